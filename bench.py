@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py — message-passing edges/s (fwd+bwd) of the GMLM GNN-encoder hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c5|c2|c3]
+
+One "step" = one forward + one backward propagate of the F=256 RGCN mean aggregation (the
+kernel pair SURVEY §8(d) defines the algorithmic bytes for: 1162 B/edge in bf16) over the whole
+synthetic graph.  N=1 runs BASELINE.json configs[3] (2M nodes / 40M edges, bf16) unless
+--workload says otherwise; N>1 runs configs[4] (10M / 200M) destination-row partitioned with
+NCCL halo exchange (gmlm_b200/partition.py).  Rank 0 prints ONE JSON line.
+
+`--impl reference` times the reference's CPU implementation of the same path — the oracle
+port of the torch_geometric index_select/scatter path (oracle/pyg_ref.py; PyG itself is not
+installable here) — on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
+NVLINK_GBS = 770.0          # measured peer copy per direction per GPU (same guide)
+# ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch, bytes
+NCU_TRAFFIC = {}            # filled from profiles/traffic.json when present
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(n_nodes, n_edges, feat, esize, live_rels):
+    """bytes one propagate must move (int32 CSR, no credit for cache hits)."""
+    fwd = n_edges * feat * esize + 4 * n_edges + 4 * (n_nodes * live_rels + 1) + n_nodes * live_rels * feat * esize
+    bwd = n_edges * feat * esize + 4 * n_edges + n_edges + 4 * (n_nodes + 1) + n_nodes * feat * esize
+    return fwd, bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_factory(sample_nodes: int, sample_edges: int, feat: int):
+    """The oracle port of the reference path on host cores: per-relation index_select +
+    index_add_ mean (fwd) and its autograd backward, fp32 (what torch_geometric runs on CPU)."""
+    from gmlm_b200 import synth
+    from oracle import edge_type_bucket_ref, rgcn_propagate_mean_ref
+
+    ei = synth.rmat_edges(sample_nodes, sample_edges, device="cpu", seed=42)
+    et = edge_type_bucket_ref(ei, sample_nodes)
+    x = synth.make_features(sample_nodes, feat, device="cpu", seed=42)
+    rels = sorted(set(et.unique().tolist()))
+    per_rel = [(ei[0, et == r].contiguous(), ei[1, et == r].contiguous()) for r in rels]
+    gh = [torch.randn(sample_nodes, feat) for _ in rels]
+
+    def step():
+        xg = x.detach().requires_grad_(True)
+        outs = [rgcn_propagate_mean_ref(xg, s, d, sample_nodes) for s, d in per_rel]
+        torch.autograd.backward(outs, gh)
+        return xg.grad
+
+    return step
+
+
+def time_cpu_reference(steps: int, warmup: int, sample_nodes: int, sample_edges: int, feat: int):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step = cpu_reference_step_factory(sample_nodes, sample_edges, feat)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return sample_edges / dt, dt * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from gmlm_b200 import synth
+    w = synth.WORKLOADS[args.workload]
+    sn, se = args.cpu_sample_nodes, args.cpu_sample_edges
+    eps, ms, cores = time_cpu_reference(args.steps, args.warmup, sn, se, w.feat)
+    sample = (f"R-MAT sample {sn} nodes / {se} edges / F={w.feat} fp32 of workload {w.key}, fwd+bwd of the "
+              f"per-relation index_select+index_add_ mean (oracle port of torch_geometric RGCNConv.propagate)")
+    line = {
+        "impl": "reference", "metric": "message-passing edges/sec fwd+bwd", "value": eps, "unit": "edges/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.title, "feat": w.feat, "sample": sample},
+        "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": eps, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- our arm, one GPU
+def run_single(args):
+    import gmlm_b200 as G
+    from gmlm_b200 import _lib, synth
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference"
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    w = synth.WORKLOADS[args.workload]
+    n = int(w.num_nodes * args.scale)
+    e = int(w.num_edges * args.scale)
+    feat = w.feat
+    dtype = torch.bfloat16 if w.dtype == "bf16" else torch.float32
+    esize = 2 if dtype == torch.bfloat16 else 4
+
+    t0 = time.perf_counter()
+    ei = synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
+    x = synth.make_features(n, feat, device=dev, dtype=dtype)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    et = G.edge_type_from_degree(ei, n)
+    torch.cuda.synchronize()
+    t_type = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g = G.get_rel_graph(ei, et, n, 5)
+    torch.cuda.synchronize()
+    t_csr = time.perf_counter() - t0
+    S = g.num_slots
+    gh = synth.make_features(n * S, feat, device=dev, seed=7, dtype=dtype)     # upstream grad of H
+
+    launches_per_step = 2 + (2 if g.fwd.n_hub else 0) + (2 if g.bwd.n_hub else 0)
+
+    def step():
+        h = G.spmm(x, g.fwd, _lib.AGG_MEAN)             # A5  forward propagate (all relations)
+        gx = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)       # A14 backward propagate
+        return h, gx
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(0)
+    sampler.start()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_start.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        h = G.spmm(x, g.fwd, _lib.AGG_MEAN)
+        ev[k][1].record()
+        gx = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)
+        ev[k][2].record()
+    t_end.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = t_start.elapsed_time(t_end)
+    ms_per_step = total_ms / args.steps
+    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in ev)
+    bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in ev)
+    value = e / (ms_per_step * 1e-3)
+
+    fwd_b, bwd_b = algorithmic_bytes(n, e, feat, esize, S)
+    peak, peak_src = peaks()
+    traffic = None
+    tj = ROOT / "profiles" / "traffic.json"
+    if tj.exists():
+        try:
+            traffic = json.loads(tj.read_text()).get(f"{w.key}_fwd")
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm", "kernel": "spmm_kernel<bf16,8,1,32> forward aggregate (A5)",
+            "achieved": fwd_b / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
+            "algorithmic_bytes": fwd_b, "ms": fwd_ms}
+    roof_bwd = {"bound": "hbm", "kernel": "spmm_kernel<bf16,8,1,32,weighted> backward aggregate (A14)",
+                "achieved": bwd_b / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": bwd_b / (bwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bwd_b, "ms": bwd_ms}
+    roof_step = {"achieved": (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9, "peak": peak,
+                 "frac": (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"}
+
+    # ---- e2e: public autograd API, x from pinned host memory every step, scalar result read back
+    x_host = x.cpu().pin_memory()
+    x_dev = torch.empty_like(x)
+    e2e_steps = max(3, min(args.steps, 10))
+    res_host = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        x_dev.copy_(x_host, non_blocking=True)
+        xg = x_dev.detach().requires_grad_(True)
+        out = G.rgcn_aggregate(xg, g)
+        out.backward(gh.view_as(out))
+        res_host.copy_(xg.grad[:: max(1, n // 4096)].float().sum().reshape(1), non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    b.record()
+    torch.cuda.synchronize()
+    e2e_ms = a.elapsed_time(b) / e2e_steps
+    e2e = {"value": e / (e2e_ms * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": x_host.numel() * esize,
+           "d2h_bytes_per_step": 4, "ms_per_step": e2e_ms,
+           "note": "x copied from pinned host memory each step; graph/CSR resident (static graph, as in the reference)"}
+
+    # ---- full message-passing layer (A5+A6+A7 fwd+bwd) for context
+    layer = None
+    if not args.no_layer:
+        try:
+            conv = G.RGCNConv(feat, w.hidden, 5, 30, out_dtype=dtype).to(dev)
+            norm = G.GraphNorm(w.hidden).to(dev)
+            xg = x.detach().requires_grad_(True)
+
+            def layer_step():
+                y = norm(conv(xg, g), fuse_gelu=True)
+                y.backward(torch.ones_like(y))
+                xg.grad = None
+
+            for _ in range(3):
+                layer_step()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(5):
+                layer_step()
+            b.record()
+            torch.cuda.synchronize()
+            lms = a.elapsed_time(b) / 5
+            layer = {"ms_fwd_bwd": lms, "edges_per_s": e / (lms * 1e-3),
+                     "what": f"RGCNConv({feat}->{w.hidden}) + GraphNorm + GELU fwd+bwd incl. weight grads"}
+        except Exception as ex:  # context only; never hides the headline
+            layer = {"error": repr(ex)[:200]}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        eps, cms, cores = time_cpu_reference(2, 1, args.cpu_sample_nodes, args.cpu_sample_edges, feat)
+        cpu = {"value": eps, "unit": "edges/s", "cores": cores, "kind": "port",
+               "sample": f"R-MAT {args.cpu_sample_nodes} nodes / {args.cpu_sample_edges} edges, F={feat} fp32, "
+                         f"fwd+bwd, oracle port of torch_geometric propagate (index_select+index_add_), "
+                         f"{cms:.0f} ms/step, best-effort 2 steps after 1 warm-up"}
+
+    line = {
+        "metric": "message-passing edges/sec fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+        "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat, "live_relations": S,
+                   "generator": f"R-MAT{synth.RMAT_ABCD} seed 42, ids mod N" if w.generator == "rmat" else "uniform seed 42",
+                   "l2": "inputs exceed L2 (x %.2f GB, H %.2f GB per step; no flush needed)" % (
+                       n * feat * esize / 1e9, n * S * feat * esize / 1e9),
+                   "step": "fwd aggregate (A5) + bwd aggregate (A14), F=%d" % feat,
+                   "hub_thresh": g.fwd.hub_thresh, "hub_rows_fwd": g.fwd.n_hub, "hub_rows_bwd": g.bwd.n_hub},
+        "roofline": roof, "roofline_bwd": roof_bwd, "roofline_step": roof_step,
+        "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+        "clocks": clocks, "layer": layer,
+        "setup_s": {"generate": t_gen, "edge_typing": t_type, "csr_build": t_csr},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-layer", action="store_true")
+    ap.add_argument("--cpu-sample-nodes", type=int, default=100_000)
+    ap.add_argument("--cpu-sample-edges", type=int, default=2_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.workload is None:
+        args.workload = "c4" if max(args.gpus, world) == 1 else "c5"
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if max(args.gpus, world) > 1:
+        from gmlm_b200.partition import run_partitioned_bench
+        run_partitioned_bench(args)
+        return
+    run_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,472 @@
+// graph_build.cu — one-off graph preprocessing on the GPU:
+// degree histogram, degree-bucket edge typing, the (dst,rel)-keyed CSR, its transpose for the
+// backward gather, and the hub plan that keeps power-law rows balanced and deterministic.
+//
+// All integer work: results are bit-exact against oracle/csr_ref.py and oracle/pyg_ref.py.
+// The radix sort / scan / select primitives are CUB (header library shipped with the CUDA
+// toolkit); everything graph-specific is written here.  This is HBM-bound byte shuffling:
+// coalesced 64-bit index reads, int32 outputs, grid sized in multiples of the SM count.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace gmlm {
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+
+static int g_spmm_variant = 1;
+static int g_spmm_unroll = 0;
+int tuning_spmm_variant() { return g_spmm_variant; }
+int tuning_spmm_unroll() { return g_spmm_unroll; }
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t n, int per_thread = 1) {
+  int64_t blocks = (n + int64_t(kThreads) * per_thread - 1) / (int64_t(kThreads) * per_thread);
+  int64_t cap = int64_t(num_sms()) * 32;  // grid-stride beyond this
+  if (blocks < 1) blocks = 1;
+  return int(blocks < cap ? blocks : cap);
+}
+
+// device-side sticky error flag (index out of range)
+__device__ int d_index_error;
+
+__global__ void clear_flag_kernel() { d_index_error = 0; }
+
+int read_flag(cudaStream_t st, int* out) {
+  int h = 0;
+  GMLM_CUDA_TRY(cudaMemcpyFromSymbolAsync(&h, d_index_error, sizeof(int), 0, cudaMemcpyDeviceToHost, st));
+  GMLM_CUDA_TRY(cudaStreamSynchronize(st));
+  *out = h;
+  return GMLM_OK;
+}
+
+// ------------------------------------------------------------------------ A1
+__global__ void degree_kernel(const int64_t* __restrict__ index, int64_t E, int64_t N, int32_t* __restrict__ deg) {
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    int64_t i = index[e];
+    if (i >= 0 && i < N) atomicAdd(deg + i, 1);   // integer atomics: order-independent result
+    else d_index_error = 1;
+  }
+}
+
+__global__ void i32_to_f32_kernel(const int32_t* __restrict__ in, float* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    out[i] = float(in[i]);
+}
+
+// ------------------------------------------------------------------------ A2
+struct Bounds { int32_t b[8]; int n; };
+
+__global__ void edge_type_kernel(const int64_t* __restrict__ src, int64_t E, const int32_t* __restrict__ deg,
+                                 int64_t N, Bounds bounds, int64_t* __restrict__ out) {
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    int64_t s = src[e];
+    int t = 0;
+    if (s >= 0 && s < N) {
+      int32_t d = deg[s];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += (k < bounds.n && d > bounds.b[k]) ? 1 : 0;
+    } else {
+      d_index_error = 1;
+    }
+    out[e] = t;
+  }
+}
+
+__global__ void rel_hist_kernel(const int64_t* __restrict__ et, int64_t E, int R, unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int sh[64];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    int64_t t = et[e];
+    if (t >= 0 && t < R) atomicAdd(&sh[t], 1u);
+    else d_index_error = 1;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < R; i += blockDim.x)
+    if (sh[i]) atomicAdd(counts + i, (unsigned long long)sh[i]);
+}
+
+// ------------------------------------------------------------------------ A3
+struct SlotMap { int32_t slot[64]; };
+
+__global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                 const int64_t* __restrict__ et, int64_t E, int64_t N, int64_t Nsrc, int R,
+                                 SlotMap sm, int S,
+                                 uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                                 int32_t* __restrict__ seg_of_edge, int32_t* __restrict__ counts) {
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    int64_t s = src[e], d = dst[e];
+    int64_t t = et ? et[e] : 0;
+    bool ok = s >= 0 && s < Nsrc && d >= 0 && d < N && t >= 0 && t < R;
+    int slot = ok ? sm.slot[t] : 0;
+    ok = ok && slot >= 0;
+    uint32_t key = 0;
+    if (ok) {
+      key = uint32_t(d * S + slot);
+      atomicAdd(counts + key, 1);
+    } else {
+      d_index_error = 1;
+    }
+    keys[e] = key;
+    vals[e] = int32_t(e);
+    if (seg_of_edge) seg_of_edge[e] = int32_t(key);
+  }
+}
+
+__global__ void gather_col_kernel(const int64_t* __restrict__ src, const int32_t* __restrict__ perm, int64_t E,
+                                  int32_t* __restrict__ col) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < E; i += int64_t(gridDim.x) * blockDim.x)
+    col[i] = int32_t(src[perm[i]]);
+}
+
+// ----------------------------------------------------------------------- A14
+__global__ void make_keys_t_kernel(const int64_t* __restrict__ row_of_edge, int64_t E, int64_t num_rows,
+                                   uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+                                   int32_t* __restrict__ counts) {
+  for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    int64_t r = row_of_edge[e];
+    uint32_t key = 0;
+    if (r >= 0 && r < num_rows) {
+      key = uint32_t(r);
+      atomicAdd(counts + key, 1);
+    } else {
+      d_index_error = 1;
+    }
+    keys[e] = key;
+    vals[e] = int32_t(e);
+  }
+}
+
+__global__ void gather_payload_t_kernel(const int32_t* __restrict__ payload, const float* __restrict__ edge_w,
+                                        const int32_t* __restrict__ fwd_rowptr, const int32_t* __restrict__ perm_t,
+                                        int64_t E, int32_t* __restrict__ payload_t, float* __restrict__ w_t) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < E; i += int64_t(gridDim.x) * blockDim.x) {
+    int32_t e = perm_t[i];
+    int32_t p = payload[e];
+    payload_t[i] = p;
+    if (fwd_rowptr) {
+      int32_t c = fwd_rowptr[p + 1] - fwd_rowptr[p];
+      w_t[i] = 1.0f / float(c);   // IEEE division: equals numpy float32(1)/float32(c)
+    } else if (edge_w) {
+      w_t[i] = edge_w[e];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ hub plan
+struct IsHub {
+  const int32_t* rowptr;
+  int32_t thresh;
+  __device__ __forceinline__ bool operator()(const int32_t& r) const { return rowptr[r + 1] - rowptr[r] > thresh; }
+};
+
+__global__ void hub_count_kernel(const int32_t* __restrict__ rowptr, int64_t num_rows, int32_t thresh,
+                                 unsigned long long* __restrict__ counts) {
+  unsigned long long hubs = 0, chunks = 0;
+  for (int64_t r = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; r < num_rows; r += int64_t(gridDim.x) * blockDim.x) {
+    int32_t len = rowptr[r + 1] - rowptr[r];
+    if (len > thresh) { hubs += 1; chunks += (len + thresh - 1) / thresh; }
+  }
+  // warp reduce then one atomic per warp (integers: deterministic result)
+  for (int o = 16; o > 0; o >>= 1) {
+    hubs += __shfl_xor_sync(0xffffffffu, hubs, o);
+    chunks += __shfl_xor_sync(0xffffffffu, chunks, o);
+  }
+  if ((threadIdx.x & 31) == 0 && hubs) { atomicAdd(counts, hubs); atomicAdd(counts + 1, chunks); }
+}
+
+__global__ void hub_nchunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ hub_row,
+                                   int64_t n_hub, int32_t thresh, int32_t* __restrict__ nch /* [n_hub+1] */) {
+  int64_t h = blockIdx.x * int64_t(blockDim.x) + threadIdx.x;
+  if (h < n_hub) {
+    int32_t r = hub_row[h];
+    nch[h] = (rowptr[r + 1] - rowptr[r] + thresh - 1) / thresh;
+  } else if (h == n_hub) {
+    nch[h] = 0;
+  }
+}
+
+__global__ void hub_fill_chunks_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ hub_row,
+                                       const int32_t* __restrict__ hub_chunk_ptr, int64_t n_hub, int32_t thresh,
+                                       int32_t* __restrict__ chunk_beg, int32_t* __restrict__ chunk_end) {
+  // one warp per hub row; lanes stride over its chunks
+  int64_t h = (blockIdx.x * int64_t(blockDim.x) + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (h >= n_hub) return;
+  int32_t r = hub_row[h];
+  int32_t b = rowptr[r], e = rowptr[r + 1];
+  int32_t c0 = hub_chunk_ptr[h], c1 = hub_chunk_ptr[h + 1];
+  for (int32_t c = c0 + lane; c < c1; c += 32) {
+    int32_t cb = b + (c - c0) * thresh;
+    int32_t ce = cb + thresh < e ? cb + thresh : e;
+    chunk_beg[c] = cb;
+    chunk_end[c] = ce;
+  }
+}
+
+int bits_for(uint64_t n_keys) {  // number of key bits needed to represent values < n_keys
+  int b = 1;
+  while ((uint64_t(1) << b) < n_keys && b < 32) ++b;
+  return b;
+}
+
+size_t sort_temp_bytes(int64_t E) {
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const int32_t*)nullptr, (int32_t*)nullptr, int(E), 0, 32, (cudaStream_t)0);
+  return bytes;
+}
+
+size_t scan_temp_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr, int(n), (cudaStream_t)0);
+  return bytes;
+}
+
+size_t select_temp_bytes(int64_t n) {
+  size_t bytes = 0;
+  cub::CountingInputIterator<int32_t> it(0);
+  IsHub pred{nullptr, 0};
+  cub::DeviceSelect::If(nullptr, bytes, it, (int32_t*)nullptr, (int32_t*)nullptr, int(n), pred, (cudaStream_t)0);
+  return bytes;
+}
+
+}  // namespace
+}  // namespace gmlm
+
+using namespace gmlm;
+
+extern "C" {
+
+int gmlm_abi_version(void) { return 1; }
+
+const char* gmlm_last_error(void) { return err_buf(); }
+
+int gmlm_set_tuning(const char* key, int value) {
+  int old = -1;
+  if (!strcmp(key, "spmm_variant")) { old = g_spmm_variant; g_spmm_variant = value; }
+  else if (!strcmp(key, "spmm_unroll")) { old = g_spmm_unroll; g_spmm_unroll = value; }
+  return old;
+}
+
+int gmlm_degree_i32(const int64_t* index, int64_t E, int64_t N, int32_t* deg, int check, void* stream) {
+  GMLM_REQUIRE(E >= 0 && N >= 0, "degree: negative size");
+  GMLM_REQUIRE(E == 0 || index != nullptr, "degree: null index");
+  cudaStream_t st = as_stream(stream);
+  if (N == 0) return GMLM_OK;
+  if (check) { clear_flag_kernel<<<1, 1, 0, st>>>(); GMLM_LAUNCH_CHECK(); }
+  GMLM_CUDA_TRY(cudaMemsetAsync(deg, 0, size_t(N) * sizeof(int32_t), st));
+  if (E > 0) {
+    degree_kernel<<<grid_for(E, 4), kThreads, 0, st>>>(index, E, N, deg);
+    GMLM_LAUNCH_CHECK();
+  }
+  if (check) {
+    int flag = 0;
+    int rc = read_flag(st, &flag);
+    if (rc) return rc;
+    if (flag) return fail(GMLM_ERR_INDEX, "degree: index out of range [0,%lld)", (long long)N);
+  }
+  return GMLM_OK;
+}
+
+int gmlm_degree_f32(const int64_t* index, int64_t E, int64_t N, float* deg, int32_t* ws, int check, void* stream) {
+  GMLM_REQUIRE(N == 0 || (deg && ws), "degree_f32: null output");
+  int rc = gmlm_degree_i32(index, E, N, ws, check, stream);
+  if (rc) return rc;
+  if (N > 0) {
+    i32_to_f32_kernel<<<grid_for(N, 4), kThreads, 0, as_stream(stream)>>>(ws, deg, N);
+    GMLM_LAUNCH_CHECK();
+  }
+  return GMLM_OK;
+}
+
+int gmlm_edge_type_bucket(const int64_t* src, int64_t E, const int32_t* deg, int64_t N, const int32_t* bounds_host,
+                          int num_bounds, int64_t* edge_type, void* stream) {
+  GMLM_REQUIRE(num_bounds >= 0 && num_bounds <= 8, "edge_type_bucket: at most 8 bounds");
+  GMLM_REQUIRE(E == 0 || (src && deg && edge_type), "edge_type_bucket: null pointer");
+  Bounds b;
+  b.n = num_bounds;
+  for (int k = 0; k < 8; ++k) b.b[k] = k < num_bounds ? bounds_host[k] : 0;
+  for (int k = 1; k < num_bounds; ++k) GMLM_REQUIRE(b.b[k] >= b.b[k - 1], "edge_type_bucket: bounds must ascend");
+  if (E == 0) return GMLM_OK;
+  edge_type_kernel<<<grid_for(E, 4), kThreads, 0, as_stream(stream)>>>(src, E, deg, N, b, edge_type);
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+int gmlm_relation_histogram(const int64_t* edge_type, int64_t E, int R, int64_t* counts, void* stream) {
+  GMLM_REQUIRE(R >= 1 && R <= 64, "relation_histogram: 1..64 relations supported");
+  cudaStream_t st = as_stream(stream);
+  GMLM_CUDA_TRY(cudaMemsetAsync(counts, 0, size_t(R) * sizeof(int64_t), st));
+  if (E > 0) {
+    rel_hist_kernel<<<grid_for(E, 8), kThreads, 0, st>>>(edge_type, E, R, reinterpret_cast<unsigned long long*>(counts));
+    GMLM_LAUNCH_CHECK();
+  }
+  return GMLM_OK;
+}
+
+size_t gmlm_csr_workspace_bytes(int64_t E, int64_t num_rows) {
+  if (E < 1) E = 1;
+  size_t t = sort_temp_bytes(E);
+  size_t s = scan_temp_bytes(num_rows + 1);
+  size_t sel = select_temp_bytes(num_rows);
+  size_t cub_bytes = t > s ? t : s;
+  if (sel > cub_bytes) cub_bytes = sel;
+  // keys_in, keys_out (u32), vals_in (i32) + hub scratch (2 x u64) + alignment slack
+  return cub_bytes + 3 * (size_t(E) * 4 + 256) + 4096;
+}
+
+int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, int64_t E, int64_t N,
+                   int64_t Nsrc, int R, const int32_t* slot_of_rel_host, int S, int32_t* rowptr, int32_t* col, int32_t* perm,
+                   int32_t* seg_of_edge, void* ws, size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(E >= 0 && N >= 0 && Nsrc >= 0 && R >= 1 && R <= 64 && S >= 1 && S <= R, "csr_build: bad sizes");
+  GMLM_REQUIRE(Nsrc < (int64_t(1) << 31) - 1, "csr_build: num_src must fit int32");
+  GMLM_REQUIRE(E < (int64_t(1) << 31) - 1, "csr_build: more than 2^31-2 edges needs a 64-bit CSR");
+  const int64_t rows = N * S;
+  GMLM_REQUIRE(rows < (int64_t(1) << 31) - 1, "csr_build: num_nodes*num_slots must fit int32");
+  GMLM_REQUIRE(rowptr != nullptr, "csr_build: null rowptr");
+  GMLM_REQUIRE(ws_bytes >= gmlm_csr_workspace_bytes(E, rows), "csr_build: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  SlotMap sm;
+  for (int r = 0; r < 64; ++r) sm.slot[r] = -1;
+  if (edge_type == nullptr) {
+    sm.slot[0] = 0;
+  } else {
+    for (int r = 0; r < R; ++r) {
+      int32_t s = slot_of_rel_host ? slot_of_rel_host[r] : r;
+      GMLM_REQUIRE(s >= -1 && s < S, "csr_build: slot_of_rel out of range");
+      sm.slot[r] = s;
+    }
+  }
+  GMLM_CUDA_TRY(cudaMemsetAsync(rowptr, 0, size_t(rows + 1) * sizeof(int32_t), st));
+  if (E == 0) return GMLM_OK;
+  GMLM_REQUIRE(src && dst && col && perm, "csr_build: null pointer");
+
+  Carver cv(ws);
+  uint32_t* keys_in = cv.take<uint32_t>(E);
+  uint32_t* keys_out = cv.take<uint32_t>(E);
+  int32_t* vals_in = cv.take<int32_t>(E);
+  void* cub_ws = cv.take<char>(0);
+  size_t cub_bytes = ws_bytes - cv.used();
+
+  clear_flag_kernel<<<1, 1, 0, st>>>();
+  GMLM_LAUNCH_CHECK();
+  make_keys_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, dst, edge_type, E, N, Nsrc, edge_type ? R : 1, sm, S, keys_in,
+                                                        vals_in, seg_of_edge, rowptr);
+  GMLM_LAUNCH_CHECK();
+  // counts -> exclusive prefix (in place); entry [rows] is 0 on input so rowptr[rows] = E
+  size_t need = scan_temp_bytes(rows + 1);
+  GMLM_REQUIRE(need <= cub_bytes, "csr_build: scan workspace");
+  GMLM_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, need, rowptr, rowptr, int(rows + 1), st));
+  need = sort_temp_bytes(E);
+  GMLM_REQUIRE(need <= cub_bytes, "csr_build: sort workspace");
+  // LSD radix sort is stable: equal (dst,slot) keys keep the original edge order
+  GMLM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, need, keys_in, keys_out, vals_in, perm, int(E), 0,
+                                                bits_for(uint64_t(rows)), st));
+  gather_col_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, perm, E, col);
+  GMLM_LAUNCH_CHECK();
+  int flag = 0;
+  int rc = read_flag(st, &flag);
+  if (rc) return rc;
+  if (flag) return fail(GMLM_ERR_INDEX, "csr_build: dst outside [0,%lld), src outside [0,%lld) or relation outside [0,%d)",
+                        (long long)N, (long long)Nsrc, R);
+  return GMLM_OK;
+}
+
+int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const float* edge_w,
+                       const int32_t* fwd_rowptr, int64_t E, int64_t num_rows, int32_t* rowptr_t,
+                       int32_t* payload_t, float* w_t, int32_t* perm_t, void* ws, size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(E >= 0 && num_rows >= 0, "csr_transpose: bad sizes");
+  GMLM_REQUIRE(E < (int64_t(1) << 31) - 1 && num_rows < (int64_t(1) << 31) - 1, "csr_transpose: int32 limits");
+  GMLM_REQUIRE(ws_bytes >= gmlm_csr_workspace_bytes(E, num_rows), "csr_transpose: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  GMLM_CUDA_TRY(cudaMemsetAsync(rowptr_t, 0, size_t(num_rows + 1) * sizeof(int32_t), st));
+  if (E == 0) return GMLM_OK;
+  GMLM_REQUIRE(row_of_edge && payload && payload_t && perm_t, "csr_transpose: null pointer");
+  GMLM_REQUIRE(!(fwd_rowptr || edge_w) || w_t, "csr_transpose: w_t required");
+
+  Carver cv(ws);
+  uint32_t* keys_in = cv.take<uint32_t>(E);
+  uint32_t* keys_out = cv.take<uint32_t>(E);
+  int32_t* vals_in = cv.take<int32_t>(E);
+  void* cub_ws = cv.take<char>(0);
+  size_t cub_bytes = ws_bytes - cv.used();
+
+  clear_flag_kernel<<<1, 1, 0, st>>>();
+  GMLM_LAUNCH_CHECK();
+  make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, E, num_rows, keys_in, vals_in, rowptr_t);
+  GMLM_LAUNCH_CHECK();
+  size_t need = scan_temp_bytes(num_rows + 1);
+  GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: scan workspace");
+  GMLM_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, need, rowptr_t, rowptr_t, int(num_rows + 1), st));
+  need = sort_temp_bytes(E);
+  GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: sort workspace");
+  GMLM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, need, keys_in, keys_out, vals_in, perm_t, int(E), 0,
+                                                bits_for(uint64_t(num_rows)), st));
+  gather_payload_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(payload, edge_w, fwd_rowptr, perm_t, E, payload_t, w_t);
+  GMLM_LAUNCH_CHECK();
+  int flag = 0;
+  int rc = read_flag(st, &flag);
+  if (rc) return rc;
+  if (flag) return fail(GMLM_ERR_INDEX, "csr_transpose: row id outside [0,%lld)", (long long)num_rows);
+  return GMLM_OK;
+}
+
+int gmlm_hub_count(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64_t* counts_host, void* ws,
+                   size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(thresh >= 1, "hub_count: thresh must be >= 1");
+  GMLM_REQUIRE(ws_bytes >= 16, "hub_count: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  counts_host[0] = counts_host[1] = 0;
+  if (num_rows == 0) return GMLM_OK;
+  unsigned long long* d = static_cast<unsigned long long*>(ws);
+  GMLM_CUDA_TRY(cudaMemsetAsync(d, 0, 16, st));
+  hub_count_kernel<<<grid_for(num_rows, 4), kThreads, 0, st>>>(rowptr, num_rows, thresh, d);
+  GMLM_LAUNCH_CHECK();
+  unsigned long long h[2];
+  GMLM_CUDA_TRY(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, st));
+  GMLM_CUDA_TRY(cudaStreamSynchronize(st));
+  counts_host[0] = int64_t(h[0]);
+  counts_host[1] = int64_t(h[1]);
+  return GMLM_OK;
+}
+
+int gmlm_hub_fill(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64_t n_hub, int64_t n_chunks,
+                  int32_t* hub_row, int32_t* hub_chunk_ptr, int32_t* chunk_beg, int32_t* chunk_end, void* ws,
+                  size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(thresh >= 1 && n_hub >= 0 && n_chunks >= 0, "hub_fill: bad sizes");
+  if (n_hub == 0) return GMLM_OK;
+  GMLM_REQUIRE(hub_row && hub_chunk_ptr && chunk_beg && chunk_end, "hub_fill: null pointer");
+  cudaStream_t st = as_stream(stream);
+  Carver cv(ws);
+  int32_t* d_num = cv.take<int32_t>(1);
+  void* cub_ws = cv.take<char>(0);
+  GMLM_REQUIRE(ws_bytes > cv.used(), "hub_fill: workspace too small");
+  size_t cub_bytes = ws_bytes - cv.used();
+  // ascending list of hub rows (DeviceSelect keeps input order)
+  cub::CountingInputIterator<int32_t> it(0);
+  IsHub pred{rowptr, thresh};
+  size_t need = select_temp_bytes(num_rows);
+  GMLM_REQUIRE(need <= cub_bytes, "hub_fill: select workspace");
+  GMLM_CUDA_TRY(cub::DeviceSelect::If(cub_ws, need, it, hub_row, d_num, int(num_rows), pred, st));
+  hub_nchunks_kernel<<<int((n_hub + 1 + kThreads - 1) / kThreads), kThreads, 0, st>>>(rowptr, hub_row, n_hub, thresh,
+                                                                                   hub_chunk_ptr);
+  GMLM_LAUNCH_CHECK();
+  need = scan_temp_bytes(n_hub + 1);
+  GMLM_REQUIRE(need <= cub_bytes, "hub_fill: scan workspace");
+  GMLM_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, need, hub_chunk_ptr, hub_chunk_ptr, int(n_hub + 1), st));
+  int64_t threads = n_hub * 32;
+  hub_fill_chunks_kernel<<<int((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(
+      rowptr, hub_row, hub_chunk_ptr, n_hub, thresh, chunk_beg, chunk_end);
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+}  // extern "C"

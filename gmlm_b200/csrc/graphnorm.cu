@@ -1,0 +1,509 @@
+// graphnorm.cu — whole-graph column statistics + normalisation (SURVEY §8a row A7:
+// [PyG] GraphNorm(batch=None), called main.py:273,286,299,309), its backward, the optional
+// fused exact-erf GELU of the layer closure (main.py:274), and the soft node masking of
+// main.py:92-99 (row A11) with its masked column-sum backward.
+//
+// All of it is HBM-bound streaming over an [N, C] matrix: 128-bit loads along the channel
+// dimension, every thread owns a fixed pack of channels and strides over rows, so the
+// per-channel constants live in registers.  Column reductions are two-stage and
+// order-fixed (per-CTA fp64 partials, then one in-order pass): no atomics, run-to-run
+// deterministic, and the fp64 accumulation makes the one-pass variance
+//   E[(x - a*mu)^2] = E[x^2] - mu^2 * (2a - a^2)
+// as accurate as the reference's two-pass form.
+#include "common.cuh"
+
+namespace gmlm {
+namespace {
+
+constexpr int kCta = 256;
+
+struct Tile {
+  int tpr;        // threads along the channel dimension (power of two <= 256)
+  int rpc;        // rows covered by one CTA pass
+  int64_t packs;  // packs per row
+  dim3 grid;
+};
+
+inline Tile make_tile(int64_t num_rows, int64_t channels, int vec, int max_row_blocks) {
+  Tile t;
+  t.packs = (channels + vec - 1) / vec;
+  int tpr = 1;
+  while (tpr < t.packs && tpr < kCta) tpr <<= 1;
+  t.tpr = tpr;
+  t.rpc = kCta / tpr;
+  int64_t col_tiles = (t.packs + tpr - 1) / tpr;
+  int64_t row_blocks = (num_rows + t.rpc - 1) / t.rpc;
+  int64_t want = std::max<int64_t>(1, int64_t(max_row_blocks) / col_tiles);
+  if (row_blocks > want) row_blocks = want;
+  if (row_blocks < 1) row_blocks = 1;
+  t.grid = dim3((unsigned)col_tiles, (unsigned)row_blocks);
+  return t;
+}
+
+__device__ __forceinline__ float gelu_f(float n) { return 0.5f * n * (1.0f + erff(n * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float n) {
+  const float cdf = 0.5f * (1.0f + erff(n * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * expf(-0.5f * n * n);
+  return cdf + n * pdf;
+}
+
+// ---------------------------------------------------------------- column sums
+// partial[(by * 2 + k) * C + c], k = 0: sum, k = 1: sum of squares.  Optional row mask.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kCta) colstats_kernel(const T* __restrict__ x, int64_t num_rows, int64_t C,
+                                                        int64_t ldx, const uint8_t* __restrict__ mask, int tpr,
+                                                        double* __restrict__ partial) {
+  __shared__ double sh[2][kCta];
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
+  const int64_t cp = int64_t(blockIdx.x) * tpr + tx;
+  const int64_t c0 = cp * VEC;
+  const bool cvalid = c0 < C;
+  double s[VEC], q[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) s[k] = q[k] = 0.0;
+  if (cvalid) {
+    for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
+      if (mask && !mask[r]) continue;
+      Pack<T, VEC> p;
+      p.load(x + r * ldx + c0);
+      float f[VEC];
+      p.unpack(f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { s[k] += double(f[k]); q[k] += double(f[k]) * double(f[k]); }
+    }
+  }
+  // reduce over ty in fixed order
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    sh[0][threadIdx.x] = s[k];
+    sh[1][threadIdx.x] = q[k];
+    __syncthreads();
+    if (ty == 0 && cvalid) {
+      double a = 0.0, b = 0.0;
+      for (int y = 0; y < rpc; ++y) { a += sh[0][y * tpr + tx]; b += sh[1][y * tpr + tx]; }
+      partial[(int64_t(blockIdx.y) * 2 + 0) * C + c0 + k] = a;
+      partial[(int64_t(blockIdx.y) * 2 + 1) * C + c0 + k] = b;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void colstats_final_kernel(const double* __restrict__ partial, int row_blocks, int64_t C,
+                                      double* __restrict__ out0, double* __restrict__ out1) {
+  const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a = 0.0, b = 0.0;
+  for (int y = 0; y < row_blocks; ++y) {
+    a += partial[(int64_t(y) * 2 + 0) * C + c];
+    b += partial[(int64_t(y) * 2 + 1) * C + c];
+  }
+  if (out0) out0[c] = a;
+  if (out1) out1[c] = b;
+}
+
+// ---------------------------------------------------------------- forward
+__global__ void graphnorm_prepare_kernel(const double* __restrict__ colsum, const double* __restrict__ colsq,
+                                         const float* __restrict__ mean_scale, int64_t num_rows, int64_t C, float eps,
+                                         float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double n = double(num_rows);
+  const double mu = colsum[c] / n;
+  const double a = double(mean_scale[c]);
+  double var = colsq[c] / n - mu * mu * (2.0 * a - a * a);
+  if (var < 0.0) var = 0.0;
+  mean_out[c] = float(mu);
+  rstd_out[c] = float(1.0 / sqrt(var + double(eps)));
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kCta) graphnorm_fwd_kernel(const T* __restrict__ x, int64_t num_rows, int64_t C,
+                                                             int64_t ldx, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd,
+                                                             const float* __restrict__ weight,
+                                                             const float* __restrict__ bias,
+                                                             const float* __restrict__ mean_scale, int fuse_gelu,
+                                                             int tpr, T* __restrict__ y, int64_t ldy) {
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
+  const int64_t c0 = (int64_t(blockIdx.x) * tpr + tx) * VEC;
+  if (c0 >= C) return;
+  float shift[VEC], k1[VEC], b[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    shift[k] = mean[c0 + k] * mean_scale[c0 + k];
+    k1[k] = weight[c0 + k] * rstd[c0 + k];
+    b[k] = bias[c0 + k];
+  }
+  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
+    Pack<T, VEC> p;
+    p.load(x + r * ldx + c0);
+    float f[VEC];
+    p.unpack(f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float n = (f[k] - shift[k]) * k1[k] + b[k];
+      f[k] = fuse_gelu ? gelu_f(n) : n;
+    }
+    p.pack(f);
+    p.store(y + r * ldy + c0);
+  }
+}
+
+// ---------------------------------------------------------------- backward
+// dn = gy * gelu'(n) (or gy); partial sums of dn and dn*ohat
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kCta) graphnorm_bwd_stats_kernel(
+    const T* __restrict__ x, const T* __restrict__ gy, int64_t num_rows, int64_t C, int64_t ldx, int64_t ldg,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
+    const float* __restrict__ bias, const float* __restrict__ mean_scale, int fuse_gelu, int tpr,
+    double* __restrict__ partial) {
+  __shared__ double sh[2][kCta];
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
+  const int64_t c0 = (int64_t(blockIdx.x) * tpr + tx) * VEC;
+  const bool cvalid = c0 < C;
+  double s[VEC], q[VEC];
+  float shift[VEC], rs[VEC], wv[VEC], b[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    s[k] = q[k] = 0.0;
+    shift[k] = rs[k] = wv[k] = b[k] = 0.f;
+  }
+  if (cvalid) {
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      shift[k] = mean[c0 + k] * mean_scale[c0 + k];
+      rs[k] = rstd[c0 + k];
+      wv[k] = weight[c0 + k];
+      b[k] = bias[c0 + k];
+    }
+    for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
+      Pack<T, VEC> px, pg;
+      px.load(x + r * ldx + c0);
+      pg.load(gy + r * ldg + c0);
+      float fx[VEC], fg[VEC];
+      px.unpack(fx);
+      pg.unpack(fg);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float oh = (fx[k] - shift[k]) * rs[k];
+        float dn = fg[k];
+        if (fuse_gelu) dn *= gelu_grad_f(oh * wv[k] + b[k]);
+        s[k] += double(dn);
+        q[k] += double(dn) * double(oh);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    sh[0][threadIdx.x] = s[k];
+    sh[1][threadIdx.x] = q[k];
+    __syncthreads();
+    if (ty == 0 && cvalid) {
+      double a = 0.0, bb = 0.0;
+      for (int y = 0; y < rpc; ++y) { a += sh[0][y * tpr + tx]; bb += sh[1][y * tpr + tx]; }
+      partial[(int64_t(blockIdx.y) * 2 + 0) * C + c0 + k] = a;
+      partial[(int64_t(blockIdx.y) * 2 + 1) * C + c0 + k] = bb;
+    }
+    __syncthreads();
+  }
+}
+
+// per-channel constants of the input gradient + parameter gradients
+//   dx = k1 * (dn - ohat * k2) - k3,  k1 = w*rstd, k2 = S2/N, k3 = (a/N) * sum(do)
+__global__ void graphnorm_bwd_params_kernel(const double* __restrict__ sum_g, const double* __restrict__ sum_go,
+                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                            const float* __restrict__ weight, const float* __restrict__ mean_scale,
+                                            int64_t num_rows, int64_t C, float* __restrict__ g_weight,
+                                            float* __restrict__ g_bias, float* __restrict__ g_mean_scale) {
+  const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double s1 = sum_g[c], s2 = sum_go[c];
+  const double mu = mean[c], rs = rstd[c], w = weight[c], a = mean_scale[c];
+  const double sum_do = w * rs * (s1 - s2 * rs * mu * (1.0 - a));
+  if (g_weight) g_weight[c] = float(s2);
+  if (g_bias) g_bias[c] = float(s1);
+  if (g_mean_scale) g_mean_scale[c] = float(-mu * sum_do);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kCta) graphnorm_bwd_apply_kernel(
+    const T* __restrict__ x, const T* __restrict__ gy, int64_t num_rows, int64_t C, int64_t ldx, int64_t ldg,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
+    const float* __restrict__ bias, const float* __restrict__ mean_scale, int fuse_gelu,
+    const double* __restrict__ sum_g, const double* __restrict__ sum_go, int tpr, T* __restrict__ gx, int64_t ldgx) {
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
+  const int64_t c0 = (int64_t(blockIdx.x) * tpr + tx) * VEC;
+  if (c0 >= C) return;
+  float shift[VEC], rs[VEC], wv[VEC], b[VEC], k1[VEC], k2[VEC], k3[VEC];
+  const double n = double(num_rows);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    const double mu = mean[c0 + k], r = rstd[c0 + k], w = weight[c0 + k], a = mean_scale[c0 + k];
+    const double s1 = sum_g[c0 + k], s2 = sum_go[c0 + k];
+    const double sum_do = w * r * (s1 - s2 * r * mu * (1.0 - a));
+    shift[k] = float(mu) * float(a);
+    rs[k] = float(r);
+    wv[k] = float(w);
+    b[k] = bias[c0 + k];
+    k1[k] = float(w * r);
+    k2[k] = float(s2 / n);
+    k3[k] = float(a * sum_do / n);
+  }
+  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
+    Pack<T, VEC> px, pg;
+    px.load(x + r * ldx + c0);
+    pg.load(gy + r * ldg + c0);
+    float fx[VEC], fg[VEC];
+    px.unpack(fx);
+    pg.unpack(fg);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float oh = (fx[k] - shift[k]) * rs[k];
+      float dn = fg[k];
+      if (fuse_gelu) dn *= gelu_grad_f(oh * wv[k] + b[k]);
+      fg[k] = k1[k] * (dn - oh * k2[k]) - k3[k];
+    }
+    pg.pack(fg);
+    pg.store(gx + r * ldgx + c0);
+  }
+}
+
+// ---------------------------------------------------------------- soft masking (A11)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kCta) soft_mask_fwd_kernel(const T* __restrict__ x, int64_t num_rows, int64_t F,
+                                                             int64_t ldx, const uint8_t* __restrict__ mask,
+                                                             const float* __restrict__ token, float beta,
+                                                             float one_minus_beta, int tpr, T* __restrict__ y,
+                                                             int64_t ldy) {
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
+  const int64_t c0 = (int64_t(blockIdx.x) * tpr + tx) * VEC;
+  if (c0 >= F) return;
+  float bt[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) bt[k] = __fmul_rn(beta, token[c0 + k]);
+  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
+    Pack<T, VEC> p;
+    p.load(x + r * ldx + c0);
+    if (mask[r]) {
+      float f[VEC];
+      p.unpack(f);
+      // (1-beta)*x + beta*t with the reference's rounding sequence (no FMA contraction)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) f[k] = __fadd_rn(__fmul_rn(one_minus_beta, f[k]), bt[k]);
+      p.pack(f);
+    }
+    p.store(y + r * ldy + c0);
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kCta) soft_mask_gx_kernel(const T* __restrict__ gy, int64_t num_rows, int64_t F,
+                                                            int64_t ldg, const uint8_t* __restrict__ mask,
+                                                            float one_minus_beta, int tpr, T* __restrict__ gx,
+                                                            int64_t ldgx) {
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
+  const int64_t c0 = (int64_t(blockIdx.x) * tpr + tx) * VEC;
+  if (c0 >= F) return;
+  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
+    Pack<T, VEC> p;
+    p.load(gy + r * ldg + c0);
+    if (mask[r]) {
+      float f[VEC];
+      p.unpack(f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) f[k] = __fmul_rn(one_minus_beta, f[k]);
+      p.pack(f);
+    }
+    p.store(gx + r * ldgx + c0);
+  }
+}
+
+__global__ void scale_to_f32_kernel(const double* __restrict__ in, float scale, int64_t n, float* __restrict__ out) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = float(double(scale) * in[i]);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+constexpr int kMaxRowBlocks = 148 * 8;
+
+// dispatch helper: calls fn.template operator()<T, VEC>()
+template <typename Fn>
+int dispatch(int dtype, bool vec_ok, Fn&& fn) {
+  if (dtype == GMLM_F32) return vec_ok ? fn.template operator()<float, 4>() : fn.template operator()<float, 1>();
+  if (dtype == GMLM_BF16)
+    return vec_ok ? fn.template operator()<__nv_bfloat16, 8>() : fn.template operator()<__nv_bfloat16, 1>();
+  return fail(GMLM_ERR_INVALID, "dtype must be GMLM_F32 or GMLM_BF16");
+}
+
+inline bool vec_ok(int dtype, int64_t C, std::initializer_list<const void*> ptrs, std::initializer_list<int64_t> lds) {
+  const int v = dtype == GMLM_F32 ? 4 : 8;
+  if (C % v) return false;
+  for (const void* p : ptrs) if (!aligned16(p)) return false;
+  for (int64_t l : lds) if (l % v) return false;
+  return true;
+}
+
+size_t partial_bytes(int64_t C) { return size_t(kMaxRowBlocks) * 2 * size_t(C) * sizeof(double) + 256; }
+
+}  // namespace
+}  // namespace gmlm
+
+using namespace gmlm;
+
+extern "C" {
+
+size_t gmlm_colstats_workspace_bytes(int64_t /*num_rows*/, int64_t channels) { return partial_bytes(channels); }
+
+static int colstats_impl(const void* x, int dtype, int64_t N, int64_t C, int64_t ldx, const uint8_t* mask,
+                         double* out0, double* out1, void* ws, size_t ws_bytes, cudaStream_t st) {
+  GMLM_REQUIRE(N >= 0 && C >= 0 && ldx >= C, "colstats: bad sizes");
+  if (C == 0) return GMLM_OK;
+  GMLM_REQUIRE(ws && ws_bytes >= partial_bytes(C), "colstats: workspace too small");
+  double* partial = static_cast<double*>(ws);
+  const bool v = vec_ok(dtype, C, {x}, {ldx});
+  int row_blocks = 1;
+  int rc = dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
+    Tile t = make_tile(N, C, VEC, kMaxRowBlocks);
+    row_blocks = int(t.grid.y);
+    colstats_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), N, C, ldx, mask, t.tpr, partial);
+    GMLM_LAUNCH_CHECK();
+    return GMLM_OK;
+  });
+  if (rc) return rc;
+  colstats_final_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(partial, row_blocks, C, out0, out1);
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+int gmlm_colstats(const void* x, int dtype, int64_t N, int64_t C, int64_t ldx, double* colsum, double* colsq,
+                  void* ws, size_t ws_bytes, void* stream) {
+  return colstats_impl(x, dtype, N, C, ldx, nullptr, colsum, colsq, ws, ws_bytes, as_stream(stream));
+}
+
+int gmlm_graphnorm_fwd(const void* x, int dtype, int64_t N, int64_t C, int64_t ldx, const double* colsum,
+                       const double* colsq, const float* weight, const float* bias, const float* mean_scale,
+                       float eps, int fuse_gelu, void* y, int64_t ldy, float* mean_out, float* rstd_out,
+                       void* stream) {
+  GMLM_REQUIRE(N >= 1 && C >= 0 && ldx >= C && ldy >= C, "graphnorm_fwd: bad sizes");
+  if (C == 0) return GMLM_OK;
+  GMLM_REQUIRE(x && y && colsum && colsq && weight && bias && mean_scale && mean_out && rstd_out,
+               "graphnorm_fwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  graphnorm_prepare_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(colsum, colsq, mean_scale, N, C, eps, mean_out,
+                                                                      rstd_out);
+  GMLM_LAUNCH_CHECK();
+  const bool v = vec_ok(dtype, C, {x, y}, {ldx, ldy});
+  return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
+    Tile t = make_tile(N, C, VEC, kMaxRowBlocks * 4);
+    graphnorm_fwd_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), N, C, ldx, mean_out, rstd_out,
+                                                          weight, bias, mean_scale, fuse_gelu, t.tpr,
+                                                          static_cast<T*>(y), ldy);
+    GMLM_LAUNCH_CHECK();
+    return GMLM_OK;
+  });
+}
+
+int gmlm_graphnorm_bwd_stats(const void* x, const void* gy, int dtype, int64_t N, int64_t C, int64_t ldx,
+                             int64_t ldg, const float* mean, const float* rstd, const float* weight,
+                             const float* bias, const float* mean_scale, int fuse_gelu, double* sum_g,
+                             double* sum_go, void* ws, size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(N >= 1 && C >= 0 && ldx >= C && ldg >= C, "graphnorm_bwd_stats: bad sizes");
+  if (C == 0) return GMLM_OK;
+  GMLM_REQUIRE(ws && ws_bytes >= partial_bytes(C), "graphnorm_bwd_stats: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  double* partial = static_cast<double*>(ws);
+  const bool v = vec_ok(dtype, C, {x, gy}, {ldx, ldg});
+  int row_blocks = 1;
+  int rc = dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
+    Tile t = make_tile(N, C, VEC, kMaxRowBlocks);
+    row_blocks = int(t.grid.y);
+    graphnorm_bwd_stats_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(gy),
+                                                                N, C, ldx, ldg, mean, rstd, weight, bias, mean_scale,
+                                                                fuse_gelu, t.tpr, partial);
+    GMLM_LAUNCH_CHECK();
+    return GMLM_OK;
+  });
+  if (rc) return rc;
+  colstats_final_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(partial, row_blocks, C, sum_g, sum_go);
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+int gmlm_graphnorm_bwd_apply(const void* x, const void* gy, int dtype, int64_t N, int64_t C, int64_t ldx,
+                             int64_t ldg, const float* mean, const float* rstd, const float* weight,
+                             const float* bias, const float* mean_scale, int fuse_gelu, const double* sum_g,
+                             const double* sum_go, void* gx, int64_t ldgx, float* g_weight, float* g_bias,
+                             float* g_mean_scale, void* stream) {
+  GMLM_REQUIRE(N >= 1 && C >= 0 && ldx >= C && ldg >= C, "graphnorm_bwd_apply: bad sizes");
+  if (C == 0) return GMLM_OK;
+  cudaStream_t st = as_stream(stream);
+  graphnorm_bwd_params_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(sum_g, sum_go, mean, rstd, weight,
+                                                                         mean_scale, N, C, g_weight, g_bias,
+                                                                         g_mean_scale);
+  GMLM_LAUNCH_CHECK();
+  if (gx == nullptr) return GMLM_OK;
+  GMLM_REQUIRE(ldgx >= C, "graphnorm_bwd_apply: bad ldgx");
+  const bool v = vec_ok(dtype, C, {x, gy, gx}, {ldx, ldg, ldgx});
+  return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
+    Tile t = make_tile(N, C, VEC, kMaxRowBlocks * 4);
+    graphnorm_bwd_apply_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(
+        static_cast<const T*>(x), static_cast<const T*>(gy), N, C, ldx, ldg, mean, rstd, weight, bias, mean_scale,
+        fuse_gelu, sum_g, sum_go, t.tpr, static_cast<T*>(gx), ldgx);
+    GMLM_LAUNCH_CHECK();
+    return GMLM_OK;
+  });
+}
+
+int gmlm_soft_mask_fwd(const void* x, int dtype, int64_t N, int64_t F, int64_t ldx, const uint8_t* mask,
+                       const float* token, float beta, void* y, int64_t ldy, void* stream) {
+  GMLM_REQUIRE(N >= 0 && F >= 0 && ldx >= F && ldy >= F, "soft_mask_fwd: bad sizes");
+  if (N == 0 || F == 0) return GMLM_OK;
+  GMLM_REQUIRE(x && y && mask && token, "soft_mask_fwd: null pointer");
+  cudaStream_t st = as_stream(stream);
+  const float omb = float(1.0 - double(beta));
+  const bool v = vec_ok(dtype, F, {x, y}, {ldx, ldy});
+  return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
+    Tile t = make_tile(N, F, VEC, kMaxRowBlocks * 4);
+    soft_mask_fwd_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), N, F, ldx, mask, token, beta, omb,
+                                                          t.tpr, static_cast<T*>(y), ldy);
+    GMLM_LAUNCH_CHECK();
+    return GMLM_OK;
+  });
+}
+
+size_t gmlm_soft_mask_bwd_workspace_bytes(int64_t /*num_rows*/, int64_t feat) {
+  return partial_bytes(feat) + size_t(feat) * sizeof(double) + 256;
+}
+
+int gmlm_soft_mask_bwd(const void* gy, int dtype, int64_t N, int64_t F, int64_t ldg, const uint8_t* mask, float beta,
+                       float* g_token, void* gx, int64_t ldgx, void* ws, size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(N >= 0 && F >= 0 && ldg >= F, "soft_mask_bwd: bad sizes");
+  if (F == 0) return GMLM_OK;
+  GMLM_REQUIRE(ws && ws_bytes >= gmlm_soft_mask_bwd_workspace_bytes(N, F), "soft_mask_bwd: workspace too small");
+  cudaStream_t st = as_stream(stream);
+  if (g_token) {
+    Carver cv(ws);
+    double* colsum = cv.take<double>(F);
+    void* part = cv.take<char>(0);
+    int rc = colstats_impl(gy, dtype, N, F, ldg, mask, colsum, nullptr, part, ws_bytes - cv.used(), st);
+    if (rc) return rc;
+    scale_to_f32_kernel<<<unsigned((F + 255) / 256), 256, 0, st>>>(colsum, beta, F, g_token);
+    GMLM_LAUNCH_CHECK();
+  }
+  if (gx && N > 0) {
+    GMLM_REQUIRE(ldgx >= F, "soft_mask_bwd: bad ldgx");
+    const float omb = float(1.0 - double(beta));
+    const bool v = vec_ok(dtype, F, {gy, gx}, {ldg, ldgx});
+    return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
+      Tile t = make_tile(N, F, VEC, kMaxRowBlocks * 4);
+      soft_mask_gx_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(gy), N, F, ldg, mask, omb, t.tpr,
+                                                           static_cast<T*>(gx), ldgx);
+      GMLM_LAUNCH_CHECK();
+      return GMLM_OK;
+    });
+  }
+  return GMLM_OK;
+}
+
+}  // extern "C"

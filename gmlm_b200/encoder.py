@@ -1,0 +1,135 @@
+"""The GNN encoder of the reference (``GraphTextLM.get_graph_embeddings``,
+``/root/reference/main.py:250-320``) on the CUDA path, with the reference's submodule names
+(``rgcn1..4``, ``gnorm1..4``, ``dropout1..4``, ``residual_proj1..3``, ``multi_scale_fusion``,
+``gnn_mask_token_embed``) so its state dict can be loaded into / out of ``GraphTextLM``.
+
+What changes relative to the reference body (results stay within the parity tolerances):
+  * edge typing (main.py:253-267) is one kernel and is cached per ``edge_index`` — the
+    reference recomputes it with a per-edge Python loop on every call;
+  * the typed CSR is built once per graph instead of five mask compactions per layer call;
+  * GraphNorm + GELU run as one fused pass (two passes in backward);
+  * the dead ``x4 + residual_proj3(x2)`` (main.py:317-318) is not computed — its result is
+    discarded by the reference, so ``residual_proj3`` gets no gradient there either;
+  * activation checkpointing (main.py:278) stays available (``use_checkpoint=True``) and is
+    re-entrant-safe: the ops use no RNG and the graph cache is read-only.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.utils.checkpoint import checkpoint
+
+from .graph import _tensor_key, get_rel_graph
+from .nn import GraphNorm, RGCNConv
+from .ops import edge_type_from_degree, soft_masking_gnn_input
+
+
+class MultiScaleFusion(nn.Module):
+    """``MultiScaleFusion`` of main.py:167-180 (dense; stock PyTorch, ends the encoder region)."""
+
+    def __init__(self, hidden_dims, output_dim):
+        super().__init__()
+        self.scale_weights = nn.Parameter(torch.ones(len(hidden_dims)) / len(hidden_dims))
+        self.projections = nn.ModuleList([nn.Linear(d, output_dim) for d in hidden_dims])
+        self.layer_norm = nn.LayerNorm(output_dim)
+
+    def forward(self, embeddings_list):
+        w = F.softmax(self.scale_weights, dim=0)
+        acc = None
+        for i, (proj, emb) in enumerate(zip(self.projections, embeddings_list)):
+            term = w[i] * proj(emb.to(proj.weight.dtype) if not torch.is_autocast_enabled("cuda") else emb)
+            acc = term if acc is None else acc + term
+        return self.layer_norm(acc)
+
+
+_ET_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
+
+
+def cached_edge_type(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    """Degree-bucket relation ids for ``edge_index`` (main.py:253-267), computed once per graph."""
+    key = (_tensor_key(edge_index), int(num_nodes))
+    hit = _ET_CACHE.get(key)
+    if hit is not None:
+        _ET_CACHE.move_to_end(key)
+        return hit[0]
+    et = edge_type_from_degree(edge_index, num_nodes)
+    _ET_CACHE[key] = (et, edge_index)          # keep the key tensor alive (see graph.py cache note)
+    while len(_ET_CACHE) > 4:
+        _ET_CACHE.popitem(last=False)
+    return et
+
+
+class GraphEncoder(nn.Module):
+    def __init__(self, gnn_in_channels: int, hidden_channels: int, out_dim: int, num_relations: int = 5,
+                 num_bases: int = 30, dropout_rate: float = 0.3, use_checkpoint: bool = False,
+                 act_dtype: Optional[torch.dtype] = None):
+        super().__init__()
+        h = hidden_channels
+        dims = [gnn_in_channels, h, 2 * h, 4 * h, 8 * h]
+        self.dims = dims
+        self.gnn_mask_token_embed = nn.Parameter(torch.zeros(1, gnn_in_channels))   # main.py:185-186
+        nn.init.xavier_uniform_(self.gnn_mask_token_embed)
+        for k in range(4):                                                          # main.py:189-203
+            setattr(self, f"rgcn{k+1}", RGCNConv(dims[k], dims[k + 1], num_relations=num_relations,
+                                                 num_bases=num_bases, out_dtype=act_dtype))
+            setattr(self, f"gnorm{k+1}", GraphNorm(dims[k + 1]))
+            setattr(self, f"dropout{k+1}", nn.Dropout(dropout_rate))
+        self.residual_proj1 = nn.Linear(gnn_in_channels, h)                         # main.py:205-207
+        self.residual_proj2 = nn.Linear(h, 2 * h)
+        self.residual_proj3 = nn.Linear(2 * h, 8 * h)
+        self.multi_scale_fusion = MultiScaleFusion(dims[1:], out_dim)
+        self.num_relations = num_relations
+        self.use_checkpoint = use_checkpoint
+
+    def _block(self, k: int):
+        conv, norm, drop = getattr(self, f"rgcn{k}"), getattr(self, f"gnorm{k}"), getattr(self, f"dropout{k}")
+
+        def run(x, graph):
+            y = conv(x, graph)
+            if y.size(0) > 1:                       # main.py:273
+                y = norm(y, fuse_gelu=True)         # GraphNorm + exact-erf GELU in one pass
+            else:
+                y = F.gelu(y)
+            return drop(y)
+        return run
+
+    def _run(self, k, x, graph):
+        if self.use_checkpoint and torch.is_grad_enabled():
+            return checkpoint(self._block(k), x, graph, use_reentrant=False)
+        return self._block(k)(x, graph)
+
+    def _lin(self, lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_autocast_enabled("cuda") or x.dtype == lin.weight.dtype:
+            return lin(x)
+        return F.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype))
+
+    def get_graph_embeddings(self, x_feat: torch.Tensor, edge_index: torch.Tensor,
+                             edge_type: Optional[torch.Tensor] = None, return_layers: bool = False):
+        n = x_feat.size(0)
+        if edge_type is None:
+            edge_type = cached_edge_type(edge_index, n)
+        graph = get_rel_graph(edge_index, edge_type, n, self.num_relations)
+        outs = []
+        x1 = self._run(1, x_feat, graph)
+        outs.append(x1)                              # pre-residual outputs feed the fusion (main.py:279)
+        x1 = x1 + self._lin(self.residual_proj1, x_feat).to(x1.dtype)
+        x2 = self._run(2, x1, graph)
+        outs.append(x2)
+        x2 = x2 + self._lin(self.residual_proj2, x1).to(x2.dtype)
+        x3 = self._run(3, x2, graph)
+        outs.append(x3)
+        x4 = self._run(4, x3, graph)
+        outs.append(x4)
+        fused = self.multi_scale_fusion(outs)
+        return (fused, outs) if return_layers else fused
+
+    def forward(self, x_feat, edge_index, edge_type=None, gnn_perturb_mask: Optional[torch.Tensor] = None,
+                beta: float = 0.7):
+        """Optionally applies the soft node masking of main.py:92-99 first (callers main.py:443,541)."""
+        if gnn_perturb_mask is not None:
+            x_feat = soft_masking_gnn_input(x_feat, gnn_perturb_mask, self.gnn_mask_token_embed, beta)
+        return self.get_graph_embeddings(x_feat, edge_index, edge_type)

@@ -1,0 +1,242 @@
+"""Graph structure cache: the (dst,rel)-keyed CSR that replaces the per-call, per-relation
+boolean-mask compaction of upstream ``RGCNConv.forward`` (call sites
+``/root/reference/main.py:272,285,298,308``), its transpose for the backward gather (A14), and
+the hub plan that keeps power-law rows balanced and deterministic.
+
+Everything is built by the CUDA library (``csr_build`` / ``csr_transpose`` / ``hub_*`` in
+include/gmlm_b200.h); this module only owns the tensors and the cache.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+DEFAULT_HUB_THRESH = int(os.environ.get("GMLM_HUB_THRESH", "1024"))
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else C.c_void_p(0)
+
+
+def _stream(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.GmlmError(
+            f"{name} must be a CUDA tensor: gmlm_b200 runs only on the GPU (no CPU fallback); got device {t.device}")
+
+
+@dataclass
+class CSR:
+    """One direction of the graph in CSR form plus its hub plan."""
+    rowptr: torch.Tensor                       # int32 [num_rows+1]
+    col: torch.Tensor                          # int32 [nnz]  (gather row of each edge)
+    num_rows: int
+    w: Optional[torch.Tensor] = None           # float32 [nnz] per-edge weight (weighted mode)
+    perm: Optional[torch.Tensor] = None        # int32 [nnz] original edge position
+    hub_thresh: int = DEFAULT_HUB_THRESH
+    n_hub: int = 0
+    n_chunks: int = 0
+    hub_row: Optional[torch.Tensor] = None
+    hub_chunk_ptr: Optional[torch.Tensor] = None
+    chunk_beg: Optional[torch.Tensor] = None
+    chunk_end: Optional[torch.Tensor] = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+    def plan_hubs(self, thresh: Optional[int] = None):
+        """Split rows longer than ``thresh`` into fixed chunks (deterministic two-stage reduce)."""
+        lib = _lib.load()
+        self.hub_thresh = int(thresh if thresh is not None else self.hub_thresh)
+        dev = self.rowptr.device
+        with torch.cuda.device(dev):
+            ws_bytes = lib.gmlm_csr_workspace_bytes(max(self.nnz, 1), self.num_rows)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            counts = (C.c_int64 * 2)()
+            _lib.check(lib.gmlm_hub_count(_ptr(self.rowptr), self.num_rows, self.hub_thresh, counts, _ptr(ws),
+                                          ws_bytes, _stream(dev)), "hub_count")
+            self.n_hub, self.n_chunks = int(counts[0]), int(counts[1])
+            if self.n_hub:
+                self.hub_row = torch.empty(self.n_hub, dtype=torch.int32, device=dev)
+                self.hub_chunk_ptr = torch.empty(self.n_hub + 1, dtype=torch.int32, device=dev)
+                self.chunk_beg = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
+                self.chunk_end = torch.empty(self.n_chunks, dtype=torch.int32, device=dev)
+                _lib.check(lib.gmlm_hub_fill(_ptr(self.rowptr), self.num_rows, self.hub_thresh, self.n_hub,
+                                             self.n_chunks, _ptr(self.hub_row), _ptr(self.hub_chunk_ptr),
+                                             _ptr(self.chunk_beg), _ptr(self.chunk_end), _ptr(ws), ws_bytes,
+                                             _stream(dev)), "hub_fill")
+            else:
+                self.hub_row = self.hub_chunk_ptr = self.chunk_beg = self.chunk_end = None
+        return self
+
+
+def build_csr(row: torch.Tensor, col: torch.Tensor, num_rows: int, num_cols: int, *,
+              rel: Optional[torch.Tensor] = None, num_relations: int = 1,
+              slot_of_rel: Optional[List[int]] = None, num_slots: int = 1,
+              want_seg_of_edge: bool = False, hub_thresh: Optional[int] = None):
+    """CSR with segments ``row*num_slots + slot_of_rel[rel]`` and gather index ``col``.
+
+    ``row``/``col``/``rel`` are int64 edge arrays (as in ``edge_index`` / ``edge_type``).
+    Returns ``(CSR, seg_of_edge or None)``.  ``row`` is validated against ``num_rows`` and ``col``
+    against ``num_cols`` (one host sync)."""
+    lib = _lib.load()
+    _require_cuda(row, "edge_index")
+    dev = row.device
+    E = int(row.numel())
+    row = row.contiguous()
+    col = col.contiguous()
+    if rel is not None:
+        rel = rel.contiguous()
+        if rel.dtype != torch.int64:
+            rel = rel.long()
+    rows_total = num_rows * num_slots
+    with torch.cuda.device(dev):
+        rowptr = torch.empty(rows_total + 1, dtype=torch.int32, device=dev)
+        colv = torch.empty(E, dtype=torch.int32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        seg = torch.empty(E, dtype=torch.int32, device=dev) if want_seg_of_edge else None
+        ws_bytes = lib.gmlm_csr_workspace_bytes(max(E, 1), rows_total)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        slots = None
+        if rel is not None:
+            slot_list = slot_of_rel if slot_of_rel is not None else list(range(num_relations))
+            slots = (C.c_int32 * num_relations)(*slot_list)
+        # csr_build keys on `dst`; here the CSR row plays that role and `col` is the gathered id
+        _lib.check(lib.gmlm_csr_build(_ptr(col), _ptr(row), _ptr(rel), E, num_rows, num_cols, num_relations, slots,
+                                      num_slots,
+                                      _ptr(rowptr), _ptr(colv), _ptr(perm), _ptr(seg), _ptr(ws), ws_bytes,
+                                      _stream(dev)), "csr_build")
+    csr = CSR(rowptr=rowptr, col=colv, num_rows=rows_total, perm=perm)
+    csr.plan_hubs(hub_thresh)
+    return csr, seg
+
+
+def transpose_csr(row_of_edge: torch.Tensor, payload: torch.Tensor, num_rows: int, *,
+                  fwd_rowptr: Optional[torch.Tensor] = None, edge_w: Optional[torch.Tensor] = None,
+                  hub_thresh: Optional[int] = None) -> CSR:
+    """CSR over ``row_of_edge`` (int64 [E]) whose gather index is ``payload`` (int32 [E], e.g. the
+    forward segment of each edge); weights are 1/|fwd segment| or ``edge_w`` permuted."""
+    lib = _lib.load()
+    dev = row_of_edge.device
+    E = int(row_of_edge.numel())
+    row_of_edge = row_of_edge.contiguous()
+    with torch.cuda.device(dev):
+        rowptr_t = torch.empty(num_rows + 1, dtype=torch.int32, device=dev)
+        payload_t = torch.empty(E, dtype=torch.int32, device=dev)
+        perm_t = torch.empty(E, dtype=torch.int32, device=dev)
+        has_w = fwd_rowptr is not None or edge_w is not None
+        w_t = torch.empty(E, dtype=torch.float32, device=dev) if has_w else None
+        ws_bytes = lib.gmlm_csr_workspace_bytes(max(E, 1), num_rows)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_csr_transpose(_ptr(row_of_edge), _ptr(payload), _ptr(edge_w), _ptr(fwd_rowptr), E,
+                                          num_rows, _ptr(rowptr_t), _ptr(payload_t), _ptr(w_t), _ptr(perm_t),
+                                          _ptr(ws), ws_bytes, _stream(dev)), "csr_transpose")
+    csr = CSR(rowptr=rowptr_t, col=payload_t, num_rows=num_rows, w=w_t, perm=perm_t)
+    csr.plan_hubs(hub_thresh)
+    return csr
+
+
+@dataclass
+class RelGraph:
+    """Typed graph prepared for relational mean aggregation.
+
+    ``fwd`` rows are the segments ``dst*num_slots + slot`` (slot = index of the relation among
+    the populated ones), gather index = source node.  ``bwd`` rows are source nodes, gather
+    index = forward segment, weight = 1/|segment|."""
+    num_nodes: int
+    num_edges: int
+    num_relations: int
+    live_rels: List[int]
+    fwd: CSR
+    bwd: CSR
+    _keepalive: list = field(default_factory=list, repr=False)
+
+    @property
+    def num_slots(self) -> int:
+        return len(self.live_rels)
+
+    @staticmethod
+    def build(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int, num_relations: int,
+              hub_thresh: Optional[int] = None) -> "RelGraph":
+        lib = _lib.load()
+        _require_cuda(edge_index, "edge_index")
+        if edge_index.dim() != 2 or edge_index.size(0) != 2:
+            raise _lib.GmlmError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
+        edge_index = edge_index.long()
+        src, dst = edge_index[0].contiguous(), edge_index[1].contiguous()
+        E = int(src.numel())
+        dev = edge_index.device
+        if edge_type is None:
+            live = [0]
+            num_relations = max(1, num_relations)
+        else:
+            _require_cuda(edge_type, "edge_type")
+            if edge_type.numel() != E:
+                raise _lib.GmlmError(f"edge_type has {edge_type.numel()} entries for {E} edges")
+            edge_type = edge_type.long().contiguous()
+            with torch.cuda.device(dev):
+                counts = torch.empty(num_relations, dtype=torch.int64, device=dev)
+                _lib.check(lib.gmlm_relation_histogram(_ptr(edge_type), E, num_relations, _ptr(counts),
+                                                       _stream(dev)), "relation_histogram")
+            counts_h = counts.cpu().tolist()
+            live = [r for r, c in enumerate(counts_h) if c > 0]
+            if sum(counts_h) != E:
+                raise _lib.GmlmError(f"edge_type has values outside [0, {num_relations})")
+            if not live:
+                live = [0]
+        slot_of_rel = [-1] * num_relations
+        for s, r in enumerate(live):
+            slot_of_rel[r] = s
+        if edge_type is None:
+            slot_of_rel[0] = 0
+        fwd, seg = build_csr(dst, src, num_nodes, num_nodes, rel=edge_type, num_relations=num_relations,
+                             slot_of_rel=slot_of_rel, num_slots=len(live), want_seg_of_edge=True,
+                             hub_thresh=hub_thresh)
+        bwd = transpose_csr(src, seg, num_nodes, fwd_rowptr=fwd.rowptr, hub_thresh=hub_thresh)
+        return RelGraph(num_nodes=num_nodes, num_edges=E, num_relations=num_relations, live_rels=live, fwd=fwd,
+                        bwd=bwd)
+
+
+# ------------------------------------------------------------------------------ cache
+# The reference rebuilds its per-relation edge lists on every conv call.  Here the structure
+# is built once per (edge_index, edge_type) pair.  Entries hold strong references to the key
+# tensors so their storage cannot be recycled under a stale key; `_version` catches in-place
+# edits.  Read-only after construction (checkpoint recompute / autograd threads only read).
+_CACHE: "OrderedDict[tuple, RelGraph]" = OrderedDict()
+_CACHE_SIZE = int(os.environ.get("GMLM_GRAPH_CACHE", "4"))
+
+
+def _tensor_key(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device))
+
+
+def get_rel_graph(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int,
+                  num_relations: int) -> RelGraph:
+    key = (_tensor_key(edge_index), _tensor_key(edge_type), int(num_nodes), int(num_relations))
+    g = _CACHE.get(key)
+    if g is not None:
+        _CACHE.move_to_end(key)
+        return g
+    g = RelGraph.build(edge_index, edge_type, num_nodes, num_relations)
+    g._keepalive = [edge_index, edge_type]
+    _CACHE[key] = g
+    while len(_CACHE) > _CACHE_SIZE:
+        _CACHE.popitem(last=False)
+    return g
+
+
+def clear_graph_cache():
+    _CACHE.clear()

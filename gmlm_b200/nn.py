@@ -1,0 +1,153 @@
+"""Drop-in modules for the three names the reference imports from torch_geometric
+(``/root/reference/main.py:6-7``): ``RGCNConv``, ``GraphNorm`` (and ``degree`` in ops.py).
+
+Constructor arguments, ``forward`` signatures, parameter names, shapes and initialisers equal
+upstream's, so ``state_dict()`` / ``load_state_dict()`` (``main.py:623,644``) and
+the name-substring optimiser grouping (``main.py:379,387,414,426``) keep working.  The
+arithmetic runs in the CUDA library; CPU tensors raise.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .graph import RelGraph, get_rel_graph
+from .ops import graph_norm, rgcn_aggregate
+
+
+def glorot_(t: Optional[torch.Tensor]):
+    """torch_geometric.nn.inits.glorot: U(-a, a), a = sqrt(6 / (size(-2) + size(-1)))."""
+    if t is not None:
+        a = math.sqrt(6.0 / (t.size(-2) + t.size(-1)))
+        with torch.no_grad():
+            t.uniform_(-a, a)
+
+
+class RGCNConv(nn.Module):
+    r"""Relational graph convolution with basis decomposition and per-relation **mean**
+    aggregation, as built at ``main.py:189,193,197,201`` and called at ``main.py:272``:
+
+        out_i = sum_r mean_{j in N_r(i)} x_j @ W_r  +  x_i @ root + bias,   W_r = sum_b comp[r,b] * weight[b]
+
+    Execution: one cached (dst,rel)-keyed CSR (A3), one deterministic segmented-mean kernel over
+    all relations (A5), then two dense GEMMs ``[N, S*Fi] @ [S*Fi, Fo]`` and ``x @ root`` (A6).
+    Relations with no edges contribute exact zeros upstream and are skipped here; their
+    ``comp`` rows receive exact-zero gradients through the index-select of the composed weight.
+    """
+
+    def __init__(self, in_channels: int, out_channels: int, num_relations: int, num_bases: Optional[int] = None,
+                 num_blocks: Optional[int] = None, aggr: str = "mean", root_weight: bool = True,
+                 is_sorted: bool = False, bias: bool = True, out_dtype: Optional[torch.dtype] = None, **kwargs):
+        super().__init__()
+        self.out_dtype = out_dtype  # None = upstream behaviour (default dtype); bf16 for the bandwidth study
+        if num_blocks is not None:
+            raise NotImplementedError("gmlm_b200.RGCNConv: block-diagonal decomposition is not on the reference "
+                                      "path (main.py uses num_bases=30)")
+        if aggr != "mean":
+            raise NotImplementedError("gmlm_b200.RGCNConv: only aggr='mean' (the upstream default the reference uses)")
+        if isinstance(in_channels, (tuple, list)):
+            raise NotImplementedError("gmlm_b200.RGCNConv: bipartite in_channels are not on the reference path")
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.num_relations = num_relations
+        self.num_bases = num_bases
+        self.num_blocks = None
+        self.is_sorted = is_sorted
+        if num_bases is not None:
+            self.weight = nn.Parameter(torch.empty(num_bases, in_channels, out_channels))
+            self.comp = nn.Parameter(torch.empty(num_relations, num_bases))
+        else:
+            self.weight = nn.Parameter(torch.empty(num_relations, in_channels, out_channels))
+            self.register_parameter("comp", None)
+        if root_weight:
+            self.root = nn.Parameter(torch.empty(in_channels, out_channels))
+        else:
+            self.register_parameter("root", None)
+        if bias:
+            self.bias = nn.Parameter(torch.empty(out_channels))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        glorot_(self.weight)
+        glorot_(self.comp)
+        glorot_(self.root)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
+
+    def composed_weight(self) -> torch.Tensor:
+        """A4: W[r] = sum_b comp[r,b] * weight[b]  -> [R, Fi, Fo]."""
+        w = self.weight
+        if self.num_bases is not None:
+            w = (self.comp @ w.view(self.num_bases, -1)).view(self.num_relations, self.in_channels,
+                                                                self.out_channels)
+        return w
+
+    def forward(self, x: torch.Tensor, edge_index, edge_type: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if isinstance(edge_index, RelGraph):
+            graph = edge_index
+        else:
+            if edge_type is None:
+                raise _lib.GmlmError("RGCNConv.forward: edge_type is required (as upstream asserts)")
+            graph = get_rel_graph(edge_index, edge_type, x.size(0), self.num_relations)
+        if not x.is_floating_point():
+            raise NotImplementedError("gmlm_b200.RGCNConv: integer node-id inputs are not on the reference path")
+        if x.size(1) != self.in_channels:
+            raise _lib.GmlmError(f"RGCNConv: x has {x.size(1)} features, layer expects {self.in_channels}")
+        h = rgcn_aggregate(x, graph)                                   # [N, S*Fi], x's dtype
+        w = self.composed_weight()
+        live = graph.live_rels
+        if len(live) != self.num_relations:
+            w = w.index_select(0, torch.as_tensor(live, device=w.device))
+        w = w.reshape(len(live) * self.in_channels, self.out_channels)
+        # upstream accumulates into `out = torch.zeros(N, Fo)` of the default dtype (fp32) while the
+        # matmuls run in the operand dtype, or in the autocast dtype under torch.amp.autocast
+        autocast = torch.is_autocast_enabled("cuda")
+        out_dtype = self.out_dtype or torch.get_default_dtype()
+
+        def mm(a, b):
+            return torch.matmul(a, b) if autocast else torch.matmul(a, b.to(a.dtype))
+
+        out = mm(h, w).to(out_dtype)
+        if self.root is not None:
+            out = out + mm(x, self.root).to(out_dtype)
+        if self.bias is not None:
+            out = out + self.bias.to(out_dtype)
+        return out
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}, {self.out_channels}, num_relations={self.num_relations}, num_bases={self.num_bases}"
+
+
+class GraphNorm(nn.Module):
+    r"""Whole-graph GraphNorm (``batch=None``) as built at ``main.py:190`` and called at
+    ``main.py:273``:  ``y = weight * (x - mean_scale*mean(x)) / sqrt(var + eps) + bias``."""
+
+    def __init__(self, in_channels: int, eps: float = 1e-5):
+        super().__init__()
+        self.in_channels = in_channels
+        self.eps = eps
+        self.weight = nn.Parameter(torch.empty(in_channels))
+        self.bias = nn.Parameter(torch.empty(in_channels))
+        self.mean_scale = nn.Parameter(torch.empty(in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.ones_(self.weight)
+        nn.init.zeros_(self.bias)
+        nn.init.ones_(self.mean_scale)
+
+    def forward(self, x: torch.Tensor, batch: Optional[torch.Tensor] = None, batch_size: Optional[int] = None,
+                fuse_gelu: bool = False) -> torch.Tensor:
+        if batch is not None:
+            raise NotImplementedError("gmlm_b200.GraphNorm: the reference always normalises the whole graph "
+                                      "(batch=None, main.py:273)")
+        return graph_norm(x, self.weight, self.bias, self.mean_scale, self.eps, fuse_gelu)
+
+    def extra_repr(self) -> str:
+        return f"{self.in_channels}"

@@ -1,0 +1,331 @@
+"""Thin torch layer over the C ABI: tensor checks, output allocation from the caching
+allocator, launch on the current stream, autograd registration.
+
+Registered ops (``torch.ops.gmlm.*``, CUDA only — calling them with CPU tensors raises from
+the dispatcher; there is no fallback):
+
+    degree_i32, edge_type_bucket, spmm_csr, colstats, graphnorm_fwd, graphnorm_bwd,
+    soft_mask_fwd, soft_mask_bwd
+
+Autograd wrappers used by the modules in ``gmlm_b200.nn``:
+
+    rgcn_aggregate(x, graph)            A5 forward / A14 backward
+    graph_norm(x, weight, bias, mean_scale, eps, fuse_gelu)   A7
+    soft_mask(x, mask, token, beta)     A11
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from .graph import CSR, RelGraph, _ptr, _require_cuda, _stream
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _dtype_code(t: torch.Tensor, what: str) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise _lib.GmlmError(f"{what}: dtype {t.dtype} unsupported (float32 and bfloat16 only)") from None
+
+
+def _rowmajor(t: torch.Tensor) -> torch.Tensor:
+    """2-D tensor with unit inner stride (a leading dimension is fine, anything else is copied)."""
+    if t.dim() != 2:
+        raise _lib.GmlmError(f"expected a 2-D tensor, got shape {tuple(t.shape)}")
+    if t.size(1) > 0 and t.stride(1) != 1 or (t.size(0) > 1 and t.stride(0) < t.size(1)):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t: torch.Tensor) -> int:
+    return int(t.stride(0)) if t.size(0) > 1 else int(t.size(1))
+
+
+_LIB = torch.library.Library("gmlm", "DEF")
+_LIB.define("degree_i32(Tensor index, int num_nodes) -> Tensor")
+_LIB.define("edge_type_bucket(Tensor src, Tensor deg, int[] bounds) -> Tensor")
+_LIB.define("spmm_csr(Tensor x, Tensor rowptr, Tensor col, Tensor? w, int num_rows, int mode, int hub_thresh, "
+            "Tensor? hub_row, Tensor? hub_chunk_ptr, Tensor? chunk_beg, Tensor? chunk_end) -> Tensor")
+_LIB.define("colstats(Tensor x) -> (Tensor, Tensor)")
+_LIB.define("graphnorm_fwd(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, bool fuse_gelu) "
+            "-> (Tensor, Tensor, Tensor)")
+_LIB.define("graphnorm_bwd(Tensor x, Tensor gy, Tensor mean, Tensor rstd, Tensor weight, Tensor bias, "
+            "Tensor mean_scale, bool fuse_gelu, bool need_gx) -> (Tensor, Tensor, Tensor, Tensor)")
+_LIB.define("soft_mask_fwd(Tensor x, Tensor mask, Tensor token, float beta) -> Tensor")
+_LIB.define("soft_mask_bwd(Tensor gy, Tensor mask, float beta, bool need_gx) -> (Tensor, Tensor)")
+
+
+# ------------------------------------------------------------------------------ A1 / A2
+def _degree_i32(index: torch.Tensor, num_nodes: int) -> torch.Tensor:
+    lib = _lib.load()
+    index = index.reshape(-1).contiguous()
+    if index.dtype != torch.int64:
+        index = index.long()
+    with torch.cuda.device(index.device):
+        deg = torch.empty(num_nodes, dtype=torch.int32, device=index.device)
+        _lib.check(lib.gmlm_degree_i32(_ptr(index), index.numel(), num_nodes, _ptr(deg), 0, _stream(index.device)),
+                   "degree")
+    return deg
+
+
+def _edge_type_bucket(src: torch.Tensor, deg: torch.Tensor, bounds: Sequence[int]) -> torch.Tensor:
+    lib = _lib.load()
+    src = src.reshape(-1).contiguous()
+    if src.dtype != torch.int64:
+        src = src.long()
+    nb = len(bounds)
+    arr = (C.c_int32 * max(nb, 1))(*[int(b) for b in bounds])
+    with torch.cuda.device(src.device):
+        out = torch.empty(src.numel(), dtype=torch.int64, device=src.device)
+        _lib.check(lib.gmlm_edge_type_bucket(_ptr(src), src.numel(), _ptr(deg), deg.numel(), arr, nb, _ptr(out),
+                                             _stream(src.device)), "edge_type_bucket")
+    return out
+
+
+# ------------------------------------------------------------------------------ A5 / A14
+def _spmm_csr(x, rowptr, col, w, num_rows, mode, hub_thresh, hub_row, hub_chunk_ptr, chunk_beg, chunk_end):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    feat = int(x.size(1))
+    dev = x.device
+    n_hub = int(hub_row.numel()) if hub_row is not None else 0
+    n_chunks = int(chunk_beg.numel()) if chunk_beg is not None else 0
+    with torch.cuda.device(dev):
+        out = torch.empty((num_rows, feat), dtype=x.dtype, device=dev)
+        hub_ws = torch.empty(n_chunks * feat, dtype=torch.float32, device=dev) if n_hub else None
+        _lib.check(lib.gmlm_spmm_csr(_ptr(x), _dtype_code(x, "spmm_csr"), feat, _ld(x), _ptr(rowptr), _ptr(col),
+                                     _ptr(w), num_rows, mode, hub_thresh, n_hub, n_chunks, _ptr(hub_row),
+                                     _ptr(hub_chunk_ptr), _ptr(chunk_beg), _ptr(chunk_end), _ptr(hub_ws), _ptr(out),
+                                     feat, _stream(dev)), "spmm_csr")
+    return out
+
+
+def spmm(x: torch.Tensor, csr: CSR, mode: int) -> torch.Tensor:
+    """out[r] = reduce over row r of csr (no autograd)."""
+    _require_cuda(x, "x")
+    return torch.ops.gmlm.spmm_csr(x, csr.rowptr, csr.col, csr.w if mode == _lib.AGG_WEIGHTED else None,
+                                   csr.num_rows, mode, csr.hub_thresh, csr.hub_row, csr.hub_chunk_ptr,
+                                   csr.chunk_beg, csr.chunk_end)
+
+
+# ------------------------------------------------------------------------------ A7
+def _colstats(x: torch.Tensor):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    n, c = x.shape
+    dev = x.device
+    with torch.cuda.device(dev):
+        colsum = torch.empty(c, dtype=torch.float64, device=dev)
+        colsq = torch.empty(c, dtype=torch.float64, device=dev)
+        ws_bytes = lib.gmlm_colstats_workspace_bytes(n, c)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_colstats(_ptr(x), _dtype_code(x, "colstats"), n, c, _ld(x), _ptr(colsum), _ptr(colsq),
+                                     _ptr(ws), ws_bytes, _stream(dev)), "colstats")
+    return colsum, colsq
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _graphnorm_fwd(x, weight, bias, mean_scale, eps, fuse_gelu):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    n, c = x.shape
+    dev = x.device
+    weight, bias, mean_scale = _f32c(weight), _f32c(bias), _f32c(mean_scale)
+    colsum, colsq = _colstats(x)
+    with torch.cuda.device(dev):
+        y = torch.empty((n, c), dtype=x.dtype, device=dev)
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        rstd = torch.empty(c, dtype=torch.float32, device=dev)
+        _lib.check(lib.gmlm_graphnorm_fwd(_ptr(x), _dtype_code(x, "graphnorm"), n, c, _ld(x), _ptr(colsum),
+                                          _ptr(colsq), _ptr(weight), _ptr(bias), _ptr(mean_scale), float(eps),
+                                          int(bool(fuse_gelu)), _ptr(y), c, _ptr(mean), _ptr(rstd), _stream(dev)),
+                   "graphnorm_fwd")
+    return y, mean, rstd
+
+
+def _graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, need_gx):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    gy = _rowmajor(gy)
+    if gy.dtype != x.dtype:
+        gy = gy.to(x.dtype)
+    n, c = x.shape
+    dev = x.device
+    weight, bias, mean_scale = _f32c(weight), _f32c(bias), _f32c(mean_scale)
+    dt = _dtype_code(x, "graphnorm_bwd")
+    with torch.cuda.device(dev):
+        s1 = torch.empty(c, dtype=torch.float64, device=dev)
+        s2 = torch.empty(c, dtype=torch.float64, device=dev)
+        ws_bytes = lib.gmlm_colstats_workspace_bytes(n, c)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_graphnorm_bwd_stats(_ptr(x), _ptr(gy), dt, n, c, _ld(x), _ld(gy), _ptr(mean), _ptr(rstd),
+                                                _ptr(weight), _ptr(bias), _ptr(mean_scale), int(bool(fuse_gelu)),
+                                                _ptr(s1), _ptr(s2), _ptr(ws), ws_bytes, _stream(dev)),
+                   "graphnorm_bwd_stats")
+        gx = torch.empty((n, c), dtype=x.dtype, device=dev) if need_gx else torch.empty(0, dtype=x.dtype, device=dev)
+        gw = torch.empty(c, dtype=torch.float32, device=dev)
+        gb = torch.empty(c, dtype=torch.float32, device=dev)
+        gms = torch.empty(c, dtype=torch.float32, device=dev)
+        _lib.check(lib.gmlm_graphnorm_bwd_apply(_ptr(x), _ptr(gy), dt, n, c, _ld(x), _ld(gy), _ptr(mean), _ptr(rstd),
+                                                _ptr(weight), _ptr(bias), _ptr(mean_scale), int(bool(fuse_gelu)),
+                                                _ptr(s1), _ptr(s2), _ptr(gx) if need_gx else C.c_void_p(0), c,
+                                                _ptr(gw), _ptr(gb), _ptr(gms), _stream(dev)), "graphnorm_bwd_apply")
+    return gx, gw, gb, gms
+
+
+# ------------------------------------------------------------------------------ A11
+def _mask_u8(mask: torch.Tensor, n: int) -> torch.Tensor:
+    mask = mask.reshape(-1)
+    if mask.numel() != n:
+        raise _lib.GmlmError(f"mask has {mask.numel()} entries for {n} rows")
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).view(torch.uint8)
+
+
+def _soft_mask_fwd(x, mask, token, beta):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    n, f = x.shape
+    dev = x.device
+    m = _mask_u8(mask.to(dev), n)
+    token = _f32c(token.to(dev)).reshape(-1)
+    if token.numel() != f:
+        raise _lib.GmlmError(f"mask token has {token.numel()} features, x has {f}")
+    with torch.cuda.device(dev):
+        y = torch.empty((n, f), dtype=x.dtype, device=dev)
+        _lib.check(lib.gmlm_soft_mask_fwd(_ptr(x), _dtype_code(x, "soft_mask"), n, f, _ld(x), _ptr(m), _ptr(token),
+                                          float(beta), _ptr(y), f, _stream(dev)), "soft_mask_fwd")
+    return y
+
+
+def _soft_mask_bwd(gy, mask, beta, need_gx):
+    lib = _lib.load()
+    gy = _rowmajor(gy)
+    n, f = gy.shape
+    dev = gy.device
+    m = _mask_u8(mask.to(dev), n)
+    with torch.cuda.device(dev):
+        g_token = torch.empty(f, dtype=torch.float32, device=dev)
+        gx = torch.empty((n, f), dtype=gy.dtype, device=dev) if need_gx else torch.empty(0, dtype=gy.dtype, device=dev)
+        ws_bytes = lib.gmlm_soft_mask_bwd_workspace_bytes(n, f)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_soft_mask_bwd(_ptr(gy), _dtype_code(gy, "soft_mask_bwd"), n, f, _ld(gy), _ptr(m),
+                                          float(beta), _ptr(g_token), _ptr(gx) if need_gx else C.c_void_p(0), f,
+                                          _ptr(ws), ws_bytes, _stream(dev)), "soft_mask_bwd")
+    return g_token, gx
+
+
+_LIB.impl("degree_i32", _degree_i32, "CUDA")
+_LIB.impl("edge_type_bucket", _edge_type_bucket, "CUDA")
+_LIB.impl("spmm_csr", _spmm_csr, "CUDA")
+_LIB.impl("colstats", _colstats, "CUDA")
+_LIB.impl("graphnorm_fwd", _graphnorm_fwd, "CUDA")
+_LIB.impl("graphnorm_bwd", _graphnorm_bwd, "CUDA")
+_LIB.impl("soft_mask_fwd", _soft_mask_fwd, "CUDA")
+_LIB.impl("soft_mask_bwd", _soft_mask_bwd, "CUDA")
+
+
+# ------------------------------------------------------------------------------ public functional API
+def degree(index: torch.Tensor, num_nodes: Optional[int] = None, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Drop-in for ``torch_geometric.utils.degree`` (``/root/reference/main.py:7``; called
+    ``main.py:65,256``): float32 [N] occurrence counts of ``index``."""
+    _require_cuda(index, "index")
+    if num_nodes is None:  # upstream maybe_num_nodes (one host sync)
+        num_nodes = int(index.max()) + 1 if index.numel() > 0 else 0
+    deg = torch.ops.gmlm.degree_i32(index, int(num_nodes))
+    return deg.to(dtype or torch.get_default_dtype())
+
+
+def edge_type_from_degree(edge_index: torch.Tensor, num_nodes: int, bounds: Sequence[int] = (2, 5, 10)) -> torch.Tensor:
+    """The reference's per-edge loop ``main.py:253-267`` as one kernel: relation id =
+    bucket of the source node's out-degree (<=2, <=5, <=10, else)."""
+    _require_cuda(edge_index, "edge_index")
+    src = edge_index[0]
+    deg = torch.ops.gmlm.degree_i32(src, int(num_nodes))
+    return torch.ops.gmlm.edge_type_bucket(src, deg, list(bounds))
+
+
+class _RGCNAggregate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, graph: RelGraph):
+        ctx.graph = graph
+        ctx.x_dtype = x.dtype
+        h = spmm(x, graph.fwd, _lib.AGG_MEAN)              # [N*S, F]
+        return h.view(graph.num_nodes, graph.num_slots * x.size(1))
+
+    @staticmethod
+    def backward(ctx, gh):
+        g: RelGraph = ctx.graph
+        gh = gh.contiguous()
+        if gh.dtype != ctx.x_dtype:
+            gh = gh.to(ctx.x_dtype)
+        feat = gh.size(1) // g.num_slots
+        gx = spmm(gh.view(g.num_nodes * g.num_slots, feat), g.bwd, _lib.AGG_WEIGHTED)   # [N, F]
+        return gx, None
+
+
+def rgcn_aggregate(x: torch.Tensor, graph: RelGraph) -> torch.Tensor:
+    """Per-(dst, relation) mean of source rows: ``[N, F] -> [N, S*F]`` (S = populated relations).
+    Forward = A5, backward = A14 (gather on the transposed CSR with 1/count folded in)."""
+    _require_cuda(x, "x")
+    if x.size(0) != graph.num_nodes:
+        raise _lib.GmlmError(f"x has {x.size(0)} rows, graph has {graph.num_nodes} nodes")
+    return _RGCNAggregate.apply(x, graph)
+
+
+class _GraphNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, mean_scale, eps, fuse_gelu):
+        y, mean, rstd = torch.ops.gmlm.graphnorm_fwd(x, weight, bias, mean_scale, float(eps), bool(fuse_gelu))
+        ctx.save_for_backward(x, mean, rstd, weight, bias, mean_scale)
+        ctx.fuse_gelu = bool(fuse_gelu)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, weight, bias, mean_scale = ctx.saved_tensors
+        gx, gw, gb, gms = torch.ops.gmlm.graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, ctx.fuse_gelu,
+                                                       ctx.needs_input_grad[0])
+        return (gx if ctx.needs_input_grad[0] else None,
+                gw.to(weight.dtype) if ctx.needs_input_grad[1] else None,
+                gb.to(bias.dtype) if ctx.needs_input_grad[2] else None,
+                gms.to(mean_scale.dtype) if ctx.needs_input_grad[3] else None, None, None)
+
+
+def graph_norm(x, weight, bias, mean_scale, eps: float = 1e-5, fuse_gelu: bool = False) -> torch.Tensor:
+    _require_cuda(x, "x")
+    return _GraphNorm.apply(x, weight, bias, mean_scale, eps, fuse_gelu)
+
+
+class _SoftMask(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, mask, token, beta):
+        ctx.save_for_backward(mask)
+        ctx.beta = float(beta)
+        ctx.token_shape = token.shape
+        ctx.token_dtype = token.dtype
+        return torch.ops.gmlm.soft_mask_fwd(x, mask, token, float(beta))
+
+    @staticmethod
+    def backward(ctx, gy):
+        (mask,) = ctx.saved_tensors
+        g_token, gx = torch.ops.gmlm.soft_mask_bwd(gy, mask, ctx.beta, ctx.needs_input_grad[0])
+        return (gx if ctx.needs_input_grad[0] else None, None,
+                g_token.view(ctx.token_shape).to(ctx.token_dtype) if ctx.needs_input_grad[2] else None, None)
+
+
+def soft_masking_gnn_input(x: torch.Tensor, gnn_perturb_mask: torch.Tensor, mask_token_embed: torch.Tensor,
+                           beta: float = 0.7) -> torch.Tensor:
+    """Drop-in for ``soft_masking_gnn_input`` (``/root/reference/main.py:92-99``): one fused pass,
+    no clone + boolean-index round trip and no ``.any()`` host sync."""
+    _require_cuda(x, "x")
+    return _SoftMask.apply(x, gnn_perturb_mask, mask_token_embed, beta)

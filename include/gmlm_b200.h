@@ -1,0 +1,149 @@
+/* gmlm_b200.h — C ABI of libgmlm_b200.so: B200 (sm_100a) kernels for the message-passing
+ * hot path of chungimungi/GMLM (the GNN encoder of /root/reference/main.py:250-320).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch/ATen types.
+ *   - Every pointer is a DEVICE pointer unless the parameter name ends in `_host`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Row-major dense matrices with an explicit leading dimension in ELEMENTS.
+ *   - Return value: 0 = ok; GMLM_ERR_* otherwise; gmlm_last_error() gives the thread-local
+ *     message.  Kernels never allocate, free or retain memory; scratch is passed in as
+ *     (ws, ws_bytes) and sized by the matching *_workspace_bytes() query.
+ *   - Nothing here touches the host CPU for arithmetic: there is no CPU fallback.
+ *
+ * Each entry point names the reference interface it replaces (file:line in
+ * /root/reference/main.py; [PyG] = the torch_geometric operator imported at main.py:6-7).
+ */
+#ifndef GMLM_B200_H_
+#define GMLM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GMLM_OK 0
+#define GMLM_ERR_INVALID 1   /* bad argument (shape / dtype / alignment / size limits) */
+#define GMLM_ERR_CUDA 2      /* a CUDA runtime call or launch failed */
+#define GMLM_ERR_INDEX 3     /* an index (node id / relation id) is out of range */
+#define GMLM_ERR_WORKSPACE 4 /* workspace too small */
+
+/* element types of dense feature matrices */
+#define GMLM_F32 0
+#define GMLM_BF16 1
+
+/* aggregation modes of gmlm_spmm_csr */
+#define GMLM_AGG_SUM 0      /* out[r] = sum_e x[col[e]]                       */
+#define GMLM_AGG_MEAN 1     /* out[r] = sum_e x[col[e]] / max(1, |row r|)     */
+#define GMLM_AGG_WEIGHTED 2 /* out[r] = sum_e w[e] * x[col[e]]                */
+
+int gmlm_abi_version(void);
+const char* gmlm_last_error(void);
+/* tuning knobs for A/B measurements: key in {"spmm_variant","spmm_unroll"}; returns old value */
+int gmlm_set_tuning(const char* key, int value);
+
+/* ---- A1  degree()  [PyG] torch_geometric.utils.degree, called main.py:65 and main.py:256 ----
+ * deg[i] = |{e : index[e] == i}|.  int32 counts are exact; the f32 variant is what the
+ * reference returns (float32[N]); identical bits while every degree < 2^24.
+ * Out-of-range indices are skipped and make the call return GMLM_ERR_INDEX when
+ * `check_host_sync` != 0 (costs one stream synchronisation). */
+int gmlm_degree_i32(const int64_t* index, int64_t num_edges, int64_t num_nodes, int32_t* deg,
+                    int check_host_sync, void* stream);
+int gmlm_degree_f32(const int64_t* index, int64_t num_edges, int64_t num_nodes, float* deg,
+                    int32_t* deg_i32_ws /* [num_nodes] scratch */, int check_host_sync, void* stream);
+
+/* ---- A2  degree-bucket edge typing, the per-edge Python loop main.py:253-267 ----
+ * edge_type[e] = #{k : deg[src[e]] > bounds_host[k]}   (bounds ascending; reference: {2,5,10}) */
+int gmlm_edge_type_bucket(const int64_t* src, int64_t num_edges, const int32_t* deg, int64_t num_nodes,
+                          const int32_t* bounds_host, int num_bounds, int64_t* edge_type, void* stream);
+
+/* per-relation edge counts (host decides which relations are populated) */
+int gmlm_relation_histogram(const int64_t* edge_type, int64_t num_edges, int num_relations,
+                            int64_t* counts /* [num_relations] */, void* stream);
+
+/* ---- A3  (dst,rel)-keyed CSR: replaces the per-relation boolean-mask compaction inside
+ *          [PyG] RGCNConv.forward (called main.py:272,285,298,308) ----
+ * Segment id s = dst*num_slots + slot_of_rel_host[edge_type[e]]  (edge_type may be NULL: slot 0).
+ * Stable in original edge order.
+ * dst in [0,num_dst), src in [0,num_src)  (equal for a whole graph; num_src > num_dst for a
+ * destination-row partition whose columns include halo rows).  Outputs:
+ *   rowptr int32[num_dst*num_slots+1], col int32[E] (= src), perm int32[E] (= original edge),
+ *   seg_of_edge int32[E] (segment of ORIGINAL edge e; may be NULL).
+ * Synchronises the stream once to report GMLM_ERR_INDEX. */
+size_t gmlm_csr_workspace_bytes(int64_t num_edges, int64_t num_rows);
+int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, int64_t num_edges,
+                   int64_t num_dst, int64_t num_src, int num_relations, const int32_t* slot_of_rel_host,
+                   int num_slots,
+                   int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* seg_of_edge,
+                   void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A14 transposed CSR for the backward gather (autograd of index_select/scatter_add in
+ *          [PyG] MessagePassing.propagate) ----
+ * rows = `row_of_edge` (e.g. src) in [0,num_rows); payload_t[i] = payload[perm_t[i]];
+ * if fwd_rowptr != NULL: w_t[i] = 1 / (fwd_rowptr[p+1]-fwd_rowptr[p]) with p = payload_t[i]
+ * (the mean divisor folded in); else if edge_w != NULL: w_t[i] = edge_w[perm_t[i]]; else w_t untouched. */
+int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const float* edge_w,
+                       const int32_t* fwd_rowptr, int64_t num_edges, int64_t num_rows,
+                       int32_t* rowptr_t, int32_t* payload_t, float* w_t, int32_t* perm_t,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- hub plan: rows longer than `thresh` are split into chunks of `thresh` edges so that the
+ *      aggregation stays balanced AND deterministic on power-law graphs ----
+ * count: counts_host[0] = #hub rows, counts_host[1] = #chunks (synchronises).
+ * fill : hub_row[n_hub], hub_chunk_ptr[n_hub+1], chunk_beg[n_chunks], chunk_end[n_chunks]. */
+int gmlm_hub_count(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64_t* counts_host,
+                   void* ws, size_t ws_bytes, void* stream);
+int gmlm_hub_fill(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64_t n_hub, int64_t n_chunks,
+                  int32_t* hub_row, int32_t* hub_chunk_ptr, int32_t* chunk_beg, int32_t* chunk_end,
+                  void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A5 / A14  aggregation: [PyG] RGCNConv.propagate + mean aggregation (forward) and the
+ *      gather-form backward.  out[r, :] = reduce_{e in row r} w[e] * x[col[e], :] ----
+ * x: [*, feat] dtype, leading dim ldx; out: [num_rows, feat] same dtype, leading dim ldo.
+ * fp32 accumulation in CSR order (deterministic).  Hub arrays may be NULL when n_hub == 0;
+ * hub_ws: float[n_chunks * feat] scratch. */
+int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx,
+                  const int32_t* rowptr, const int32_t* col, const float* w, int64_t num_rows, int mode,
+                  int32_t hub_thresh, int64_t n_hub, int64_t n_chunks, const int32_t* hub_row,
+                  const int32_t* hub_chunk_ptr, const int32_t* chunk_beg, const int32_t* chunk_end,
+                  float* hub_ws, void* out, int64_t ldo, void* stream);
+
+/* ---- A7  GraphNorm  [PyG] torch_geometric.nn.GraphNorm(batch=None), called main.py:273,286,299,309 ----
+ * stats: colsum[c] = sum_i x[i,c], colsq[c] = sum_i x[i,c]^2 in fp64 (deterministic two-stage).
+ * fwd  : mu = colsum/N; o = x - mu*mean_scale; var = E[o^2]; y = weight*o/sqrt(var+eps)+bias,
+ *        optionally followed by exact-erf GELU (main.py:274) when fuse_gelu != 0.
+ * bwd  : grads for x, weight, bias, mean_scale (through the optional GELU). */
+size_t gmlm_colstats_workspace_bytes(int64_t num_rows, int64_t channels);
+int gmlm_colstats(const void* x, int dtype, int64_t num_rows, int64_t channels, int64_t ldx,
+                  double* colsum, double* colsq, void* ws, size_t ws_bytes, void* stream);
+int gmlm_graphnorm_fwd(const void* x, int dtype, int64_t num_rows, int64_t channels, int64_t ldx,
+                       const double* colsum, const double* colsq, const float* weight, const float* bias,
+                       const float* mean_scale, float eps, int fuse_gelu, void* y, int64_t ldy,
+                       float* mean_out /* [C] */, float* rstd_out /* [C] */, void* stream);
+int gmlm_graphnorm_bwd_stats(const void* x, const void* gy, int dtype, int64_t num_rows, int64_t channels,
+                             int64_t ldx, int64_t ldg, const float* mean, const float* rstd,
+                             const float* weight, const float* bias, const float* mean_scale, int fuse_gelu,
+                             double* sum_g /* [C] sum of dL/dn */, double* sum_go /* [C] sum dL/dn * ohat */,
+                             void* ws, size_t ws_bytes, void* stream);
+int gmlm_graphnorm_bwd_apply(const void* x, const void* gy, int dtype, int64_t num_rows, int64_t channels,
+                             int64_t ldx, int64_t ldg, const float* mean, const float* rstd,
+                             const float* weight, const float* bias, const float* mean_scale, int fuse_gelu,
+                             const double* sum_g, const double* sum_go, void* gx, int64_t ldgx,
+                             float* g_weight, float* g_bias, float* g_mean_scale, void* stream);
+
+/* ---- A11 soft node masking, soft_masking_gnn_input main.py:92-99 ----
+ * fwd: y = x; y[m] = (1-beta)*x[m] + beta*token.   bwd: g_token = beta * sum_{m} gy[m]; gx (optional)
+ * = gy * (m ? 1-beta : 1). */
+int gmlm_soft_mask_fwd(const void* x, int dtype, int64_t num_rows, int64_t feat, int64_t ldx,
+                       const uint8_t* mask, const float* token, float beta, void* y, int64_t ldy, void* stream);
+size_t gmlm_soft_mask_bwd_workspace_bytes(int64_t num_rows, int64_t feat);
+int gmlm_soft_mask_bwd(const void* gy, int dtype, int64_t num_rows, int64_t feat, int64_t ldg,
+                       const uint8_t* mask, float beta, float* g_token /* [feat] */, void* gx /* may be NULL */,
+                       int64_t ldgx, void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMLM_B200_H_ */

@@ -1,0 +1,52 @@
+"""oracle/ — TEST INFRASTRUCTURE ONLY.  Never imported by the product package.
+
+CPU restatement (plain PyTorch / numpy, fp64-capable) of the reference hot path of
+chungimungi/GMLM: the GNN encoder's message-passing layers, ``main.py:250-320``,
+plus the helpers that feed them (``main.py:92-99`` soft masking, ``main.py:253-267``
+degree-bucket edge typing).
+
+**PARITY UNPINNED.**  The arithmetic of the path lives in a third-party dependency,
+``torch_geometric`` (PyPI ``torch-geometric``; version unpinned by the reference —
+it ships no requirements/lock file; API clues put it in the 2.5–2.6 era), which is
+imported at ``main.py:5-7,20`` but is not vendored under /root/reference, is not
+installed in this image and cannot be fetched (no network).  The reference has no
+tests, golden vectors or fixtures.  This oracle therefore restates
+the *published* upstream algorithms of ``RGCNConv``, ``GraphNorm``, ``degree``
+(and, for the extension variants, ``GCNConv`` / ``GATConv``) and anchors on the
+reference's own call sites:
+
+  * ``degree``     — called ``main.py:65,256``
+  * ``RGCNConv``   — built ``main.py:189,193,197,201``; called ``main.py:272,285,298,308``
+  * ``GraphNorm``  — built ``main.py:190,194,198,202``; called ``main.py:273,286,299,309``
+  * edge typing    — ``main.py:253-267`` (restated verbatim as a Python loop AND as a
+                     vectorised bucketize; the two are cross-checked in tests/)
+  * soft masking   — ``main.py:92-99``
+  * encoder body   — ``main.py:250-320``
+  * fusion         — ``main.py:167-180``
+
+The only pins available are internal: (i) the verbatim per-edge loop vs the
+vectorised form, (ii) the per-relation-loop formulation (what upstream executes)
+vs the single-(dst,rel)-CSR / single-GEMM formulation the CUDA path uses, both in
+fp64, (iii) hand-derived backward vs autograd of the restatement, (iv) committed
+golden vectors under tests/golden/ generated *from this oracle* by
+``tests/golden/make_golden.py`` (they pin the oracle against regressions, not
+against PyG).
+
+Who may import this package: ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs — as the checker or the
+timed CPU baseline, never as the product.
+"""
+from .pyg_ref import (  # noqa: F401
+    degree_ref,
+    edge_type_loop_ref,
+    edge_type_bucket_ref,
+    glorot_,
+    RGCNConvRef,
+    GraphNormRef,
+    GCNConvRef,
+    GATConvRef,
+    soft_masking_ref,
+    rgcn_propagate_mean_ref,
+)
+from .csr_ref import rel_csr_ref, transposed_csr_ref  # noqa: F401
+from .encoder_ref import EncoderRef, MultiScaleFusionRef  # noqa: F401

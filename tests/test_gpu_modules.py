@@ -1,0 +1,195 @@
+"""GPU parity of the drop-in modules against the oracle restatement of the reference path:
+RGCNConv (main.py:189/272), GraphNorm (main.py:190/273), soft masking (main.py:92-99) and the
+whole encoder body (main.py:250-320), forward and parameter/input gradients."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import gmlm_b200 as G
+from gmlm_b200 import synth
+from oracle import (EncoderRef, GraphNormRef, RGCNConvRef, edge_type_bucket_ref, soft_masking_ref)
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+def _copy_params(dst: torch.nn.Module, src: torch.nn.Module):
+    missing, unexpected = dst.load_state_dict(src.state_dict(), strict=False)
+    return missing, unexpected
+
+
+@pytest.mark.parametrize("n,e,fi,fo", [(183, 300, 1703, 64), (500, 4000, 300, 96), (64, 900, 32, 256), (1, 3, 16, 8)])
+def test_rgcn_conv_matches_oracle(cuda_dev, n, e, fi, fo):
+    torch.manual_seed(0)
+    ei = synth.uniform_edges(n, e, seed=n)
+    et = edge_type_bucket_ref(ei, n)
+    ref = RGCNConvRef(fi, fo, num_relations=5, num_bases=30).double()
+    with torch.no_grad():
+        ref.bias.uniform_(-0.1, 0.1)
+    mod = G.RGCNConv(fi, fo, num_relations=5, num_bases=30)
+    assert set(mod.state_dict()) == set(ref.state_dict()) == {"weight", "comp", "root", "bias"}
+    for k, v in mod.state_dict().items():
+        assert v.shape == ref.state_dict()[k].shape
+    mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mod = mod.to(cuda_dev)
+    x = torch.randn(n, fi)
+    gout = torch.randn(n, fo)
+
+    x64 = x.double().requires_grad_(True)
+    y_ref = ref(x64, ei, et)
+    y_ref.backward(gout.double())
+
+    xg = x.to(cuda_dev).requires_grad_(True)
+    y = mod(xg, ei.to(cuda_dev), et.to(cuda_dev))
+    assert y.dtype == torch.float32
+    y.backward(gout.to(cuda_dev))
+    assert rel_err(y, y_ref) <= FP32_TOL
+    assert rel_err(xg.grad, x64.grad) <= FP32_TOL
+    for name in ("weight", "comp", "root", "bias"):
+        assert rel_err(getattr(mod, name).grad, getattr(ref, name).grad) <= 2e-5, name
+    # relation 4 is never produced by the degree buckets: exact-zero comp gradient
+    assert torch.count_nonzero(mod.comp.grad[4]) == 0
+
+
+def test_rgcn_conv_autocast(cuda_dev):
+    """Callers run the encoder under torch.amp.autocast (main.py:446,543): fp32 in, fp32 out,
+    half-precision GEMMs; tolerance 2e-2."""
+    n, e, fi, fo = 300, 2500, 128, 64
+    ei = synth.uniform_edges(n, e, seed=9)
+    et = edge_type_bucket_ref(ei, n)
+    ref = RGCNConvRef(fi, fo, 5, 30).double()
+    mod = G.RGCNConv(fi, fo, 5, 30)
+    mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mod = mod.to(cuda_dev)
+    x = torch.randn(n, fi)
+    with torch.amp.autocast("cuda"):
+        y = mod(x.to(cuda_dev), ei.to(cuda_dev), et.to(cuda_dev))
+    assert y.dtype == torch.float32
+    assert rel_err(y, ref(x.double(), ei, et)) <= BF16_TOL
+
+
+@pytest.mark.parametrize("n,c", [(2, 8), (183, 512), (1000, 300), (4097, 64), (333, 1703)])
+@pytest.mark.parametrize("fuse_gelu", [False, True])
+def test_graph_norm_matches_oracle(cuda_dev, n, c, fuse_gelu):
+    torch.manual_seed(1)
+    ref = GraphNormRef(c).double()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.uniform_(-0.5, 0.5)
+        ref.mean_scale.uniform_(0.2, 1.2)
+    mod = G.GraphNorm(c)
+    assert set(mod.state_dict()) == {"weight", "bias", "mean_scale"}
+    mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mod = mod.to(cuda_dev)
+    x = torch.randn(n, c) * 2.0 + 3.0          # non-zero mean: exercises the shifted-variance identity
+    gout = torch.randn(n, c)
+    x64 = x.double().requires_grad_(True)
+    y_ref = ref(x64)
+    if fuse_gelu:
+        y_ref = F.gelu(y_ref)
+    y_ref.backward(gout.double())
+    xg = x.to(cuda_dev).requires_grad_(True)
+    y = mod(xg, fuse_gelu=fuse_gelu)
+    y.backward(gout.to(cuda_dev))
+    assert rel_err(y, y_ref) <= FP32_TOL
+    assert rel_err(xg.grad, x64.grad) <= 2e-5
+    for name in ("weight", "bias", "mean_scale"):
+        assert rel_err(getattr(mod, name).grad, getattr(ref, name).grad) <= 2e-5, name
+
+
+def test_graph_norm_bf16(cuda_dev):
+    n, c = 2000, 256
+    ref = GraphNormRef(c).double()
+    mod = G.GraphNorm(c).to(cuda_dev)
+    x = (torch.randn(n, c) + 1.0).bfloat16()
+    y = mod(x.to(cuda_dev), fuse_gelu=True)
+    assert y.dtype == torch.bfloat16
+    assert rel_err(y, F.gelu(ref(x.double()))) <= BF16_TOL
+
+
+@pytest.mark.parametrize("n,f", [(183, 1703), (1000, 300), (50, 256)])
+@pytest.mark.parametrize("ratio", [0.0, 0.3, 1.0])
+def test_soft_mask_bit_exact_and_grad(cuda_dev, n, f, ratio):
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(n, f, generator=gen)
+    mask = torch.rand(n, generator=gen) < ratio
+    token = torch.randn(1, f, generator=gen) * 0.1
+    ref = soft_masking_ref(x, mask, token, beta=0.7)
+    tok = token.to(cuda_dev).requires_grad_(True)
+    xg = x.to(cuda_dev).requires_grad_(True)
+    got = G.soft_masking_gnn_input(xg, mask.to(cuda_dev), tok, beta=0.7)
+    assert torch.equal(got.cpu(), ref)                       # same rounding sequence as main.py:98
+    gout = torch.randn(n, f, generator=gen)
+    got.backward(gout.to(cuda_dev))
+    t64 = token.double().requires_grad_(True)
+    x64 = x.double().requires_grad_(True)
+    soft_masking_ref(x64, mask, t64, beta=0.7).backward(gout.double())
+    if t64.grad is None:
+        assert torch.count_nonzero(tok.grad) == 0
+    else:
+        assert rel_err(tok.grad, t64.grad) <= FP32_TOL
+    assert rel_err(xg.grad, x64.grad) <= FP32_TOL
+
+
+def _encoder_pair(fin, hidden, out_dim, dropout=0.0):
+    torch.manual_seed(5)
+    ref = EncoderRef(fin, hidden, out_dim, dropout_rate=dropout, use_checkpoint=False).double()
+    with torch.no_grad():
+        for k in range(1, 5):
+            getattr(ref, f"gnorm{k}").mean_scale.uniform_(0.5, 1.0)
+            getattr(ref, f"rgcn{k}").bias.uniform_(-0.1, 0.1)
+    mod = G.GraphEncoder(fin, hidden, out_dim, dropout_rate=dropout)
+    missing, unexpected = mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()}, strict=False)
+    assert unexpected == [] and missing == ["gnn_mask_token_embed"]
+    return ref, mod
+
+
+@pytest.mark.parametrize("n,e,fin,hidden", [(183, 300, 1703, 32), (2000, 9000, 300, 16), (1, 2, 24, 8)])
+@pytest.mark.parametrize("use_checkpoint", [False, True])
+def test_encoder_matches_oracle(cuda_dev, n, e, fin, hidden, use_checkpoint):
+    """Whole get_graph_embeddings body (main.py:250-320), eval-free (dropout p=0), fp32."""
+    ref, mod = _encoder_pair(fin, hidden, 48)
+    mod = mod.to(cuda_dev)
+    mod.use_checkpoint = use_checkpoint
+    ei = synth.uniform_edges(n, e, seed=n + 1)
+    x = torch.randn(n, fin)
+    fused_ref, layers_ref = ref(x.double(), ei, return_layers=True)
+    fused, layers = mod.get_graph_embeddings(x.to(cuda_dev), ei.to(cuda_dev), return_layers=True)
+    for a, b in zip(layers, layers_ref):
+        assert rel_err(a, b) <= 5e-5     # four stacked layers: per-layer 1e-5 compounds
+    assert rel_err(fused, fused_ref) <= 5e-5
+    gout = torch.randn(n, 48)
+    fused_ref.backward(gout.double())
+    fused.backward(gout.to(cuda_dev))
+    sd_ref = dict(ref.named_parameters())
+    for name, p in mod.named_parameters():
+        if name == "gnn_mask_token_embed":
+            continue
+        if name.startswith("residual_proj3"):
+            assert p.grad is None and sd_ref[name].grad is None      # dead branch, main.py:317-318
+            continue
+        assert p.grad is not None, name
+        assert rel_err(p.grad, sd_ref[name].grad) <= 2e-4, name
+
+
+def test_encoder_with_soft_mask_and_autocast(cuda_dev):
+    """Caller #1/#2 shape (main.py:443-448): soft-masked input, autocast region."""
+    n, e, fin, hidden = 600, 3000, 300, 16
+    ref, mod = _encoder_pair(fin, hidden, 32)
+    mod = mod.to(cuda_dev)
+    ei = synth.uniform_edges(n, e, seed=77)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.randn(n, fin, generator=gen)
+    mask = torch.rand(n, generator=gen) < 0.3
+    tok = mod.gnn_mask_token_embed.detach().cpu()
+    fused_ref = ref(soft_masking_ref(x.double(), mask, tok.double()), ei)
+    with torch.amp.autocast("cuda"):
+        fused = mod(x.to(cuda_dev), ei.to(cuda_dev), gnn_perturb_mask=mask.to(cuda_dev))
+    assert rel_err(fused, fused_ref) <= BF16_TOL
+    fused.float().sum().backward()
+    assert mod.gnn_mask_token_embed.grad is not None
+    assert torch.isfinite(mod.gnn_mask_token_embed.grad).all()

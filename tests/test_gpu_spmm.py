@@ -1,0 +1,174 @@
+"""GPU parity of the aggregation kernel (SURVEY §8a rows A5 forward, A14 backward) against the
+oracle's per-relation index_select/index_add_ restatement of [PyG] RGCNConv.propagate (called
+main.py:272,285,298,308).  Gates: <= 1e-5 relative (fp32), <= 2e-2 (bf16) — north_star."""
+import pytest
+import torch
+
+import gmlm_b200 as G
+from gmlm_b200 import synth
+from oracle import edge_type_bucket_ref, rgcn_propagate_mean_ref
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-5
+BF16_TOL = 2e-2
+
+
+def oracle_aggregate(x64, ei, et, n, live):
+    """[N, S*F] per-(dst, live relation) means, fp64, relation loop as upstream executes it."""
+    outs = []
+    for r in live:
+        m = et == r
+        outs.append(rgcn_propagate_mean_ref(x64, ei[0, m], ei[1, m], n))
+    return torch.cat(outs, dim=1)
+
+
+def _case(n, e, seed, kind="uniform"):
+    ei = synth.rmat_edges(n, e, seed=seed) if kind == "rmat" else synth.uniform_edges(n, e, seed=seed)
+    return n, ei
+
+
+@pytest.mark.parametrize("feat", [1, 5, 64, 96, 128, 256, 300, 512, 1000, 1703])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_aggregate_fp32_widths(cuda_dev, feat, variant):
+    n, ei = _case(257, 2000, seed=feat)
+    et = edge_type_bucket_ref(ei, n)
+    x = torch.randn(n, feat, generator=torch.Generator().manual_seed(1))
+    old = G.set_tuning("spmm_variant", variant)
+    try:
+        g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=64)
+        got = G.rgcn_aggregate(x.to(cuda_dev), g)
+    finally:
+        G.set_tuning("spmm_variant", old)
+    ref = oracle_aggregate(x.double(), ei, et, n, g.live_rels)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= FP32_TOL
+
+
+@pytest.mark.parametrize("feat", [8, 64, 128, 256, 264, 512, 257])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_aggregate_bf16_widths(cuda_dev, feat, variant):
+    n, ei = _case(300, 3000, seed=feat + 1)
+    et = edge_type_bucket_ref(ei, n)
+    x = torch.randn(n, feat, generator=torch.Generator().manual_seed(2)).bfloat16()
+    old = G.set_tuning("spmm_variant", variant)
+    try:
+        g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=64)
+        got = G.rgcn_aggregate(x.to(cuda_dev), g)
+    finally:
+        G.set_tuning("spmm_variant", old)
+    assert got.dtype == torch.bfloat16
+    ref = oracle_aggregate(x.double(), ei, et, n, g.live_rels)
+    assert rel_err(got, ref) <= BF16_TOL
+    # accumulation is fp32: the only bf16 rounding is the final store
+    assert rel_err(got, ref.bfloat16()) <= 1e-2
+
+
+@pytest.mark.parametrize("hub_thresh", [1, 3, 16, 100000])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_aggregate_hub_rows_and_determinism(cuda_dev, hub_thresh, variant):
+    """A star-like graph: the hub path (chunk partials + in-order final sum) must agree with the
+    oracle and be bit-identical run to run (the stock scatter_add_ path is not)."""
+    gen = torch.Generator().manual_seed(5)
+    n, e, feat = 400, 20000, 256
+    dst = torch.where(torch.rand(e, generator=gen) < 0.6, torch.randint(0, 3, (e,), generator=gen),
+                      torch.randint(0, n, (e,), generator=gen))
+    src = torch.randint(0, n, (e,), generator=gen)
+    ei = torch.stack([src, dst])
+    et = edge_type_bucket_ref(ei, n)
+    x = torch.randn(n, feat, generator=gen)
+    old = G.set_tuning("spmm_variant", variant)
+    try:
+        g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh)
+        xs = x.to(cuda_dev)
+        a = G.rgcn_aggregate(xs, g)
+        b = G.rgcn_aggregate(xs, g)
+    finally:
+        G.set_tuning("spmm_variant", old)
+    assert torch.equal(a, b)
+    ref = oracle_aggregate(x.double(), ei, et, n, g.live_rels)
+    assert rel_err(a, ref) <= FP32_TOL
+    if hub_thresh < 100000:
+        assert g.fwd.n_hub > 0
+
+
+@pytest.mark.parametrize("name,n,e,kind", [("empty", 7, 0, "uniform"), ("one_node", 1, 4, "uniform"),
+                                           ("cornell", 183, 300, "uniform"), ("rmat", 4096, 50000, "rmat")])
+def test_aggregate_edge_cases(cuda_dev, name, n, e, kind):
+    _, ei = _case(n, e, seed=11, kind=kind)
+    et = edge_type_bucket_ref(ei, n)
+    x = torch.randn(n, 40, generator=torch.Generator().manual_seed(3))
+    g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5)
+    got = G.rgcn_aggregate(x.to(cuda_dev), g)
+    ref = oracle_aggregate(x.double(), ei, et, n, g.live_rels)
+    assert got.shape == ref.shape
+    if e == 0:
+        assert torch.count_nonzero(got) == 0
+    else:
+        assert rel_err(got, ref) <= FP32_TOL
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
+@pytest.mark.parametrize("hub_thresh", [8, 1024])
+def test_aggregate_backward_matches_autograd_of_oracle(cuda_dev, dtype, tol, hub_thresh):
+    """A14: gather on the transposed CSR with 1/count folded in == autograd through
+    index_select + index_add_ + divide (what the reference's backward executes)."""
+    n, ei = _case(500, 6000, seed=21, kind="rmat")
+    et = edge_type_bucket_ref(ei, n)
+    gen = torch.Generator().manual_seed(4)
+    feat = 128
+    x = torch.randn(n, feat, generator=gen).to(dtype)
+    g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh)
+    gh = torch.randn(n, g.num_slots * feat, generator=gen).to(dtype)
+
+    xg = x.to(cuda_dev).requires_grad_(True)
+    out = G.rgcn_aggregate(xg, g)
+    out.backward(gh.to(cuda_dev))
+
+    x64 = x.double().requires_grad_(True)
+    ref = oracle_aggregate(x64, ei, et, n, g.live_rels)
+    ref.backward(gh.double())
+    assert rel_err(out, ref) <= tol
+    assert rel_err(xg.grad, x64.grad) <= tol
+
+
+def test_aggregate_linearity_full_size_property(cuda_dev):
+    """Size-independent property used at BASELINE sizes: aggregation is linear, and aggregating a
+    constant-one feature returns exactly 1 on non-empty (dst,rel) segments and 0 on empty ones."""
+    n, e, feat = 200_000, 4_000_000, 64
+    ei = synth.rmat_edges(n, e, device=cuda_dev, seed=42)
+    et = G.edge_type_from_degree(ei, n)
+    g = G.get_rel_graph(ei, et, n, 5)
+    ones = torch.ones(n, feat, device=cuda_dev)
+    h = G.rgcn_aggregate(ones, g).view(n * g.num_slots, feat)
+    lens = (g.fwd.rowptr[1:] - g.fwd.rowptr[:-1]).long()
+    # mean of ones: exact for short rows, within fp32 rounding of len*(1/len) for long ones
+    expect = (lens > 0).float().unsqueeze(1).expand_as(h)
+    assert float((h - expect).abs().max()) <= 1e-6
+    assert int(lens.sum()) == e
+    x = synth.make_features(n, feat, device=cuda_dev, seed=1)
+    y = synth.make_features(n, feat, device=cuda_dev, seed=2)
+    lhs = G.rgcn_aggregate(2.0 * x + y, g)
+    rhs = 2.0 * G.rgcn_aggregate(x, g) + G.rgcn_aggregate(y, g)
+    assert rel_err(lhs, rhs) <= 1e-5
+    # adjoint identity <A x, g> == <x, A^T g> ties the backward kernel to the forward one
+    gh = torch.randn_like(lhs)
+    xg = x.clone().requires_grad_(True)
+    out = G.rgcn_aggregate(xg, g)
+    out.backward(gh)
+    lhs_ip = (out.double() * gh.double()).sum()
+    rhs_ip = (x.double() * xg.grad.double()).sum()
+    scale = float(out.double().norm() * gh.double().norm())
+    assert abs(float(lhs_ip - rhs_ip)) <= 1e-5 * scale
+
+
+def test_cpu_tensors_raise(lib_built):
+    x = torch.randn(4, 8)
+    with pytest.raises(Exception):
+        G.degree(torch.tensor([0, 1, 2]), 4)
+    ei = torch.tensor([[0, 1], [1, 2]])
+    with pytest.raises(Exception):
+        G.RelGraph.build(ei, torch.tensor([0, 0]), 4, 5)
+    del x
