@@ -30,8 +30,10 @@ SIGNATURES = {
     "gmlm_csr_transpose": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "gmlm_hub_count": (_int, [_p, _i64, _i32, C.POINTER(_i64), _p, _sz, _p]),
     "gmlm_hub_fill": (_int, [_p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
-    "gmlm_spmm_csr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i64, _int, _i32, _i64, _i64, _p, _p, _p, _p, _p,
-                             _p, _i64, _p]),
+    "gmlm_group_plan_size": (_i64, [_i64, _i64, _i64]),
+    "gmlm_group_plan": (_int, [_p, _i64, _i64, _i64, _p, _p]),
+    "gmlm_spmm_csr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i64, _int, _p, _i64, _i32, _i64, _i64, _p, _p, _p,
+                             _p, _p, _p, _i64, _p]),
     "gmlm_colstats_workspace_bytes": (_sz, [_i64, _i64]),
     "gmlm_colstats": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "gmlm_graphnorm_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f32, _int, _p, _i64, _p, _p, _p]),

@@ -84,6 +84,7 @@ struct Pack<float, 4> {
   __device__ __forceinline__ void store(float* p) const { __stcs(reinterpret_cast<float4*>(p), v); }
   __device__ __forceinline__ void unpack(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
   __device__ __forceinline__ void pack(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
 };
 
 template <>
@@ -93,6 +94,7 @@ struct Pack<float, 1> {
   __device__ __forceinline__ void store(float* p) const { *p = v; }
   __device__ __forceinline__ void unpack(float* f) const { f[0] = v; }
   __device__ __forceinline__ void pack(const float* f) { v = f[0]; }
+  __device__ __forceinline__ void zero() { v = 0.f; }
 };
 
 template <>
@@ -115,6 +117,7 @@ struct Pack<__nv_bfloat16, 8> {
     v.x = *reinterpret_cast<uint32_t*>(&a); v.y = *reinterpret_cast<uint32_t*>(&b);
     v.z = *reinterpret_cast<uint32_t*>(&c); v.w = *reinterpret_cast<uint32_t*>(&d);
   }
+  __device__ __forceinline__ void zero() { v = make_uint4(0u, 0u, 0u, 0u); }
 };
 
 template <>
@@ -124,6 +127,7 @@ struct Pack<__nv_bfloat16, 1> {
   __device__ __forceinline__ void store(__nv_bfloat16* p) const { *p = v; }
   __device__ __forceinline__ void unpack(float* f) const { f[0] = __bfloat162float(v); }
   __device__ __forceinline__ void pack(const float* f) { v = __float2bfloat16_rn(f[0]); }
+  __device__ __forceinline__ void zero() { v = __float2bfloat16_rn(0.f); }
 };
 
 __device__ __forceinline__ float to_float(float v) { return v; }

@@ -18,7 +18,8 @@ import torch
 
 from . import _lib
 
-DEFAULT_HUB_THRESH = int(os.environ.get("GMLM_HUB_THRESH", "1024"))
+DEFAULT_HUB_THRESH = int(os.environ.get("GMLM_HUB_THRESH", "256"))
+DEFAULT_QUANTUM = int(os.environ.get("GMLM_GROUP_QUANTUM", "512"))   # 0 = uniform 32-row groups
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -50,10 +51,29 @@ class CSR:
     hub_chunk_ptr: Optional[torch.Tensor] = None
     chunk_beg: Optional[torch.Tensor] = None
     chunk_end: Optional[torch.Tensor] = None
+    quantum: int = 0                           # cost-balanced group plan (0 = uniform groups)
+    n_groups: int = 0
+    grp_row: Optional[torch.Tensor] = None     # int32 [n_groups+1]
 
     @property
     def nnz(self) -> int:
         return int(self.col.numel())
+
+    def plan_groups(self, quantum: Optional[int] = None):
+        """Cut the rows into groups of about ``quantum`` units of work (edges + rows)."""
+        lib = _lib.load()
+        q = DEFAULT_QUANTUM if quantum is None else int(quantum)
+        self.quantum = q
+        if q <= 0 or self.num_rows == 0:
+            self.n_groups, self.grp_row = 0, None
+            return self
+        dev = self.rowptr.device
+        with torch.cuda.device(dev):
+            self.n_groups = int(lib.gmlm_group_plan_size(self.num_rows, self.nnz, q))
+            self.grp_row = torch.empty(self.n_groups + 1, dtype=torch.int32, device=dev)
+            _lib.check(lib.gmlm_group_plan(_ptr(self.rowptr), self.num_rows, self.nnz, q, _ptr(self.grp_row),
+                                           _stream(dev)), "group_plan")
+        return self
 
     def plan_hubs(self, thresh: Optional[int] = None):
         """Split rows longer than ``thresh`` into fixed chunks (deterministic two-stage reduce)."""
@@ -84,7 +104,8 @@ class CSR:
 def build_csr(row: torch.Tensor, col: torch.Tensor, num_rows: int, num_cols: int, *,
               rel: Optional[torch.Tensor] = None, num_relations: int = 1,
               slot_of_rel: Optional[List[int]] = None, num_slots: int = 1,
-              want_seg_of_edge: bool = False, hub_thresh: Optional[int] = None):
+              want_seg_of_edge: bool = False, hub_thresh: Optional[int] = None,
+              quantum: Optional[int] = None):
     """CSR with segments ``row*num_slots + slot_of_rel[rel]`` and gather index ``col``.
 
     ``row``/``col``/``rel`` are int64 edge arrays (as in ``edge_index`` / ``edge_type``).
@@ -119,12 +140,13 @@ def build_csr(row: torch.Tensor, col: torch.Tensor, num_rows: int, num_cols: int
                                       _stream(dev)), "csr_build")
     csr = CSR(rowptr=rowptr, col=colv, num_rows=rows_total, perm=perm)
     csr.plan_hubs(hub_thresh)
+    csr.plan_groups(quantum)
     return csr, seg
 
 
 def transpose_csr(row_of_edge: torch.Tensor, payload: torch.Tensor, num_rows: int, *,
                   fwd_rowptr: Optional[torch.Tensor] = None, edge_w: Optional[torch.Tensor] = None,
-                  hub_thresh: Optional[int] = None) -> CSR:
+                  hub_thresh: Optional[int] = None, quantum: Optional[int] = None) -> CSR:
     """CSR over ``row_of_edge`` (int64 [E]) whose gather index is ``payload`` (int32 [E], e.g. the
     forward segment of each edge); weights are 1/|fwd segment| or ``edge_w`` permuted."""
     lib = _lib.load()
@@ -144,6 +166,7 @@ def transpose_csr(row_of_edge: torch.Tensor, payload: torch.Tensor, num_rows: in
                                           _ptr(ws), ws_bytes, _stream(dev)), "csr_transpose")
     csr = CSR(rowptr=rowptr_t, col=payload_t, num_rows=num_rows, w=w_t, perm=perm_t)
     csr.plan_hubs(hub_thresh)
+    csr.plan_groups(quantum)
     return csr
 
 
@@ -154,13 +177,18 @@ class RelGraph:
     ``fwd`` rows are the segments ``dst*num_slots + slot`` (slot = index of the relation among
     the populated ones), gather index = source node.  ``bwd`` rows are source nodes, gather
     index = forward segment, weight = 1/|segment|."""
-    num_nodes: int
+    num_nodes: int                 # destination rows (== source rows for a whole graph)
     num_edges: int
     num_relations: int
     live_rels: List[int]
     fwd: CSR
     bwd: CSR
+    num_src: int = -1              # source rows; > num_nodes for a partition with halo rows
     _keepalive: list = field(default_factory=list, repr=False)
+
+    def __post_init__(self):
+        if self.num_src < 0:
+            self.num_src = self.num_nodes
 
     @property
     def num_slots(self) -> int:
@@ -168,8 +196,13 @@ class RelGraph:
 
     @staticmethod
     def build(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int, num_relations: int,
-              hub_thresh: Optional[int] = None) -> "RelGraph":
+              hub_thresh: Optional[int] = None, quantum: Optional[int] = None, num_src: Optional[int] = None,
+              live_rels: Optional[List[int]] = None) -> "RelGraph":
+        """``num_src`` > ``num_nodes`` builds the rectangular CSR of a destination-row partition
+        (columns = local rows followed by halo rows).  ``live_rels`` pins the relation->slot
+        layout (ranks of a partition must agree on it); default = the populated relations."""
         lib = _lib.load()
+        n_src = num_nodes if num_src is None else int(num_src)
         _require_cuda(edge_index, "edge_index")
         if edge_index.dim() != 2 or edge_index.size(0) != 2:
             raise _lib.GmlmError(f"edge_index must have shape [2, E], got {tuple(edge_index.shape)}")
@@ -191,6 +224,10 @@ class RelGraph:
                                                        _stream(dev)), "relation_histogram")
             counts_h = counts.cpu().tolist()
             live = [r for r, c in enumerate(counts_h) if c > 0]
+            if live_rels is not None:
+                if not set(live) <= set(live_rels):
+                    raise _lib.GmlmError(f"live_rels {live_rels} does not cover the populated relations {live}")
+                live = sorted(live_rels)
             if sum(counts_h) != E:
                 raise _lib.GmlmError(f"edge_type has values outside [0, {num_relations})")
             if not live:
@@ -200,12 +237,12 @@ class RelGraph:
             slot_of_rel[r] = s
         if edge_type is None:
             slot_of_rel[0] = 0
-        fwd, seg = build_csr(dst, src, num_nodes, num_nodes, rel=edge_type, num_relations=num_relations,
+        fwd, seg = build_csr(dst, src, num_nodes, n_src, rel=edge_type, num_relations=num_relations,
                              slot_of_rel=slot_of_rel, num_slots=len(live), want_seg_of_edge=True,
-                             hub_thresh=hub_thresh)
-        bwd = transpose_csr(src, seg, num_nodes, fwd_rowptr=fwd.rowptr, hub_thresh=hub_thresh)
+                             hub_thresh=hub_thresh, quantum=quantum)
+        bwd = transpose_csr(src, seg, n_src, fwd_rowptr=fwd.rowptr, hub_thresh=hub_thresh, quantum=quantum)
         return RelGraph(num_nodes=num_nodes, num_edges=E, num_relations=num_relations, live_rels=live, fwd=fwd,
-                        bwd=bwd)
+                        bwd=bwd, num_src=n_src)
 
 
 # ------------------------------------------------------------------------------ cache

@@ -49,8 +49,8 @@ def _ld(t: torch.Tensor) -> int:
 _LIB = torch.library.Library("gmlm", "DEF")
 _LIB.define("degree_i32(Tensor index, int num_nodes) -> Tensor")
 _LIB.define("edge_type_bucket(Tensor src, Tensor deg, int[] bounds) -> Tensor")
-_LIB.define("spmm_csr(Tensor x, Tensor rowptr, Tensor col, Tensor? w, int num_rows, int mode, int hub_thresh, "
-            "Tensor? hub_row, Tensor? hub_chunk_ptr, Tensor? chunk_beg, Tensor? chunk_end) -> Tensor")
+_LIB.define("spmm_csr(Tensor x, Tensor rowptr, Tensor col, Tensor? w, int num_rows, int mode, Tensor? grp_row, "
+            "int hub_thresh, Tensor? hub_row, Tensor? hub_chunk_ptr, Tensor? chunk_beg, Tensor? chunk_end) -> Tensor")
 _LIB.define("colstats(Tensor x) -> (Tensor, Tensor)")
 _LIB.define("graphnorm_fwd(Tensor x, Tensor weight, Tensor bias, Tensor mean_scale, float eps, bool fuse_gelu) "
             "-> (Tensor, Tensor, Tensor)")
@@ -88,18 +88,20 @@ def _edge_type_bucket(src: torch.Tensor, deg: torch.Tensor, bounds: Sequence[int
 
 
 # ------------------------------------------------------------------------------ A5 / A14
-def _spmm_csr(x, rowptr, col, w, num_rows, mode, hub_thresh, hub_row, hub_chunk_ptr, chunk_beg, chunk_end):
+def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, hub_chunk_ptr, chunk_beg, chunk_end):
     lib = _lib.load()
     x = _rowmajor(x)
     feat = int(x.size(1))
     dev = x.device
     n_hub = int(hub_row.numel()) if hub_row is not None else 0
     n_chunks = int(chunk_beg.numel()) if chunk_beg is not None else 0
+    n_groups = int(grp_row.numel()) - 1 if grp_row is not None else 0
     with torch.cuda.device(dev):
         out = torch.empty((num_rows, feat), dtype=x.dtype, device=dev)
         hub_ws = torch.empty(n_chunks * feat, dtype=torch.float32, device=dev) if n_hub else None
         _lib.check(lib.gmlm_spmm_csr(_ptr(x), _dtype_code(x, "spmm_csr"), feat, _ld(x), _ptr(rowptr), _ptr(col),
-                                     _ptr(w), num_rows, mode, hub_thresh, n_hub, n_chunks, _ptr(hub_row),
+                                     _ptr(w), num_rows, mode, _ptr(grp_row), n_groups, hub_thresh, n_hub, n_chunks,
+                                     _ptr(hub_row),
                                      _ptr(hub_chunk_ptr), _ptr(chunk_beg), _ptr(chunk_end), _ptr(hub_ws), _ptr(out),
                                      feat, _stream(dev)), "spmm_csr")
     return out
@@ -109,7 +111,7 @@ def spmm(x: torch.Tensor, csr: CSR, mode: int) -> torch.Tensor:
     """out[r] = reduce over row r of csr (no autograd)."""
     _require_cuda(x, "x")
     return torch.ops.gmlm.spmm_csr(x, csr.rowptr, csr.col, csr.w if mode == _lib.AGG_WEIGHTED else None,
-                                   csr.num_rows, mode, csr.hub_thresh, csr.hub_row, csr.hub_chunk_ptr,
+                                   csr.num_rows, mode, csr.grp_row, csr.hub_thresh, csr.hub_row, csr.hub_chunk_ptr,
                                    csr.chunk_beg, csr.chunk_end)
 
 
@@ -277,8 +279,8 @@ def rgcn_aggregate(x: torch.Tensor, graph: RelGraph) -> torch.Tensor:
     """Per-(dst, relation) mean of source rows: ``[N, F] -> [N, S*F]`` (S = populated relations).
     Forward = A5, backward = A14 (gather on the transposed CSR with 1/count folded in)."""
     _require_cuda(x, "x")
-    if x.size(0) != graph.num_nodes:
-        raise _lib.GmlmError(f"x has {x.size(0)} rows, graph has {graph.num_nodes} nodes")
+    if x.size(0) != graph.num_src:
+        raise _lib.GmlmError(f"x has {x.size(0)} rows, graph has {graph.num_src} source nodes")
     return _RGCNAggregate.apply(x, graph)
 
 

@@ -1,0 +1,267 @@
+"""Destination-row partitioning of a graph across ranks with a halo exchange of source rows
+(SURVEY §8e).  The reference has no distributed code at all (single process, single device,
+``/root/reference/main.py:43``); this is the B200-box scaling path north_star asks for: one
+process per GPU, nodes split into contiguous destination-row ranges balanced by work, every
+rank owns the in-edges of its rows, and before each layer's aggregation the distinct remote
+source rows ("halo") are fetched over NVLink.
+
+Host logic here is device-agnostic torch (tested on CPU with the gloo backend, world_size 2);
+the aggregation itself is the CUDA kernel on the rank's local CSR, whose column space is
+``[local rows ‖ halo rows]``.
+
+Forward:  X = [x_local ‖ all_to_all(x_local[send_ids])];  H = aggregate(X, local CSR)
+Backward: gX = aggregate^T(gH);  gx_local = gX[:n_local] + scatter(all_to_all^T(gX[n_local:]))
+          (added peer by peer in rank order, indices unique within a peer -> deterministic)
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def partition_ranges(in_deg: torch.Tensor, world: int, node_cost: float = 1.0) -> List[Tuple[int, int]]:
+    """Contiguous node ranges with about equal  (#in-edges + node_cost * #nodes)  each —
+    the same cost the aggregation kernel's group plan balances."""
+    n = int(in_deg.numel())
+    cost = in_deg.to(torch.float64) + node_cost
+    csum = torch.cumsum(cost, 0)
+    total = float(csum[-1]) if n else 0.0
+    targets = torch.tensor([total * (p + 1) / world for p in range(world - 1)], dtype=torch.float64,
+                           device=in_deg.device)
+    cuts = torch.searchsorted(csum, targets, right=False).tolist() if n else [0] * (world - 1)
+    bounds = [0] + [min(int(c) + 1, n) for c in cuts] + [n]
+    for i in range(1, len(bounds)):           # monotone, even for degenerate inputs
+        bounds[i] = max(bounds[i], bounds[i - 1])
+    return [(bounds[p], bounds[p + 1]) for p in range(world)]
+
+
+@dataclass
+class LocalPart:
+    rank: int
+    world: int
+    ranges: List[Tuple[int, int]]
+    n_local: int
+    n_halo: int
+    halo_gid: torch.Tensor           # int64 [n_halo] global ids of the remote source rows, ascending
+    recv_splits: List[int]           # rows received from each peer (sums to n_halo)
+    send_ids: torch.Tensor           # int64 [n_send] LOCAL ids of the rows each peer needs, peer-major
+    send_splits: List[int]
+    edge_index: torch.Tensor         # int64 [2, E_local]: src in [0, n_local+n_halo), dst in [0, n_local)
+    edge_type: Optional[torch.Tensor]
+
+    @property
+    def lo(self) -> int:
+        return self.ranges[self.rank][0]
+
+    @property
+    def n_src(self) -> int:
+        return self.n_local + self.n_halo
+
+
+def select_local(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], ranges, rank: int):
+    """Communication-free half of the partition build: this rank's in-edges with sources
+    renumbered into [local ‖ halo].  Returns (edge_index_local, edge_type_local, halo_gid, recv_splits)."""
+    lo, hi = ranges[rank]
+    dev = edge_index.device
+    src, dst = edge_index[0], edge_index[1]
+    mine = (dst >= lo) & (dst < hi)
+    src_m, dst_m = src[mine], dst[mine] - lo
+    et_m = edge_type[mine] if edge_type is not None else None
+    n_local = hi - lo
+    is_local = (src_m >= lo) & (src_m < hi)
+    halo_gid = torch.unique(src_m[~is_local])                     # sorted ascending => grouped by owner
+    src_new = torch.empty_like(src_m)
+    src_new[is_local] = src_m[is_local] - lo
+    src_new[~is_local] = n_local + torch.searchsorted(halo_gid, src_m[~is_local])
+    starts = torch.tensor([r[0] for r in ranges] + [ranges[-1][1]], dtype=torch.int64, device=dev)
+    owner_bounds = torch.searchsorted(halo_gid, starts)           # halo rows owned by peer q: [b[q], b[q+1])
+    recv_splits = (owner_bounds[1:] - owner_bounds[:-1]).tolist()
+    return torch.stack([src_new, dst_m]), et_m, halo_gid, recv_splits
+
+
+def build_local_part(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], ranges, rank: int,
+                     group=None) -> LocalPart:
+    """Select this rank's in-edges, renumber sources into [local ‖ halo] and agree the send
+    lists with the peers (one all_to_all of counts, one of ids)."""
+    world = len(ranges)
+    lo, hi = ranges[rank]
+    dev = edge_index.device
+    ei_local, et_m, halo_gid, recv_splits = select_local(edge_index, edge_type, ranges, rank)
+    n_local = hi - lo
+    n_halo = int(halo_gid.numel())
+    # tell every owner which of its rows we need
+    if world > 1:
+        recv_cnt = torch.tensor(recv_splits, dtype=torch.int64, device=dev)
+        send_cnt = torch.empty_like(recv_cnt)
+        dist.all_to_all_single(send_cnt, recv_cnt, group=group)
+        send_splits = send_cnt.tolist()
+        send_gid = torch.empty(int(sum(send_splits)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_gid, halo_gid, output_split_sizes=send_splits, input_split_sizes=recv_splits,
+                               group=group)
+        send_ids = send_gid - lo
+    else:
+        send_splits = [0]
+        send_ids = torch.empty(0, dtype=torch.int64, device=dev)
+    return LocalPart(rank=rank, world=world, ranges=list(ranges), n_local=n_local, n_halo=n_halo, halo_gid=halo_gid,
+                     recv_splits=recv_splits, send_ids=send_ids, send_splits=send_splits,
+                     edge_index=ei_local, edge_type=et_m)
+
+
+class _HaloExchange(torch.autograd.Function):
+    """x_local [n_local, F] -> X [n_local + n_halo, F] (rows of remote sources appended)."""
+
+    @staticmethod
+    def forward(ctx, x_local, part: LocalPart, group):
+        ctx.part, ctx.group = part, group
+        feat = x_local.size(1)
+        X = torch.empty((part.n_src, feat), dtype=x_local.dtype, device=x_local.device)
+        X[: part.n_local] = x_local
+        if part.world > 1:
+            send = x_local.index_select(0, part.send_ids)
+            dist.all_to_all_single(X[part.n_local:], send, output_split_sizes=part.recv_splits,
+                                   input_split_sizes=part.send_splits, group=group)
+        return X
+
+    @staticmethod
+    def backward(ctx, gX):
+        part: LocalPart = ctx.part
+        gx = gX[: part.n_local].clone()
+        if part.world > 1:
+            g_halo = gX[part.n_local:].contiguous()
+            back = torch.empty((int(sum(part.send_splits)), gX.size(1)), dtype=gX.dtype, device=gX.device)
+            dist.all_to_all_single(back, g_halo, output_split_sizes=part.send_splits,
+                                   input_split_sizes=part.recv_splits, group=ctx.group)
+            off = 0
+            for cnt in part.send_splits:      # fixed peer order; ids unique within a peer
+                if cnt:
+                    gx.index_add_(0, part.send_ids[off:off + cnt], back[off:off + cnt])
+                off += cnt
+        return gx, None, None
+
+
+def halo_exchange(x_local: torch.Tensor, part: LocalPart, group=None) -> torch.Tensor:
+    return _HaloExchange.apply(x_local, part, group)
+
+
+# ----------------------------------------------------------------------------- multi-GPU bench
+def run_partitioned_bench(args):
+    """bench.py --gpus N (N > 1): BASELINE.json configs[4] — the 10M-node / 200M-edge power-law
+    graph, destination-row partitioned, halo exchange + aggregation forward and backward."""
+    import json
+    import os
+    import statistics
+    import sys
+    import time
+
+    import gmlm_b200 as G
+    from gmlm_b200 import _lib, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world == 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    try:
+        w = synth.WORKLOADS[args.workload]
+        n = int(w.num_nodes * args.scale)
+        e = int(w.num_edges * args.scale)
+        feat = w.feat
+        dtype = torch.bfloat16 if w.dtype == "bf16" else torch.float32
+        esize = 2 if dtype == torch.bfloat16 else 4
+
+        # every rank generates the same seeded graph (device RNG streams are identical across
+        # identical GPUs) and keeps only its destination range
+        t0 = time.perf_counter()
+        ei = synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
+        et = G.edge_type_from_degree(ei, n)                      # A2 needs the GLOBAL out-degree
+        in_deg = torch.ops.gmlm.degree_i32(ei[1], n)
+        ranges = partition_ranges(in_deg, world)
+        live = sorted(torch.unique(et).tolist())                 # one relation->slot layout for all ranks
+        part = build_local_part(ei, et, ranges, rank)
+        del ei, et, in_deg
+        torch.cuda.empty_cache()
+        g = G.RelGraph.build(part.edge_index, part.edge_type, part.n_local, 5, num_src=part.n_src, live_rels=live)
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter() - t0
+        S = g.num_slots
+        x_local = synth.make_features(part.n_local, feat, device=dev, seed=42 + rank, dtype=dtype)
+        gh = synth.make_features(part.n_local * S, feat, device=dev, seed=7 + rank, dtype=dtype)
+
+        def step():
+            X = halo_exchange(x_local, part)                    # NCCL all-to-all over NVLink
+            h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                 # A5 on [local ‖ halo]
+            gX = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)           # A14: grads for local and halo rows
+            gx = _HaloExchange.backward(_Ctx(part), gX)[0]      # halo grads back to their owners
+            return h, gx
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = None
+        if rank == 0:
+            from bench import ClockSampler
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+        a.record()
+        for _ in range(args.steps):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # device time, max over ranks
+        halo_rows = torch.tensor([float(part.n_halo), float(part.edge_index.size(1)), float(part.n_local)],
+                                 device=dev, dtype=torch.float64)
+        halo_all = [torch.zeros_like(halo_rows) for _ in range(world)]
+        dist.all_gather(halo_all, halo_rows)
+        if rank == 0:
+            clocks = sampler.stop()
+            from bench import NVLINK_GBS, algorithmic_bytes, peaks
+            ms_step = float(ms.item())
+            value = e / (ms_step * 1e-3)
+            peak, peak_src = peaks()
+            max_halo = max(float(t[0]) for t in halo_all)
+            max_edges = max(float(t[1]) for t in halo_all)
+            max_rows = max(float(t[2]) for t in halo_all)
+            fwd_b, bwd_b = algorithmic_bytes(int(max_rows), int(max_edges), feat, esize, S)
+            t_hbm = (fwd_b + bwd_b) / (peak * 1e9)
+            t_link = 2 * max_halo * feat * esize / (NVLINK_GBS * 1e9)        # fwd + bwd exchange
+            roof_t = max(t_hbm, t_link)
+            line = {
+                "metric": "message-passing edges/sec fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+                "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat,
+                           "parallelism": f"dst-row partition x{world}, NCCL all_to_all halo exchange",
+                           "l2": "inputs exceed L2", "halo_rows_per_rank": [int(t[0]) for t in halo_all],
+                           "edges_per_rank": [int(t[1]) for t in halo_all],
+                           "rows_per_rank": [int(t[2]) for t in halo_all]},
+                "roofline": {"bound": "nvlink" if t_link > t_hbm else "hbm", "achieved": roof_t / (ms_step * 1e-3),
+                             "peak": 1.0, "unit": "fraction of max(HBM, NVLink) time", "frac": roof_t / (ms_step * 1e-3),
+                             "t_hbm_ms": t_hbm * 1e3, "t_nvlink_ms": t_link * 1e3, "traffic": None,
+                             "peak_source": peak_src + f"; NVLink {NVLINK_GBS} GB/s per direction (B200_PROFILING.md)"},
+                "cpu_baseline": None,
+                "e2e": None,
+                "gpu_launches": (2 + (2 if g.fwd.n_hub else 0) + (2 if g.bwd.n_hub else 0)) * args.steps,
+                "clocks": clocks, "setup_s": t_setup,
+            }
+            print(json.dumps(line), flush=True)
+    finally:
+        dist.destroy_process_group()
+
+
+class _Ctx:
+    """minimal stand-in for an autograd ctx so the bench can call the exchange backward directly"""
+
+    def __init__(self, part):
+        self.part, self.group = part, None

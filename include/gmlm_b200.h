@@ -99,13 +99,23 @@ int gmlm_hub_fill(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64
                   int32_t* hub_row, int32_t* hub_chunk_ptr, int32_t* chunk_beg, int32_t* chunk_end,
                   void* ws, size_t ws_bytes, void* stream);
 
+/* ---- cost-balanced group plan for gmlm_spmm_csr ----
+ * Cuts the row sequence where (r + rowptr[r]) crosses multiples of `quantum`, so that every
+ * group of lanes moves about `quantum` row-sized units (one per gathered edge + one per written
+ * row) whatever the degree distribution.  n_groups = gmlm_group_plan_size(); grp_row has
+ * n_groups+1 entries, grp_row[g] = first row of group g, grp_row[n_groups] = num_rows. */
+int64_t gmlm_group_plan_size(int64_t num_rows, int64_t nnz, int64_t quantum);
+int gmlm_group_plan(const int32_t* rowptr, int64_t num_rows, int64_t nnz, int64_t quantum,
+                    int32_t* grp_row, void* stream);
+
 /* ---- A5 / A14  aggregation: [PyG] RGCNConv.propagate + mean aggregation (forward) and the
  *      gather-form backward.  out[r, :] = reduce_{e in row r} w[e] * x[col[e], :] ----
  * x: [*, feat] dtype, leading dim ldx; out: [num_rows, feat] same dtype, leading dim ldo.
- * fp32 accumulation in CSR order (deterministic).  Hub arrays may be NULL when n_hub == 0;
- * hub_ws: float[n_chunks * feat] scratch. */
+ * fp32 accumulation in CSR order (deterministic).  grp_row may be NULL (uniform 32-row groups).
+ * Hub arrays may be NULL when n_hub == 0; hub_ws: float[n_chunks * feat] scratch. */
 int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx,
                   const int32_t* rowptr, const int32_t* col, const float* w, int64_t num_rows, int mode,
+                  const int32_t* grp_row, int64_t n_groups,
                   int32_t hub_thresh, int64_t n_hub, int64_t n_chunks, const int32_t* hub_row,
                   const int32_t* hub_chunk_ptr, const int32_t* chunk_beg, const int32_t* chunk_end,
                   float* hub_ws, void* out, int64_t ldo, void* stream);

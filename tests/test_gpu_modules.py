@@ -165,15 +165,24 @@ def test_encoder_matches_oracle(cuda_dev, n, e, fin, hidden, use_checkpoint):
     gout = torch.randn(n, 48)
     fused_ref.backward(gout.double())
     fused.backward(gout.to(cuda_dev))
+    # yardstick for the gradients: the SAME oracle run in fp32 on the CPU.  Back-propagating
+    # through four GraphNorms is ill-conditioned enough that fp32 itself sits near 2e-4 here.
+    import copy
+    ref32 = copy.deepcopy(ref).float()
+    ref32.zero_grad()
+    ref32(x, ei).backward(gout)
     sd_ref = dict(ref.named_parameters())
+    sd32 = dict(ref32.named_parameters())
     for name, p in mod.named_parameters():
         if name == "gnn_mask_token_embed":
             continue
-        if name.startswith("residual_proj3"):
-            assert p.grad is None and sd_ref[name].grad is None      # dead branch, main.py:317-318
+        if sd_ref[name].grad is None:
+            # residual_proj3 is dead (main.py:317-318); GraphNorm is skipped when N == 1 (main.py:273)
+            assert p.grad is None, name
             continue
         assert p.grad is not None, name
-        assert rel_err(p.grad, sd_ref[name].grad) <= 2e-4, name
+        noise = rel_err(sd32[name].grad, sd_ref[name].grad)
+        assert rel_err(p.grad, sd_ref[name].grad) <= max(2e-5, 3.0 * noise), (name, noise)
 
 
 def test_encoder_with_soft_mask_and_autocast(cuda_dev):

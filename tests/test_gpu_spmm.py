@@ -68,7 +68,8 @@ def test_aggregate_bf16_widths(cuda_dev, feat, variant):
 
 @pytest.mark.parametrize("hub_thresh", [1, 3, 16, 100000])
 @pytest.mark.parametrize("variant", [0, 1])
-def test_aggregate_hub_rows_and_determinism(cuda_dev, hub_thresh, variant):
+@pytest.mark.parametrize("quantum", [0, 7, 256])
+def test_aggregate_hub_rows_and_determinism(cuda_dev, hub_thresh, variant, quantum):
     """A star-like graph: the hub path (chunk partials + in-order final sum) must agree with the
     oracle and be bit-identical run to run (the stock scatter_add_ path is not)."""
     gen = torch.Generator().manual_seed(5)
@@ -81,7 +82,7 @@ def test_aggregate_hub_rows_and_determinism(cuda_dev, hub_thresh, variant):
     x = torch.randn(n, feat, generator=gen)
     old = G.set_tuning("spmm_variant", variant)
     try:
-        g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh)
+        g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh, quantum=quantum)
         xs = x.to(cuda_dev)
         a = G.rgcn_aggregate(xs, g)
         b = G.rgcn_aggregate(xs, g)
@@ -112,7 +113,8 @@ def test_aggregate_edge_cases(cuda_dev, name, n, e, kind):
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, FP32_TOL), (torch.bfloat16, BF16_TOL)])
 @pytest.mark.parametrize("hub_thresh", [8, 1024])
-def test_aggregate_backward_matches_autograd_of_oracle(cuda_dev, dtype, tol, hub_thresh):
+@pytest.mark.parametrize("quantum", [0, 33, 256])
+def test_aggregate_backward_matches_autograd_of_oracle(cuda_dev, dtype, tol, hub_thresh, quantum):
     """A14: gather on the transposed CSR with 1/count folded in == autograd through
     index_select + index_add_ + divide (what the reference's backward executes)."""
     n, ei = _case(500, 6000, seed=21, kind="rmat")
@@ -120,7 +122,7 @@ def test_aggregate_backward_matches_autograd_of_oracle(cuda_dev, dtype, tol, hub
     gen = torch.Generator().manual_seed(4)
     feat = 128
     x = torch.randn(n, feat, generator=gen).to(dtype)
-    g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh)
+    g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh, quantum=quantum)
     gh = torch.randn(n, g.num_slots * feat, generator=gen).to(dtype)
 
     xg = x.to(cuda_dev).requires_grad_(True)
@@ -132,6 +134,24 @@ def test_aggregate_backward_matches_autograd_of_oracle(cuda_dev, dtype, tol, hub
     ref.backward(gh.double())
     assert rel_err(out, ref) <= tol
     assert rel_err(xg.grad, x64.grad) <= tol
+
+
+def test_group_plan_covers_rows_in_order(cuda_dev):
+    """The cost-balanced cuts are monotone, start at 0, end at num_rows, and no group exceeds
+    quantum + (longest non-hub row) units of work."""
+    n, e = 5000, 80000
+    ei = synth.rmat_edges(n, e, seed=13)
+    et = edge_type_bucket_ref(ei, n)
+    for q in (1, 16, 256, 100000):
+        g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=64, quantum=q)
+        for csr in (g.fwd, g.bwd):
+            cuts = csr.grp_row.cpu().long()
+            rp = csr.rowptr.cpu().long()
+            assert cuts[0] == 0 and cuts[-1] == csr.num_rows and bool((cuts[1:] >= cuts[:-1]).all())
+            assert cuts.numel() == csr.n_groups + 1
+            cost = (cuts[1:] - cuts[:-1]) + (rp[cuts[1:]] - rp[cuts[:-1]])
+            max_row = int((rp[1:] - rp[:-1]).max())
+            assert int(cost.max()) <= q + max_row + 1
 
 
 def test_aggregate_linearity_full_size_property(cuda_dev):
@@ -172,3 +192,35 @@ def test_cpu_tensors_raise(lib_built):
     with pytest.raises(Exception):
         G.RelGraph.build(ei, torch.tensor([0, 0]), 4, 5)
     del x
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_aggregate_equals_whole_graph(cuda_dev, world):
+    """SURVEY §8e on one GPU: for every rank of a destination-row partition, the kernel on the
+    rectangular local CSR over [local ‖ halo] rows reproduces that rank's slice of the
+    whole-graph result bit for bit (same per-row edge order), forward and backward-adjoint."""
+    from gmlm_b200.partition import partition_ranges, select_local
+    n, e, feat = 3000, 40000, 64
+    ei = synth.rmat_edges(n, e, seed=17).to(cuda_dev)
+    et = G.edge_type_from_degree(ei, n)
+    x = synth.make_features(n, feat, device=cuda_dev, seed=3)
+    g_full = G.RelGraph.build(ei, et, n, 5)
+    h_full = G.rgcn_aggregate(x, g_full)
+    in_deg = torch.ops.gmlm.degree_i32(ei[1], n)
+    ranges = partition_ranges(in_deg, world)
+    gh = torch.randn_like(h_full)
+    gx_sum = torch.zeros_like(x)
+    for rank in range(world):
+        lo, hi = ranges[rank]
+        ei_l, et_l, halo_gid, _ = select_local(ei, et, ranges, rank)
+        n_local, n_src = hi - lo, hi - lo + int(halo_gid.numel())
+        g = G.RelGraph.build(ei_l, et_l, n_local, 5, num_src=n_src, live_rels=g_full.live_rels)
+        X = torch.cat([x[lo:hi], x[halo_gid]]).requires_grad_(True)
+        h = G.rgcn_aggregate(X, g)
+        assert torch.equal(h, h_full[lo:hi])
+        h.backward(gh[lo:hi])
+        gx_sum[lo:hi] += X.grad[:n_local]
+        gx_sum.index_add_(0, halo_gid, X.grad[n_local:])
+    xg = x.clone().requires_grad_(True)
+    G.rgcn_aggregate(xg, g_full).backward(gh)
+    assert rel_err(gx_sum, xg.grad) <= 1e-5

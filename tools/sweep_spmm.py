@@ -34,7 +34,9 @@ def main():
     ap.add_argument("--workload", default="c4")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--thresh", type=int, nargs="*", default=[256, 1024, 4096])
-    ap.add_argument("--variants", type=int, nargs="*", default=[0, 1])
+    ap.add_argument("--variants", type=int, nargs="*", default=[1])
+    ap.add_argument("--quantum", type=int, nargs="*", default=[0, 128, 256, 512])
+    ap.add_argument("--unroll", type=int, nargs="*", default=[8, 4])
     ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -47,18 +49,19 @@ def main():
     et = G.edge_type_from_degree(ei, n)
     Path(args.out).parent.mkdir(exist_ok=True)
     rows = []
-    for th in args.thresh:
-        g = G.RelGraph.build(ei, et, n, 5, hub_thresh=th)
+    for th, qn in [(t, q) for t in args.thresh for q in args.quantum]:
+        g = G.RelGraph.build(ei, et, n, 5, hub_thresh=th, quantum=qn)
         S = g.num_slots
         gh = synth.make_features(n * S, feat, device=dev, seed=7, dtype=dtype)
         fb, bb = algorithmic_bytes(n, e, feat, esz, S)
         lens = (g.fwd.rowptr[1:] - g.fwd.rowptr[:-1])
         lens_t = (g.bwd.rowptr[1:] - g.bwd.rowptr[:-1])
-        for v in args.variants:
+        for v, un in [(v, u) for v in args.variants for u in args.unroll]:
             G.set_tuning("spmm_variant", v)
+            G.set_tuning("spmm_unroll", un)
             f_ms = timeit(lambda: G.spmm(x, g.fwd, _lib.AGG_MEAN))
             b_ms = timeit(lambda: G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED))
-            row = {"thresh": th, "variant": v, "fwd_ms": f_ms, "bwd_ms": b_ms, "fwd_gbs": fb / f_ms / 1e6,
+            row = {"thresh": th, "quantum": qn, "variant": v, "unroll": un, "fwd_ms": f_ms, "bwd_ms": b_ms, "fwd_gbs": fb / f_ms / 1e6,
                    "bwd_gbs": bb / b_ms / 1e6, "edges_per_s": e / ((f_ms + b_ms) * 1e-3),
                    "hub_fwd": g.fwd.n_hub, "chunks_fwd": g.fwd.n_chunks, "hub_bwd": g.bwd.n_hub,
                    "chunks_bwd": g.bwd.n_chunks, "max_len_fwd": int(lens.max()), "max_len_bwd": int(lens_t.max()),
