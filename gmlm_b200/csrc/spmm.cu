@@ -310,23 +310,34 @@ __global__ void __launch_bounds__(256, MINB) chunk_kernel(const ChunkParams p) {
   }
 }
 
-// final in-order reduction of the hub partials: one warp per hub row, scalar feature loop
+// final in-order reduction of the hub partials: `tpr` threads per hub row, each thread owns the
+// features f = t, t+tpr, ...; chunk partials are loaded 8 at a time (independent loads) and added
+// in chunk order (fixed order => deterministic).
 template <typename T>
 __global__ void __launch_bounds__(256) hub_final_kernel(const float* __restrict__ ws, int64_t feat,
                                                         const int32_t* __restrict__ rowptr,
                                                         const int32_t* __restrict__ hub_row,
                                                         const int32_t* __restrict__ hub_chunk_ptr, int64_t n_hub,
-                                                        int mean, T* __restrict__ out, int64_t ldo) {
-  const int64_t h = (int64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+                                                        int tpr, int mean, T* __restrict__ out, int64_t ldo) {
+  const int rows_per_cta = blockDim.x / tpr;
+  const int64_t h = int64_t(blockIdx.x) * rows_per_cta + threadIdx.x / tpr;
+  const int t = threadIdx.x % tpr;
   if (h >= n_hub) return;
-  const int32_t r = hub_row[h];
-  const int32_t c0 = hub_chunk_ptr[h], c1 = hub_chunk_ptr[h + 1];
-  const int len = rowptr[r + 1] - rowptr[r];
+  const int32_t r = __ldg(hub_row + h);
+  const int32_t c0 = __ldg(hub_chunk_ptr + h), c1 = __ldg(hub_chunk_ptr + h + 1);
+  const int len = __ldg(rowptr + r + 1) - __ldg(rowptr + r);
   const float scale = (mean && len > 1) ? 1.0f / float(len) : 1.0f;
-  for (int64_t f = lane; f < feat; f += 32) {
+  for (int64_t f = t; f < feat; f += tpr) {
     float a = 0.f;
-    for (int32_t c = c0; c < c1; ++c) a += ws[int64_t(c) * feat + f];
+    int32_t c = c0;
+    for (; c + 8 <= c1; c += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = __ldcs(ws + int64_t(c + u) * feat + f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a += v[u];
+    }
+    for (; c < c1; ++c) a += __ldcs(ws + int64_t(c) * feat + f);
     out[int64_t(r) * ldo + f] = from_float<T>(a * scale);
   }
 }
@@ -474,13 +485,16 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   if (rc) return rc;
   if (n_hub == 0) return GMLM_OK;
 
-  const int64_t threads = n_hub * 32;
-  const unsigned blocks = unsigned((threads + 255) / 256);
+  int tpr = 256;
+  if (feat <= 128) tpr = int((feat + 31) / 32) * 32;
+  if (tpr == 96) tpr = 128;
+  const int rows_per_cta = 256 / tpr;
+  const unsigned blocks = unsigned((n_hub + rows_per_cta - 1) / rows_per_cta);
   if (dtype == GMLM_F32)
-    hub_final_kernel<float><<<blocks, 256, 0, st>>>(hub_ws, feat, rowptr, hub_row, hub_chunk_ptr, n_hub, p.mean,
+    hub_final_kernel<float><<<blocks, 256, 0, st>>>(hub_ws, feat, rowptr, hub_row, hub_chunk_ptr, n_hub, tpr, p.mean,
                                                     static_cast<float*>(out), ldo);
   else
-    hub_final_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(hub_ws, feat, rowptr, hub_row, hub_chunk_ptr, n_hub,
+    hub_final_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(hub_ws, feat, rowptr, hub_row, hub_chunk_ptr, n_hub, tpr,
                                                             p.mean, static_cast<__nv_bfloat16*>(out), ldo);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
