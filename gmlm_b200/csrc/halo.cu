@@ -1,0 +1,90 @@
+// halo.cu — row pack / unpack for the halo exchange of a destination-row partitioned graph
+// (no reference counterpart — /root/reference is single-process).
+//
+//   gather_rows      : out[k, :]      = x[ids[k], :]          (pack the rows a peer needs)
+//   scatter_add_rows : dst[ids[k], :] += src[k, :]            (return halo gradients to owners)
+//
+// `ids` must be unique within one call (true for one peer's send list), so the scatter needs no
+// atomics and the sum order is fixed by the order of the calls (peer by peer): deterministic.
+// HBM-bound: 128-bit accesses, one row handled by feat/VEC consecutive threads.
+#include "common.cuh"
+
+namespace gmlm {
+namespace {
+
+template <typename T, int VEC, bool ADD>
+__global__ void __launch_bounds__(256) rows_move_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst,
+                                                        int64_t ldd, const int64_t* __restrict__ ids, int64_t n,
+                                                        int64_t feat, int64_t src_rows) {
+  const int64_t packs = (feat + VEC - 1) / VEC;
+  const int64_t total = n * packs;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t k = i / packs;
+    const int64_t f = (i - k * packs) * VEC;
+    const int64_t id = __ldg(ids + k);
+    if (ADD) {  // dst[id] += src[k]
+      Pack<T, VEC> a, b;
+      a.load(src + k * lds + f);
+      b.load(dst + id * ldd + f);
+      float fa[VEC], fb[VEC];
+      a.unpack(fa);
+      b.unpack(fb);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) fb[j] += fa[j];
+      b.pack(fb);
+      b.store(dst + id * ldd + f);
+    } else {    // dst[k] = src[id]
+      Pack<T, VEC> a;
+      a.load(src + id * lds + f);
+      a.store(dst + k * ldd + f);
+    }
+  }
+}
+
+template <bool ADD>
+int launch(const void* src, int64_t lds, void* dst, int64_t ldd, const int64_t* ids, int64_t n, int64_t feat,
+           int dtype, cudaStream_t st) {
+  if (n == 0 || feat == 0) return GMLM_OK;
+  const int v = dtype == GMLM_F32 ? 4 : 8;
+  const bool vec = feat % v == 0 && lds % v == 0 && ldd % v == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+  const int64_t packs = vec ? feat / v : feat;
+  int64_t blocks = (n * packs + 255) / 256;
+  const int64_t cap = int64_t(num_sms()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (dtype == GMLM_F32) {
+    if (vec) rows_move_kernel<float, 4, ADD><<<unsigned(blocks), 256, 0, st>>>(
+        static_cast<const float*>(src), lds, static_cast<float*>(dst), ldd, ids, n, feat, 0);
+    else rows_move_kernel<float, 1, ADD><<<unsigned(blocks), 256, 0, st>>>(
+        static_cast<const float*>(src), lds, static_cast<float*>(dst), ldd, ids, n, feat, 0);
+  } else {
+    using B = __nv_bfloat16;
+    if (vec) rows_move_kernel<B, 8, ADD><<<unsigned(blocks), 256, 0, st>>>(
+        static_cast<const B*>(src), lds, static_cast<B*>(dst), ldd, ids, n, feat, 0);
+    else rows_move_kernel<B, 1, ADD><<<unsigned(blocks), 256, 0, st>>>(
+        static_cast<const B*>(src), lds, static_cast<B*>(dst), ldd, ids, n, feat, 0);
+  }
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+}  // namespace
+}  // namespace gmlm
+
+using namespace gmlm;
+
+extern "C" int gmlm_gather_rows(const void* x, int dtype, int64_t feat, int64_t ldx, const int64_t* ids, int64_t n,
+                                void* out, int64_t ldo, void* stream) {
+  GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "gather_rows: dtype must be GMLM_F32 or GMLM_BF16");
+  GMLM_REQUIRE(n >= 0 && feat >= 0 && ldx >= feat && ldo >= feat, "gather_rows: bad sizes");
+  GMLM_REQUIRE(n == 0 || (x && ids && out), "gather_rows: null pointer");
+  return launch<false>(x, ldx, out, ldo, ids, n, feat, dtype, as_stream(stream));
+}
+
+extern "C" int gmlm_scatter_add_rows(void* dst, int dtype, int64_t feat, int64_t ldd, const int64_t* ids, int64_t n,
+                                     const void* src, int64_t lds, void* stream) {
+  GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "scatter_add_rows: dtype must be GMLM_F32 or GMLM_BF16");
+  GMLM_REQUIRE(n >= 0 && feat >= 0 && ldd >= feat && lds >= feat, "scatter_add_rows: bad sizes");
+  GMLM_REQUIRE(n == 0 || (dst && ids && src), "scatter_add_rows: null pointer");
+  return launch<true>(src, lds, dst, ldd, ids, n, feat, dtype, as_stream(stream));
+}

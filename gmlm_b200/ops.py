@@ -236,6 +236,37 @@ _LIB.impl("soft_mask_fwd", _soft_mask_fwd, "CUDA")
 _LIB.impl("soft_mask_bwd", _soft_mask_bwd, "CUDA")
 
 
+# ------------------------------------------------------------------------------ halo pack / unpack
+def gather_rows(x: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[k] = x[ids[k]] (pack the rows a peer needs)."""
+    lib = _lib.load()
+    _require_cuda(x, "x")
+    x = _rowmajor(x)
+    ids = ids.contiguous()
+    n, feat = int(ids.numel()), int(x.size(1))
+    with torch.cuda.device(x.device):
+        if out is None:
+            out = torch.empty((n, feat), dtype=x.dtype, device=x.device)
+        _lib.check(lib.gmlm_gather_rows(_ptr(x), _dtype_code(x, "gather_rows"), feat, _ld(x), _ptr(ids), n, _ptr(out),
+                                        _ld(out) if n > 1 else feat, _stream(x.device)), "gather_rows")
+    return out
+
+
+def scatter_add_rows_(dst: torch.Tensor, ids: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+    """dst[ids[k]] += src[k] in place; ``ids`` must be unique (no atomics, deterministic)."""
+    lib = _lib.load()
+    _require_cuda(dst, "dst")
+    if dst.dim() != 2 or dst.stride(1) != 1 or src.dim() != 2 or src.stride(1) != 1:
+        raise _lib.GmlmError("scatter_add_rows_: row-major 2-D tensors required")
+    ids = ids.contiguous()
+    n, feat = int(ids.numel()), int(dst.size(1))
+    with torch.cuda.device(dst.device):
+        _lib.check(lib.gmlm_scatter_add_rows(_ptr(dst), _dtype_code(dst, "scatter_add_rows"), feat, _ld(dst), _ptr(ids),
+                                             n, _ptr(src), _ld(src) if n > 1 else feat, _stream(dst.device)),
+                   "scatter_add_rows")
+    return dst
+
+
 # ------------------------------------------------------------------------------ public functional API
 def degree(index: torch.Tensor, num_nodes: Optional[int] = None, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Drop-in for ``torch_geometric.utils.degree`` (``/root/reference/main.py:7``; called

@@ -110,6 +110,23 @@ def build_local_part(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor]
                      edge_index=ei_local, edge_type=et_m)
 
 
+def _pack(x_local: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Rows a peer needs.  CUDA tensors always take the library kernel; the torch path exists only
+    so that the exchange plumbing can be exercised on CPU with gloo (tests/test_partition.py)."""
+    if x_local.is_cuda:
+        from .ops import gather_rows
+        return gather_rows(x_local, ids, out=out)
+    return torch.index_select(x_local, 0, ids, out=out) if out is not None else x_local.index_select(0, ids)
+
+
+def _unpack_add(gx: torch.Tensor, ids: torch.Tensor, rows: torch.Tensor):
+    if gx.is_cuda:
+        from .ops import scatter_add_rows_
+        scatter_add_rows_(gx, ids, rows)
+    else:
+        gx.index_add_(0, ids, rows)
+
+
 class _HaloExchange(torch.autograd.Function):
     """x_local [n_local, F] -> X [n_local + n_halo, F] (rows of remote sources appended)."""
 
@@ -120,7 +137,7 @@ class _HaloExchange(torch.autograd.Function):
         X = torch.empty((part.n_src, feat), dtype=x_local.dtype, device=x_local.device)
         X[: part.n_local] = x_local
         if part.world > 1:
-            send = x_local.index_select(0, part.send_ids)
+            send = _pack(x_local, part.send_ids)
             dist.all_to_all_single(X[part.n_local:], send, output_split_sizes=part.recv_splits,
                                    input_split_sizes=part.send_splits, group=group)
         return X
@@ -137,7 +154,7 @@ class _HaloExchange(torch.autograd.Function):
             off = 0
             for cnt in part.send_splits:      # fixed peer order; ids unique within a peer
                 if cnt:
-                    gx.index_add_(0, part.send_ids[off:off + cnt], back[off:off + cnt])
+                    _unpack_add(gx, part.send_ids[off:off + cnt], back[off:off + cnt])
                 off += cnt
         return gx, None, None
 
@@ -190,14 +207,39 @@ def run_partitioned_bench(args):
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
         S = g.num_slots
-        x_local = synth.make_features(part.n_local, feat, device=dev, seed=42 + rank, dtype=dtype)
+        # persistent buffers: the node features live in the head of the gather matrix X, the halo
+        # rows are received straight into its tail (no per-step concat / clone)
+        X = torch.empty((part.n_src, feat), dtype=dtype, device=dev)
+        X[: part.n_local] = synth.make_features(part.n_local, feat, device=dev, seed=42 + rank, dtype=dtype)
+        x_local = X[: part.n_local]
         gh = synth.make_features(part.n_local * S, feat, device=dev, seed=7 + rank, dtype=dtype)
+        n_send = int(sum(part.send_splits))
+        send_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
+        back_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
+        PH = 5
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(PH + 1)] for _ in range(args.steps)]
 
-        def step():
-            X = halo_exchange(x_local, part)                    # NCCL all-to-all over NVLink
-            h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                 # A5 on [local ‖ halo]
-            gX = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)           # A14: grads for local and halo rows
-            gx = _HaloExchange.backward(_Ctx(part), gX)[0]      # halo grads back to their owners
+        def step(k=None):
+            rec = (lambda i: ev[k][i].record()) if k is not None else (lambda i: None)
+            rec(0)
+            _pack(x_local, part.send_ids, out=send_buf)                          # pack (gmlm_gather_rows)
+            rec(1)
+            dist.all_to_all_single(X[part.n_local:], send_buf, output_split_sizes=part.recv_splits,
+                                   input_split_sizes=part.send_splits)           # halo rows over NVLink
+            rec(2)
+            h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                                  # A5 on [local ‖ halo]
+            rec(3)
+            gX = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)                            # A14: grads for local AND halo rows
+            rec(4)
+            dist.all_to_all_single(back_buf, gX[part.n_local:], output_split_sizes=part.send_splits,
+                                   input_split_sizes=part.recv_splits)           # halo grads back to their owners
+            gx = gX[: part.n_local]
+            off = 0
+            for cnt in part.send_splits:                                         # peer order, unique ids per peer
+                if cnt:
+                    _unpack_add(gx, part.send_ids[off:off + cnt], back_buf[off:off + cnt])
+                off += cnt
+            rec(5)
             return h, gx
 
         for _ in range(args.warmup):
@@ -212,12 +254,16 @@ def run_partitioned_bench(args):
             sampler = ClockSampler(local_rank)
             sampler.start()
         a.record()
-        for _ in range(args.steps):
-            step()
+        for k in range(args.steps):
+            step(k)
         b.record()
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        phases = torch.tensor([statistics.mean(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps))
+                               for i in range(PH)], device=dev, dtype=torch.float64)
+        phases_all = [torch.zeros_like(phases) for _ in range(world)]
+        dist.all_gather(phases_all, phases)
         ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # device time, max over ranks
         halo_rows = torch.tensor([float(part.n_halo), float(part.edge_index.size(1)), float(part.n_local)],
@@ -254,6 +300,9 @@ def run_partitioned_bench(args):
                 "e2e": None,
                 "gpu_launches": (2 + (2 if g.fwd.n_hub else 0) + (2 if g.bwd.n_hub else 0)) * args.steps,
                 "clocks": clocks, "setup_s": t_setup,
+                "phases_ms_per_rank": {"order": ["pack", "all_to_all_fwd", "aggregate_fwd", "aggregate_bwd",
+                                                 "all_to_all_bwd+scatter"],
+                                       "ranks": [[round(float(v), 3) for v in t] for t in phases_all]},
             }
             print(json.dumps(line), flush=True)
     finally:

@@ -153,6 +153,15 @@ int gmlm_soft_mask_bwd(const void* gy, int dtype, int64_t num_rows, int64_t feat
                        const uint8_t* mask, float beta, float* g_token /* [feat] */, void* gx /* may be NULL */,
                        int64_t ldgx, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- halo pack / unpack for the destination-row partition (the reference has no
+ *      multi-GPU path) ----
+ * gather_rows     : out[k,:]      = x[ids[k],:]
+ * scatter_add_rows: dst[ids[k],:] += src[k,:]   ids unique within a call => no atomics, deterministic */
+int gmlm_gather_rows(const void* x, int dtype, int64_t feat, int64_t ldx, const int64_t* ids, int64_t n,
+                     void* out, int64_t ldo, void* stream);
+int gmlm_scatter_add_rows(void* dst, int dtype, int64_t feat, int64_t ldd, const int64_t* ids, int64_t n,
+                          const void* src, int64_t lds, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,22 @@ def test_partitioned_aggregate_equals_whole_graph(cuda_dev, world):
     xg = x.clone().requires_grad_(True)
     G.rgcn_aggregate(xg, g_full).backward(gh)
     assert rel_err(gx_sum, xg.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("feat", [256, 300, 7])
+def test_halo_pack_and_unpack_kernels(cuda_dev, dtype, feat):
+    """gather_rows == index_select bit for bit; scatter_add_rows_ (unique ids) == index_add_ with the
+    addition done in fp32 and rounded once."""
+    from gmlm_b200.ops import gather_rows, scatter_add_rows_
+    gen = torch.Generator().manual_seed(9)
+    n, k = 1000, 400
+    x = torch.randn(n, feat, generator=gen).to(dtype).to(cuda_dev)
+    ids = torch.randperm(n, generator=gen)[:k].to(cuda_dev)
+    assert torch.equal(gather_rows(x, ids), x.index_select(0, ids))
+    rows = torch.randn(k, feat, generator=gen).to(dtype).to(cuda_dev)
+    want = x.float()
+    want[ids] += rows.float()
+    got = scatter_add_rows_(x.clone(), ids, rows)
+    assert torch.equal(got, want.to(dtype))
+    assert gather_rows(x, ids[:0]).shape == (0, feat)
