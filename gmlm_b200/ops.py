@@ -88,7 +88,8 @@ def _edge_type_bucket(src: torch.Tensor, deg: torch.Tensor, bounds: Sequence[int
 
 
 # ------------------------------------------------------------------------------ A5 / A14
-def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, hub_chunk_ptr, chunk_beg, chunk_end):
+def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, hub_chunk_ptr, chunk_beg, chunk_end,
+              out=None):
     lib = _lib.load()
     x = _rowmajor(x)
     feat = int(x.size(1))
@@ -97,7 +98,10 @@ def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, h
     n_chunks = int(chunk_beg.numel()) if chunk_beg is not None else 0
     n_groups = int(grp_row.numel()) - 1 if grp_row is not None else 0
     with torch.cuda.device(dev):
-        out = torch.empty((num_rows, feat), dtype=x.dtype, device=dev)
+        if out is None:
+            out = torch.empty((num_rows, feat), dtype=x.dtype, device=dev)
+        elif out.shape != (num_rows, feat) or out.dtype != x.dtype or not out.is_contiguous():
+            raise _lib.GmlmError("spmm: `out` must be a contiguous [num_rows, feat] tensor of x's dtype")
         hub_ws = torch.empty(n_chunks * feat, dtype=torch.float32, device=dev) if n_hub else None
         _lib.check(lib.gmlm_spmm_csr(_ptr(x), _dtype_code(x, "spmm_csr"), feat, _ld(x), _ptr(rowptr), _ptr(col),
                                      _ptr(w), num_rows, mode, _ptr(grp_row), n_groups, hub_thresh, n_hub, n_chunks,
@@ -107,9 +111,14 @@ def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, h
     return out
 
 
-def spmm(x: torch.Tensor, csr: CSR, mode: int) -> torch.Tensor:
-    """out[r] = reduce over row r of csr (no autograd)."""
+def spmm(x: torch.Tensor, csr: CSR, mode: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[r] = reduce over row r of csr (no autograd).  ``out`` lets the result land in a caller-owned
+    buffer (e.g. NVLink-peer-visible symmetric memory for the halo exchange)."""
     _require_cuda(x, "x")
+    if out is not None:
+        return _spmm_csr(x, csr.rowptr, csr.col, csr.w if mode == _lib.AGG_WEIGHTED else None, csr.num_rows, mode,
+                         csr.grp_row, csr.hub_thresh, csr.hub_row, csr.hub_chunk_ptr, csr.chunk_beg, csr.chunk_end,
+                         out=out)
     return torch.ops.gmlm.spmm_csr(x, csr.rowptr, csr.col, csr.w if mode == _lib.AGG_WEIGHTED else None,
                                    csr.num_rows, mode, csr.grp_row, csr.hub_thresh, csr.hub_row, csr.hub_chunk_ptr,
                                    csr.chunk_beg, csr.chunk_end)

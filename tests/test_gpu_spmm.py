@@ -238,7 +238,7 @@ def test_halo_pack_and_unpack_kernels(cuda_dev, dtype, feat):
     ids = torch.randperm(n, generator=gen)[:k].to(cuda_dev)
     assert torch.equal(gather_rows(x, ids), x.index_select(0, ids))
     rows = torch.randn(k, feat, generator=gen).to(dtype).to(cuda_dev)
-    want = x.float()
+    want = x.float().clone()
     want[ids] += rows.float()
     got = scatter_add_rows_(x.clone(), ids, rows)
     assert torch.equal(got, want.to(dtype))
