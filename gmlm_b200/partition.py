@@ -279,7 +279,8 @@ def run_partitioned_bench(args):
         ei = synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
         et = G.edge_type_from_degree(ei, n)                      # A2 needs the GLOBAL out-degree
         in_deg = torch.ops.gmlm.degree_i32(ei[1], n)
-        ranges = partition_ranges(in_deg, world)
+        # cost per node in edge units: fwd writes S (dst,rel) rows, bwd writes 1; each edge is read twice
+        ranges = partition_ranges(in_deg, world, node_cost=2.5)
         live = sorted(torch.unique(et).tolist())                 # one relation->slot layout for all ranks
         part = build_local_part(ei, et, ranges, rank)
         del ei, et, in_deg
