@@ -104,3 +104,35 @@ def test_partition_ranges_balance_and_degenerate():
     r = partition_ranges(torch.tensor([3, 1]), 4)
     assert r[0][0] == 0 and r[-1][1] == 2 and all(a <= b for a, b in r)
     assert sum(b - a for a, b in r) == 2
+
+
+def test_cyclic_relabel_is_a_permutation_and_balances():
+    from gmlm_b200.partition import cyclic_relabel
+    n, world = 1003, 4
+    ei = synth.rmat_edges(n, 20000, seed=3)
+    new, ranges, perm = cyclic_relabel(ei, n, world)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n
+    assert sorted(perm.tolist()) == list(range(n))
+    assert torch.equal(perm[new], ei)                        # new -> old round trip
+    for p, (lo, hi) in enumerate(ranges):
+        assert bool((perm[lo:hi] % world == p).all())        # rank p owns the ids congruent to p
+        assert abs((hi - lo) - n / world) <= 1
+    # degrees are invariant under the relabelling, so edge typing is too
+    assert torch.equal(edge_type_bucket_ref(new, n), edge_type_bucket_ref(ei, n))
+
+
+def test_random_relabel_is_a_seeded_permutation_and_balances_edges():
+    from gmlm_b200.partition import random_relabel
+    n, world = 20011, 8
+    ei = synth.rmat_edges(n, 400000, seed=3)
+    new, ranges, perm = random_relabel(ei, n, world)
+    new2, ranges2, perm2 = random_relabel(ei, n, world)
+    assert torch.equal(new, new2) and ranges == ranges2 and torch.equal(perm, perm2)   # every rank derives the same
+    assert sorted(perm.tolist()) == list(range(n))
+    assert torch.equal(perm[new], ei)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(abs((b - a) - n / world) <= 1 for a, b in ranges)
+    assert torch.equal(edge_type_bucket_ref(new, n), edge_type_bucket_ref(ei, n))
+    starts = torch.tensor([r[0] for r in ranges] + [n])
+    own = torch.searchsorted(starts, new[1], right=True) - 1
+    per_rank = torch.bincount(own, minlength=world).double()
+    assert float(per_rank.max() / per_rank.mean()) < 1.5      # i mod P ownership gives 3.5x on this graph
