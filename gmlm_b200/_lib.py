@@ -43,7 +43,7 @@ SIGNATURES = {
                                         _p, _i64, _p, _p, _p, _p]),
     "gmlm_gather_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "gmlm_scatter_add_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
-    "gmlm_gather_rows_ptr": (_int, [_p, _int, _i64, _i64, _p, _i64, _p]),
+    "gmlm_gather_rows_ptr": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _p]),
     "gmlm_reduce_rows_ptr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i64, _p]),
     "gmlm_soft_mask_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _f32, _p, _i64, _p]),
     "gmlm_soft_mask_bwd_workspace_bytes": (_sz, [_i64, _i64]),

@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(256) rows_move_kernel(const T* __restrict__ sr
 // out[k, :] = *(row_ptrs[k])[0:feat]   — every row has its own 64-bit source address, so one
 // launch pulls from all NVLink peers at once (addresses in peer-mapped symmetric memory).
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) gather_ptr_kernel(const T* const* __restrict__ row_ptrs, int64_t n,
+__global__ void __launch_bounds__(256) gather_ptr_kernel(const T* const* __restrict__ row_ptrs,
+                                                         const int64_t* __restrict__ out_ids, int64_t n,
                                                          int64_t feat, T* __restrict__ out, int64_t ldo) {
   const int64_t packs = feat / VEC;
   const int64_t total = n * packs;
@@ -52,9 +53,10 @@ __global__ void __launch_bounds__(256) gather_ptr_kernel(const T* const* __restr
     const int64_t k = i / packs;
     const int64_t f = (i - k * packs) * VEC;
     const T* src = row_ptrs[k];
+    const int64_t o = out_ids ? out_ids[k] : k;
     Pack<T, VEC> a;
     a.load(src + f);
-    a.store(out + k * ldo + f);
+    a.store(out + o * ldo + f);
   }
 }
 
@@ -152,8 +154,8 @@ extern "C" int gmlm_scatter_add_rows(void* dst, int dtype, int64_t feat, int64_t
   return launch<true>(src, lds, dst, ldd, ids, n, feat, dtype, as_stream(stream));
 }
 
-extern "C" int gmlm_gather_rows_ptr(const void* const* row_ptrs, int dtype, int64_t feat, int64_t n, void* out,
-                                    int64_t ldo, void* stream) {
+extern "C" int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
+                                    int64_t n, void* out, int64_t ldo, void* stream) {
   GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "gather_rows_ptr: dtype must be GMLM_F32 or GMLM_BF16");
   const int v = dtype == GMLM_F32 ? 4 : 8;
   GMLM_REQUIRE(n >= 0 && feat >= 0 && ldo >= feat, "gather_rows_ptr: bad sizes");
@@ -166,11 +168,12 @@ extern "C" int gmlm_gather_rows_ptr(const void* const* row_ptrs, int dtype, int6
   if (blocks > cap) blocks = cap;
   cudaStream_t st = as_stream(stream);
   if (dtype == GMLM_F32)
-    gather_ptr_kernel<float, 4><<<unsigned(blocks), 256, 0, st>>>(reinterpret_cast<const float* const*>(row_ptrs), n,
-                                                                  feat, static_cast<float*>(out), ldo);
+    gather_ptr_kernel<float, 4><<<unsigned(blocks), 256, 0, st>>>(reinterpret_cast<const float* const*>(row_ptrs),
+                                                                  out_ids, n, feat, static_cast<float*>(out), ldo);
   else
     gather_ptr_kernel<__nv_bfloat16, 8><<<unsigned(blocks), 256, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16* const*>(row_ptrs), n, feat, static_cast<__nv_bfloat16*>(out), ldo);
+        reinterpret_cast<const __nv_bfloat16* const*>(row_ptrs), out_ids, n, feat, static_cast<__nv_bfloat16*>(out),
+        ldo);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }

@@ -251,14 +251,20 @@ class PeerHalo:
         order = sorted(range(world), key=lambda q: (q - rank) % world)      # fixed per-rank peer order
         # forward plan: one 64-bit source address per halo row (peer X head + remote local id)
         ptrs = torch.empty(part.n_halo, dtype=torch.int64, device=dev)
+        key = torch.empty(part.n_halo, dtype=torch.int64, device=dev)
         off = 0
         for p in range(world):
             cnt = part.recv_splits[p]
             if cnt:
                 base = self.hx.get_buffer(p, (self.max_rows, feat), dtype).data_ptr()
                 ptrs[off:off + cnt] = base + (part.halo_gid[off:off + cnt] - part.ranges[p][0]) * row_bytes
+                key[off:off + cnt] = torch.arange(cnt, dtype=torch.int64, device=dev) * world + (p - rank) % world
             off += cnt
-        self.fwd_ptrs = ptrs
+        # list the rows round-robin over the owners (and start each rank on a different owner):
+        # the halo list itself is grouped by owner, and walking it in order makes every rank pull
+        # from the same peer at the same time — measured 5.9 ms instead of 2 on 8 GPUs
+        self.fwd_order = torch.argsort(key)
+        self.fwd_ptrs = ptrs[self.fwd_order].contiguous()
         # backward plan: for every local row that some peer used, the addresses of its gradient rows
         # in those peers' gX tails, grouped by row, peers in the fixed order above
         rows, addrs, keys = [], [], []
@@ -296,8 +302,9 @@ class PeerHalo:
         self.hx.barrier()                                   # every rank's x_local is final
         if self.part.n_halo:
             tail = self.X[self.part.n_local:]
-            _check(lib.gmlm_gather_rows_ptr(_p(self.fwd_ptrs), _dt(self.dtype), self.feat, self.part.n_halo, _p(tail),
-                                            self.feat, _st(tail.device)), "gather_rows_ptr")
+            _check(lib.gmlm_gather_rows_ptr(_p(self.fwd_ptrs), _p(self.fwd_order), _dt(self.dtype), self.feat,
+                                            self.part.n_halo, _p(tail), self.feat, _st(tail.device)),
+                   "gather_rows_ptr")
         self.hx.barrier()                                   # every rank is done reading
         return self.X
 

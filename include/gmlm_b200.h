@@ -164,12 +164,13 @@ int gmlm_scatter_add_rows(void* dst, int dtype, int64_t feat, int64_t ldd, const
 
 /* ---- halo exchange over NVLink peer memory: every row carries its own 64-bit source address
  *      (a pointer into a peer-mapped symmetric buffer), so ONE launch moves rows from all peers ----
- * gather_rows_ptr : out[k,:] = row_ptrs[k][0:feat]
+ * gather_rows_ptr : out[out_ids[k],:] = row_ptrs[k][0:feat]   (out_ids NULL = identity; callers list the
+ *                   rows round-robin over the peers so that no peer's egress is hit by everyone at once)
  * reduce_rows_ptr : dst[row_ids[r],:] += sum over entries e of row r of entry_ptrs[e][0:feat]
  *                   (fp32 accumulation in entry order, one rounding; one owner per row => no atomics).
  * Rows must be multiples of 16 bytes and 16-byte aligned. */
-int gmlm_gather_rows_ptr(const void* const* row_ptrs, int dtype, int64_t feat, int64_t n, void* out,
-                         int64_t ldo, void* stream);
+int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
+                         int64_t n, void* out, int64_t ldo, void* stream);
 int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t ldd, const int64_t* row_ids,
                          const int32_t* rowptr, const void* const* entry_ptrs, int64_t n_rows, void* stream);
 
