@@ -32,8 +32,8 @@ SIGNATURES = {
     "gmlm_hub_fill": (_int, [_p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "gmlm_group_plan_size": (_i64, [_i64, _i64, _i64]),
     "gmlm_group_plan": (_int, [_p, _i64, _i64, _i64, _p, _p]),
-    "gmlm_spmm_csr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i64, _int, _p, _i64, _i32, _i64, _i64, _p, _p, _p,
-                             _p, _p, _p, _i64, _p]),
+    "gmlm_spmm_csr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i32, _i64, _int, _p, _i64, _i32, _i64, _i64, _p, _p,
+                             _p, _p, _p, _p, _i64, _p]),
     "gmlm_colstats_workspace_bytes": (_sz, [_i64, _i64]),
     "gmlm_colstats": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
     "gmlm_graphnorm_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f32, _int, _p, _i64, _p, _p, _p]),
@@ -41,6 +41,10 @@ SIGNATURES = {
                                         _p, _sz, _p]),
     "gmlm_graphnorm_bwd_apply": (_int, [_p, _p, _int, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _int, _p, _p,
                                         _p, _i64, _p, _p, _p, _p]),
+    "gmlm_gcn_edge_weights": (_int, [_p, _p, _i64, _p, _p, _p]),
+    "gmlm_gat_alpha_fwd": (_int, [_p, _p, _i64, _p, _p, _int, _f32, _p, _p]),
+    "gmlm_gat_alpha_bwd": (_int, [_p, _p, _i64, _p, _i64, _p, _i64, _int, _int, _int, _p, _p, _p, _f32, _p, _p, _p]),
+    "gmlm_segment_sum_f32": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
     "gmlm_gather_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "gmlm_scatter_add_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "gmlm_gather_rows_ptr": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _p]),

@@ -40,7 +40,10 @@ struct RowsParams {
   int64_t feat;
   const int32_t* rowptr;   // [num_rows+1]
   const int32_t* col;
-  const float* w;
+  const float* w;          // [nnz, w_stride]; head h (= grid.y slab) reads column h when w_stride > 1
+  int64_t w_stride;
+  int64_t slab_stride;     // features between consecutive slabs (0 = LPR*VEC*CH)
+  int64_t slab_width;      // valid features inside a slab (0 = slab_stride)
   int64_t num_rows;
   const int32_t* grp_row;  // [n_groups+1] cost-balanced row cuts, or nullptr = uniform LPR rows
   int64_t n_groups;
@@ -59,6 +62,9 @@ struct ChunkParams {
   const int32_t* chunk_end;
   const int32_t* col;
   const float* w;
+  int64_t w_stride;
+  int64_t slab_stride;
+  int64_t slab_width;
   int64_t n_chunks;
   float* out;              // float [n_chunks, feat]
 };
@@ -97,11 +103,16 @@ __global__ void __launch_bounds__(256, MINB) rows_kernel(const RowsParams p) {
     r_hi = min(r_lo + LPR, p.num_rows);
   }
 
-  const int64_t f0 = int64_t(blockIdx.y) * (LPR * VEC * CH) + gl * VEC;
+  const int64_t slab_stride = p.slab_stride ? p.slab_stride : int64_t(LPR) * VEC * CH;
+  const int64_t slab_width = p.slab_width ? p.slab_width : slab_stride;
+  const int64_t f0 = int64_t(blockIdx.y) * slab_stride + gl * VEC;
   bool fvalid[CH];
 #pragma unroll
-  for (int ch = 0; ch < CH; ++ch) fvalid[ch] = f0 + ch * LPR * VEC < p.feat;
+  for (int ch = 0; ch < CH; ++ch)
+    fvalid[ch] = (gl * VEC + ch * LPR * VEC < slab_width) && (f0 + ch * LPR * VEC < p.feat);
   const T* __restrict__ xf = static_cast<const T*>(p.x) + f0;
+  const float* __restrict__ wp = WEIGHTED ? p.w + (p.w_stride > 1 ? int64_t(blockIdx.y) : 0) : nullptr;
+  const int64_t wst = p.w_stride;
 
   float acc[CH][VEC];
 #pragma unroll
@@ -137,7 +148,7 @@ __global__ void __launch_bounds__(256, MINB) rows_kernel(const RowsParams p) {
         const int idx = base + gl;
         const int my_col = idx < e1 ? ld_stream(p.col + idx) : 0;
         float my_w = 0.f;
-        if (WEIGHTED) my_w = idx < e1 ? ld_stream(p.w + idx) : 0.f;
+        if (WEIGHTED) my_w = idx < e1 ? ld_stream(wp + int64_t(idx) * wst) : 0.f;
         const int nb = min(LPR, e1 - base);
         for (int j0 = 0; j0 < nb; j0 += U) {
           Pack<T, VEC> v[U][CH];
@@ -228,11 +239,16 @@ __global__ void __launch_bounds__(256, MINB) chunk_kernel(const ChunkParams p) {
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
   const int64_t c_id = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + g;
   if (c_id >= p.n_chunks) return;
-  const int64_t f0 = int64_t(blockIdx.y) * (LPR * VEC * CH) + gl * VEC;
+  const int64_t slab_stride = p.slab_stride ? p.slab_stride : int64_t(LPR) * VEC * CH;
+  const int64_t slab_width = p.slab_width ? p.slab_width : slab_stride;
+  const int64_t f0 = int64_t(blockIdx.y) * slab_stride + gl * VEC;
   bool fvalid[CH];
 #pragma unroll
-  for (int ch = 0; ch < CH; ++ch) fvalid[ch] = f0 + ch * LPR * VEC < p.feat;
+  for (int ch = 0; ch < CH; ++ch)
+    fvalid[ch] = (gl * VEC + ch * LPR * VEC < slab_width) && (f0 + ch * LPR * VEC < p.feat);
   const T* __restrict__ xf = static_cast<const T*>(p.x) + f0;
+  const float* __restrict__ wp = WEIGHTED ? p.w + (p.w_stride > 1 ? int64_t(blockIdx.y) : 0) : nullptr;
+  const int64_t wst = p.w_stride;
   const int beg = __ldg(p.chunk_beg + c_id);
   const int end = __ldg(p.chunk_end + c_id);
 
@@ -247,7 +263,7 @@ __global__ void __launch_bounds__(256, MINB) chunk_kernel(const ChunkParams p) {
   for (; base + LPR <= end; base += LPR) {
     const int my_col = ld_stream(p.col + base + gl);
     float my_w = 0.f;
-    if (WEIGHTED) my_w = ld_stream(p.w + base + gl);
+    if (WEIGHTED) my_w = ld_stream(wp + int64_t(base + gl) * wst);
 #pragma unroll
     for (int j0 = 0; j0 < LPR; j0 += U) {
       Pack<T, VEC> v[U][CH];
@@ -271,7 +287,7 @@ __global__ void __launch_bounds__(256, MINB) chunk_kernel(const ChunkParams p) {
     const int idx = base + gl;
     const int my_col = idx < end ? ld_stream(p.col + idx) : 0;
     float my_w = 0.f;
-    if (WEIGHTED) my_w = idx < end ? ld_stream(p.w + idx) : 0.f;
+    if (WEIGHTED) my_w = idx < end ? ld_stream(wp + int64_t(idx) * wst) : 0.f;
     const int nb = end - base;
     for (int j0 = 0; j0 < nb; j0 += U) {
       Pack<T, VEC> v[U][CH];
@@ -376,7 +392,8 @@ int launch_geo(Job& job, cudaStream_t st) {
     RowsParams& p = job.rows;
     if (p.grp_row == nullptr) p.n_groups = (p.num_rows + LPR - 1) / LPR;
     const int64_t gx = (p.n_groups + groups_per_cta - 1) / groups_per_cta;
-    const int64_t gy = (p.feat + slab - 1) / slab;
+    const int64_t sstride = p.slab_stride ? p.slab_stride : slab;
+    const int64_t gy = (p.feat + sstride - 1) / sstride;
     GMLM_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large");
     if (gx > 0) {
       dim3 grid((unsigned)gx, (unsigned)gy);
@@ -388,7 +405,8 @@ int launch_geo(Job& job, cudaStream_t st) {
   if (job.do_chunks) {
     ChunkParams& q = job.chunks;
     const int64_t gx = (q.n_chunks + groups_per_cta - 1) / groups_per_cta;
-    const int64_t gy = (q.feat + slab - 1) / slab;
+    const int64_t sstride = q.slab_stride ? q.slab_stride : slab;
+    const int64_t gy = (q.feat + sstride - 1) / sstride;
     GMLM_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large");
     if (gx > 0) {
       dim3 grid((unsigned)gx, (unsigned)gy);
@@ -402,7 +420,9 @@ int launch_geo(Job& job, cudaStream_t st) {
 
 template <typename T, int VEC>
 int launch_vec(Job& job, cudaStream_t st) {
-  const int64_t nvec = (job.rows.feat + VEC - 1) / VEC;
+  const int64_t width = job.rows.slab_width ? job.rows.slab_width : job.rows.feat;
+  const int64_t nvec = (width + VEC - 1) / VEC;
+  if (job.rows.slab_width) GMLM_REQUIRE(nvec <= 128, "spmm: per-head width above 128 packs is not supported");
   if (nvec <= 8) return launch_geo<T, VEC, 1, 8, 8, 3>(job, st);
   if (nvec <= 16) return launch_geo<T, VEC, 1, 16, 8, 3>(job, st);
   if (nvec <= 32) {
@@ -440,7 +460,7 @@ extern "C" int gmlm_group_plan(const int32_t* rowptr, int64_t num_rows, int64_t 
 }
 
 extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx, const int32_t* rowptr,
-                             const int32_t* col, const float* w, int64_t num_rows, int mode,
+                             const int32_t* col, const float* w, int32_t w_heads, int64_t num_rows, int mode,
                              const int32_t* grp_row, int64_t n_groups, int32_t hub_thresh, int64_t n_hub,
                              int64_t n_chunks, const int32_t* hub_row, const int32_t* hub_chunk_ptr,
                              const int32_t* chunk_beg, const int32_t* chunk_end, float* hub_ws, void* out,
@@ -449,6 +469,8 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   GMLM_REQUIRE(mode == GMLM_AGG_SUM || mode == GMLM_AGG_MEAN || mode == GMLM_AGG_WEIGHTED, "spmm: bad mode");
   GMLM_REQUIRE(feat >= 0 && num_rows >= 0 && ldx >= feat && ldo >= feat, "spmm: bad sizes");
   GMLM_REQUIRE(mode != GMLM_AGG_WEIGHTED || w != nullptr, "spmm: weighted mode needs w");
+  GMLM_REQUIRE(w_heads >= 1 && (w_heads == 1 || (mode == GMLM_AGG_WEIGHTED && feat % w_heads == 0)),
+               "spmm: w_heads must divide feat (and needs weighted mode)");
   GMLM_REQUIRE(n_hub >= 0 && n_chunks >= n_hub, "spmm: bad hub plan");
   GMLM_REQUIRE(grp_row == nullptr || n_groups >= 0, "spmm: bad group plan");
   if (num_rows == 0 || feat == 0) return GMLM_OK;
@@ -458,8 +480,9 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   cudaStream_t st = as_stream(stream);
   const int esz = dtype == GMLM_F32 ? 4 : 2;
   const int fullvec = 16 / esz;
+  const int64_t head_width = w_heads > 1 ? feat / w_heads : 0;
   const bool aligned = aligned16(x) && aligned16(out) && aligned16(hub_ws) && feat % fullvec == 0 &&
-                       ldx % fullvec == 0 && ldo % fullvec == 0;
+                       ldx % fullvec == 0 && ldo % fullvec == 0 && head_width % fullvec == 0;
 
   Job job;
   job.weighted = mode == GMLM_AGG_WEIGHTED;
@@ -469,6 +492,7 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   RowsParams& p = job.rows;
   p.x = x; p.ldx = ldx; p.feat = feat;
   p.rowptr = rowptr; p.col = col; p.w = w; p.num_rows = num_rows;
+  p.w_stride = w_heads; p.slab_stride = head_width; p.slab_width = head_width;
   p.grp_row = grp_row; p.n_groups = n_groups;
   p.mean = mode == GMLM_AGG_MEAN;
   p.single = tuning_spmm_variant() == 0;
@@ -477,6 +501,7 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   ChunkParams& q = job.chunks;
   q.x = x; q.ldx = ldx; q.feat = feat;
   q.chunk_beg = chunk_beg; q.chunk_end = chunk_end; q.col = col; q.w = w;
+  q.w_stride = w_heads; q.slab_stride = head_width; q.slab_width = head_width;
   q.n_chunks = n_chunks; q.out = hub_ws;
 
   int rc;

@@ -97,6 +97,7 @@ def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, h
     n_hub = int(hub_row.numel()) if hub_row is not None else 0
     n_chunks = int(chunk_beg.numel()) if chunk_beg is not None else 0
     n_groups = int(grp_row.numel()) - 1 if grp_row is not None else 0
+    w_heads = int(w.size(1)) if (w is not None and w.dim() == 2) else 1
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((num_rows, feat), dtype=x.dtype, device=dev)
@@ -104,7 +105,8 @@ def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, h
             raise _lib.GmlmError("spmm: `out` must be a contiguous [num_rows, feat] tensor of x's dtype")
         hub_ws = torch.empty(n_chunks * feat, dtype=torch.float32, device=dev) if n_hub else None
         _lib.check(lib.gmlm_spmm_csr(_ptr(x), _dtype_code(x, "spmm_csr"), feat, _ld(x), _ptr(rowptr), _ptr(col),
-                                     _ptr(w), num_rows, mode, _ptr(grp_row), n_groups, hub_thresh, n_hub, n_chunks,
+                                     _ptr(w), w_heads, num_rows, mode, _ptr(grp_row), n_groups, hub_thresh, n_hub,
+                                     n_chunks,
                                      _ptr(hub_row),
                                      _ptr(hub_chunk_ptr), _ptr(chunk_beg), _ptr(chunk_end), _ptr(hub_ws), _ptr(out),
                                      feat, _stream(dev)), "spmm_csr")

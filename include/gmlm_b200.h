@@ -112,10 +112,12 @@ int gmlm_group_plan(const int32_t* rowptr, int64_t num_rows, int64_t nnz, int64_
  *      gather-form backward.  out[r, :] = reduce_{e in row r} w[e] * x[col[e], :] ----
  * x: [*, feat] dtype, leading dim ldx; out: [num_rows, feat] same dtype, leading dim ldo.
  * fp32 accumulation in CSR order (deterministic).  grp_row may be NULL (uniform 32-row groups).
+ * w is [nnz, w_heads]: w_heads = 1 is one scalar per edge; w_heads = H > 1 (GAT attention, row A9)
+ * gives head h its own weight column for the features [h*feat/H, (h+1)*feat/H).
  * Hub arrays may be NULL when n_hub == 0; hub_ws: float[n_chunks * feat] scratch. */
 int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx,
-                  const int32_t* rowptr, const int32_t* col, const float* w, int64_t num_rows, int mode,
-                  const int32_t* grp_row, int64_t n_groups,
+                  const int32_t* rowptr, const int32_t* col, const float* w, int32_t w_heads,
+                  int64_t num_rows, int mode, const int32_t* grp_row, int64_t n_groups,
                   int32_t hub_thresh, int64_t n_hub, int64_t n_chunks, const int32_t* hub_row,
                   const int32_t* hub_chunk_ptr, const int32_t* chunk_beg, const int32_t* chunk_end,
                   float* hub_ws, void* out, int64_t ldo, void* stream);
@@ -152,6 +154,25 @@ size_t gmlm_soft_mask_bwd_workspace_bytes(int64_t num_rows, int64_t feat);
 int gmlm_soft_mask_bwd(const void* gy, int dtype, int64_t num_rows, int64_t feat, int64_t ldg,
                        const uint8_t* mask, float beta, float* g_token /* [feat] */, void* gx /* may be NULL */,
                        int64_t ldgx, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference): per-edge scalars
+ *      of the GCN symmetric normalisation and the GAT edge-softmax on a dst-keyed CSR.  The
+ *      feature aggregation itself is gmlm_spmm_csr in weighted mode (w_heads = 1 / = heads). ----
+ * gcn_edge_weights: w[e] = deg[col[e]]^-1/2 * deg[row]^-1/2, deg = CSR row length (self-loops included)
+ * gat_alpha_fwd   : alpha[e,h] = softmax over row(e) of leaky_relu(a_src[col[e],h] + a_dst[row,h])  (+1e-16)
+ * gat_alpha_bwd   : d_score[e,h] = d/d(raw score); da_dst[r,h] = sum over row r of d_score
+ * segment_sum_f32 : out[r,h] = sum_{i in row r} vals[idx[i],h]  (idx NULL = identity) */
+int gmlm_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, int64_t num_rows, float* dis_ws /* [rows] */,
+                          float* w /* [nnz] */, void* stream);
+int gmlm_gat_alpha_fwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, const float* a_src,
+                       const float* a_dst, int heads, float negative_slope, float* alpha /* [nnz,heads] */,
+                       void* stream);
+int gmlm_gat_alpha_bwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, const void* z, int64_t ldz,
+                       const void* g, int64_t ldg, int dtype, int heads, int head_dim, const float* a_src,
+                       const float* a_dst, const float* alpha, float negative_slope, float* d_score /* [nnz,heads] */,
+                       float* da_dst /* [rows,heads] */, void* stream);
+int gmlm_segment_sum_f32(const float* vals, const int64_t* idx, const int32_t* rowptr, int64_t num_rows, int heads,
+                         float* out, void* stream);
 
 /* ---- halo pack / unpack for the destination-row partition (the reference has no
  *      multi-GPU path) ----

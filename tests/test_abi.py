@@ -52,10 +52,10 @@ def test_argument_validation_without_gpu(lib_built):
     lib = _lib.load()
     null = C.c_void_p(0)
     # bad dtype code
-    rc = lib.gmlm_spmm_csr(null, 7, 4, 4, null, null, null, 1, 0, null, 0, 0, 0, 0, null, null, null, null, null, null, 4, null)
+    rc = lib.gmlm_spmm_csr(null, 7, 4, 4, null, null, null, 1, 1, 0, null, 0, 0, 0, 0, null, null, null, null, null, null, 4, null)
     assert rc == 1 and b"dtype" in lib.gmlm_last_error()
     # weighted mode without weights
-    rc = lib.gmlm_spmm_csr(null, 0, 4, 4, null, null, null, 1, 2, null, 0, 0, 0, 0, null, null, null, null, null, null, 4, null)
+    rc = lib.gmlm_spmm_csr(null, 0, 4, 4, null, null, null, 1, 1, 2, null, 0, 0, 0, 0, null, null, null, null, null, null, 4, null)
     assert rc == 1
     # too many bucket bounds
     rc = lib.gmlm_edge_type_bucket(null, 0, null, 0, (C.c_int32 * 9)(*range(9)), 9, null, null)

@@ -202,3 +202,82 @@ def test_encoder_with_soft_mask_and_autocast(cuda_dev):
     fused.float().sum().backward()
     assert mod.gnn_mask_token_embed.grad is not None
     assert torch.isfinite(mod.gnn_mask_token_embed.grad).all()
+
+
+# ------------------------------------------------------------------ extensions A8 / A9 (parity unpinned by the reference)
+from oracle import GATConvRef, GCNConvRef  # noqa: E402
+
+
+def _loopy_graph(n, e, seed):
+    """random graph with duplicate edges and a few self-loops (upstream removes then re-adds them)"""
+    ei = synth.uniform_edges(n, e, seed=seed)
+    ei[1, : e // 20] = ei[0, : e // 20]
+    return ei
+
+
+@pytest.mark.parametrize("n,e,fi,fo", [(183, 300, 64, 32), (2000, 15000, 300, 64), (3, 0, 8, 8)])
+def test_gcn_conv_matches_oracle(cuda_dev, n, e, fi, fo):
+    torch.manual_seed(2)
+    ei = _loopy_graph(n, e, seed=n)
+    ref = GCNConvRef(fi, fo).double()
+    with torch.no_grad():
+        ref.bias.uniform_(-0.1, 0.1)
+    mod = G.GCNConv(fi, fo)
+    assert set(mod.state_dict()) == set(ref.state_dict()) == {"lin.weight", "bias"}
+    mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mod = mod.to(cuda_dev)
+    x, gout = torch.randn(n, fi), torch.randn(n, fo)
+    x64 = x.double().requires_grad_(True)
+    y_ref = ref(x64, ei)
+    y_ref.backward(gout.double())
+    xg = x.to(cuda_dev).requires_grad_(True)
+    y = mod(xg, ei.to(cuda_dev))
+    y.backward(gout.to(cuda_dev))
+    assert rel_err(y, y_ref) <= FP32_TOL
+    assert rel_err(xg.grad, x64.grad) <= FP32_TOL
+    assert rel_err(mod.lin.weight.grad, ref.lin.weight.grad) <= 2e-5
+    assert rel_err(mod.bias.grad, ref.bias.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("n,e,fi,c,heads,concat", [(183, 300, 64, 16, 4, True), (2449, 9305, 300, 64, 8, True),
+                                                   (500, 6000, 32, 8, 3, False), (1, 2, 8, 4, 2, True)])
+def test_gat_conv_matches_oracle(cuda_dev, n, e, fi, c, heads, concat):
+    """Amazon-ratings-shaped config (BASELINE configs[2], 1/10 scale here) with 8 heads, plus odd
+    head counts / widths (scalar-pack path) and the mean-over-heads variant."""
+    torch.manual_seed(3)
+    ei = _loopy_graph(n, e, seed=n + 7)
+    ref = GATConvRef(fi, c, heads=heads, concat=concat).double()
+    with torch.no_grad():
+        ref.bias.uniform_(-0.1, 0.1)
+    mod = G.GATConv(fi, c, heads=heads, concat=concat)
+    assert set(mod.state_dict()) == set(ref.state_dict()) == {"lin.weight", "att_src", "att_dst", "bias"}
+    mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    mod = mod.to(cuda_dev)
+    out_dim = heads * c if concat else c
+    x, gout = torch.randn(n, fi), torch.randn(n, out_dim)
+    x64 = x.double().requires_grad_(True)
+    y_ref = ref(x64, ei)
+    y_ref.backward(gout.double())
+    xg = x.to(cuda_dev).requires_grad_(True)
+    y = mod(xg, ei.to(cuda_dev))
+    y.backward(gout.to(cuda_dev))
+    assert rel_err(y, y_ref) <= FP32_TOL
+    assert rel_err(xg.grad, x64.grad) <= 2e-5
+    for name in ("att_src", "att_dst", "bias"):
+        assert rel_err(getattr(mod, name).grad, getattr(ref, name).grad) <= 2e-5, name
+    assert rel_err(mod.lin.weight.grad, ref.lin.weight.grad) <= 2e-5
+
+
+def test_gat_attention_rows_sum_to_one_and_bf16(cuda_dev):
+    n, e, heads, c = 3000, 40000, 8, 32
+    ei = synth.rmat_edges(n, e, seed=4).to(cuda_dev)
+    g = G.get_loop_graph(ei, n)
+    z = torch.ones(n, heads * c, device=cuda_dev)
+    a_s = torch.randn(n, heads, device=cuda_dev)
+    a_d = torch.randn(n, heads, device=cuda_dev)
+    out = G.gat_aggregate(z, a_s, a_d, g)        # softmax-weighted mean of identical rows == the row
+    assert float((out - 1).abs().max()) <= 1e-5
+    zb = torch.randn(n, heads * c, device=cuda_dev)
+    o32 = G.gat_aggregate(zb, a_s, a_d, g)
+    o16 = G.gat_aggregate(zb.bfloat16(), a_s, a_d, g)
+    assert o16.dtype == torch.bfloat16 and rel_err(o16, o32) <= BF16_TOL
