@@ -247,6 +247,44 @@ _LIB.impl("soft_mask_fwd", _soft_mask_fwd, "CUDA")
 _LIB.impl("soft_mask_bwd", _soft_mask_bwd, "CUDA")
 
 
+# ------------------------------------------------------------------------------ A6 dense transform (tcgen05)
+def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None, split: int = 0):
+    """``[a1 | a2] @ b.T + bias`` on the tcgen05 tensor cores (bf16 in, fp32 accumulate).
+
+    a1 [M,K1], a2 [M,K2] (optional), b [N,K1+K2], all bf16 with unit inner stride; returns C [M,N],
+    or (C[:, :split], C[:, split:]) as two contiguous tensors when ``split`` > 0."""
+    lib = _lib.load()
+    _require_cuda(a1, "a1")
+    if a1.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or (a2 is not None and a2.dtype != torch.bfloat16):
+        raise _lib.GmlmError("gemm_nt: operands must be bfloat16")
+    a1, b = _rowmajor(a1), _rowmajor(b)
+    a2 = _rowmajor(a2) if a2 is not None else None
+    m, k1 = a1.shape
+    k2 = int(a2.size(1)) if a2 is not None else 0
+    n = int(b.size(0))
+    if b.size(1) != k1 + k2 or (a2 is not None and a2.size(0) != m):
+        raise _lib.GmlmError(f"gemm_nt: shape mismatch a1 {tuple(a1.shape)} a2 {None if a2 is None else tuple(a2.shape)} "
+                             f"b {tuple(b.shape)}")
+    out_dtype = out_dtype or torch.bfloat16
+    code = _DT[out_dtype]
+    dev = a1.device
+    bias32 = bias.detach().float().contiguous() if bias is not None else None
+    with torch.cuda.device(dev):
+        if split and 0 < split < n:
+            c1 = torch.empty((m, split), dtype=out_dtype, device=dev)
+            c2 = torch.empty((m, n - split), dtype=out_dtype, device=dev)
+        else:
+            split = 0
+            c1 = torch.empty((m, n), dtype=out_dtype, device=dev)
+            c2 = None
+        _lib.check(lib.gmlm_gemm_nt_bf16(_ptr(a1), _ld(a1), k1, _ptr(a2), _ld(a2) if a2 is not None else 0, k2,
+                                         _ptr(b), _ld(b), _ptr(bias32), m, n, _ptr(c1), c1.size(1), split,
+                                         _ptr(c2), c2.size(1) if c2 is not None else 0, code, _stream(dev)),
+                   "gemm_nt_bf16")
+    return (c1, c2) if c2 is not None else c1
+
+
 # ------------------------------------------------------------------------------ halo pack / unpack
 def gather_rows(x: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[k] = x[ids[k]] (pack the rows a peer needs)."""

@@ -155,6 +155,15 @@ int gmlm_soft_mask_bwd(const void* gy, int dtype, int64_t num_rows, int64_t feat
                        const uint8_t* mask, float beta, float* g_token /* [feat] */, void* gx /* may be NULL */,
                        int64_t ldgx, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- A6  dense feature transform on tcgen05 tensor cores (TMA tiles, TMEM accumulator):
+ *          [PyG] RGCNConv.forward `out += h @ W[r]` / `out += x @ root` / `+ bias`, main.py:272 ----
+ * C[M,N] = [A1 | A2][M, K1+K2] * B[N, K1+K2]^T + bias[N];  A1, A2, B bf16 row-major (K contiguous),
+ * fp32 accumulation, C bf16 or fp32.  Output columns [0,N1) go to C1 and [N1,N) to C2 (N1 <= 0 or
+ * >= N: everything to C1).  K1, K2 multiples of 64; N multiple of 32; N1 on a tile boundary. */
+int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                      const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
+                      int64_t N1, void* C2, int64_t ldc2, int out_dtype, void* stream);
+
 /* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference): per-edge scalars
  *      of the GCN symmetric normalisation and the GAT edge-softmax on a dst-keyed CSR.  The
  *      feature aggregation itself is gmlm_spmm_csr in weighted mode (w_heads = 1 / = heads). ----

@@ -1,0 +1,57 @@
+"""tcgen05 GEMM (the dense transform of [PyG] RGCNConv.forward, main.py:272)
+against a plain PyTorch fp32 reference of the same op on the same bf16 inputs."""
+import pytest
+import torch
+
+from gmlm_b200.ops import gemm_nt
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a1, b, bias, a2):
+    a = a1.float() if a2 is None else torch.cat([a1.float(), a2.float()], dim=1)
+    out = a @ b.float().t()
+    return out + bias if bias is not None else out
+
+
+@pytest.mark.parametrize("m,n,k1,k2", [(128, 64, 64, 0), (300, 64, 128, 0), (389, 256, 64, 0), (1000, 128, 256, 64),
+                                       (4097, 64, 1024, 256), (77, 32, 192, 0), (513, 512, 128, 128), (5, 96, 64, 0)])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_gemm_nt_matches_fp32_reference(cuda_dev, m, n, k1, k2, out_dtype, use_bias):
+    g = torch.Generator().manual_seed(m + n + k1)
+    a1 = torch.randn(m, k1, generator=g).bfloat16().to(cuda_dev)
+    a2 = torch.randn(m, k2, generator=g).bfloat16().to(cuda_dev) if k2 else None
+    b = (torch.randn(n, k1 + k2, generator=g) / (k1 + k2) ** 0.5).bfloat16().to(cuda_dev)
+    bias = torch.randn(n, generator=g).to(cuda_dev) if use_bias else None
+    got = gemm_nt(a1, b, bias=bias, a2=a2, out_dtype=out_dtype)
+    ref = _ref(a1, b, bias, a2)
+    assert got.shape == (m, n) and got.dtype == out_dtype
+    tol = 1e-5 if out_dtype == torch.float32 else 1e-2     # fp32 accumulate; bf16 only rounds the store
+    assert rel_err(got, ref) <= tol
+
+
+def test_gemm_nt_split_outputs_and_strided_operands(cuda_dev):
+    """backward use: [dH | dx] = g @ [W ; root]^T written to two contiguous tensors; A given as a
+    column slice (leading dimension > K)."""
+    g = torch.Generator().manual_seed(1)
+    m, n, k = 777, 1024 + 256, 64
+    big = torch.randn(m, 192, generator=g).bfloat16().to(cuda_dev)
+    a = big[:, 64:128]                                   # lda = 192
+    b = (torch.randn(n, k, generator=g) / 8).bfloat16().to(cuda_dev)
+    c1, c2 = gemm_nt(a, b, split=1024)
+    ref = a.float() @ b.float().t()
+    assert c1.shape == (m, 1024) and c2.shape == (m, 256) and c1.is_contiguous() and c2.is_contiguous()
+    assert rel_err(c1, ref[:, :1024]) <= 1e-2 and rel_err(c2, ref[:, 1024:]) <= 1e-2
+
+
+def test_gemm_nt_rejects_bad_shapes(cuda_dev):
+    from gmlm_b200 import GmlmError
+    a = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)      # K not a multiple of 64
+    b = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)
+    with pytest.raises(GmlmError):
+        gemm_nt(a, b)
+    with pytest.raises(GmlmError):
+        gemm_nt(a.float(), b.float())
