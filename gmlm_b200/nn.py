@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .graph import RelGraph, get_rel_graph
-from .ops import graph_norm, rgcn_aggregate
+from .ops import graph_norm, rgcn_aggregate, rgcn_transform, rgcn_transform_ok
 
 
 def glorot_(t: Optional[torch.Tensor]):
@@ -44,6 +44,7 @@ class RGCNConv(nn.Module):
                  is_sorted: bool = False, bias: bool = True, out_dtype: Optional[torch.dtype] = None, **kwargs):
         super().__init__()
         self.out_dtype = out_dtype  # None = upstream behaviour (default dtype); bf16 for the bandwidth study
+        self.use_tcgen05 = True     # bf16 activations: dense transform on the tcgen05 GEMM (else cuBLAS)
         if num_blocks is not None:
             raise NotImplementedError("gmlm_b200.RGCNConv: block-diagonal decomposition is not on the reference "
                                       "path (main.py uses num_bases=30)")
@@ -109,6 +110,10 @@ class RGCNConv(nn.Module):
         # matmuls run in the operand dtype, or in the autocast dtype under torch.amp.autocast
         autocast = torch.is_autocast_enabled("cuda")
         out_dtype = self.out_dtype or torch.get_default_dtype()
+        if (self.use_tcgen05 and not autocast and self.root is not None and out_dtype in (torch.float32, torch.bfloat16)
+                and rgcn_transform_ok(h, x, self.out_channels)):
+            # bf16 pipeline: one tcgen05 GEMM over [h | x] with the bias in its epilogue
+            return rgcn_transform(h, x, w, self.root, self.bias, out_dtype)
 
         def mm(a, b):
             return torch.matmul(a, b) if autocast else torch.matmul(a, b.to(a.dtype))

@@ -285,6 +285,46 @@ def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = No
     return (c1, c2) if c2 is not None else c1
 
 
+class _RGCNTransform(torch.autograd.Function):
+    """out = [h | x] @ [w ; root] + bias on tcgen05 (A6), with the matching backward:
+    [dh | dx] = g @ [w ; root]^T (tcgen05, two outputs), dW = h^T g, droot = x^T g (cuBLAS: the
+    2M-deep reduction is a plain library GEMM), dbias = column sum."""
+
+    @staticmethod
+    def forward(ctx, h, x, w, root, bias, out_dtype):
+        wc = torch.cat([w, root], dim=0).to(torch.bfloat16)            # [K1+K2, Fo]
+        out = gemm_nt(h, wc.t().contiguous(), bias=bias, a2=x, out_dtype=out_dtype)
+        ctx.save_for_backward(h, x, wc)
+        ctx.k1 = h.size(1)
+        ctx.dtypes = (w.dtype, root.dtype, None if bias is None else bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, x, wc = ctx.saved_tensors
+        gb = g.to(torch.bfloat16).contiguous()
+        dh = dx = dw = droot = dbias = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dh, dx = gemm_nt(gb, wc, split=ctx.k1)                     # [M,K1], [M,K2]
+        if ctx.needs_input_grad[2]:
+            dw = (h.t() @ gb).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[3]:
+            droot = (x.t() @ gb).to(ctx.dtypes[1])
+        if ctx.needs_input_grad[4]:
+            dbias = g.float().sum(0).to(ctx.dtypes[2])
+        return dh, dx, dw, droot, dbias, None
+
+
+def rgcn_transform_ok(h: torch.Tensor, x: torch.Tensor, fo: int) -> bool:
+    """Shapes the tcgen05 path covers: bf16 activations, K blocks of 64, Fo a multiple of 64."""
+    return (h.is_cuda and h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and h.size(1) % 64 == 0
+            and x.size(1) % 64 == 0 and fo % 64 == 0 and h.size(1) > 0)
+
+
+def rgcn_transform(h, x, w, root, bias, out_dtype) -> torch.Tensor:
+    return _RGCNTransform.apply(h, x, w, root, bias, out_dtype)
+
+
 # ------------------------------------------------------------------------------ halo pack / unpack
 def gather_rows(x: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[k] = x[ids[k]] (pack the rows a peer needs)."""

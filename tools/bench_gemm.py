@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""Development micro-benchmark (GPU): tcgen05 gemm_nt vs torch.matmul (cuBLAS) on the layer shapes."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from gmlm_b200.ops import gemm_nt
+
+
+def t(fn, it=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(it):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / it
+
+
+dev = torch.device("cuda:0")
+for (m, n, k1, k2) in [(2_000_000, 64, 1024, 256), (2_000_000, 128, 256, 64), (2_000_000, 256, 512, 128),
+                       (2_000_000, 1024 + 256, 64, 0)]:
+    a1 = torch.randn(m, k1, device=dev).bfloat16()
+    a2 = torch.randn(m, k2, device=dev).bfloat16() if k2 else None
+    b = torch.randn(n, k1 + k2, device=dev).bfloat16()
+    bias = torch.randn(n, device=dev)
+    ms_tc = t(lambda: gemm_nt(a1, b, bias=bias, a2=a2))
+    bt = b.t().contiguous()
+    if a2 is not None:
+        ms_cb = t(lambda: torch.addmm(bias.bfloat16(), a1, bt[:k1]) + a2 @ bt[k1:])
+    else:
+        ms_cb = t(lambda: torch.addmm(bias.bfloat16(), a1, bt))
+    bytes_ = (m * (k1 + k2) + m * n) * 2
+    print(f"M={m} N={n} K={k1}+{k2}: tcgen05 {ms_tc:.3f} ms ({bytes_/ms_tc/1e6:.0f} GB/s, "
+          f"{2*m*n*(k1+k2)/ms_tc/1e9:.0f} TFLOP/s)  cuBLAS {ms_cb:.3f} ms ({bytes_/ms_cb/1e6:.0f} GB/s)", flush=True)
+    del a1, a2, b
