@@ -189,38 +189,53 @@ __global__ void __launch_bounds__(kThreads) gemm_nt_kernel(const __grid_constant
       umma_commit(smem_u32(tmem_full));        // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warp w owns TMEM lanes [32*(w%4), 32*(w%4)+32) = 32 output rows
+    // ---------------- epilogue: warp w owns TMEM lanes [32*(w%4), 32*(w%4)+32) = 32 output rows.
+    // TMEM -> registers (one row per lane) -> shared memory (the drained pipeline stages, padded
+    // rows: conflict-free 16-byte writes) -> global with fully coalesced 128-bit row segments.
     const int quad = warp & 3;
     mbar_wait(smem_u32(tmem_full), 0);
     tc_fence_after();
-    const int row = m0 + quad * 32 + lane;
-    const bool second = n0 >= p.N1;
-    OutT* crow = second ? static_cast<OutT*>(p.C2) + int64_t(row) * p.ldc2 + (n0 - p.N1)
-                        : static_cast<OutT*>(p.C1) + int64_t(row) * p.ldc1 + n0;
+    constexpr int ROW_BYTES = BLOCK_N * int(sizeof(OutT));
+    constexpr int STRIDE = ROW_BYTES + 16;                 // odd multiple of 16 bytes
+    uint8_t* stage = smem + quad * 32 * STRIDE;            // K loop is over: the operand ring is free
+    uint8_t* my_row = stage + lane * STRIDE;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       uint32_t r[32];
       tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
-      if (row < p.M) {
-        float v[32];
+      float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[j] = __uint_as_float(r[j]);
-          if (p.bias) v[j] += __ldg(p.bias + n0 + c0 + j);
+      for (int j = 0; j < 32; ++j) {
+        v[j] = __uint_as_float(r[j]);
+        if (p.bias) v[j] += __ldg(p.bias + n0 + c0 + j);
+      }
+      if constexpr (sizeof(OutT) == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          Pack<__nv_bfloat16, 8> o;
+          o.pack(v + j);
+          *reinterpret_cast<uint4*>(my_row + (c0 + j) * 2) = o.v;
         }
-        if constexpr (sizeof(OutT) == 2) {
+      } else {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            Pack<__nv_bfloat16, 8> o;
-            o.pack(v + j);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(crow) + c0 + j) = o.v;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(crow) + c0 + j) =
-                make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(my_row + (c0 + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+    __syncwarp();
+    const bool second = n0 >= p.N1;
+    uint8_t* cbase = second ? static_cast<uint8_t*>(p.C2) + int64_t(n0 - p.N1) * sizeof(OutT)
+                            : static_cast<uint8_t*>(p.C1) + int64_t(n0) * sizeof(OutT);
+    const int64_t ldc_bytes = (second ? p.ldc2 : p.ldc1) * int64_t(sizeof(OutT));
+    constexpr int CHUNKS = ROW_BYTES / 16;                 // 16-byte chunks per output row
+    const int row0 = m0 + quad * 32;
+#pragma unroll 4
+    for (int idx = lane; idx < 32 * CHUNKS; idx += 32) {
+      const int rr = idx / CHUNKS;
+      const int cc = idx - rr * CHUNKS;
+      if (row0 + rr < p.M) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * STRIDE + cc * 16);
+        __stcs(reinterpret_cast<uint4*>(cbase + int64_t(row0 + rr) * ldc_bytes + cc * 16), val);
       }
     }
   }
@@ -309,6 +324,16 @@ extern "C" int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const
   GMLM_REQUIRE((reinterpret_cast<uintptr_t>(C1) & 15) == 0 && (reinterpret_cast<uintptr_t>(C2) & 15) == 0 &&
                    (ldc1 * esz) % 16 == 0 && (ldc2 * esz) % 16 == 0,
                "gemm: outputs must be 16-byte aligned");
+  // cuTensorMapEncodeTiled is a driver entry point: it needs a current context on THIS thread.
+  // Autograd worker threads may not have one bound yet in this library's runtime instance, so
+  // bind the device that owns the operands.
+  {
+    cudaPointerAttributes attr;
+    GMLM_CUDA_TRY(cudaPointerGetAttributes(&attr, A1));
+    GMLM_REQUIRE(attr.type == cudaMemoryTypeDevice, "gemm: A1 is not device memory");
+    GMLM_CUDA_TRY(cudaSetDevice(attr.device));
+    GMLM_CUDA_TRY(cudaFree(nullptr));
+  }
   CUtensorMap ma1, ma2, mb;
   int rc = make_map(&ma1, A1, M, K1, lda1, BLOCK_M);
   if (rc) return rc;

