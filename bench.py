@@ -317,6 +317,39 @@ def run_single(args):
         except Exception as ex:  # context only; never hides the headline
             layer = {"error": repr(ex)[:200]}
 
+    # ---- whole GNN encoder (get_graph_embeddings, main.py:250-320): four layers + residuals + fusion,
+    #      forward + backward ("epoch" of the encoder on this graph); edges/s counts 4*E per pass
+    encoder = None
+    if not args.no_layer:
+        try:
+            del gh
+            torch.cuda.empty_cache()
+            enc = G.GraphEncoder(feat, w.hidden, 768, dropout_rate=0.0, act_dtype=dtype).to(dev)
+            if dtype == torch.bfloat16:
+                enc.residual_proj1.to(dtype), enc.residual_proj2.to(dtype), enc.multi_scale_fusion.to(dtype)
+            xg = x.detach().requires_grad_(True)
+
+            def enc_step():
+                y = enc.get_graph_embeddings(xg, ei, et)
+                y.backward(torch.ones_like(y))
+                xg.grad = None
+
+            for _ in range(2):
+                enc_step()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(3):
+                enc_step()
+            b.record()
+            torch.cuda.synchronize()
+            ems = a.elapsed_time(b) / 3
+            encoder = {"ms_fwd_bwd": ems, "edges_per_s": 4 * e / (ems * 1e-3), "hidden_channels": w.hidden,
+                       "what": "GraphEncoder.get_graph_embeddings fwd+bwd: 4x(RGCNConv+GraphNorm+GELU), residual "
+                               "projections, MultiScaleFusion(->768); edges/s counts the 4 propagates"}
+            del enc
+        except Exception as ex:
+            encoder = {"error": repr(ex)[:300]}
+
     cpu = None
     if not args.no_cpu_baseline:
         eps, cms, cores = time_cpu_reference(2, 1, args.cpu_sample_nodes, args.cpu_sample_edges, feat)
@@ -337,7 +370,7 @@ def run_single(args):
                    "hub_thresh": g.fwd.hub_thresh, "hub_rows_fwd": g.fwd.n_hub, "hub_rows_bwd": g.bwd.n_hub},
         "roofline": roof, "roofline_bwd": roof_bwd, "roofline_step": roof_step,
         "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-        "clocks": clocks, "layer": layer,
+        "clocks": clocks, "layer": layer, "encoder": encoder,
         "setup_s": {"generate": t_gen, "edge_typing": t_type, "csr_build": t_csr},
     }
     print(json.dumps(line), flush=True)
