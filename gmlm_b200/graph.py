@@ -62,7 +62,16 @@ class CSR:
     def plan_groups(self, quantum: Optional[int] = None):
         """Cut the rows into groups of about ``quantum`` units of work (edges + rows)."""
         lib = _lib.load()
-        q = DEFAULT_QUANTUM if quantum is None else int(quantum)
+        if quantum is None:
+            # DEFAULT_QUANTUM units per group on big graphs; small graphs (the reference's own
+            # datasets) get smaller groups so that there are >= ~32 groups per SM to hide latency
+            # (measured on the Roman-empire shape: 105 us at 512 vs 45 us at 32)
+            q = DEFAULT_QUANTUM
+            if q > 0:
+                sms = torch.cuda.get_device_properties(self.rowptr.device).multi_processor_count
+                q = max(32, min(q, (self.num_rows + self.nnz) // (sms * 32)))
+        else:
+            q = int(quantum)
         self.quantum = q
         if q <= 0 or self.num_rows == 0:
             self.n_groups, self.grp_row = 0, None
