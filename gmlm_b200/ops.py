@@ -315,7 +315,7 @@ class _RGCNTransform(torch.autograd.Function):
         if ctx.needs_input_grad[3]:
             droot = (x.t() @ gb).to(ctx.dtypes[1])
         if ctx.needs_input_grad[4]:
-            dbias = g.float().sum(0).to(ctx.dtypes[2])
+            dbias = torch.ops.gmlm.colstats(gb)[0].to(ctx.dtypes[2])   # one pass, fp64 accumulate, deterministic
         return dh, dx, dw, droot, dbias, None
 
 

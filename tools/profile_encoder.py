@@ -1,0 +1,36 @@
+#!/usr/bin/env python
+"""Development: kernel-time breakdown of one encoder fwd+bwd on a workload (torch profiler)."""
+import sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import torch
+from torch.profiler import profile, ProfilerActivity
+import gmlm_b200 as G
+from gmlm_b200 import synth
+
+key = sys.argv[1] if len(sys.argv) > 1 else "c4"
+dev = torch.device("cuda:0")
+w = synth.WORKLOADS[key]
+dtype = torch.bfloat16 if w.dtype == "bf16" else torch.float32
+ei = synth.make_graph(w, device=dev)
+x = synth.make_features(w.num_nodes, w.feat, device=dev, dtype=dtype)
+et = G.edge_type_from_degree(ei, w.num_nodes)
+enc = G.GraphEncoder(w.feat, w.hidden, 768, dropout_rate=0.0, act_dtype=dtype).to(dev)
+if dtype == torch.bfloat16:
+    enc.residual_proj1.to(dtype), enc.residual_proj2.to(dtype), enc.multi_scale_fusion.to(dtype)
+xg = x.detach().requires_grad_(True)
+
+
+def step():
+    y = enc.get_graph_embeddings(xg, ei, et)
+    y.backward(torch.ones_like(y))
+    xg.grad = None
+
+
+for _ in range(2):
+    step()
+torch.cuda.synchronize()
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step()
+    torch.cuda.synchronize()
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
