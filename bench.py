@@ -389,6 +389,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: halo exchange implementation")
+    ap.add_argument("--no-bwd-pipeline", action="store_true", help="N>1: disable the sliced/pipelined backward")
     ap.add_argument("--partition", default="random", choices=["random", "cyclic", "range"],
                     help="N>1: node ownership")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -193,6 +193,7 @@ class RelGraph:
     fwd: CSR
     bwd: CSR
     num_src: int = -1              # source rows; > num_nodes for a partition with halo rows
+    seg_of_edge: Optional[torch.Tensor] = None   # int32 [E] forward segment of each ORIGINAL edge (kept on request)
     _keepalive: list = field(default_factory=list, repr=False)
 
     def __post_init__(self):
@@ -206,7 +207,7 @@ class RelGraph:
     @staticmethod
     def build(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int, num_relations: int,
               hub_thresh: Optional[int] = None, quantum: Optional[int] = None, num_src: Optional[int] = None,
-              live_rels: Optional[List[int]] = None) -> "RelGraph":
+              live_rels: Optional[List[int]] = None, keep_seg: bool = False) -> "RelGraph":
         """``num_src`` > ``num_nodes`` builds the rectangular CSR of a destination-row partition
         (columns = local rows followed by halo rows).  ``live_rels`` pins the relation->slot
         layout (ranks of a partition must agree on it); default = the populated relations."""
@@ -251,7 +252,7 @@ class RelGraph:
                              hub_thresh=hub_thresh, quantum=quantum)
         bwd = transpose_csr(src, seg, n_src, fwd_rowptr=fwd.rowptr, hub_thresh=hub_thresh, quantum=quantum)
         return RelGraph(num_nodes=num_nodes, num_edges=E, num_relations=num_relations, live_rels=live, fwd=fwd,
-                        bwd=bwd, num_src=n_src)
+                        bwd=bwd, num_src=n_src, seg_of_edge=seg if keep_seg else None)
 
 
 # ------------------------------------------------------------------------------ cache

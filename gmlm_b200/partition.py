@@ -268,6 +268,7 @@ class PeerHalo:
         # backward plan: for every local row that some peer used, the addresses of its gradient rows
         # in those peers' gX tails, grouped by row, peers in the fixed order above
         rows, addrs, keys = [], [], []
+        self.bwd_seq = []
         offs = [0]
         for q in range(world):
             offs.append(offs[-1] + part.send_splits[q])
@@ -277,7 +278,9 @@ class PeerHalo:
                 continue
             n_local_q = part.ranges[q][1] - part.ranges[q][0]
             start = n_local_q + int(all_splits[q, :rank].sum())
-            base = self.hg.get_buffer(q, (self.max_rows, feat), dtype).data_ptr()
+            peer_g = self.hg.get_buffer(q, (self.max_rows, feat), dtype)
+            base = peer_g.data_ptr()
+            self.bwd_seq.append((q, peer_g[start:start + cnt], part.send_ids[offs[q]:offs[q] + cnt].contiguous()))
             rows.append(part.send_ids[offs[q]:offs[q] + cnt])
             addrs.append(base + (start + torch.arange(cnt, dtype=torch.int64, device=dev)) * row_bytes)
         if rows:
@@ -307,6 +310,69 @@ class PeerHalo:
                    "gather_rows_ptr")
         self.hx.barrier()                                   # every rank is done reading
         return self.X
+
+    # ---- pipelined backward: aggregate the halo gradients owner by owner and let each owner pull
+    #      its slice over NVLink while the next slice is being computed
+    def build_backward_slices(self, graph):
+        """Split the transposed CSR of ``graph`` (built with keep_seg=True) into row slices: the local
+        rows, then the halo rows owner by owner in this rank's rotated peer order."""
+        from .graph import transpose_csr
+        part, world, rank = self.part, self.part.world, self.part.rank
+        if graph.seg_of_edge is None:
+            raise ValueError("build_backward_slices needs RelGraph.build(..., keep_seg=True)")
+        src = part.edge_index[0]
+        seg = graph.seg_of_edge
+
+        def make(a, b):
+            m = (src >= a) & (src < b)
+            return transpose_csr((src[m] - a).contiguous(), seg[m].contiguous(), b - a, fwd_rowptr=graph.fwd.rowptr)
+
+        self.slice_local = make(0, part.n_local)
+        offs = [0]
+        for p in range(world):
+            offs.append(offs[-1] + part.recv_splits[p])
+        send_offs = [0]
+        for q in range(world):
+            send_offs.append(send_offs[-1] + part.send_splits[q])
+        self.slices = []
+        for k in range(1, world):
+            owner = (rank + k) % world                       # the slice I compute at step k belongs to `owner`
+            a, b = part.n_local + offs[owner], part.n_local + offs[owner + 1]
+            src_rank = (rank - k) % world                    # ... and at step k I can pull my slice from `src_rank`
+            cnt = part.send_splits[src_rank]
+            pull = None
+            for q, rows, ids in self.bwd_seq:
+                if q == src_rank:
+                    pull = (rows, ids)
+            self.slices.append((make(a, b) if b > a else None, a, b, pull))
+        self.comm_stream = torch.cuda.Stream(device=src.device)
+        return self
+
+    def backward_pipelined(self, gh: torch.Tensor) -> torch.Tensor:
+        """gX = aggregate^T(gh) slice by slice; slice k is pulled by its owner while slice k+1 is
+        computed.  Summation order per local row is the fixed step order => deterministic."""
+        from . import _lib
+        from .ops import scatter_add_rows_, spmm
+        main = torch.cuda.current_stream()
+        n_local = self.part.n_local
+        self.hg.barrier()                                    # peers finished reading gX of the previous step
+        spmm(gh, self.slice_local, _lib.AGG_WEIGHTED, out=self.gX[:n_local])
+        gx = self.gX[:n_local]
+        done_local = torch.cuda.Event()
+        done_local.record(main)
+        self.comm_stream.wait_event(done_local)
+        for csr, a, b, pull in self.slices:
+            if csr is not None:
+                spmm(gh, csr, _lib.AGG_WEIGHTED, out=self.gX[a:b])
+            self.hg.barrier()                                # every rank has finished this step's slice
+            ev = torch.cuda.Event()
+            ev.record(main)
+            if pull is not None:
+                with torch.cuda.stream(self.comm_stream):
+                    self.comm_stream.wait_event(ev)
+                    scatter_add_rows_(gx, pull[1], pull[0])  # contiguous remote rows -> my gradient rows
+        main.wait_stream(self.comm_stream)
+        return gx
 
     def pull_backward(self) -> torch.Tensor:
         """gX holds the transposed aggregation's output; returns grad wrt the local rows."""
@@ -394,7 +460,8 @@ def run_partitioned_bench(args):
         part = build_local_part(ei, et, ranges, rank)
         del ei, et, in_deg
         torch.cuda.empty_cache()
-        g = G.RelGraph.build(part.edge_index, part.edge_type, part.n_local, 5, num_src=part.n_src, live_rels=live)
+        g = G.RelGraph.build(part.edge_index, part.edge_type, part.n_local, 5, num_src=part.n_src, live_rels=live,
+                             keep_seg=True)
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
         S = g.num_slots
@@ -413,6 +480,9 @@ def run_partitioned_bench(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             peer, halo_mode = None, "nccl"
+        pipelined = peer is not None and not getattr(args, "no_bwd_pipeline", False)
+        if pipelined:
+            peer.build_backward_slices(g)
         if peer is not None:
             X, gX_buf = peer.X, peer.gX
         else:
@@ -442,6 +512,11 @@ def run_partitioned_bench(args):
             rec(2)
             h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                                      # A5 on [local ‖ halo]
             rec(3)
+            if peer is not None and pipelined:
+                gx = peer.backward_pipelined(gh)      # A14 slice by slice, owners pull while the next slice runs
+                rec(4)
+                rec(5)
+                return h, gx
             gX = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED, out=gX_buf)                    # A14: grads for local AND halo rows
             rec(4)
             if peer is not None:
@@ -506,7 +581,8 @@ def run_partitioned_bench(args):
                 "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat,
                            "parallelism": f"dst-row partition x{world} ({getattr(args, 'partition', 'random')} ownership), "
                                           "halo exchange: " + (
-                               "NVLink peer-memory pull kernels" if peer is not None else "NCCL all_to_all"),
+                               ("NVLink peer-memory pull kernels" + (", backward pipelined by owner slice" if pipelined else ""))
+                               if peer is not None else "NCCL all_to_all"),
                            "l2": "inputs exceed L2", "halo_rows_per_rank": [int(t[0]) for t in halo_all],
                            "edges_per_rank": [int(t[1]) for t in halo_all],
                            "rows_per_rank": [int(t[2]) for t in halo_all]},
