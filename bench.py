@@ -333,8 +333,13 @@ def run_single(args):
                 enc.residual_proj1.to(dtype), enc.residual_proj2.to(dtype), enc.multi_scale_fusion.to(dtype)
             xg = x.detach().requires_grad_(True)
 
+            # fp32 workloads (the reference's own dataset shapes) run the encoder under autocast, as the
+            # reference's training loops do (main.py:446,543); the bf16 study runs bf16 end to end
+            use_autocast = dtype == torch.float32
+
             def enc_step():
-                y = enc.get_graph_embeddings(xg, ei, et)
+                with torch.amp.autocast("cuda", enabled=use_autocast):
+                    y = enc.get_graph_embeddings(xg, ei, et)
                 y.backward(torch.ones_like(y))
                 xg.grad = None
 
@@ -348,6 +353,7 @@ def run_single(args):
             torch.cuda.synchronize()
             ems = a.elapsed_time(b) / 3
             encoder = {"ms_fwd_bwd": ems, "edges_per_s": 4 * e / (ems * 1e-3), "hidden_channels": w.hidden,
+                       "autocast": use_autocast,
                        "what": "GraphEncoder.get_graph_embeddings fwd+bwd: 4x(RGCNConv+GraphNorm+GELU), residual "
                                "projections, MultiScaleFusion(->768); edges/s counts the 4 propagates"}
             del enc

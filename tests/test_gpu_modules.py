@@ -281,3 +281,30 @@ def test_gat_attention_rows_sum_to_one_and_bf16(cuda_dev):
     o32 = G.gat_aggregate(zb, a_s, a_d, g)
     o16 = G.gat_aggregate(zb.bfloat16(), a_s, a_d, g)
     assert o16.dtype == torch.bfloat16 and rel_err(o16, o32) <= BF16_TOL
+
+
+def test_rgcn_conv_arbitrary_relation_ids_and_no_basis(cuda_dev):
+    """General RGCNConv use beyond the reference's degree buckets: all five relations populated,
+    and the num_bases=None (one weight per relation) variant of upstream."""
+    torch.manual_seed(4)
+    n, e, fi, fo = 400, 5000, 48, 40
+    ei = synth.uniform_edges(n, e, seed=5)
+    et = torch.randint(0, 5, (e,), generator=torch.Generator().manual_seed(6))
+    for num_bases in (30, None):
+        ref = RGCNConvRef(fi, fo, 5, num_bases).double()
+        mod = G.RGCNConv(fi, fo, 5, num_bases)
+        mod.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+        mod = mod.to(cuda_dev)
+        x = torch.randn(n, fi)
+        gout = torch.randn(n, fo)
+        x64 = x.double().requires_grad_(True)
+        y_ref = ref(x64, ei, et)
+        y_ref.backward(gout.double())
+        xg = x.to(cuda_dev).requires_grad_(True)
+        y = mod(xg, ei.to(cuda_dev), et.to(cuda_dev))
+        y.backward(gout.to(cuda_dev))
+        assert rel_err(y, y_ref) <= FP32_TOL
+        assert rel_err(xg.grad, x64.grad) <= FP32_TOL
+        assert rel_err(mod.weight.grad, ref.weight.grad) <= 2e-5
+        if num_bases is not None:
+            assert rel_err(mod.comp.grad, ref.comp.grad) <= 2e-5 and torch.count_nonzero(mod.comp.grad[4]) > 0
