@@ -243,3 +243,35 @@ def test_halo_pack_and_unpack_kernels(cuda_dev, dtype, feat):
     got = scatter_add_rows_(x.clone(), ids, rows)
     assert torch.equal(got, want.to(dtype))
     assert gather_rows(x, ids[:0]).shape == (0, feat)
+
+
+from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E402
+
+
+@given(n=st.integers(1, 300), e=st.integers(0, 3000), feat=st.sampled_from([3, 8, 20, 64, 72, 256]),
+       seed=st.integers(0, 10_000), hub_thresh=st.sampled_from([2, 17, 256]), quantum=st.sampled_from([0, 5, 64]),
+       bf16=st.booleans())
+@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+def test_aggregate_property_random_graphs(cuda_dev, n, e, feat, seed, hub_thresh, quantum, bf16):
+    """Random graphs (isolated nodes, multi-edges, self-loops, empty relations, N=1), random widths and
+    every plan setting: forward and backward agree with the oracle and the integer structure is consistent."""
+    g_ = torch.Generator().manual_seed(seed)
+    ei = torch.randint(0, n, (2, e), generator=g_)
+    et = edge_type_bucket_ref(ei, n)
+    dtype = torch.bfloat16 if bf16 else torch.float32
+    tol = BF16_TOL if bf16 else FP32_TOL
+    x = torch.randn(n, feat, generator=g_).to(dtype)
+    g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh, quantum=quantum)
+    assert int(g.fwd.rowptr[-1]) == e and int(g.bwd.rowptr[-1]) == e
+    xg = x.to(cuda_dev).requires_grad_(True)
+    out = G.rgcn_aggregate(xg, g)
+    gh = torch.randn(out.shape, generator=g_).to(dtype)
+    out.backward(gh.to(cuda_dev))
+    x64 = x.double().requires_grad_(True)
+    ref = oracle_aggregate(x64, ei, et, n, g.live_rels)
+    ref.backward(gh.double())
+    if e == 0:
+        assert torch.count_nonzero(out) == 0 and torch.count_nonzero(xg.grad) == 0
+    else:
+        assert rel_err(out, ref) <= tol
+        assert rel_err(xg.grad, x64.grad) <= tol
