@@ -557,6 +557,31 @@ def run_partitioned_bench(args):
         dist.all_gather(phases_all, phases)
         ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # device time, max over ranks
+        # ---- e2e: every step each rank copies its node features from pinned host memory and reads a
+        #      scalar of the result back (graph / CSR / halo plan stay resident: the graph is static)
+        x_host = x_local.cpu().pin_memory()
+        res_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        e2e_steps = max(3, min(args.steps, 5))
+
+        def e2e_step():
+            x_local.copy_(x_host, non_blocking=True)
+            _, gx_ = step()
+            res_host.copy_(gx_[:: max(1, part.n_local // 4096)].float().sum().reshape(1), non_blocking=True)
+
+        e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_ms = torch.tensor([a.elapsed_time(b) / e2e_steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([float(x_host.numel() * esize)], device=dev, dtype=torch.float64)
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
         halo_rows = torch.tensor([float(part.n_halo), float(part.edge_index.size(1)), float(part.n_local)],
                                  device=dev, dtype=torch.float64)
         halo_all = [torch.zeros_like(halo_rows) for _ in range(world)]
@@ -591,7 +616,11 @@ def run_partitioned_bench(args):
                              "t_hbm_ms": t_hbm * 1e3, "t_nvlink_ms": t_link * 1e3, "traffic": None,
                              "peak_source": peak_src + f"; NVLink {NVLINK_GBS} GB/s per direction (B200_PROFILING.md)"},
                 "cpu_baseline": None,
-                "e2e": None,
+                "e2e": {"value": e / (float(e2e_ms.item()) * 1e-3), "unit": "edges/s",
+                        "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world,
+                        "ms_per_step": float(e2e_ms.item()),
+                        "note": "each rank copies its node features from pinned host memory every step and reads a "
+                                "scalar back; PCIe-bound"},
                 "gpu_launches": (2 + (2 if g.fwd.n_hub else 0) + (2 if g.bwd.n_hub else 0)) * args.steps,
                 "clocks": clocks, "setup_s": t_setup,
                 "phases_ms_per_rank": {"order": ["pack", "all_to_all_fwd", "aggregate_fwd", "aggregate_bwd",
