@@ -98,6 +98,8 @@ def _spmm_csr(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, h
     n_chunks = int(chunk_beg.numel()) if chunk_beg is not None else 0
     n_groups = int(grp_row.numel()) - 1 if grp_row is not None else 0
     w_heads = int(w.size(1)) if (w is not None and w.dim() == 2) else 1
+    if col.numel() == 0 and mode == _lib.AGG_WEIGHTED:
+        mode, w, w_heads = _lib.AGG_SUM, None, 1          # no edges: every row is empty, the result is zeros
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((num_rows, feat), dtype=x.dtype, device=dev)
