@@ -135,6 +135,59 @@ def time_cpu_reference(steps: int, warmup: int, sample_nodes: int, sample_edges:
     return sample_edges / dt, dt * 1e3, cores
 
 
+def baseline_extras(ei, x, et, n, e, gpu_typing_s, dev):
+    """Two more reported baselines of SURVEY §8(d), same leg as cpu_baseline (the only place bench.py runs
+    oracle code): (i) the edge-typing step — the reference's verbatim per-edge Python loop
+    (main.py:253-267) on a bounded sample and its vectorised form on the host, next to our kernel;
+    (ii) the stock-PyTorch path (index_select + index_add_ atomics per relation, what torch_geometric
+    executes) run ON THE B200 on the full workload — what the reference would get from the same GPU."""
+    from oracle import edge_type_bucket_ref, edge_type_loop_ref, rgcn_propagate_mean_ref
+    out = {}
+    try:
+        m = min(e, 20_000)
+        ei_s = ei[:, :m].cpu()
+        t0 = time.perf_counter()
+        edge_type_loop_ref(ei_s, n)
+        loop_s = time.perf_counter() - t0
+        ei_c = ei.cpu() if e <= 50_000_000 else ei[:, :50_000_000].cpu()
+        t0 = time.perf_counter()
+        edge_type_bucket_ref(ei_c, n)
+        vec_s = time.perf_counter() - t0
+        out["edge_typing"] = {"reference_python_loop_us_per_edge": loop_s / max(m, 1) * 1e6,
+                              "reference_loop_extrapolated_s": loop_s / max(m, 1) * e,
+                              "vectorised_cpu_s": vec_s * (e / max(ei_c.size(1), 1)),
+                              "our_kernel_s": gpu_typing_s, "sample_edges_for_loop": m}
+    except Exception as ex:
+        out["edge_typing"] = {"error": repr(ex)[:200]}
+    try:
+        rels = sorted(torch.unique(et).tolist())
+        per_rel = [(ei[0, et == r].contiguous(), ei[1, et == r].contiguous()) for r in rels]
+        gh = [torch.randn(n, x.size(1), device=dev, dtype=x.dtype) for _ in rels]
+
+        def step():
+            xg = x.detach().requires_grad_(True)
+            outs = [rgcn_propagate_mean_ref(xg, s_, d_, n) for s_, d_ in per_rel]
+            torch.autograd.backward(outs, gh)
+
+        step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(3):
+            step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        out["stock_torch_on_gpu"] = {"value": e / (ms * 1e-3), "unit": "edges/s", "ms_per_step": ms,
+                                     "what": "oracle port (index_select + index_add_ per relation, autograd "
+                                             "backward) on the same B200, same graph and dtype"}
+        del per_rel, gh
+        torch.cuda.empty_cache()
+    except Exception as ex:
+        out["stock_torch_on_gpu"] = {"error": repr(ex)[:200]}
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -367,6 +420,7 @@ def run_single(args):
                "sample": f"R-MAT {args.cpu_sample_nodes} nodes / {args.cpu_sample_edges} edges, F={feat} fp32, "
                          f"fwd+bwd, oracle port of torch_geometric propagate (index_select+index_add_), "
                          f"{cms:.0f} ms/step, best-effort 2 steps after 1 warm-up"}
+        cpu.update(baseline_extras(ei, x, et, n, e, t_type, dev))
 
     line = {
         "metric": "message-passing edges/sec fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": 1,
