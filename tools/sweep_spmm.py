@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--variants", type=int, nargs="*", default=[1])
     ap.add_argument("--quantum", type=int, nargs="*", default=[0, 128, 256, 512])
     ap.add_argument("--unroll", type=int, nargs="*", default=[8, 4])
+    ap.add_argument("--uniform", action="store_true", help="uniform random edges instead of the workload's generator")
     ap.add_argument("--out", default="gpurun_out/sweep.jsonl")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -44,7 +45,7 @@ def main():
     n, e, feat = int(w.num_nodes * args.scale), int(w.num_edges * args.scale), w.feat
     dtype = torch.bfloat16 if w.dtype == "bf16" else torch.float32
     esz = 2 if dtype == torch.bfloat16 else 4
-    ei = synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
+    ei = synth.uniform_edges(n, e, device=dev) if args.uniform else synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
     x = synth.make_features(n, feat, device=dev, dtype=dtype)
     et = G.edge_type_from_degree(ei, n)
     Path(args.out).parent.mkdir(exist_ok=True)
