@@ -346,6 +346,10 @@ class PeerHalo:
                     pull = (rows, ids)
             self.slices.append((make(a, b) if b > a else None, a, b, pull))
         self.comm_stream = torch.cuda.Stream(device=src.device)
+        # one local staging buffer: each owner slice is fetched from the peer by a plain device-to-device
+        # copy (copy engine, no SM time taken from the aggregation kernels), then added locally
+        max_cnt = max([int(pl[0].size(0)) for _, _, _, pl in self.slices if pl is not None] + [1])
+        self.staging = torch.empty((max_cnt, self.feat), dtype=self.dtype, device=src.device)
         return self
 
     def backward_pipelined(self, gh: torch.Tensor) -> torch.Tensor:
@@ -370,7 +374,9 @@ class PeerHalo:
             if pull is not None:
                 with torch.cuda.stream(self.comm_stream):
                     self.comm_stream.wait_event(ev)
-                    scatter_add_rows_(gx, pull[1], pull[0])  # contiguous remote rows -> my gradient rows
+                    stg = self.staging[: pull[0].size(0)]
+                    stg.copy_(pull[0], non_blocking=True)    # contiguous remote rows over NVLink (copy engine)
+                    scatter_add_rows_(gx, pull[1], stg)      # ... added into my gradient rows
         main.wait_stream(self.comm_stream)
         return gx
 
