@@ -19,6 +19,7 @@ from .ops import (  # noqa: F401
     degree,
     edge_type_from_degree,
     graph_norm,
+    layer_norm,
     rgcn_aggregate,
     soft_masking_gnn_input,
     spmm,

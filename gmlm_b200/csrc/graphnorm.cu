@@ -10,12 +10,15 @@
 // deterministic, and the fp64 accumulation makes the one-pass variance
 //   E[(x - a*mu)^2] = E[x^2] - mu^2 * (2a - a^2)
 // as accurate as the reference's two-pass form.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gmlm {
 namespace {
 
 constexpr int kCta = 256;
+constexpr int kU = 4;    // row loads in flight per thread
 
 struct Tile {
   int tpr;        // threads along the channel dimension (power of two <= 256)
@@ -40,11 +43,51 @@ inline Tile make_tile(int64_t num_rows, int64_t channels, int vec, int max_row_b
   return t;
 }
 
-__device__ __forceinline__ float gelu_f(float n) { return 0.5f * n * (1.0f + erff(n * 0.70710678118654752440f)); }
+// Exact-erf GELU (main.py:274, F.gelu default).  fp32 activations use erff/expf; bf16 activations
+// (resolution 2^-8) use the Abramowitz-Stegun 7.1.26 rational form on MUFU.RCP/EX2: |error| of
+// gelu and gelu' <= 5e-7 absolute (checked against fp64 over [-9, 9]) for a third of the
+// instructions -- these kernels are issue-bound on the transcendental, not on HBM, otherwise.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void phi_fast(float n, float& cdf, float& e) {
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(n), 1.0f));
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  e = ex2_approx((n * n) * (-0.5f * 1.4426950408889634f));   // exp(-n^2/2)
+  const float h = 0.5f * (p * t) * e;
+  cdf = n >= 0.f ? 1.0f - h : h;
+}
+template <typename T>
+__device__ __forceinline__ float gelu_f(float n) {
+  if constexpr (sizeof(T) == 4) {
+    return 0.5f * n * (1.0f + erff(n * 0.70710678118654752440f));
+  } else {
+    float cdf, e;
+    phi_fast(n, cdf, e);
+    return n * cdf;
+  }
+}
+template <typename T>
 __device__ __forceinline__ float gelu_grad_f(float n) {
-  const float cdf = 0.5f * (1.0f + erff(n * 0.70710678118654752440f));
-  const float pdf = 0.39894228040143267794f * expf(-0.5f * n * n);
-  return cdf + n * pdf;
+  if constexpr (sizeof(T) == 4) {
+    const float cdf = 0.5f * (1.0f + erff(n * 0.70710678118654752440f));
+    const float pdf = 0.39894228040143267794f * expf(-0.5f * n * n);
+    return cdf + n * pdf;
+  } else {
+    float cdf, e;
+    phi_fast(n, cdf, e);
+    return fmaf(n * 0.39894228040143267794f, e, cdf);
+  }
 }
 
 // ---------------------------------------------------------------- column sums
@@ -62,14 +105,31 @@ __global__ void __launch_bounds__(kCta) colstats_kernel(const T* __restrict__ x,
 #pragma unroll
   for (int k = 0; k < VEC; ++k) s[k] = q[k] = 0.0;
   if (cvalid) {
-    for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
-      if (mask && !mask[r]) continue;
-      Pack<T, VEC> p;
-      p.load(x + r * ldx + c0);
-      float f[VEC];
-      p.unpack(f);
+    // kU row loads in flight per thread (latency, not issue, bounds a one-load loop); fp32 partials
+    // over those rows, flushed into the fp64 accumulators: error of a partial <= kU ulp(fp32)
+    const int64_t stride = int64_t(gridDim.y) * rpc;
+    for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += stride * kU) {
+      Pack<T, VEC> p[kU];
+      bool ok[kU];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) { s[k] += double(f[k]); q[k] += double(f[k]) * double(f[k]); }
+      for (int u = 0; u < kU; ++u) {
+        const int64_t rr = r + u * stride;
+        ok[u] = rr < num_rows && (mask == nullptr || mask[rr] != 0);
+        if (ok[u]) p[u].load(x + rr * ldx + c0);
+      }
+      float ps[VEC], pq[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) ps[k] = pq[k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (!ok[u]) continue;
+        float f[VEC];
+        p[u].unpack(f);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) { ps[k] += f[k]; pq[k] = fmaf(f[k], f[k], pq[k]); }
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { s[k] += double(ps[k]); q[k] += double(pq[k]); }
     }
   }
   // reduce over ty in fixed order
@@ -134,25 +194,33 @@ __global__ void __launch_bounds__(kCta) graphnorm_fwd_kernel(const T* __restrict
     k1[k] = weight[c0 + k] * rstd[c0 + k];
     b[k] = bias[c0 + k];
   }
-  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
-    Pack<T, VEC> p;
-    p.load(x + r * ldx + c0);
-    float f[VEC];
-    p.unpack(f);
+  const int64_t stride = int64_t(gridDim.y) * rpc;
+  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += stride * kU) {
+    Pack<T, VEC> p[kU];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      float n = (f[k] - shift[k]) * k1[k] + b[k];
-      f[k] = fuse_gelu ? gelu_f(n) : n;
+    for (int u = 0; u < kU; ++u)
+      if (r + u * stride < num_rows) p[u].load(x + (r + u * stride) * ldx + c0);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t rr = r + u * stride;
+      if (rr >= num_rows) break;
+      float f[VEC];
+      p[u].unpack(f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float n = (f[k] - shift[k]) * k1[k] + b[k];
+        f[k] = fuse_gelu ? gelu_f<T>(n) : n;
+      }
+      p[u].pack(f);
+      p[u].store(y + rr * ldy + c0);
     }
-    p.pack(f);
-    p.store(y + r * ldy + c0);
   }
 }
 
 // ---------------------------------------------------------------- backward
 // dn = gy * gelu'(n) (or gy); partial sums of dn and dn*ohat
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kCta) graphnorm_bwd_stats_kernel(
+__global__ void __launch_bounds__(kCta, 2) graphnorm_bwd_stats_kernel(
     const T* __restrict__ x, const T* __restrict__ gy, int64_t num_rows, int64_t C, int64_t ldx, int64_t ldg,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
     const float* __restrict__ bias, const float* __restrict__ mean_scale, int fuse_gelu, int tpr,
@@ -176,21 +244,37 @@ __global__ void __launch_bounds__(kCta) graphnorm_bwd_stats_kernel(
       wv[k] = weight[c0 + k];
       b[k] = bias[c0 + k];
     }
-    for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
-      Pack<T, VEC> px, pg;
-      px.load(x + r * ldx + c0);
-      pg.load(gy + r * ldg + c0);
-      float fx[VEC], fg[VEC];
-      px.unpack(fx);
-      pg.unpack(fg);
+    const int64_t stride = int64_t(gridDim.y) * rpc;
+    for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += stride * kU) {
+      Pack<T, VEC> px[kU], pg[kU];
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) {
-        const float oh = (fx[k] - shift[k]) * rs[k];
-        float dn = fg[k];
-        if (fuse_gelu) dn *= gelu_grad_f(oh * wv[k] + b[k]);
-        s[k] += double(dn);
-        q[k] += double(dn) * double(oh);
+      for (int u = 0; u < kU; ++u) {
+        const int64_t rr = r + u * stride;
+        if (rr < num_rows) {
+          px[u].load(x + rr * ldx + c0);
+          pg[u].load(gy + rr * ldg + c0);
+        }
       }
+      float ps[VEC], pq[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) ps[k] = pq[k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < kU; ++u) {
+        if (r + u * stride >= num_rows) break;
+        float fx[VEC], fg[VEC];
+        px[u].unpack(fx);
+        pg[u].unpack(fg);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float oh = (fx[k] - shift[k]) * rs[k];
+          float dn = fg[k];
+          if (fuse_gelu) dn *= gelu_grad_f<T>(oh * wv[k] + b[k]);
+          ps[k] += dn;
+          pq[k] = fmaf(dn, oh, pq[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) { s[k] += double(ps[k]); q[k] += double(pq[k]); }
     }
   }
 #pragma unroll
@@ -226,7 +310,7 @@ __global__ void graphnorm_bwd_params_kernel(const double* __restrict__ sum_g, co
 }
 
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kCta) graphnorm_bwd_apply_kernel(
+__global__ void __launch_bounds__(kCta, 2) graphnorm_bwd_apply_kernel(
     const T* __restrict__ x, const T* __restrict__ gy, int64_t num_rows, int64_t C, int64_t ldx, int64_t ldg,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
     const float* __restrict__ bias, const float* __restrict__ mean_scale, int fuse_gelu,
@@ -249,22 +333,34 @@ __global__ void __launch_bounds__(kCta) graphnorm_bwd_apply_kernel(
     k2[k] = float(s2 / n);
     k3[k] = float(a * sum_do / n);
   }
-  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += int64_t(gridDim.y) * rpc) {
-    Pack<T, VEC> px, pg;
-    px.load(x + r * ldx + c0);
-    pg.load(gy + r * ldg + c0);
-    float fx[VEC], fg[VEC];
-    px.unpack(fx);
-    pg.unpack(fg);
+  const int64_t stride = int64_t(gridDim.y) * rpc;
+  for (int64_t r = int64_t(blockIdx.y) * rpc + ty; r < num_rows; r += stride * kU) {
+    Pack<T, VEC> px[kU], pg[kU];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const float oh = (fx[k] - shift[k]) * rs[k];
-      float dn = fg[k];
-      if (fuse_gelu) dn *= gelu_grad_f(oh * wv[k] + b[k]);
-      fg[k] = k1[k] * (dn - oh * k2[k]) - k3[k];
+    for (int u = 0; u < kU; ++u) {
+      const int64_t rr = r + u * stride;
+      if (rr < num_rows) {
+        px[u].load(x + rr * ldx + c0);
+        pg[u].load(gy + rr * ldg + c0);
+      }
     }
-    pg.pack(fg);
-    pg.store(gx + r * ldgx + c0);
+#pragma unroll
+    for (int u = 0; u < kU; ++u) {
+      const int64_t rr = r + u * stride;
+      if (rr >= num_rows) break;
+      float fx[VEC], fg[VEC];
+      px[u].unpack(fx);
+      pg[u].unpack(fg);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float oh = (fx[k] - shift[k]) * rs[k];
+        float dn = fg[k];
+        if (fuse_gelu) dn *= gelu_grad_f<T>(oh * wv[k] + b[k]);
+        fg[k] = k1[k] * (dn - oh * k2[k]) - k3[k];
+      }
+      pg[u].pack(fg);
+      pg[u].store(gx + rr * ldgx + c0);
+    }
   }
 }
 
@@ -327,6 +423,19 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 constexpr int kMaxRowBlocks = 148 * 8;
 
+// CTAs of `kernel` that are resident at once on the whole device: the streaming kernels run exactly one
+// wave of them (each thread strides over the rows), so there is no partial last wave.
+template <auto Kernel>
+int resident_ctas() {
+  static int cached = 0;   // per kernel instantiation; benign race (same value)
+  if (cached == 0) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kernel, kCta, 0) != cudaSuccess || occ < 1) occ = 1;
+    cached = std::min(occ * num_sms(), kMaxRowBlocks);
+  }
+  return cached;
+}
+
 // dispatch helper: calls fn.template operator()<T, VEC>()
 template <typename Fn>
 int dispatch(int dtype, bool vec_ok, Fn&& fn) {
@@ -364,7 +473,7 @@ static int colstats_impl(const void* x, int dtype, int64_t N, int64_t C, int64_t
   const bool v = vec_ok(dtype, C, {x}, {ldx});
   int row_blocks = 1;
   int rc = dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
-    Tile t = make_tile(N, C, VEC, kMaxRowBlocks);
+    Tile t = make_tile(N, C, VEC, resident_ctas<colstats_kernel<T, VEC>>());
     row_blocks = int(t.grid.y);
     colstats_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), N, C, ldx, mask, t.tpr, partial);
     GMLM_LAUNCH_CHECK();
@@ -395,7 +504,7 @@ int gmlm_graphnorm_fwd(const void* x, int dtype, int64_t N, int64_t C, int64_t l
   GMLM_LAUNCH_CHECK();
   const bool v = vec_ok(dtype, C, {x, y}, {ldx, ldy});
   return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
-    Tile t = make_tile(N, C, VEC, kMaxRowBlocks * 4);
+    Tile t = make_tile(N, C, VEC, resident_ctas<graphnorm_fwd_kernel<T, VEC>>());
     graphnorm_fwd_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), N, C, ldx, mean_out, rstd_out,
                                                           weight, bias, mean_scale, fuse_gelu, t.tpr,
                                                           static_cast<T*>(y), ldy);
@@ -416,7 +525,7 @@ int gmlm_graphnorm_bwd_stats(const void* x, const void* gy, int dtype, int64_t N
   const bool v = vec_ok(dtype, C, {x, gy}, {ldx, ldg});
   int row_blocks = 1;
   int rc = dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
-    Tile t = make_tile(N, C, VEC, kMaxRowBlocks);
+    Tile t = make_tile(N, C, VEC, resident_ctas<graphnorm_bwd_stats_kernel<T, VEC>>());
     row_blocks = int(t.grid.y);
     graphnorm_bwd_stats_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(static_cast<const T*>(x), static_cast<const T*>(gy),
                                                                 N, C, ldx, ldg, mean, rstd, weight, bias, mean_scale,
@@ -446,7 +555,7 @@ int gmlm_graphnorm_bwd_apply(const void* x, const void* gy, int dtype, int64_t N
   GMLM_REQUIRE(ldgx >= C, "graphnorm_bwd_apply: bad ldgx");
   const bool v = vec_ok(dtype, C, {x, gy, gx}, {ldx, ldg, ldgx});
   return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
-    Tile t = make_tile(N, C, VEC, kMaxRowBlocks * 4);
+    Tile t = make_tile(N, C, VEC, resident_ctas<graphnorm_bwd_apply_kernel<T, VEC>>());
     graphnorm_bwd_apply_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(
         static_cast<const T*>(x), static_cast<const T*>(gy), N, C, ldx, ldg, mean, rstd, weight, bias, mean_scale,
         fuse_gelu, sum_g, sum_go, t.tpr, static_cast<T*>(gx), ldgx);

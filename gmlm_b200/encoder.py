@@ -25,7 +25,7 @@ from torch.utils.checkpoint import checkpoint
 
 from .graph import _tensor_key, get_rel_graph
 from .nn import GraphNorm, RGCNConv
-from .ops import edge_type_from_degree, soft_masking_gnn_input
+from .ops import edge_type_from_degree, layer_norm, layer_norm_ok, soft_masking_gnn_input
 
 
 class MultiScaleFusion(nn.Module):
@@ -48,7 +48,13 @@ class MultiScaleFusion(nn.Module):
         weight = torch.cat([w[i] * p.weight for i, p in enumerate(self.projections)], dim=1)
         bias = sum(w[i] * p.bias for i, p in enumerate(self.projections))
         xs = torch.cat([e if autocast else e.to(dt) for e in embeddings_list], dim=1)
-        return self.layer_norm(F.linear(xs, weight, bias))
+        fused = F.linear(xs, weight, bias)
+        ln = self.layer_norm
+        if autocast:                      # torch.autocast runs layer_norm in fp32
+            fused = fused.float()
+        if ln.elementwise_affine and ln.bias is not None and layer_norm_ok(fused):
+            return layer_norm(fused, ln.weight, ln.bias, ln.eps)     # row-wise kernel (csrc/layernorm.cu)
+        return ln(fused)                  # widths the kernel does not take: stock, as in the reference
 
 
 _ET_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()

@@ -5,13 +5,14 @@ Registered ops (``torch.ops.gmlm.*``, CUDA only — calling them with CPU tensor
 the dispatcher; there is no fallback):
 
     degree_i32, edge_type_bucket, spmm_csr, colstats, graphnorm_fwd, graphnorm_bwd,
-    soft_mask_fwd, soft_mask_bwd
+    layernorm_fwd, layernorm_bwd, soft_mask_fwd, soft_mask_bwd
 
 Autograd wrappers used by the modules in ``gmlm_b200.nn``:
 
     rgcn_aggregate(x, graph)            A5 forward / A14 backward
     graph_norm(x, weight, bias, mean_scale, eps, fuse_gelu)   A7
     soft_mask(x, mask, token, beta)     A11
+    layer_norm(x, weight, bias, eps)    A13 (the LayerNorm closing MultiScaleFusion)
 """
 from __future__ import annotations
 
@@ -56,6 +57,9 @@ _LIB.define("graphnorm_fwd(Tensor x, Tensor weight, Tensor bias, Tensor mean_sca
             "-> (Tensor, Tensor, Tensor)")
 _LIB.define("graphnorm_bwd(Tensor x, Tensor gy, Tensor mean, Tensor rstd, Tensor weight, Tensor bias, "
             "Tensor mean_scale, bool fuse_gelu, bool need_gx) -> (Tensor, Tensor, Tensor, Tensor)")
+_LIB.define("layernorm_fwd(Tensor x, Tensor weight, Tensor bias, float eps) -> (Tensor, Tensor, Tensor)")
+_LIB.define("layernorm_bwd(Tensor x, Tensor gy, Tensor mean, Tensor rstd, Tensor weight, bool need_gx) "
+            "-> (Tensor, Tensor, Tensor)")
 _LIB.define("soft_mask_fwd(Tensor x, Tensor mask, Tensor token, float beta) -> Tensor")
 _LIB.define("soft_mask_bwd(Tensor gy, Tensor mask, float beta, bool need_gx) -> (Tensor, Tensor)")
 
@@ -196,6 +200,53 @@ def _graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, need_
     return gx, gw, gb, gms
 
 
+# ------------------------------------------------------------------------------ A13 LayerNorm
+def layer_norm_ok(x: torch.Tensor) -> bool:
+    """Shapes the row-wise kernel takes: CUDA fp32/bf16 [N, C], C a multiple of the 16-byte pack, C <= 1024."""
+    if not (x.is_cuda and x.dim() == 2 and x.dtype in _DT and x.size(0) >= 1):
+        return False
+    vec = 4 if x.dtype == torch.float32 else 8
+    return x.size(1) % vec == 0 and 0 < x.size(1) <= _lib.load().gmlm_layernorm_max_channels(_DT[x.dtype])
+
+
+def _layernorm_fwd(x, weight, bias, eps):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    n, c = x.shape
+    dev = x.device
+    weight, bias = _f32c(weight), _f32c(bias)
+    with torch.cuda.device(dev):
+        y = torch.empty((n, c), dtype=x.dtype, device=dev)
+        mean = torch.empty(n, dtype=torch.float32, device=dev)
+        rstd = torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.check(lib.gmlm_layernorm_fwd(_ptr(x), _dtype_code(x, "layernorm"), n, c, _ld(x), _ptr(weight), _ptr(bias),
+                                          float(eps), _ptr(y), c, _ptr(mean), _ptr(rstd), _stream(dev)),
+                   "layernorm_fwd")
+    return y, mean, rstd
+
+
+def _layernorm_bwd(x, gy, mean, rstd, weight, need_gx):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    gy = _rowmajor(gy)
+    if gy.dtype != x.dtype:
+        gy = gy.to(x.dtype)
+    n, c = x.shape
+    dev = x.device
+    weight = _f32c(weight)
+    with torch.cuda.device(dev):
+        gx = torch.empty((n, c), dtype=x.dtype, device=dev) if need_gx else torch.empty(0, dtype=x.dtype, device=dev)
+        gw = torch.empty(c, dtype=torch.float32, device=dev)
+        gb = torch.empty(c, dtype=torch.float32, device=dev)
+        ws_bytes = lib.gmlm_layernorm_bwd_workspace_bytes(n, c)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_layernorm_bwd(_ptr(x), _ptr(gy), _dtype_code(x, "layernorm_bwd"), n, c, _ld(x), _ld(gy),
+                                          _ptr(weight), _ptr(mean), _ptr(rstd),
+                                          _ptr(gx) if need_gx else C.c_void_p(0), c, _ptr(gw), _ptr(gb), _ptr(ws),
+                                          ws_bytes, _stream(dev)), "layernorm_bwd")
+    return gx, gw, gb
+
+
 # ------------------------------------------------------------------------------ A11
 def _mask_u8(mask: torch.Tensor, n: int) -> torch.Tensor:
     mask = mask.reshape(-1)
@@ -245,6 +296,8 @@ _LIB.impl("spmm_csr", _spmm_csr, "CUDA")
 _LIB.impl("colstats", _colstats, "CUDA")
 _LIB.impl("graphnorm_fwd", _graphnorm_fwd, "CUDA")
 _LIB.impl("graphnorm_bwd", _graphnorm_bwd, "CUDA")
+_LIB.impl("layernorm_fwd", _layernorm_fwd, "CUDA")
+_LIB.impl("layernorm_bwd", _layernorm_bwd, "CUDA")
 _LIB.impl("soft_mask_fwd", _soft_mask_fwd, "CUDA")
 _LIB.impl("soft_mask_bwd", _soft_mask_bwd, "CUDA")
 
@@ -432,6 +485,33 @@ class _GraphNorm(torch.autograd.Function):
 def graph_norm(x, weight, bias, mean_scale, eps: float = 1e-5, fuse_gelu: bool = False) -> torch.Tensor:
     _require_cuda(x, "x")
     return _GraphNorm.apply(x, weight, bias, mean_scale, eps, fuse_gelu)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        y, mean, rstd = torch.ops.gmlm.layernorm_fwd(x, weight, bias, float(eps))
+        ctx.save_for_backward(x, mean, rstd, weight)
+        ctx.bias_dtype = bias.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, mean, rstd, weight = ctx.saved_tensors
+        gx, gw, gb = torch.ops.gmlm.layernorm_bwd(x, gy, mean, rstd, weight, ctx.needs_input_grad[0])
+        return (gx if ctx.needs_input_grad[0] else None,
+                gw.to(weight.dtype) if ctx.needs_input_grad[1] else None,
+                gb.to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None, None)
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """``nn.LayerNorm(C)`` over the last dimension of a 2-D CUDA tensor (the ``self.layer_norm(fused)`` of
+    ``MultiScaleFusion``, ``/root/reference/main.py:171,180``): one read + one write forward, two reads +
+    one write backward, deterministic parameter gradients."""
+    _require_cuda(x, "x")
+    if not layer_norm_ok(x):
+        raise _lib.GmlmError(f"layer_norm: unsupported input {tuple(x.shape)} {x.dtype} (see layer_norm_ok)")
+    return _LayerNorm.apply(x, weight, bias, eps)
 
 
 class _SoftMask(torch.autograd.Function):

@@ -155,6 +155,20 @@ int gmlm_soft_mask_bwd(const void* gy, int dtype, int64_t num_rows, int64_t feat
                        const uint8_t* mask, float beta, float* g_token /* [feat] */, void* gx /* may be NULL */,
                        int64_t ldgx, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- A13 LayerNorm closing MultiScaleFusion (main.py:171,180 `self.layer_norm(fused)`, the last op of
+ *          get_graph_embeddings main.py:320) ----
+ * fwd: y = (x - mean_row) * rstd_row * gamma + beta   (biased variance, eps inside the sqrt; nn.LayerNorm)
+ * bwd: gx (may be NULL), g_gamma[c] = sum_i gy*xhat, g_beta[c] = sum_i gy  (either may be NULL).
+ * channels: multiple of 4 (f32) / 8 (bf16), <= gmlm_layernorm_max_channels(dtype); 16-byte aligned rows. */
+int64_t gmlm_layernorm_max_channels(int dtype);
+int gmlm_layernorm_fwd(const void* x, int dtype, int64_t num_rows, int64_t channels, int64_t ldx,
+                       const float* gamma, const float* beta, float eps, void* y, int64_t ldy,
+                       float* mean_out /* [rows] */, float* rstd_out /* [rows] */, void* stream);
+size_t gmlm_layernorm_bwd_workspace_bytes(int64_t num_rows, int64_t channels);
+int gmlm_layernorm_bwd(const void* x, const void* gy, int dtype, int64_t num_rows, int64_t channels, int64_t ldx,
+                       int64_t ldg, const float* gamma, const float* mean, const float* rstd, void* gx,
+                       int64_t ldgx, float* g_gamma, float* g_beta, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- A6  dense feature transform on tcgen05 tensor cores (TMA tiles, TMEM accumulator):
  *          [PyG] RGCNConv.forward `out += h @ W[r]` / `out += x @ root` / `+ bias`, main.py:272 ----
  * C[M,N] = [A1 | A2][M, K1+K2] * B[N, K1+K2]^T + bias[N];  A1, A2, B bf16 row-major (K contiguous),

@@ -111,6 +111,52 @@ def test_graph_norm_bf16(cuda_dev):
     assert rel_err(y, F.gelu(ref(x.double()))) <= BF16_TOL
 
 
+@pytest.mark.parametrize("n,c", [(1, 8), (183, 768), (1000, 300), (4097, 64), (50, 1024), (300000, 96)])
+def test_layer_norm_matches_torch_fp64(cuda_dev, n, c):
+    """A13: the LayerNorm closing MultiScaleFusion (main.py:171,180) is nn.LayerNorm in the reference, so
+    nn.LayerNorm in fp64 is the oracle; forward, input gradient and both parameter gradients."""
+    torch.manual_seed(2)
+    ref = torch.nn.LayerNorm(c).double()
+    with torch.no_grad():
+        ref.weight.uniform_(0.5, 1.5)
+        ref.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(n, c) * 2.0 + 3.0
+    gout = torch.randn(n, c)
+    x64 = x.double().requires_grad_(True)
+    ref(x64).backward(gout.double())
+    w = ref.weight.detach().float().to(cuda_dev).requires_grad_(True)
+    b = ref.bias.detach().float().to(cuda_dev).requires_grad_(True)
+    xg = x.to(cuda_dev).requires_grad_(True)
+    y = G.layer_norm(xg, w, b, ref.eps)
+    y.backward(gout.to(cuda_dev))
+    assert rel_err(y, ref(x64)) <= FP32_TOL
+    assert rel_err(xg.grad, x64.grad) <= 2e-5
+    assert rel_err(w.grad, ref.weight.grad) <= 2e-5
+    assert rel_err(b.grad, ref.bias.grad) <= 2e-5
+    # deterministic parameter gradients (fixed-order two-stage sums)
+    w2 = w.detach().clone().requires_grad_(True)
+    G.layer_norm(xg.detach(), w2, b.detach(), ref.eps).backward(gout.to(cuda_dev))
+    assert torch.equal(w2.grad, w.grad)
+
+
+def test_layer_norm_bf16_and_fusion_module(cuda_dev):
+    n, c = 3000, 768
+    x = (torch.randn(n, c) + 0.5).bfloat16()
+    ref = torch.nn.LayerNorm(c).double()
+    y = G.layer_norm(x.to(cuda_dev), ref.weight.float().to(cuda_dev), ref.bias.float().to(cuda_dev), ref.eps)
+    assert y.dtype == torch.bfloat16
+    assert rel_err(y, ref(x.double())) <= BF16_TOL
+    # the module routes through the kernel on CUDA and equals its stock formulation
+    fus = G.MultiScaleFusion([16, 32], 64).to(cuda_dev)
+    xs = [torch.randn(40, 16, device=cuda_dev), torch.randn(40, 32, device=cuda_dev)]
+    w = F.softmax(fus.scale_weights, dim=0)
+    want = fus.layer_norm(sum(w[i] * fus.projections[i](xs[i]) for i in range(2)))
+    assert rel_err(fus(xs), want) <= FP32_TOL
+    with pytest.raises(G.GmlmError):
+        G.layer_norm(torch.randn(4, 6, device=cuda_dev), torch.ones(6, device=cuda_dev),
+                     torch.zeros(6, device=cuda_dev))
+
+
 @pytest.mark.parametrize("n,f", [(183, 1703), (1000, 300), (50, 256)])
 @pytest.mark.parametrize("ratio", [0.0, 0.3, 1.0])
 def test_soft_mask_bit_exact_and_grad(cuda_dev, n, f, ratio):
