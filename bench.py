@@ -5,9 +5,10 @@
 
 One "step" = one forward + one backward propagate of the F=256 RGCN mean aggregation (the
 kernel pair SURVEY §8(d) defines the algorithmic bytes for: 1162 B/edge in bf16) over the whole
-synthetic graph.  N=1 runs BASELINE.json configs[3] (2M nodes / 40M edges, bf16) unless
---workload says otherwise; N>1 runs configs[4] (10M / 200M) destination-row partitioned with
-NCCL halo exchange (gmlm_b200/partition.py).  Rank 0 prints ONE JSON line.
+synthetic graph.  Every N runs BASELINE.json configs[4]'s graph (10M nodes / 200M edges, bf16): whole
+on one GPU at N=1 (the denominator of the 1/2/4/8 scaling the metric names; the same line carries
+configs[3] — 2M / 40M, the HBM-roofline study — under "c4"), destination-row partitioned with the
+NVLink halo exchange of gmlm_b200/partition.py at N>1.  Rank 0 prints ONE JSON line.
 
 `--impl reference` times the reference's CPU implementation of the same path — the oracle
 port of the torch_geometric index_select/scatter path (oracle/pyg_ref.py; PyG itself is not
@@ -212,14 +213,15 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- our arm, one GPU
-def run_single(args):
+def measure_single(args, key: str, extras: bool, with_cpu: bool):
+    """One workload on one GPU -> the fields of the JSON line (value, roofline, e2e, context legs)."""
     import gmlm_b200 as G
     from gmlm_b200 import _lib, synth
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback); use --impl reference"
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
-    w = synth.WORKLOADS[args.workload]
+    w = synth.WORKLOADS[key]
     n = int(w.num_nodes * args.scale)
     e = int(w.num_edges * args.scale)
     feat = w.feat
@@ -355,7 +357,7 @@ def run_single(args):
 
     # ---- full message-passing layer (A5+A6+A7 fwd+bwd) for context
     layer = None
-    if not args.no_layer:
+    if extras and not args.no_layer:
         try:
             conv = G.RGCNConv(feat, w.hidden, 5, 30, out_dtype=dtype).to(dev)
             norm = G.GraphNorm(w.hidden).to(dev)
@@ -383,7 +385,7 @@ def run_single(args):
     # ---- whole GNN encoder (get_graph_embeddings, main.py:250-320): four layers + residuals + fusion,
     #      forward + backward ("epoch" of the encoder on this graph); edges/s counts 4*E per pass
     encoder = None
-    if not args.no_layer:
+    if extras and not args.no_layer:
         try:
             del gh
             torch.cuda.empty_cache()
@@ -420,7 +422,7 @@ def run_single(args):
             encoder = {"error": repr(ex)[:300]}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if with_cpu and not args.no_cpu_baseline:
         eps, cms, cores = time_cpu_reference(2, 1, args.cpu_sample_nodes, args.cpu_sample_edges, feat)
         cpu = {"value": eps, "unit": "edges/s", "cores": cores, "kind": "port",
                "sample": f"R-MAT {args.cpu_sample_nodes} nodes / {args.cpu_sample_edges} edges, F={feat} fp32, "
@@ -443,6 +445,34 @@ def run_single(args):
         "clocks": clocks, "layer": layer, "encoder": encoder,
         "setup_s": {"generate": t_gen, "edge_typing": t_type, "csr_build": t_csr},
     }
+    del g, ei, et, x
+    G.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_single(args):
+    """N=1.  Default: BASELINE.json configs[4]'s graph (10M nodes / 200M edges) whole on one GPU — the
+    denominator of the 1/2/4/8-GPU scaling the metric names — followed by configs[3] (2M / 40M, the
+    HBM-roofline study, with the layer / encoder / stock-torch context legs) under the key "c4"."""
+    if args.workload != "c5":
+        print(json.dumps(measure_single(args, args.workload, extras=True, with_cpu=True)), flush=True)
+        return
+    line = measure_single(args, "c5", extras=False, with_cpu=False)
+    if not args.no_c4:
+        c4 = measure_single(args, "c4", extras=True, with_cpu=True)
+        line["cpu_baseline"] = c4.pop("cpu_baseline")          # bounded R-MAT sample: the same for both graphs
+        line["layer"], line["encoder"] = c4.pop("layer"), c4.pop("encoder")
+        for d in (line["layer"], line["encoder"]):
+            if isinstance(d, dict):
+                d["workload"] = c4["config"]["workload"]
+        line["c4"] = {k: c4[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "roofline_bwd",
+                                          "roofline_step", "e2e", "gpu_launches", "setup_s")}
+    elif not args.no_cpu_baseline:
+        eps, cms, cores = time_cpu_reference(2, 1, args.cpu_sample_nodes, args.cpu_sample_edges, 256)
+        line["cpu_baseline"] = {"value": eps, "unit": "edges/s", "cores": cores, "kind": "port",
+                                "sample": f"R-MAT {args.cpu_sample_nodes} nodes / {args.cpu_sample_edges} edges, F=256 "
+                                          f"fp32, fwd+bwd, oracle port of torch_geometric propagate, {cms:.0f} ms/step"}
     print(json.dumps(line), flush=True)
 
 
@@ -456,9 +486,16 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: halo exchange implementation")
     ap.add_argument("--no-bwd-pipeline", action="store_true", help="N>1: disable the sliced/pipelined backward")
+    ap.add_argument("--bwd", default="push", choices=["push", "pipeline", "plain"],
+                    help="N>1: halo-gradient return (push = remote stores from the aggregation kernel)")
+    ap.add_argument("--fwd-stages", type=int, default=1,
+                    help="N>1: halo pull stages overlapped with the aggregation (1 = one pull; measured on 8 GPUs: "
+                         "6 stages 8.52 ms vs 8.55 ms, see DESIGN.md §6)")
+    ap.add_argument("--pull-ctas", type=int, default=0, help="N>1: CTA cap of the overlapped pull kernels (0 = 1 per SM)")
     ap.add_argument("--partition", default="random", choices=["random", "cyclic", "range"],
                     help="N>1: node ownership")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="N=1 default run: skip the configs[3] roofline-study leg")
     ap.add_argument("--no-layer", action="store_true")
     ap.add_argument("--cpu-sample-nodes", type=int, default=100_000)
     ap.add_argument("--cpu-sample-edges", type=int, default=2_000_000)
@@ -466,7 +503,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.workload is None:
-        args.workload = "c4" if max(args.gpus, world) == 1 else "c5"
+        args.workload = "c5"          # same graph at every N: the driver's scaling ratio compares like with like
     if args.impl == "reference":
         run_reference(args)
         return

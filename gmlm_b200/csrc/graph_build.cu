@@ -21,6 +21,8 @@ static int g_spmm_variant = 1;
 static int g_spmm_unroll = 0;
 int tuning_spmm_variant() { return g_spmm_variant; }
 int tuning_spmm_unroll() { return g_spmm_unroll; }
+static int g_halo_pull_ctas = 0;
+int tuning_halo_pull_ctas() { return g_halo_pull_ctas; }
 
 namespace {
 
@@ -253,6 +255,7 @@ int gmlm_set_tuning(const char* key, int value) {
   int old = -1;
   if (!strcmp(key, "spmm_variant")) { old = g_spmm_variant; g_spmm_variant = value; }
   else if (!strcmp(key, "spmm_unroll")) { old = g_spmm_unroll; g_spmm_unroll = value; }
+  else if (!strcmp(key, "halo_pull_ctas")) { old = g_halo_pull_ctas; g_halo_pull_ctas = value; }
   return old;
 }
 

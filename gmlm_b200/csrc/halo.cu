@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 namespace gmlm {
+int tuning_halo_pull_ctas();   // graph_build.cu: CTA cap of gather_rows_ptr (0 = 16 per SM)
 namespace {
 
 template <typename T, int VEC, bool ADD>
@@ -47,16 +48,30 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256) gather_ptr_kernel(const T* const* __restrict__ row_ptrs,
                                                          const int64_t* __restrict__ out_ids, int64_t n,
                                                          int64_t feat, T* __restrict__ out, int64_t ldo) {
+  // eight 16-byte remote loads in flight per thread: a launch capped to one CTA per SM (so that it can
+  // share the GPU with an aggregation kernel) still keeps the NVLink pipe full (148 x 256 x 128 B = 4.8 MB)
+  constexpr int U = 8;
   const int64_t packs = feat / VEC;
   const int64_t total = n * packs;
-  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-    const int64_t k = i / packs;
-    const int64_t f = (i - k * packs) * VEC;
-    const T* src = row_ptrs[k];
-    const int64_t o = out_ids ? out_ids[k] : k;
-    Pack<T, VEC> a;
-    a.load(src + f);
-    a.store(out + o * ldo + f);
+  const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+  for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride * U) {
+    Pack<T, VEC> a[U];
+    T* dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t j = i + u * stride;
+      dst[u] = nullptr;
+      if (j < total) {
+        const int64_t k = j / packs;
+        const int64_t f = (j - k * packs) * VEC;
+        const int64_t o = out_ids ? out_ids[k] : k;
+        a[u].load(row_ptrs[k] + f);
+        dst[u] = out + o * ldo + f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] != nullptr) a[u].store(dst[u]);
   }
 }
 
@@ -164,7 +179,8 @@ extern "C" int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* 
   if (n == 0 || feat == 0) return GMLM_OK;
   GMLM_REQUIRE(row_ptrs && out, "gather_rows_ptr: null pointer");
   int64_t blocks = (n * (feat / v) + 255) / 256;
-  const int64_t cap = int64_t(num_sms()) * 16;
+  const int tuned = tuning_halo_pull_ctas();
+  const int64_t cap = tuned > 0 ? int64_t(tuned) : int64_t(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = as_stream(stream);
   if (dtype == GMLM_F32)

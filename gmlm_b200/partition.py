@@ -246,6 +246,10 @@ class PeerHalo:
         self.hg = symm_mem.rendezvous(self.gX_sym, group=group.group_name)
         self.X = self.X_sym[: part.n_src]
         self.gX = self.gX_sym[: part.n_src]
+        self.all_splits = all_splits
+        self._symm = symm_mem
+        self._group = group
+        self.stage_sym = None                                        # built by build_backward_push()
         esz = torch.empty(0, dtype=dtype).element_size()
         row_bytes = feat * esz
         order = sorted(range(world), key=lambda q: (q - rank) % world)      # fixed per-rank peer order
@@ -380,6 +384,211 @@ class PeerHalo:
         main.wait_stream(self.comm_stream)
         return gx
 
+
+    # ---- pushed backward: every owner slice of the transposed aggregation is written by the
+    #      aggregation kernel itself straight into the OWNER's staging area over NVLink (remote
+    #      stores are posted, so the transfer rides under the kernel's gathers); after one barrier
+    #      each owner adds the staged rows into its gradient locally at HBM speed.
+    def build_backward_push(self, graph):
+        """Needs ``build_backward_slices(graph)`` semantics (calls it when missing).  Allocates the
+        symmetric staging area ``[rows peers use from me, feat]`` (peer-major, rank order) and the
+        local reduce plan (per local row: its staged copies in this rank's fixed peer order)."""
+        if not hasattr(self, "slices"):
+            self.build_backward_slices(graph)
+        part, world, rank = self.part, self.part.world, self.part.rank
+        dev = part.edge_index.device
+        feat, dtype = self.feat, self.dtype
+        n_send = int(sum(part.send_splits))
+        m = torch.tensor([max(n_send, 1)], dtype=torch.int64, device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self._group)
+        self.max_stage = int(m.item())
+        self.stage_sym = self._symm.empty((self.max_stage, feat), dtype=dtype, device=dev)
+        self.hs = self._symm.rendezvous(self.stage_sym, group=self._group.group_name)
+        offs = [0]
+        for q in range(world):
+            offs.append(offs[-1] + part.send_splits[q])
+        # where my slice for `owner` lands in the owner's staging area: after the rows of the ranks before me
+        self.push_out = []
+        for k in range(1, world):
+            owner = (rank + k) % world
+            cnt = part.recv_splits[owner]
+            off = int(self.all_splits[:rank, owner].sum())
+            buf = self.hs.get_buffer(owner, (self.max_stage, feat), dtype)
+            self.push_out.append(buf[off:off + cnt] if cnt else None)
+        # local reduce plan over my own staging area, peers in the fixed rotated order
+        esz = torch.empty(0, dtype=dtype).element_size()
+        row_bytes = feat * esz
+        base = self.stage_sym.data_ptr()
+        order = sorted(range(world), key=lambda q: (q - rank) % world)
+        rows, addrs = [], []
+        for q in order:
+            cnt = part.send_splits[q]
+            if not cnt or q == rank:
+                continue
+            rows.append(part.send_ids[offs[q]:offs[q] + cnt])
+            addrs.append(base + (offs[q] + torch.arange(cnt, dtype=torch.int64, device=dev)) * row_bytes)
+        if rows:
+            rows_c, addrs_c = torch.cat(rows), torch.cat(addrs)
+            srt, idx = torch.sort(rows_c, stable=True)
+            self.push_ptrs = addrs_c[idx].contiguous()
+            self.push_rows, counts = torch.unique_consecutive(srt, return_counts=True)
+            rp = torch.zeros(self.push_rows.numel() + 1, dtype=torch.int64, device=dev)
+            rp[1:] = torch.cumsum(counts, 0)
+            self.push_rowptr = rp.to(torch.int32)
+        else:
+            self.push_ptrs = torch.empty(0, dtype=torch.int64, device=dev)
+            self.push_rows = torch.empty(0, dtype=torch.int64, device=dev)
+            self.push_rowptr = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self
+
+    def backward_pushed(self, gh: torch.Tensor) -> torch.Tensor:
+        """gX = aggregate^T(gh): local rows into my gradient, every owner's halo slice straight into that
+        owner's staging area; then the staged rows are added locally (fixed peer order per row =>
+        deterministic, fp32 accumulation, one rounding)."""
+        from . import _lib
+        from .ops import spmm
+        lib = _liblib()
+        n_local = self.part.n_local
+        gx = self.gX[:n_local]
+        main = torch.cuda.current_stream()
+        self.hs.barrier()                                    # every owner has consumed last step's staged rows
+        # the owner slices are bound by the NVLink store rate, not by the SMs (measured on 8 GPUs: 450 GB/s of
+        # remote stores vs 0.27 ms of compute per slice), so the local rows are aggregated next to them on a
+        # second stream instead of in front of them
+        start = torch.cuda.Event()
+        start.record(main)
+        self.comm_stream.wait_event(start)
+        with torch.cuda.stream(self.comm_stream):
+            spmm(gh, self.slice_local, _lib.AGG_WEIGHTED, out=gx)
+        for (csr, a, b, _), out in zip(self.slices, self.push_out):
+            if csr is not None and out is not None:
+                spmm(gh, csr, _lib.AGG_WEIGHTED, out=out)    # remote stores over NVLink
+        main.wait_stream(self.comm_stream)
+        self.hs.barrier()                                    # every rank's slices have landed
+        n_rows = int(self.push_rows.numel())
+        if n_rows:
+            _check(lib.gmlm_reduce_rows_ptr(_p(gx), _dt(self.dtype), self.feat, self.feat, _p(self.push_rows),
+                                            _p(self.push_rowptr), _p(self.push_ptrs), n_rows, _st(gx.device)),
+                   "reduce_rows_ptr")
+        return gx
+
+    # ---- staged forward: the destination rows are cut into blocks of equal edge count; a halo row is
+    #      pulled in the stage of the FIRST block that gathers it, on a second (high-priority) stream, so
+    #      only stage 0 is exposed and every later pull runs under the previous block's aggregation.
+    def build_forward_stages(self, graph, n_stages: int = 6, pull_ctas_overlapped: int = 0, fractions=None):
+        """``fractions``: relative edge counts of the blocks; default grows like Fibonacci (1,2,3,5,8,13):
+        the first pull is the only exposed one, so the first block is small, and the late blocks are big
+        because by then most of the halo has arrived (simulated on the 10M/200M graph at 8 ranks: forward
+        4.9 ms one-shot -> 3.6 ms; equal blocks 3.7 ms)."""
+        from .graph import CSR
+        part = self.part
+        fwd = graph.fwd
+        dev = fwd.rowptr.device
+        K = max(1, int(n_stages))
+        if fractions is None:
+            fractions = [1.0, 2.0]
+            while len(fractions) < K:
+                fractions.append(fractions[-1] + fractions[-2])
+            fractions = fractions[:K]
+        assert len(fractions) == K and all(f > 0 for f in fractions)
+        nnz, n_rows = fwd.nnz, fwd.num_rows
+        rowptr64 = fwd.rowptr.long()
+        tot, acc, tg = float(sum(fractions)), 0.0, []
+        for f in fractions[:-1]:
+            acc += f
+            tg.append(int(nnz * acc / tot))
+        targets = torch.tensor(tg, dtype=torch.int64, device=dev)
+        cuts = [0] + torch.searchsorted(rowptr64, targets, right=False).clamp(max=n_rows).tolist() + [n_rows]
+        for i in range(1, len(cuts)):
+            cuts[i] = max(cuts[i], cuts[i - 1])
+        ebounds = rowptr64[torch.tensor(cuts, dtype=torch.int64, device=dev)]            # edge offset of every cut
+        # first block that gathers each halo row
+        first = torch.full((max(part.n_halo, 1),), K, dtype=torch.int64, device=dev)
+        if part.n_halo and nnz:
+            col = fwd.col
+            is_halo = col >= part.n_local
+            pos = torch.nonzero(is_halo).squeeze(1)
+            blk = torch.searchsorted(ebounds, pos, right=True) - 1
+            first.scatter_reduce_(0, (col[pos].long() - part.n_local), blk, reduce="amin")
+            del is_halo, pos, blk
+        first = first[: part.n_halo]
+        self.fwd_stages = []
+        sel_stage = first[self.fwd_order] if part.n_halo else first
+        for k in range(K):
+            r0, r1 = cuts[k], cuts[k + 1]
+            e0, e1 = int(ebounds[k].item()), int(ebounds[k + 1].item())
+            csr = None
+            if r1 > r0:
+                csr = CSR(rowptr=(fwd.rowptr[r0:r1 + 1] - e0).contiguous(), col=fwd.col[e0:e1], num_rows=r1 - r0,
+                          hub_thresh=fwd.hub_thresh)
+                csr.plan_hubs()
+                csr.plan_groups()
+            if part.n_halo:
+                m = sel_stage == k
+                ptrs, outs = self.fwd_ptrs[m].contiguous(), self.fwd_order[m].contiguous()
+            else:
+                ptrs = outs = torch.empty(0, dtype=torch.int64, device=dev)
+            self.fwd_stages.append((csr, r0, r1, ptrs, outs))
+        # halo rows no block gathers cannot exist (the halo IS the set of gathered remote rows)
+        assert not part.n_halo or int((first >= K).sum().item()) == 0
+        lo_pri, hi_pri = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
+        self.pull_stream = torch.cuda.Stream(device=dev, priority=hi_pri)
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        # one CTA per SM keeps ~4.8 MB of remote loads in flight (8 x 16 B per thread), enough for the NVLink
+        # pipe, and takes one of the aggregation's four CTA slots only where it lands
+        self.pull_ctas_overlapped = int(pull_ctas_overlapped) or sms
+        self.fwd_stage_rows = [int(st[3].numel()) for st in self.fwd_stages]
+        return self
+
+    def forward_staged(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """H = mean-aggregate([x_local ‖ halo]) with the halo pulled stage by stage under the aggregation.
+        Bit-identical to ``pull_forward()`` + one whole-CSR aggregation (same rows, same per-row edge order)."""
+        from . import _lib
+        from .ops import spmm
+        lib = _liblib()
+        part = self.part
+        main = torch.cuda.current_stream()
+        n_rows = self.fwd_stages[-1][2]
+        if out is None:
+            out = torch.empty((n_rows, self.feat), dtype=self.dtype, device=self.X.device)
+        tail = self.X[part.n_local:]
+        timing = bool(getattr(self, "stage_timing", False))
+        self.hx.barrier()                                   # every rank's x_local is final
+        ready = torch.cuda.Event(enable_timing=timing)
+        ready.record(main)
+        self.pull_stream.wait_event(ready)
+        events, agg_done = [], []
+        with torch.cuda.stream(self.pull_stream):
+            for k, (_, _, _, ptrs, outs) in enumerate(self.fwd_stages):
+                cnt = int(ptrs.numel())
+                if cnt:
+                    # stage 0 has the GPU to itself; later stages share it with an aggregation kernel
+                    lib.gmlm_set_tuning(b"halo_pull_ctas", 0 if k == 0 else self.pull_ctas_overlapped)
+                    _check(lib.gmlm_gather_rows_ptr(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
+                                                    self.feat, _st(tail.device)), "gather_rows_ptr")
+                ev = torch.cuda.Event(enable_timing=timing)
+                ev.record(self.pull_stream)
+                events.append(ev)
+            lib.gmlm_set_tuning(b"halo_pull_ctas", 0)
+        for (csr, r0, r1, _, _), ev in zip(self.fwd_stages, events):
+            main.wait_event(ev)
+            if csr is not None:
+                spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
+            if timing:
+                d = torch.cuda.Event(enable_timing=True)
+                d.record(main)
+                agg_done.append(d)
+        self.hx.barrier()                                   # every rank is done reading
+        if timing:
+            self.last_timeline = (ready, events, agg_done)
+        return out
+
+    def timeline_ms(self):
+        """(pull-stage end times, block end times) of the last ``forward_staged`` call, in ms after its first
+        barrier; needs ``stage_timing = True`` and a device synchronisation by the caller."""
+        t0, pulls, aggs = self.last_timeline
+        return [round(t0.elapsed_time(e), 3) for e in pulls], [round(t0.elapsed_time(e), 3) for e in aggs]
+
     def pull_backward(self) -> torch.Tensor:
         """gX holds the transposed aggregation's output; returns grad wrt the local rows."""
         lib = _liblib()
@@ -486,9 +695,18 @@ def run_partitioned_bench(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if int(ok.item()) == 0:
             peer, halo_mode = None, "nccl"
-        pipelined = peer is not None and not getattr(args, "no_bwd_pipeline", False)
+        bwd_mode = getattr(args, "bwd", "push") if peer is not None else "plain"
+        if getattr(args, "no_bwd_pipeline", False) and peer is not None:
+            bwd_mode = "plain"
+        pipelined = bwd_mode in ("push", "pipeline")
         if pipelined:
             peer.build_backward_slices(g)
+        if bwd_mode == "push":
+            peer.build_backward_push(g)
+        fwd_stages = int(getattr(args, "fwd_stages", 1)) if peer is not None else 0
+        if fwd_stages > 1:
+            peer.build_forward_stages(g, n_stages=fwd_stages, pull_ctas_overlapped=int(getattr(args, "pull_ctas", 0)))
+            h_buf = torch.empty((part.n_local * S, feat), dtype=dtype, device=dev)
         if peer is not None:
             X, gX_buf = peer.X, peer.gX
         else:
@@ -501,13 +719,30 @@ def run_partitioned_bench(args):
         if peer is None:
             send_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
             back_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
+        # kernels of libgmlm_b200.so per step (symmetric-memory barriers and copies are not counted)
+        def _nk(csr):
+            return 0 if csr is None else 1 + (2 if csr.n_hub else 0)
+        if peer is not None and fwd_stages > 1:
+            launches_per_step = sum(_nk(st[0]) + (1 if st[3].numel() else 0) for st in peer.fwd_stages)
+        else:
+            launches_per_step = _nk(g.fwd) + 1
+        if bwd_mode == "push":
+            launches_per_step += _nk(peer.slice_local) + sum(_nk(sl[0]) for sl in peer.slices) + 1
+        elif bwd_mode == "pipeline":
+            launches_per_step += _nk(peer.slice_local) + sum(_nk(sl[0]) + 1 for sl in peer.slices)
+        else:
+            launches_per_step += _nk(g.bwd) + 1
         PH = 5
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(PH + 1)] for _ in range(args.steps)]
 
         def step(k=None):
             rec = (lambda i: ev[k][i].record()) if k is not None else (lambda i: None)
             rec(0)
-            if peer is not None:
+            if peer is not None and fwd_stages > 1:
+                rec(1)
+                rec(2)
+                h = peer.forward_staged(out=h_buf)        # halo pulled stage by stage under the aggregation
+            elif peer is not None:
                 rec(1)
                 peer.pull_forward()                                                  # rows read over NVLink peer memory
             else:
@@ -515,11 +750,15 @@ def run_partitioned_bench(args):
                 rec(1)
                 dist.all_to_all_single(X[part.n_local:], send_buf, output_split_sizes=part.recv_splits,
                                        input_split_sizes=part.send_splits)           # halo rows via NCCL
-            rec(2)
-            h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                                      # A5 on [local ‖ halo]
+            if not (peer is not None and fwd_stages > 1):
+                rec(2)
+                h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                                  # A5 on [local ‖ halo]
             rec(3)
             if peer is not None and pipelined:
-                gx = peer.backward_pipelined(gh)      # A14 slice by slice, owners pull while the next slice runs
+                if bwd_mode == "push":
+                    gx = peer.backward_pushed(gh)     # A14 slice by slice, written straight into the owners' staging
+                else:
+                    gx = peer.backward_pipelined(gh)  # A14 slice by slice, owners pull while the next slice runs
                 rec(4)
                 rec(5)
                 return h, gx
@@ -557,6 +796,15 @@ def run_partitioned_bench(args):
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
+        timeline = None
+        if peer is not None and fwd_stages > 1:            # one extra, untimed step with per-stage events
+            peer.stage_timing = True
+            step()
+            torch.cuda.synchronize()
+            peer.stage_timing = False
+            timeline = {"pull_end_ms": peer.timeline_ms()[0], "block_end_ms": peer.timeline_ms()[1],
+                        "rows_per_stage": peer.fwd_stage_rows}
+            dist.barrier()
         phases = torch.tensor([statistics.mean(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps))
                                for i in range(PH)], device=dev, dtype=torch.float64)
         phases_all = [torch.zeros_like(phases) for _ in range(world)]
@@ -612,7 +860,11 @@ def run_partitioned_bench(args):
                 "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat,
                            "parallelism": f"dst-row partition x{world} ({getattr(args, 'partition', 'random')} ownership), "
                                           "halo exchange: " + (
-                               ("NVLink peer-memory pull kernels" + (", backward pipelined by owner slice" if pipelined else ""))
+                               ("NVLink peer memory; forward: " +
+                                (f"{fwd_stages}-stage pull under the aggregation" if fwd_stages > 1 else "one pull kernel") +
+                                "; backward: " + {"push": "owner slices stored into the owners' staging by the aggregation "
+                                                          "kernel, local reduce", "pipeline": "owner slices pulled by copy engine",
+                                                  "plain": "pull-reduce kernel"}[bwd_mode])
                                if peer is not None else "NCCL all_to_all"),
                            "l2": "inputs exceed L2", "halo_rows_per_rank": [int(t[0]) for t in halo_all],
                            "edges_per_rank": [int(t[1]) for t in halo_all],
@@ -627,8 +879,8 @@ def run_partitioned_bench(args):
                         "ms_per_step": float(e2e_ms.item()),
                         "note": "each rank copies its node features from pinned host memory every step and reads a "
                                 "scalar back; PCIe-bound"},
-                "gpu_launches": (2 + (2 if g.fwd.n_hub else 0) + (2 if g.bwd.n_hub else 0)) * args.steps,
-                "clocks": clocks, "setup_s": t_setup,
+                "gpu_launches": launches_per_step * args.steps,
+                "clocks": clocks, "setup_s": t_setup, "fwd_timeline_rank0": timeline,
                 "phases_ms_per_rank": {"order": ["pack", "all_to_all_fwd", "aggregate_fwd", "aggregate_bwd",
                                                  "all_to_all_bwd+scatter"],
                                        "ranks": [[round(float(v), 3) for v in t] for t in phases_all]},

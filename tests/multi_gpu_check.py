@@ -6,7 +6,9 @@ rank, that
   * aggregation over [local ‖ halo] reproduces this rank's slice of the whole-graph result
     bit for bit (same kernel, same per-row edge order),
   * the backward (transposed aggregation + peer pull-reduce) matches the whole-graph gradient
-    and the NCCL path within the bf16/fp32 tolerance, and is bit-identical run to run.
+    and the NCCL path within the bf16/fp32 tolerance, and is bit-identical run to run,
+  * the staged forward (halo pulled under the aggregation) is bit-identical to the one-shot forward and
+    the pushed backward (remote stores into the owners' staging areas) matches within tolerance.
 
 The whole-graph reference is computed on each rank with the same CUDA library (its own parity
 against the oracle is established by the single-GPU tests)."""
@@ -84,6 +86,24 @@ def main():
             assert torch.equal(p1, p2), "pipelined backward is not deterministic"
             e_pipe = rel(p1, xg.grad[lo:hi])
             assert e_pipe <= tol, e_pipe
+            # staged forward (halo pulled block by block under the aggregation): bit-identical to the one-shot path
+            for stages in (1, 3, 5):
+                peer.build_forward_stages(g, n_stages=stages)
+                for _ in range(2):
+                    h_st = peer.forward_staged().view(part.n_local, S * feat)
+                    assert torch.equal(h_st, h_full.detach()[lo:hi]), f"staged forward ({stages}) differs"
+            assert sum(peer.fwd_stage_rows) == part.n_halo
+            # pushed backward (owner slices written into the owners' staging areas by the aggregation kernel)
+            peer.build_backward_push(g)
+            q1 = peer.backward_pushed(ghl).clone()
+            q2 = peer.backward_pushed(ghl).clone()
+            torch.cuda.synchronize()
+            assert torch.equal(q1, q2), "pushed backward is not deterministic"
+            e_push = rel(q1, xg.grad[lo:hi])
+            assert e_push <= tol, e_push
+            assert rel(q1, p1) <= tol
+            print(f"[rank {rank}] {dtype}: staged fwd ok (rows per stage {peer.fwd_stage_rows}), pushed grad err {e_push:.2e}",
+                  flush=True)
             print(f"[rank {rank}] {dtype}: halo {part.n_halo} rows ok, pipelined grad err {e_pipe:.2e}, grad err vs whole graph {e_full:.2e}, "
                   f"vs NCCL path {e_nccl:.2e}", flush=True)
             del peer

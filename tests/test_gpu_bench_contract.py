@@ -35,6 +35,11 @@ def test_bench_line_contract(lib_built):
     assert e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0 and 0 < e2e["value"] < r["value"]
     assert r["gpu_launches"] >= 2 * r["steps"]
     assert r["value"] > 0 and r["ms_per_step"] > 0
+    # N=1 default: the 10M/200M graph of the scaling study, with the 2M/40M roofline study riding along
+    assert "10M nodes" in r["config"]["workload"]
+    c4 = r["c4"]
+    assert "2M nodes" in c4["config"]["workload"] and c4["value"] > 0 and c4["roofline"]["achieved"] > 0
+    assert r["encoder"] is None or "ms_fwd_bwd" in r["encoder"] or "error" in r["encoder"]
 
 
 def test_reference_arm_contract(lib_built):
