@@ -491,7 +491,7 @@ def main():
     ap.add_argument("--fwd-stages", type=int, default=1,
                     help="N>1: halo pull stages overlapped with the aggregation (1 = one pull; measured on 8 GPUs: "
                          "6 stages 8.52 ms vs 8.55 ms, see DESIGN.md §6)")
-    ap.add_argument("--pull-ctas", type=int, default=0, help="N>1: CTA cap of the overlapped pull kernels (0 = 1 per SM)")
+    ap.add_argument("--pull-ctas", type=int, default=0, help="N>1: CTA cap of the overlapped pull kernels (0 = 32 CTAs of 1024 threads)")
     ap.add_argument("--partition", default="random", choices=["random", "cyclic", "range"],
                     help="N>1: node ownership")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -23,6 +23,8 @@ int tuning_spmm_variant() { return g_spmm_variant; }
 int tuning_spmm_unroll() { return g_spmm_unroll; }
 static int g_halo_pull_ctas = 0;
 int tuning_halo_pull_ctas() { return g_halo_pull_ctas; }
+static int g_halo_pull_threads = 0;
+int tuning_halo_pull_threads() { return g_halo_pull_threads; }
 
 namespace {
 
@@ -256,6 +258,7 @@ int gmlm_set_tuning(const char* key, int value) {
   if (!strcmp(key, "spmm_variant")) { old = g_spmm_variant; g_spmm_variant = value; }
   else if (!strcmp(key, "spmm_unroll")) { old = g_spmm_unroll; g_spmm_unroll = value; }
   else if (!strcmp(key, "halo_pull_ctas")) { old = g_halo_pull_ctas; g_halo_pull_ctas = value; }
+  else if (!strcmp(key, "halo_pull_threads")) { old = g_halo_pull_threads; g_halo_pull_threads = value; }
   return old;
 }
 

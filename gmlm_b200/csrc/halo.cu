@@ -7,10 +7,13 @@
 // `ids` must be unique within one call (true for one peer's send list), so the scatter needs no
 // atomics and the sum order is fixed by the order of the calls (peer by peer): deterministic.
 // HBM-bound: 128-bit accesses, one row handled by feat/VEC consecutive threads.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gmlm {
-int tuning_halo_pull_ctas();   // graph_build.cu: CTA cap of gather_rows_ptr (0 = 16 per SM)
+int tuning_halo_pull_ctas();     // graph_build.cu: CTA cap of gather_rows_ptr (0 = 16 per SM)
+int tuning_halo_pull_threads();  // threads per CTA of gather_rows_ptr (0 = 256)
 namespace {
 
 template <typename T, int VEC, bool ADD>
@@ -45,33 +48,36 @@ __global__ void __launch_bounds__(256) rows_move_kernel(const T* __restrict__ sr
 // out[k, :] = *(row_ptrs[k])[0:feat]   — every row has its own 64-bit source address, so one
 // launch pulls from all NVLink peers at once (addresses in peer-mapped symmetric memory).
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) gather_ptr_kernel(const T* const* __restrict__ row_ptrs,
-                                                         const int64_t* __restrict__ out_ids, int64_t n,
-                                                         int64_t feat, T* __restrict__ out, int64_t ldo) {
-  // eight 16-byte remote loads in flight per thread: a launch capped to one CTA per SM (so that it can
-  // share the GPU with an aggregation kernel) still keeps the NVLink pipe full (148 x 256 x 128 B = 4.8 MB)
+__global__ void __launch_bounds__(1024) gather_ptr_kernel(const T* const* __restrict__ row_ptrs,
+                                                          const int64_t* __restrict__ out_ids, int64_t n,
+                                                          int64_t feat, T* __restrict__ out, int64_t ldo) {
+  // eight 16-byte remote loads in flight per thread.  Two launch shapes: alone on the GPU, many 256-thread
+  // CTAs; next to an aggregation kernel, a FEW 1024-thread CTAs -- a pull CTA fills its SM's outstanding-load
+  // capacity with 3 us NVLink requests and halves the aggregation on that SM (measured), so the pull is
+  // confined to a few SMs instead of being sprinkled over all of them
   constexpr int U = 8;
   const int64_t packs = feat / VEC;
   const int64_t total = n * packs;
   const int64_t stride = int64_t(gridDim.x) * blockDim.x;
   for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride * U) {
     Pack<T, VEC> a[U];
-    T* dst[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t j = i + u * stride;
-      dst[u] = nullptr;
       if (j < total) {
         const int64_t k = j / packs;
-        const int64_t f = (j - k * packs) * VEC;
-        const int64_t o = out_ids ? out_ids[k] : k;
-        a[u].load(row_ptrs[k] + f);
-        dst[u] = out + o * ldo + f;
+        a[u].load(row_ptrs[k] + (j - k * packs) * VEC);
       }
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (dst[u] != nullptr) a[u].store(dst[u]);
+    for (int u = 0; u < U; ++u) {
+      const int64_t j = i + u * stride;
+      if (j < total) {
+        const int64_t k = j / packs;
+        const int64_t o = out_ids ? out_ids[k] : k;
+        a[u].store(out + o * ldo + (j - k * packs) * VEC);
+      }
+    }
   }
 }
 
@@ -178,16 +184,19 @@ extern "C" int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* 
                "gather_rows_ptr: rows must be 16-byte multiples and 16-byte aligned");
   if (n == 0 || feat == 0) return GMLM_OK;
   GMLM_REQUIRE(row_ptrs && out, "gather_rows_ptr: null pointer");
-  int64_t blocks = (n * (feat / v) + 255) / 256;
+  int threads = tuning_halo_pull_threads();
+  if (threads <= 0) threads = 256;
+  threads = std::min(1024, (threads + 31) / 32 * 32);
+  int64_t blocks = (n * (feat / v) + threads - 1) / threads;
   const int tuned = tuning_halo_pull_ctas();
   const int64_t cap = tuned > 0 ? int64_t(tuned) : int64_t(num_sms()) * 16;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = as_stream(stream);
   if (dtype == GMLM_F32)
-    gather_ptr_kernel<float, 4><<<unsigned(blocks), 256, 0, st>>>(reinterpret_cast<const float* const*>(row_ptrs),
-                                                                  out_ids, n, feat, static_cast<float*>(out), ldo);
+    gather_ptr_kernel<float, 4><<<unsigned(blocks), threads, 0, st>>>(reinterpret_cast<const float* const*>(row_ptrs),
+                                                                      out_ids, n, feat, static_cast<float*>(out), ldo);
   else
-    gather_ptr_kernel<__nv_bfloat16, 8><<<unsigned(blocks), 256, 0, st>>>(
+    gather_ptr_kernel<__nv_bfloat16, 8><<<unsigned(blocks), threads, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16* const*>(row_ptrs), out_ids, n, feat, static_cast<__nv_bfloat16*>(out),
         ldo);
   GMLM_LAUNCH_CHECK();

@@ -210,6 +210,53 @@ def halo_exchange(x_local: torch.Tensor, part: LocalPart, group=None) -> torch.T
     return _HaloExchange.apply(x_local, part, group)
 
 
+
+def default_stage_fractions(n_stages: int) -> List[float]:
+    """Relative block sizes of the staged forward: 1, 2, 3, 5, 8, 13, ... (the first pull is the only exposed
+    one, so the first block is small; the late blocks are big because most of the halo has arrived by then)."""
+    fr = [1.0, 2.0]
+    while len(fr) < n_stages:
+        fr.append(fr[-1] + fr[-2])
+    return fr[:max(1, n_stages)]
+
+
+def stage_row_cuts(rowptr: torch.Tensor, fractions) -> Tuple[List[int], torch.Tensor]:
+    """Cut the CSR rows into ``len(fractions)`` consecutive blocks whose edge counts follow ``fractions``.
+    Returns (row cuts [K+1], edge offset of every cut as an int64 tensor [K+1])."""
+    n_rows = int(rowptr.numel()) - 1
+    rowptr64 = rowptr.long()
+    nnz = int(rowptr64[-1].item()) if n_rows >= 0 else 0
+    tot, acc, tg = float(sum(fractions)), 0.0, []
+    for f in list(fractions)[:-1]:
+        acc += f
+        tg.append(int(nnz * acc / tot))
+    targets = torch.tensor(tg, dtype=torch.int64, device=rowptr.device)
+    cuts = [0] + torch.searchsorted(rowptr64, targets, right=False).clamp(max=n_rows).tolist() + [n_rows]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    ebounds = rowptr64[torch.tensor(cuts, dtype=torch.int64, device=rowptr.device)]
+    return cuts, ebounds
+
+
+def first_use_stage(col: torch.Tensor, n_local: int, n_halo: int, ebounds: torch.Tensor) -> torch.Tensor:
+    """For every halo row (CSR column ``n_local + h``) the first block whose edges gather it; ``K`` (= number
+    of blocks) for a halo row no edge gathers."""
+    K = int(ebounds.numel()) - 1
+    first = torch.full((max(n_halo, 1),), K, dtype=torch.int64, device=col.device)
+    if n_halo and col.numel():
+        pos = torch.nonzero(col >= n_local).squeeze(1)
+        blk = torch.searchsorted(ebounds, pos, right=True) - 1
+        first.scatter_reduce_(0, col[pos].long() - n_local, blk, reduce="amin")
+    return first[:n_halo]
+
+
+def push_offset(all_splits: torch.Tensor, rank: int, owner: int) -> int:
+    """Row offset, inside ``owner``'s staging area, of the gradient rows ``rank`` pushes to it.
+    ``all_splits[q, p]`` = halo rows rank q gathers from rank p; the staging area is peer-major in rank
+    order, i.e. laid out exactly like the owner's ``send_ids`` / ``send_splits``."""
+    return int(all_splits[:rank, owner].sum())
+
+
 class PeerHalo:
     """Halo exchange over NVLink peer memory (no NCCL, no pack buffers).
 
@@ -412,7 +459,7 @@ class PeerHalo:
         for k in range(1, world):
             owner = (rank + k) % world
             cnt = part.recv_splits[owner]
-            off = int(self.all_splits[:rank, owner].sum())
+            off = push_offset(self.all_splits, rank, owner)
             buf = self.hs.get_buffer(owner, (self.max_stage, feat), dtype)
             self.push_out.append(buf[off:off + cnt] if cnt else None)
         # local reduce plan over my own staging area, peers in the fixed rotated order
@@ -486,32 +533,10 @@ class PeerHalo:
         dev = fwd.rowptr.device
         K = max(1, int(n_stages))
         if fractions is None:
-            fractions = [1.0, 2.0]
-            while len(fractions) < K:
-                fractions.append(fractions[-1] + fractions[-2])
-            fractions = fractions[:K]
+            fractions = default_stage_fractions(K)
         assert len(fractions) == K and all(f > 0 for f in fractions)
-        nnz, n_rows = fwd.nnz, fwd.num_rows
-        rowptr64 = fwd.rowptr.long()
-        tot, acc, tg = float(sum(fractions)), 0.0, []
-        for f in fractions[:-1]:
-            acc += f
-            tg.append(int(nnz * acc / tot))
-        targets = torch.tensor(tg, dtype=torch.int64, device=dev)
-        cuts = [0] + torch.searchsorted(rowptr64, targets, right=False).clamp(max=n_rows).tolist() + [n_rows]
-        for i in range(1, len(cuts)):
-            cuts[i] = max(cuts[i], cuts[i - 1])
-        ebounds = rowptr64[torch.tensor(cuts, dtype=torch.int64, device=dev)]            # edge offset of every cut
-        # first block that gathers each halo row
-        first = torch.full((max(part.n_halo, 1),), K, dtype=torch.int64, device=dev)
-        if part.n_halo and nnz:
-            col = fwd.col
-            is_halo = col >= part.n_local
-            pos = torch.nonzero(is_halo).squeeze(1)
-            blk = torch.searchsorted(ebounds, pos, right=True) - 1
-            first.scatter_reduce_(0, (col[pos].long() - part.n_local), blk, reduce="amin")
-            del is_halo, pos, blk
-        first = first[: part.n_halo]
+        cuts, ebounds = stage_row_cuts(fwd.rowptr, fractions)
+        first = first_use_stage(fwd.col, part.n_local, part.n_halo, ebounds)   # first block that gathers each halo row
         self.fwd_stages = []
         sel_stage = first[self.fwd_order] if part.n_halo else first
         for k in range(K):
@@ -534,9 +559,9 @@ class PeerHalo:
         lo_pri, hi_pri = torch.cuda.Stream.priority_range() if hasattr(torch.cuda.Stream, "priority_range") else (0, -1)
         self.pull_stream = torch.cuda.Stream(device=dev, priority=hi_pri)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        # one CTA per SM keeps ~4.8 MB of remote loads in flight (8 x 16 B per thread), enough for the NVLink
-        # pipe, and takes one of the aggregation's four CTA slots only where it lands
-        self.pull_ctas_overlapped = int(pull_ctas_overlapped) or sms
+        # overlapped pulls run as a FEW 1024-thread CTAs (32 x 1024 x 128 B = 4 MB of remote loads in flight):
+        # sprinkled over every SM they halved the aggregation's throughput (8 GPUs, 148 x 256 threads)
+        self.pull_ctas_overlapped = int(pull_ctas_overlapped) or 32
         self.fwd_stage_rows = [int(st[3].numel()) for st in self.fwd_stages]
         return self
 
@@ -564,12 +589,14 @@ class PeerHalo:
                 if cnt:
                     # stage 0 has the GPU to itself; later stages share it with an aggregation kernel
                     lib.gmlm_set_tuning(b"halo_pull_ctas", 0 if k == 0 else self.pull_ctas_overlapped)
+                    lib.gmlm_set_tuning(b"halo_pull_threads", 0 if k == 0 else 1024)
                     _check(lib.gmlm_gather_rows_ptr(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
                                                     self.feat, _st(tail.device)), "gather_rows_ptr")
                 ev = torch.cuda.Event(enable_timing=timing)
                 ev.record(self.pull_stream)
                 events.append(ev)
             lib.gmlm_set_tuning(b"halo_pull_ctas", 0)
+            lib.gmlm_set_tuning(b"halo_pull_threads", 0)
         for (csr, r0, r1, _, _), ev in zip(self.fwd_stages, events):
             main.wait_event(ev)
             if csr is not None:

@@ -41,8 +41,8 @@ extern "C" {
 
 int gmlm_abi_version(void);
 const char* gmlm_last_error(void);
-/* tuning knobs for A/B measurements: key in {"spmm_variant","spmm_unroll","halo_pull_ctas"}; returns old value
- * (halo_pull_ctas: CTA cap of gmlm_gather_rows_ptr so that a pull can share the GPU with an aggregation) */
+/* tuning knobs for A/B measurements: key in {"spmm_variant","spmm_unroll","halo_pull_ctas","halo_pull_threads"};
+ * returns old value (halo_pull_*: launch shape of gmlm_gather_rows_ptr when a pull shares the GPU with an aggregation) */
 int gmlm_set_tuning(const char* key, int value);
 
 /* ---- A1  degree()  [PyG] torch_geometric.utils.degree, called main.py:65 and main.py:256 ----

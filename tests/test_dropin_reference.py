@@ -153,3 +153,27 @@ def test_oracle_encoder_is_pinned_by_the_reference_body(ref_main_on_oracle, n, e
         got = enc(x, ei)
     assert torch.equal(captured["edge_type"], edge_type_bucket_ref(ei, n))
     assert torch.allclose(got, want, rtol=0, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------- §8f N4: NT-Xent consumer
+@pytest.mark.parametrize("n,bs", [(0, 8), (1, 8), (8, 8), (9, 8), (10, 8), (37, 8), (64, 8), (23, 5), (12, None), (7, 16)])
+def test_batched_nt_xent_equals_the_reference_function(ref_main_on_oracle, n, bs):
+    """gmlm_b200.nt_xent_loss (one bmm over all chunks) against the reference's own chunk loop
+    (main.py:102-136) on the same inputs: value and both input gradients, fp64."""
+    from gmlm_b200.losses import nt_xent_loss
+    g = torch.Generator().manual_seed(100 + n)
+    z1 = torch.randn(n, 24, dtype=torch.float64, generator=g)
+    z2 = torch.randn(n, 24, dtype=torch.float64, generator=g)
+    a1, a2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+    b1, b2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+    want = ref_main_on_oracle.nt_xent_loss(a1, a2, temperature=0.5, batch_size=bs)
+    got = nt_xent_loss(b1, b2, temperature=0.5, batch_size=bs)
+    assert got.shape == want.shape and got.requires_grad == want.requires_grad
+    assert abs(float(got) - float(want)) <= 1e-12 * max(1.0, abs(float(want)))
+    if want.grad_fn is not None:
+        want.backward()
+        got.backward()
+        assert torch.allclose(b1.grad, a1.grad, rtol=1e-11, atol=1e-13)
+        assert torch.allclose(b2.grad, a2.grad, rtol=1e-11, atol=1e-13)
+    else:
+        assert float(got) == 0.0 and got.grad_fn is None

@@ -56,3 +56,17 @@ def test_cuda_path_matches_golden(cuda_dev, name, hub_thresh):
         assert rel_err(fused, torch.from_numpy(z["fused"])) <= 5e-5
         fused_m = enc(x, ei, gnn_perturb_mask=mask)
         assert rel_err(fused_m, torch.from_numpy(z["fused_masked"])) <= 5e-5
+
+
+def test_nt_xent_matches_reference_golden(cuda_dev):
+    """§8f N4: the batched NT-Xent on CUDA against vectors produced by the reference's own function
+    (tests/golden/make_nt_xent_golden.py), value and input gradients, fp32 tolerance."""
+    z = np.load(GOLDEN / "nt_xent.npz")
+    for i, ((n, d, b), t) in enumerate(zip(z["cases"].tolist(), z["temperature"].tolist())):
+        z1 = torch.from_numpy(z[f"z1_{i}"]).to(cuda_dev).requires_grad_(True)
+        z2 = torch.from_numpy(z[f"z2_{i}"]).to(cuda_dev).requires_grad_(True)
+        loss = G.nt_xent_loss(z1, z2, temperature=t, batch_size=None if b < 0 else b)
+        loss.backward()
+        assert abs(float(loss) - float(z[f"loss_{i}"])) <= 1e-5 * abs(float(z[f"loss_{i}"])), i
+        assert rel_err(z1.grad, torch.from_numpy(z[f"g1_{i}"])) <= 1e-4, i      # fp32 (TF32 off) vs the fp64 reference
+        assert rel_err(z2.grad, torch.from_numpy(z[f"g2_{i}"])) <= 1e-4, i

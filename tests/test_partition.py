@@ -136,3 +136,81 @@ def test_random_relabel_is_a_seeded_permutation_and_balances_edges():
     own = torch.searchsorted(starts, new[1], right=True) - 1
     per_rank = torch.bincount(own, minlength=world).double()
     assert float(per_rank.max() / per_rank.mean()) < 1.5      # i mod P ownership gives 3.5x on this graph
+
+
+# ----------------------------------------------------------------------------- staged forward / pushed backward
+# Index logic of the overlapped exchange (PeerHalo.build_forward_stages / build_backward_push); the
+# kernels and the symmetric-memory plumbing themselves are covered on real GPUs by tests/multi_gpu_check.py.
+def _csr_by_dst(ei, n_dst):
+    order = torch.argsort(ei[1], stable=True)
+    col = ei[0][order].to(torch.int32)
+    rowptr = torch.zeros(n_dst + 1, dtype=torch.int64)
+    rowptr[1:] = torch.cumsum(torch.bincount(ei[1], minlength=n_dst), 0)
+    return rowptr.to(torch.int32), col
+
+
+@pytest.mark.parametrize("world,stages", [(2, 1), (3, 4), (4, 6)])
+def test_stage_plan_covers_every_halo_row_before_its_first_use(world, stages):
+    from gmlm_b200.partition import (default_stage_fractions, first_use_stage, random_relabel, select_local,
+                                     stage_row_cuts)
+    n, e = 3000, 40000
+    ei = synth.rmat_edges(n, e, seed=3)
+    ei, ranges, _ = random_relabel(ei, n, world)
+    for rank in range(world):
+        ei_l, _, halo_gid, recv_splits = select_local(ei, None, ranges, rank)
+        n_local, n_halo = ranges[rank][1] - ranges[rank][0], int(halo_gid.numel())
+        rowptr, col = _csr_by_dst(ei_l, n_local)
+        fr = default_stage_fractions(stages)
+        assert len(fr) == stages and fr == sorted(fr)
+        cuts, eb = stage_row_cuts(rowptr, fr)
+        assert cuts[0] == 0 and cuts[-1] == n_local and cuts == sorted(cuts) and len(cuts) == stages + 1
+        assert int(eb[0]) == 0 and int(eb[-1]) == col.numel()
+        first = first_use_stage(col, n_local, n_halo, eb)
+        assert first.numel() == n_halo and (n_halo == 0 or int(first.max()) < stages)   # every halo row is gathered
+        # brute force: the block of every edge is >= the stage its halo row arrives in, with equality somewhere
+        blk_of_edge = torch.searchsorted(eb, torch.arange(col.numel()), right=True) - 1
+        seen = torch.full((n_halo,), stages, dtype=torch.int64)
+        for pos in torch.nonzero(col >= n_local).squeeze(1).tolist():
+            h = int(col[pos]) - n_local
+            assert int(blk_of_edge[pos]) >= int(first[h])
+            seen[h] = min(int(seen[h]), int(blk_of_edge[pos]))
+        assert torch.equal(seen, first)
+        # block edge counts follow the fractions to within one row's worth of edges
+        max_row = int((rowptr[1:] - rowptr[:-1]).max())
+        tot = float(sum(fr))
+        acc = 0.0
+        for k in range(stages - 1):
+            acc += fr[k]
+            assert abs(int(eb[k + 1]) - col.numel() * acc / tot) <= max_row + 1
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_push_offsets_tile_every_owners_staging_area(world):
+    """Rank p's slice for owner o lands at push_offset(all_splits, p, o); over all p these ranges must tile
+    o's staging area in exactly the layout of o's send lists (peer-major, rank order, ascending ids)."""
+    from gmlm_b200.partition import push_offset, random_relabel, select_local
+    n, e = 2000, 30000
+    ei = synth.rmat_edges(n, e, seed=8)
+    ei, ranges, _ = random_relabel(ei, n, world)
+    halo = [select_local(ei, None, ranges, r) for r in range(world)]
+    all_splits = torch.tensor([h[3] for h in halo], dtype=torch.int64)          # [q, p] rows q gathers from p
+    assert int(torch.diagonal(all_splits).sum()) == 0
+    for owner in range(world):
+        lo = ranges[owner][0]
+        send_splits = all_splits[:, owner].tolist()                             # what build_local_part agrees on
+        staged = torch.full((sum(send_splits),), -1, dtype=torch.int64)
+        for p in range(world):
+            cnt = send_splits[p]
+            off = push_offset(all_splits, p, owner)
+            assert off == sum(send_splits[:p])
+            gid = halo[p][2]                                                    # p's halo rows, ascending, grouped by owner
+            start = int(all_splits[p, :owner].sum())
+            staged[off:off + cnt] = gid[start:start + cnt] - lo                 # local id (at the owner) of each pushed row
+        assert int((staged < 0).sum()) == 0
+        assert int(staged.min()) >= 0 and int(staged.max()) < ranges[owner][1] - lo
+        # within one sender the ids ascend, so the owner's send_ids (same construction) match position by position
+        off = 0
+        for p in range(world):
+            seg = staged[off:off + send_splits[p]]
+            assert torch.equal(seg, torch.sort(seg).values) and seg.unique().numel() == seg.numel()
+            off += send_splits[p]
