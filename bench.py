@@ -202,7 +202,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "message-passing edges/sec fwd+bwd", "value": eps, "unit": "edges/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": "strong" if w.key == "c5" else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.title, "feat": w.feat, "sample": sample},
         "cpu_baseline": {"value": eps, "unit": "edges/s", "cores": cores, "kind": "port", "sample": sample},
@@ -286,13 +286,14 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
 
     fwd_b, bwd_b = algorithmic_bytes(n, e, feat, esize, S)
     peak, peak_src = peaks()
-    traffic = None
+    traffic = traffic_bwd = None
     tj = ROOT / "profiles" / "traffic.json"
-    if tj.exists():
+    if tj.exists() and args.scale == 1.0:
         try:
-            traffic = json.loads(tj.read_text()).get(f"{w.key}_fwd")
+            tr = json.loads(tj.read_text())
+            traffic, traffic_bwd = tr.get(f"{w.key}_fwd"), tr.get(f"{w.key}_bwd")
         except Exception:
-            traffic = None
+            traffic = traffic_bwd = None
     roof = {"bound": "hbm", "kernel": "forward aggregate (A5): rows_kernel + chunk_kernel + hub_final_kernel",
             "achieved": fwd_b / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
@@ -305,7 +306,10 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
                         "(L2 hit rate ~12 %) the same kernels measure 1.02x the copy peak (profiles/).")
     roof_bwd = {"bound": "hbm", "kernel": "backward aggregate (A14): rows_kernel<weighted> + chunk_kernel<weighted> + hub_final_kernel",
                 "achieved": bwd_b / (bwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": bwd_b / (bwd_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bwd_b, "ms": bwd_ms}
+                "frac": bwd_b / (bwd_ms * 1e-3) / 1e9 / peak, "traffic": traffic_bwd, "algorithmic_bytes": bwd_b,
+                "ms": bwd_ms}
+    if traffic_bwd:
+        roof_bwd["dram_gbs"] = traffic_bwd / (bwd_ms * 1e-3) / 1e9
     roof_step = {"achieved": (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9, "peak": peak,
                  "frac": (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"}
 
@@ -433,7 +437,7 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
     line = {
         "metric": "message-passing edges/sec fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": 1,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+        "scaling": "strong" if key == "c5" else "weak", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
         "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat, "live_relations": S,
                    "generator": f"R-MAT{synth.RMAT_ABCD} seed 42, ids mod N" if w.generator == "rmat" else "uniform seed 42",
                    "l2": "inputs exceed L2 (x %.2f GB, H %.2f GB per step; no flush needed)" % (

@@ -523,10 +523,15 @@ class PeerHalo:
     #      pulled in the stage of the FIRST block that gathers it, on a second (high-priority) stream, so
     #      only stage 0 is exposed and every later pull runs under the previous block's aggregation.
     def build_forward_stages(self, graph, n_stages: int = 6, pull_ctas_overlapped: int = 0, fractions=None):
-        """``fractions``: relative edge counts of the blocks; default grows like Fibonacci (1,2,3,5,8,13):
-        the first pull is the only exposed one, so the first block is small, and the late blocks are big
-        because by then most of the halo has arrived (simulated on the 10M/200M graph at 8 ranks: forward
-        4.9 ms one-shot -> 3.6 ms; equal blocks 3.7 ms)."""
+        """``fractions``: relative edge counts of the blocks; default grows like Fibonacci (1,2,3,5,8,13): the
+        first pull is the only exposed one, so the first block is small.
+
+        MEASURED (round 1, 10M/200M graph): not a win with SM-driven pulls, so bench.py leaves it off.  A pull
+        kernel that shares the GPU with the aggregation fills its SMs' outstanding-load capacity with 3 us
+        NVLink requests: sprinkled over all SMs (148 x 256 threads) it halved the aggregation's throughput
+        (8 GPUs: 8.52 ms vs 8.55 ms one-shot); confined to 32 SMs (32 x 1024 threads) it only reaches
+        260 GB/s (4 GPUs: 13.0 ms vs 12.0 ms).  The overlap needs the copy engines (owner-side pack +
+        contiguous CE copies), see DESIGN.md §6."""
         from .graph import CSR
         part = self.part
         fwd = graph.fwd

@@ -22,7 +22,8 @@ xg = x.detach().requires_grad_(True)
 
 
 def step():
-    y = enc.get_graph_embeddings(xg, ei, et)
+    with torch.amp.autocast("cuda", enabled=dtype == torch.float32):     # as bench.py: fp32 workloads under autocast
+        y = enc.get_graph_embeddings(xg, ei, et)
     y.backward(torch.ones_like(y))
     xg.grad = None
 
