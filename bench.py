@@ -492,6 +492,9 @@ def main():
     ap.add_argument("--no-bwd-pipeline", action="store_true", help="N>1: disable the sliced/pipelined backward")
     ap.add_argument("--bwd", default="push", choices=["push", "pipeline", "plain"],
                     help="N>1: halo-gradient return (push = remote stores from the aggregation kernel)")
+    ap.add_argument("--fwd", default="pull", choices=["pull", "packed"],
+                    help="N>1: forward halo transport (pull = one SM pull kernel; packed = owner-side pack + "
+                         "copy-engine fetch by (owner, stage), correctness-tested, not yet measured at 8 GPUs)")
     ap.add_argument("--fwd-stages", type=int, default=1,
                     help="N>1: halo pull stages overlapped with the aggregation (1 = one pull; measured on 8 GPUs: "
                          "6 stages 8.52 ms vs 8.55 ms, see DESIGN.md §6)")

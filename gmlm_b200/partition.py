@@ -98,6 +98,9 @@ class LocalPart:
     send_splits: List[int]
     edge_index: torch.Tensor         # int64 [2, E_local]: src in [0, n_local+n_halo), dst in [0, n_local)
     edge_type: Optional[torch.Tensor]
+    # set by restage_part(): halo rows ordered (owner, stage of first use, id) instead of (owner, id)
+    stage_fractions: Optional[List[float]] = None
+    recv_stage_counts: Optional[torch.Tensor] = None     # int64 [world, K] on the host: rows per (owner, stage)
 
     @property
     def lo(self) -> int:
@@ -248,6 +251,61 @@ def first_use_stage(col: torch.Tensor, n_local: int, n_halo: int, ebounds: torch
         blk = torch.searchsorted(ebounds, pos, right=True) - 1
         first.scatter_reduce_(0, col[pos].long() - n_local, blk, reduce="amin")
     return first[:n_halo]
+
+
+def halo_first_use_stage(part: "LocalPart", live_rels: List[int], fractions) -> torch.Tensor:
+    """Stage of first use of every halo row, computed from the raw local edge list exactly as
+    ``build_forward_stages`` later computes it from the CSR: edges in (dst*S + slot, original order) order
+    -- the order ``gmlm_csr_build`` produces -- are cut into blocks by ``stage_row_cuts`` and a halo row
+    belongs to the first block that gathers it."""
+    src, dst = part.edge_index[0], part.edge_index[1]
+    S = max(1, len(live_rels))
+    if part.edge_type is not None:
+        lut = torch.full((max(live_rels) + 1,), -1, dtype=torch.int64, device=src.device)
+        lut[torch.tensor(live_rels, dtype=torch.int64, device=src.device)] = torch.arange(S, device=src.device)
+        key = dst * S + lut[part.edge_type]
+    else:
+        key = dst * S
+    n_rows = part.n_local * S
+    order = torch.argsort(key, stable=True)
+    rowptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=src.device)
+    rowptr[1:] = torch.cumsum(torch.bincount(key, minlength=n_rows), 0)
+    _, ebounds = stage_row_cuts(rowptr, fractions)
+    return first_use_stage(src[order], part.n_local, part.n_halo, ebounds)
+
+
+def restage_part(part: "LocalPart", stage: torch.Tensor, fractions, group=None) -> "LocalPart":
+    """Renumber the halo rows from (owner, id) order to (owner, stage, id) order, so that the rows one stage
+    needs from one owner are CONTIGUOUS both in this rank's gather matrix and in the owner's packed send
+    buffer -- what a copy engine needs (contiguous peer-to-peer copies that take no SM from the aggregation).
+    Owner grouping is kept, so the per-owner backward slices stay contiguous.  The send lists are agreed
+    again with the owners (one all_to_all of ids), which therefore pack in the new order."""
+    K = len(fractions)
+    world, rank, dev = part.world, part.rank, part.edge_index.device
+    n_local, n_halo = part.n_local, part.n_halo
+    owner = torch.repeat_interleave(torch.arange(world, device=dev),
+                                    torch.tensor(part.recv_splits, dtype=torch.int64, device=dev))
+    new_order = torch.argsort(owner * (K + 1) + stage, stable=True)          # stable: ids stay ascending inside
+    inv = torch.empty_like(new_order)
+    inv[new_order] = torch.arange(n_halo, dtype=torch.int64, device=dev)
+    halo_gid = part.halo_gid[new_order]
+    src = part.edge_index[0].clone()
+    is_halo = src >= n_local
+    src[is_halo] = n_local + inv[src[is_halo] - n_local]
+    counts = torch.zeros((world, K), dtype=torch.int64, device=dev)
+    if n_halo:
+        counts.view(-1).index_add_(0, owner * K + stage, torch.ones(n_halo, dtype=torch.int64, device=dev))
+    if world > 1:
+        send_gid = torch.empty(int(sum(part.send_splits)), dtype=torch.int64, device=dev)
+        dist.all_to_all_single(send_gid, halo_gid, output_split_sizes=part.send_splits,
+                               input_split_sizes=part.recv_splits, group=group)
+        send_ids = send_gid - part.lo
+    else:
+        send_ids = part.send_ids
+    return LocalPart(rank=rank, world=world, ranges=part.ranges, n_local=n_local, n_halo=n_halo, halo_gid=halo_gid,
+                     recv_splits=part.recv_splits, send_ids=send_ids, send_splits=part.send_splits,
+                     edge_index=torch.stack([src, part.edge_index[1]]), edge_type=part.edge_type,
+                     stage_fractions=list(fractions), recv_stage_counts=counts.cpu())
 
 
 def push_offset(all_splits: torch.Tensor, rank: int, owner: int) -> int:
@@ -621,6 +679,88 @@ class PeerHalo:
         t0, pulls, aggs = self.last_timeline
         return [round(t0.elapsed_time(e), 3) for e in pulls], [round(t0.elapsed_time(e), 3) for e in aggs]
 
+    # ---- packed forward: owners pack the rows every peer needs into a contiguous symmetric send buffer
+    #      (one local gather), peers fetch their (owner, stage) ranges with plain device-to-device copies
+    #      -- copy engines, no SM taken from the aggregation, unlike the SM-driven staged pull above --
+    #      and block k of the aggregation starts when stage k has landed.  Needs a part from restage_part().
+    def build_forward_packed(self, graph):
+        from .graph import CSR
+        part = self.part
+        if part.recv_stage_counts is None:
+            raise ValueError("build_forward_packed needs a LocalPart from restage_part()")
+        world, rank = part.world, part.rank
+        fwd = graph.fwd
+        dev = fwd.rowptr.device
+        feat, dtype = self.feat, self.dtype
+        K = len(part.stage_fractions)
+        cuts, ebounds = stage_row_cuts(fwd.rowptr, part.stage_fractions)
+        n_send = int(sum(part.send_splits))
+        m = torch.tensor([max(n_send, 1)], dtype=torch.int64, device=dev)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self._group)
+        self.max_send = int(m.item())
+        self.send_sym = self._symm.empty((self.max_send, feat), dtype=dtype, device=dev)
+        self.hp = self._symm.rendezvous(self.send_sym, group=self._group.group_name)
+        self.send_buf = self.send_sym[:n_send] if n_send else None
+        tail_off = [0]
+        for o in range(world):
+            tail_off.append(tail_off[-1] + part.recv_splits[o])
+        cnt = part.recv_stage_counts                                     # [owner, stage]
+        self.packed_stages = []
+        for k in range(K):
+            r0, r1 = cuts[k], cuts[k + 1]
+            e0, e1 = int(ebounds[k].item()), int(ebounds[k + 1].item())
+            csr = None
+            if r1 > r0:
+                csr = CSR(rowptr=(fwd.rowptr[r0:r1 + 1] - e0).contiguous(), col=fwd.col[e0:e1], num_rows=r1 - r0,
+                          hub_thresh=fwd.hub_thresh)
+                csr.plan_hubs()
+                csr.plan_groups()
+            copies = []
+            for j in range(1, world):                                    # rotated owner order: no two ranks start on the same peer
+                o = (rank + j) % world
+                c = int(cnt[o, k])
+                if not c:
+                    continue
+                within = int(cnt[o, :k].sum())
+                dst = self.X[part.n_local + tail_off[o] + within: part.n_local + tail_off[o] + within + c]
+                base = push_offset(self.all_splits, rank, o)            # my rows inside owner o's send buffer
+                src = self.hp.get_buffer(o, (self.max_send, feat), dtype)[base + within: base + within + c]
+                copies.append((dst, src))
+            self.packed_stages.append((csr, r0, r1, copies))
+        if not hasattr(self, "copy_stream"):
+            self.copy_stream = torch.cuda.Stream(device=dev)
+        return self
+
+    def forward_packed(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """H = mean-aggregate([x_local ‖ halo]); bit-identical to the one-shot forward."""
+        from . import _lib
+        from .ops import gather_rows, spmm
+        part = self.part
+        main = torch.cuda.current_stream()
+        n_rows = self.packed_stages[-1][2]
+        if out is None:
+            out = torch.empty((n_rows, self.feat), dtype=self.dtype, device=self.X.device)
+        if self.send_buf is not None:
+            gather_rows(self.x_local, part.send_ids, out=self.send_buf)     # pack: [peer][stage][id]
+        self.hp.barrier()                                                   # every owner's send buffer is final
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.copy_stream.wait_event(ready)
+        events = []
+        with torch.cuda.stream(self.copy_stream):
+            for _, _, _, copies in self.packed_stages:
+                for dst, src in copies:
+                    dst.copy_(src, non_blocking=True)                       # contiguous rows over NVLink (copy engine)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append(ev)
+        for (csr, r0, r1, _), ev in zip(self.packed_stages, events):
+            main.wait_event(ev)
+            if csr is not None:
+                spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
+        self.hp.barrier()                                                   # every peer has fetched its rows
+        return out
+
     def pull_backward(self) -> torch.Tensor:
         """gX holds the transposed aggregation's output; returns grad wrt the local rows."""
         lib = _liblib()
@@ -707,6 +847,12 @@ def run_partitioned_bench(args):
         part = build_local_part(ei, et, ranges, rank)
         del ei, et, in_deg
         torch.cuda.empty_cache()
+        fwd_mode = getattr(args, "fwd", "pull")
+        if fwd_mode == "packed" and getattr(args, "halo", "p2p") == "p2p":
+            # halo rows renumbered (owner, stage of first use, id): contiguous ranges for copy-engine transfers
+            k_req = int(getattr(args, "fwd_stages", 1))
+            fr = default_stage_fractions(k_req if k_req > 1 else 4)
+            part = restage_part(part, halo_first_use_stage(part, live, fr), fr)
         g = G.RelGraph.build(part.edge_index, part.edge_type, part.n_local, 5, num_src=part.n_src, live_rels=live,
                              keep_seg=True)
         torch.cuda.synchronize()
@@ -736,6 +882,11 @@ def run_partitioned_bench(args):
         if bwd_mode == "push":
             peer.build_backward_push(g)
         fwd_stages = int(getattr(args, "fwd_stages", 1)) if peer is not None else 0
+        packed = peer is not None and fwd_mode == "packed" and part.recv_stage_counts is not None
+        if packed:
+            peer.build_forward_packed(g)
+            fwd_stages = 0
+            h_buf = torch.empty((part.n_local * S, feat), dtype=dtype, device=dev)
         if fwd_stages > 1:
             peer.build_forward_stages(g, n_stages=fwd_stages, pull_ctas_overlapped=int(getattr(args, "pull_ctas", 0)))
             h_buf = torch.empty((part.n_local * S, feat), dtype=dtype, device=dev)
@@ -754,7 +905,9 @@ def run_partitioned_bench(args):
         # kernels of libgmlm_b200.so per step (symmetric-memory barriers and copies are not counted)
         def _nk(csr):
             return 0 if csr is None else 1 + (2 if csr.n_hub else 0)
-        if peer is not None and fwd_stages > 1:
+        if packed:
+            launches_per_step = sum(_nk(st[0]) for st in peer.packed_stages) + 1
+        elif peer is not None and fwd_stages > 1:
             launches_per_step = sum(_nk(st[0]) + (1 if st[3].numel() else 0) for st in peer.fwd_stages)
         else:
             launches_per_step = _nk(g.fwd) + 1
@@ -770,7 +923,11 @@ def run_partitioned_bench(args):
         def step(k=None):
             rec = (lambda i: ev[k][i].record()) if k is not None else (lambda i: None)
             rec(0)
-            if peer is not None and fwd_stages > 1:
+            if packed:
+                rec(1)
+                rec(2)
+                h = peer.forward_packed(out=h_buf)        # owners pack, copy engines fetch under the aggregation
+            elif peer is not None and fwd_stages > 1:
                 rec(1)
                 rec(2)
                 h = peer.forward_staged(out=h_buf)        # halo pulled stage by stage under the aggregation
@@ -782,7 +939,7 @@ def run_partitioned_bench(args):
                 rec(1)
                 dist.all_to_all_single(X[part.n_local:], send_buf, output_split_sizes=part.recv_splits,
                                        input_split_sizes=part.send_splits)           # halo rows via NCCL
-            if not (peer is not None and fwd_stages > 1):
+            if not (packed or (peer is not None and fwd_stages > 1)):
                 rec(2)
                 h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                                  # A5 on [local ‖ halo]
             rec(3)
@@ -893,7 +1050,9 @@ def run_partitioned_bench(args):
                            "parallelism": f"dst-row partition x{world} ({getattr(args, 'partition', 'random')} ownership), "
                                           "halo exchange: " + (
                                ("NVLink peer memory; forward: " +
-                                (f"{fwd_stages}-stage pull under the aggregation" if fwd_stages > 1 else "one pull kernel") +
+                                ("owner-side pack + copy-engine fetch by (owner, stage) under the aggregation" if packed
+                                 else f"{fwd_stages}-stage pull under the aggregation" if fwd_stages > 1
+                                 else "one pull kernel") +
                                 "; backward: " + {"push": "owner slices stored into the owners' staging by the aggregation "
                                                           "kernel, local reduce", "pipeline": "owner slices pulled by copy engine",
                                                   "plain": "pull-reduce kernel"}[bwd_mode])

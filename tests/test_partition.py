@@ -70,6 +70,44 @@ def _worker(rank, world, port, n, e, feat, q):
         xg = x.clone().requires_grad_(True)
         _aggregate_all_rel(xg, ei, et, n, rels).backward(gh_full)
         assert torch.allclose(x_local.grad, xg.grad[lo:hi], rtol=0, atol=1e-12)
+
+        # restaged halo order (owner, stage of first use, id): same rows, same result, contiguous (owner, stage)
+        # ranges -- the layout the copy-engine forward (PeerHalo.forward_packed) relies on
+        from gmlm_b200.partition import (default_stage_fractions, first_use_stage, halo_first_use_stage, restage_part,
+                                         stage_row_cuts)
+        fr = default_stage_fractions(4)
+        stage = halo_first_use_stage(part, rels, fr)
+        part2 = restage_part(part, stage, fr)
+        assert part2.recv_splits == part.recv_splits and part2.send_splits == part.send_splits
+        assert torch.equal(torch.sort(part2.halo_gid).values, part.halo_gid)
+        assert int(part2.recv_stage_counts.sum()) == part.n_halo
+        assert part2.recv_stage_counts.sum(1).tolist() == part.recv_splits
+        x_local2 = x[lo:hi].clone().requires_grad_(True)
+        X2 = halo_exchange(x_local2, part2)                               # owners pack in the NEW order
+        assert torch.equal(X2[part2.n_local:], x[part2.halo_gid])
+        # same global source behind every local edge
+        gid_of = torch.cat([torch.arange(lo, hi), part.halo_gid])
+        gid_of2 = torch.cat([torch.arange(lo, hi), part2.halo_gid])
+        assert torch.equal(gid_of[part.edge_index[0]], gid_of2[part2.edge_index[0]])
+        assert torch.equal(part.edge_index[1], part2.edge_index[1])
+        h2 = _aggregate_all_rel(X2, part2.edge_index, part2.edge_type, part2.n_local, rels)
+        assert torch.equal(h2, h_local.detach())
+        h2.backward(gh_full[lo:hi])
+        assert torch.allclose(x_local2.grad, xg.grad[lo:hi], rtol=0, atol=1e-12)
+        # layout: within every owner group the stages are ascending and contiguous, ids ascending inside a stage,
+        # and the stage of a row (recomputed on the renumbered part) is the block of its first use
+        stage2 = halo_first_use_stage(part2, rels, fr)
+        off = 0
+        for o in range(world):
+            seg = stage2[off:off + part2.recv_splits[o]]
+            assert torch.equal(seg, torch.sort(seg).values)
+            assert torch.bincount(seg, minlength=len(fr)).tolist() == part2.recv_stage_counts[o].tolist()
+            gseg = part2.halo_gid[off:off + part2.recv_splits[o]]
+            for k in range(len(fr)):
+                ids = gseg[seg == k]
+                assert torch.equal(ids, torch.sort(ids).values)
+            assert part2.recv_splits[o] == 0 or (int(gseg.min()) >= ranges[o][0] and int(gseg.max()) < ranges[o][1])
+            off += part2.recv_splits[o]
         q.put((rank, "ok", part.n_halo))
     except Exception as ex:  # surface the failure in the parent
         import traceback
