@@ -1079,10 +1079,3 @@ def run_partitioned_bench(args):
             print(json.dumps(line), flush=True)
     finally:
         dist.destroy_process_group()
-
-
-class _Ctx:
-    """minimal stand-in for an autograd ctx so the bench can call the exchange backward directly"""
-
-    def __init__(self, part):
-        self.part, self.group = part, None

@@ -177,3 +177,52 @@ def test_batched_nt_xent_equals_the_reference_function(ref_main_on_oracle, n, bs
         assert torch.allclose(b2.grad, a2.grad, rtol=1e-11, atol=1e-13)
     else:
         assert float(got) == 0.0 and got.grad_fn is None
+
+
+# ----------------------------------------------------------------------------- §8f N2: active-node mask sampler
+@pytest.mark.parametrize("case", ["train_mask", "no_mask", "split_edge", "zero_degree", "empty_mask", "one_select"])
+@pytest.mark.parametrize("seed", [0, 7])
+def test_mask_sampler_is_bit_identical_to_the_reference(ref_main_on_oracle, case, seed):
+    """gmlm_b200.generate_active_node_mask against the reference's own function (main.py:47-89) under the
+    same seed: same branches, same random stream (multinomial == exponential race + topk) => same mask."""
+    from types import SimpleNamespace
+    from gmlm_b200.sampling import generate_active_node_mask
+    from oracle import degree_ref
+    ref = ref_main_on_oracle
+    g = torch.Generator().manual_seed(seed)
+    n, e = 400, 3000
+    ei = torch.randint(0, n, (2, e), generator=g)
+    x = torch.randn(n, 4, generator=g)
+    kw, ratio = {}, 0.3
+    train_mask = torch.rand(n, generator=g) < 0.6
+    if case == "zero_degree":
+        ei = ei[:, :0]
+    if case == "empty_mask":
+        train_mask = torch.zeros(n, dtype=torch.bool)
+    if case == "one_select":
+        ratio = 0.0                                             # num_select = max(1, 0) = 1 -> argmax branch
+    data = SimpleNamespace(x=x, edge_index=ei, num_nodes=n, train_mask=train_mask)
+    if case == "no_mask":
+        data.train_mask = None
+    if case == "split_edge":
+        kw = {"split_edge": {"train": {"edge": ei[:, :500].t()}}, "base_mask_name": None}
+    torch.manual_seed(100 + seed)
+    want = ref.generate_active_node_mask(data, ratio, **kw)
+    torch.manual_seed(100 + seed)
+    got = generate_active_node_mask(data, ratio, deg=degree_ref(ei[0], n), **kw)
+    assert got.dtype == torch.bool and torch.equal(got, want)
+    if case not in ("empty_mask",):
+        assert int(got.sum()) >= 1
+
+
+def test_weighted_sampler_distribution_and_zero_weights():
+    from gmlm_b200.sampling import weighted_sample_without_replacement
+    w = torch.tensor([0.0, 1.0, 2.0, 0.0, 5.0, 0.5])
+    g = torch.Generator().manual_seed(0)
+    first = torch.zeros(6)
+    for _ in range(4000):
+        idx = weighted_sample_without_replacement(w, 3, g)
+        assert idx.unique().numel() == 3 and not bool(((idx == 0) | (idx == 3)).any())     # zero weights never drawn
+        first[idx[0]] += 1                                     # topk is sorted: idx[0] is the first draw
+    p = w / w.sum()
+    assert float((first / first.sum() - p).abs().max()) < 0.03   # first draw ~ weights

@@ -354,3 +354,25 @@ def test_rgcn_conv_arbitrary_relation_ids_and_no_basis(cuda_dev):
         assert rel_err(mod.weight.grad, ref.weight.grad) <= 2e-5
         if num_bases is not None:
             assert rel_err(mod.comp.grad, ref.comp.grad) <= 2e-5 and torch.count_nonzero(mod.comp.grad[4]) > 0
+
+
+def test_mask_sampler_on_cuda(cuda_dev):
+    """§8f N2 on the device: the exponential-race sampler reproduces torch.multinomial for the same seed, and
+    generate_active_node_mask (degrees from the gmlm_degree kernel) selects exactly num_select base nodes with
+    positive out-degree."""
+    from types import SimpleNamespace
+    n, e = 5000, 60000
+    ei = synth.rmat_edges(n, e, seed=4).to(cuda_dev)
+    w = G.degree(ei[0], n)
+    p = w / w.sum()
+    torch.manual_seed(11)
+    want = torch.multinomial(p, 500, replacement=False)
+    torch.manual_seed(11)
+    got = G.weighted_sample_without_replacement(p, 500)
+    assert torch.equal(got, want)
+    train_mask = torch.rand(n, device=cuda_dev) < 0.5
+    data = SimpleNamespace(x=torch.zeros(n, 1, device=cuda_dev), edge_index=ei, num_nodes=n, train_mask=train_mask)
+    m = G.generate_active_node_mask(data, 0.3)
+    k = max(1, int(0.3 * int(train_mask.sum())))
+    assert m.dtype == torch.bool and int(m.sum()) == k
+    assert bool(train_mask[m].all()) and bool((w[m] > 0).all())
