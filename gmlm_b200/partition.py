@@ -5,9 +5,9 @@ process per GPU, nodes split into contiguous destination-row ranges balanced by 
 rank owns the in-edges of its rows, and before each layer's aggregation the distinct remote
 source rows ("halo") are fetched over NVLink.
 
-Host logic here is device-agnostic torch (tested on CPU with the gloo backend, world_size 2);
-the aggregation itself is the CUDA kernel on the rank's local CSR, whose column space is
-``[local rows ‖ halo rows]``.
+The index logic here is device-agnostic torch (tested on CPU with the gloo backend, world_size 2 and 3,
+with test-side row movers and the oracle aggregation); the row movers and the aggregation of the product
+are the CUDA kernels, on the rank's local CSR whose column space is ``[local rows ‖ halo rows]``.
 
 Forward:  X = [x_local ‖ all_to_all(x_local[send_ids])];  H = aggregate(X, local CSR)
 Backward: gX = aggregate^T(gH);  gx_local = gX[:n_local] + scatter(all_to_all^T(gX[n_local:]))
@@ -161,33 +161,32 @@ def build_local_part(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor]
 
 
 def _pack(x_local: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Rows a peer needs.  CUDA tensors always take the library kernel; the torch path exists only
-    so that the exchange plumbing can be exercised on CPU with gloo (tests/test_partition.py)."""
-    if x_local.is_cuda:
-        from .ops import gather_rows
-        return gather_rows(x_local, ids, out=out)
-    return torch.index_select(x_local, 0, ids, out=out) if out is not None else x_local.index_select(0, ids)
+    """Rows a peer needs: the library kernel ``gmlm_gather_rows`` (raises on CPU tensors — no fallback)."""
+    from .ops import gather_rows
+    return gather_rows(x_local, ids, out=out)
 
 
 def _unpack_add(gx: torch.Tensor, ids: torch.Tensor, rows: torch.Tensor):
-    if gx.is_cuda:
-        from .ops import scatter_add_rows_
-        scatter_add_rows_(gx, ids, rows)
-    else:
-        gx.index_add_(0, ids, rows)
+    """gx[ids] += rows: the library kernel ``gmlm_scatter_add_rows`` (raises on CPU tensors — no fallback)."""
+    from .ops import scatter_add_rows_
+    scatter_add_rows_(gx, ids, rows)
 
 
 class _HaloExchange(torch.autograd.Function):
-    """x_local [n_local, F] -> X [n_local + n_halo, F] (rows of remote sources appended)."""
+    """x_local [n_local, F] -> X [n_local + n_halo, F] (rows of remote sources appended).
+
+    ``pack`` / ``unpack_add`` are the row movers; the product uses the CUDA kernels above.  The CPU tests of
+    the multi-rank host logic (gloo) inject torch-indexing movers of their own — test infrastructure that
+    lives in tests/, like the oracle aggregation those tests use."""
 
     @staticmethod
-    def forward(ctx, x_local, part: LocalPart, group):
-        ctx.part, ctx.group = part, group
+    def forward(ctx, x_local, part: LocalPart, group, pack, unpack_add):
+        ctx.part, ctx.group, ctx.unpack_add = part, group, unpack_add
         feat = x_local.size(1)
         X = torch.empty((part.n_src, feat), dtype=x_local.dtype, device=x_local.device)
         X[: part.n_local] = x_local
         if part.world > 1:
-            send = _pack(x_local, part.send_ids)
+            send = pack(x_local, part.send_ids)
             dist.all_to_all_single(X[part.n_local:], send, output_split_sizes=part.recv_splits,
                                    input_split_sizes=part.send_splits, group=group)
         return X
@@ -204,13 +203,15 @@ class _HaloExchange(torch.autograd.Function):
             off = 0
             for cnt in part.send_splits:      # fixed peer order; ids unique within a peer
                 if cnt:
-                    _unpack_add(gx, part.send_ids[off:off + cnt], back[off:off + cnt])
+                    ctx.unpack_add(gx, part.send_ids[off:off + cnt], back[off:off + cnt])
                 off += cnt
-        return gx, None, None
+        return gx, None, None, None, None
 
 
-def halo_exchange(x_local: torch.Tensor, part: LocalPart, group=None) -> torch.Tensor:
-    return _HaloExchange.apply(x_local, part, group)
+def halo_exchange(x_local: torch.Tensor, part: LocalPart, group=None, *, pack=None, unpack_add=None) -> torch.Tensor:
+    """Autograd halo exchange over ``torch.distributed`` (NCCL on the GPUs).  Row movers default to the CUDA
+    library kernels; CPU tensors raise unless a test injects its own movers."""
+    return _HaloExchange.apply(x_local, part, group, pack or _pack, unpack_add or _unpack_add)
 
 
 

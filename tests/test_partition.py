@@ -35,6 +35,15 @@ def _aggregate_all_rel(x, ei, et, n_dst, rels):
     return torch.cat(outs, 1)
 
 
+def _cpu_pack(x_local, ids, out=None):
+    """Test-side row movers for the gloo runs (the product's are CUDA kernels and refuse CPU tensors)."""
+    return x_local.index_select(0, ids)
+
+
+def _cpu_unpack_add(gx, ids, rows):
+    gx.index_add_(0, ids, rows)
+
+
 def _worker(rank, world, port, n, e, feat, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -57,7 +66,9 @@ def _worker(rank, world, port, n, e, feat, q):
         assert sum(part.recv_splits) == part.n_halo and part.recv_splits[rank] == 0
 
         x_local = x[lo:hi].clone().requires_grad_(True)
-        X = halo_exchange(x_local, part)
+        with pytest.raises(Exception):                                   # product movers: CUDA only, no CPU fallback
+            halo_exchange(x_local, part)
+        X = halo_exchange(x_local, part, pack=_cpu_pack, unpack_add=_cpu_unpack_add)
         assert torch.equal(X[: part.n_local], x[lo:hi])
         assert torch.equal(X[part.n_local:], x[part.halo_gid])           # the right remote rows arrived
 
@@ -83,7 +94,7 @@ def _worker(rank, world, port, n, e, feat, q):
         assert int(part2.recv_stage_counts.sum()) == part.n_halo
         assert part2.recv_stage_counts.sum(1).tolist() == part.recv_splits
         x_local2 = x[lo:hi].clone().requires_grad_(True)
-        X2 = halo_exchange(x_local2, part2)                               # owners pack in the NEW order
+        X2 = halo_exchange(x_local2, part2, pack=_cpu_pack, unpack_add=_cpu_unpack_add)   # owners pack in the NEW order
         assert torch.equal(X2[part2.n_local:], x[part2.halo_gid])
         # same global source behind every local edge
         gid_of = torch.cat([torch.arange(lo, hi), part.halo_gid])
