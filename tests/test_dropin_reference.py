@@ -226,3 +226,32 @@ def test_weighted_sampler_distribution_and_zero_weights():
         first[idx[0]] += 1                                     # topk is sorted: idx[0] is the first draw
     p = w / w.sum()
     assert float((first / first.sum() - p).abs().max()) < 0.03   # first draw ~ weights
+
+
+def test_batched_nt_xent_property(ref_main_on_oracle):
+    """Random shapes / chunk sizes / temperatures: batched == reference loop (value and gradients)."""
+    from hypothesis import given, settings, strategies as st
+    from gmlm_b200.losses import nt_xent_loss
+    ref = ref_main_on_oracle
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(0, 70), d=st.integers(1, 17), bs=st.one_of(st.none(), st.integers(1, 12)),
+           temp=st.floats(0.05, 2.0), seed=st.integers(0, 10_000))
+    def check(n, d, bs, temp, seed):
+        g = torch.Generator().manual_seed(seed)
+        z1 = torch.randn(n, d, dtype=torch.float64, generator=g) + 0.1
+        z2 = torch.randn(n, d, dtype=torch.float64, generator=g) + 0.1
+        a1, a2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+        b1, b2 = z1.clone().requires_grad_(True), z2.clone().requires_grad_(True)
+        want = ref.nt_xent_loss(a1, a2, temperature=temp, batch_size=bs)
+        got = nt_xent_loss(b1, b2, temperature=temp, batch_size=bs)
+        assert abs(float(got.detach()) - float(want.detach())) <= 1e-10 * max(1.0, abs(float(want.detach())))
+        if want.grad_fn is not None:
+            want.backward()
+            got.backward()
+            assert torch.allclose(b1.grad, a1.grad, rtol=1e-9, atol=1e-11)
+            assert torch.allclose(b2.grad, a2.grad, rtol=1e-9, atol=1e-11)
+        else:
+            assert got.grad_fn is None
+
+    check()
