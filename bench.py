@@ -490,8 +490,9 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: halo exchange implementation")
     ap.add_argument("--no-bwd-pipeline", action="store_true", help="N>1: disable the sliced/pipelined backward")
-    ap.add_argument("--bwd", default="push", choices=["push", "pipeline", "plain"],
-                    help="N>1: halo-gradient return (push = remote stores from the aggregation kernel)")
+    ap.add_argument("--bwd", default="push", choices=["push", "fetch", "pipeline", "plain"],
+                    help="N>1: halo-gradient return (push = remote stores from the aggregation kernel; fetch = "
+                         "copy-engine fetch into staging + one reduce, not yet measured)")
     ap.add_argument("--fwd", default="pull", choices=["pull", "packed"],
                     help="N>1: forward halo transport (pull = one SM pull kernel; packed = owner-side pack + "
                          "copy-engine fetch by (owner, stage), correctness-tested, not yet measured at 8 GPUs)")

@@ -521,6 +521,12 @@ class PeerHalo:
             off = push_offset(self.all_splits, rank, owner)
             buf = self.hs.get_buffer(owner, (self.max_stage, feat), dtype)
             self.push_out.append(buf[off:off + cnt] if cnt else None)
+        # where the slice I FETCH at step k (computed for me by rank - k) lands in my own staging area
+        self.fetch_dst = []
+        for k in range(1, world):
+            src_rank = (rank - k) % world
+            cnt = part.send_splits[src_rank]
+            self.fetch_dst.append(self.stage_sym[offs[src_rank]:offs[src_rank] + cnt] if cnt else None)
         # local reduce plan over my own staging area, peers in the fixed rotated order
         esz = torch.empty(0, dtype=dtype).element_size()
         row_bytes = feat * esz
@@ -571,6 +577,46 @@ class PeerHalo:
                 spmm(gh, csr, _lib.AGG_WEIGHTED, out=out)    # remote stores over NVLink
         main.wait_stream(self.comm_stream)
         self.hs.barrier()                                    # every rank's slices have landed
+        n_rows = int(self.push_rows.numel())
+        if n_rows:
+            _check(lib.gmlm_reduce_rows_ptr(_p(gx), _dt(self.dtype), self.feat, self.feat, _p(self.push_rows),
+                                            _p(self.push_rowptr), _p(self.push_ptrs), n_rows, _st(gx.device)),
+                   "reduce_rows_ptr")
+        return gx
+
+    def backward_fetched(self, gh: torch.Tensor) -> torch.Tensor:
+        """Variant of ``backward_pushed`` whose halo gradients travel by copy engine instead of by the
+        aggregation kernel's remote stores (measured ~450 GB/s, which bounds the pushed slices): every owner
+        slice is aggregated into my own gX tail at HBM speed; after a barrier its owner fetches it with ONE
+        contiguous device-to-device copy into its staging area while the next slice is being aggregated;
+        one local reduce at the end (same plan, same fixed order per row as the pushed variant).
+        NOT YET MEASURED (written at the end of round 1 with the GPU budget spent): `bench.py --bwd fetch`."""
+        from . import _lib
+        from .ops import spmm
+        lib = _liblib()
+        main = torch.cuda.current_stream()
+        n_local = self.part.n_local
+        gx = self.gX[:n_local]
+        if not hasattr(self, "copy_stream"):
+            self.copy_stream = torch.cuda.Stream(device=gx.device)
+        self.hg.barrier()                                    # peers have fetched last step's slices from my gX tail
+        start = torch.cuda.Event()
+        start.record(main)
+        self.comm_stream.wait_event(start)
+        with torch.cuda.stream(self.comm_stream):
+            spmm(gh, self.slice_local, _lib.AGG_WEIGHTED, out=gx)
+        for (csr, a, b, pull), dst in zip(self.slices, self.fetch_dst):
+            if csr is not None:
+                spmm(gh, csr, _lib.AGG_WEIGHTED, out=self.gX[a:b])
+            self.hg.barrier()                                # every rank has finished this step's slice
+            ev = torch.cuda.Event()
+            ev.record(main)
+            if pull is not None and dst is not None:
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_event(ev)
+                    dst.copy_(pull[0], non_blocking=True)    # contiguous remote rows over NVLink (copy engine)
+        main.wait_stream(self.comm_stream)
+        main.wait_stream(self.copy_stream)
         n_rows = int(self.push_rows.numel())
         if n_rows:
             _check(lib.gmlm_reduce_rows_ptr(_p(gx), _dt(self.dtype), self.feat, self.feat, _p(self.push_rows),
@@ -877,10 +923,10 @@ def run_partitioned_bench(args):
         bwd_mode = getattr(args, "bwd", "push") if peer is not None else "plain"
         if getattr(args, "no_bwd_pipeline", False) and peer is not None:
             bwd_mode = "plain"
-        pipelined = bwd_mode in ("push", "pipeline")
+        pipelined = bwd_mode in ("push", "pipeline", "fetch")
         if pipelined:
             peer.build_backward_slices(g)
-        if bwd_mode == "push":
+        if bwd_mode in ("push", "fetch"):
             peer.build_backward_push(g)
         fwd_stages = int(getattr(args, "fwd_stages", 1)) if peer is not None else 0
         packed = peer is not None and fwd_mode == "packed" and part.recv_stage_counts is not None
@@ -912,7 +958,7 @@ def run_partitioned_bench(args):
             launches_per_step = sum(_nk(st[0]) + (1 if st[3].numel() else 0) for st in peer.fwd_stages)
         else:
             launches_per_step = _nk(g.fwd) + 1
-        if bwd_mode == "push":
+        if bwd_mode in ("push", "fetch"):
             launches_per_step += _nk(peer.slice_local) + sum(_nk(sl[0]) for sl in peer.slices) + 1
         elif bwd_mode == "pipeline":
             launches_per_step += _nk(peer.slice_local) + sum(_nk(sl[0]) + 1 for sl in peer.slices)
@@ -947,6 +993,8 @@ def run_partitioned_bench(args):
             if peer is not None and pipelined:
                 if bwd_mode == "push":
                     gx = peer.backward_pushed(gh)     # A14 slice by slice, written straight into the owners' staging
+                elif bwd_mode == "fetch":
+                    gx = peer.backward_fetched(gh)    # A14 slice by slice, owners fetch by copy engine, one reduce
                 else:
                     gx = peer.backward_pipelined(gh)  # A14 slice by slice, owners pull while the next slice runs
                 rec(4)
@@ -1056,6 +1104,7 @@ def run_partitioned_bench(args):
                                  else "one pull kernel") +
                                 "; backward: " + {"push": "owner slices stored into the owners' staging by the aggregation "
                                                           "kernel, local reduce", "pipeline": "owner slices pulled by copy engine",
+                                                  "fetch": "owner slices fetched by copy engine into staging, one local reduce",
                                                   "plain": "pull-reduce kernel"}[bwd_mode])
                                if peer is not None else "NCCL all_to_all"),
                            "l2": "inputs exceed L2", "halo_rows_per_rank": [int(t[0]) for t in halo_all],

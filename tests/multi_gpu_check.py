@@ -103,6 +103,10 @@ def main():
             e_push = rel(q1, xg.grad[lo:hi])
             assert e_push <= tol, e_push
             assert rel(q1, p1) <= tol
+            # fetched backward (owner slices travel by copy engine into the same staging plan): bit-equal to pushed
+            f1 = peer.backward_fetched(ghl).clone()
+            torch.cuda.synchronize()
+            assert torch.equal(f1, q1), "fetched and pushed backward differ"
             print(f"[rank {rank}] {dtype}: staged fwd ok (rows per stage {peer.fwd_stage_rows}), pushed grad err {e_push:.2e}",
                   flush=True)
             # packed forward on a restaged part (owners pack, peers fetch contiguous (owner, stage) ranges with

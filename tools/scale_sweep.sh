@@ -16,6 +16,8 @@ run() {
 run                                   # default: one pull kernel forward, pushed backward
 run --fwd packed                      # owner-side pack + copy-engine fetch, 4 stages
 run --fwd packed --fwd-stages 6
+run --bwd fetch                       # copy-engine fetch of the owner slices into staging + one reduce
+run --fwd packed --bwd fetch          # both transports on copy engines
 run --bwd pipeline                    # previous backward (copy-engine pulls per owner slice)
 python - "$OUT" <<'PY'
 import json, sys
