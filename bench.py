@@ -33,8 +33,6 @@ import torch  # noqa: E402
 
 FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md fallback
 NVLINK_GBS = 770.0          # measured peer copy per direction per GPU (same guide)
-# ncu --set full captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum per launch, bytes
-NCU_TRAFFIC = {}            # filled from profiles/traffic.json when present
 
 
 def peaks():

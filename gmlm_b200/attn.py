@@ -10,7 +10,6 @@ CSR, backward on its transpose.  The per-edge scalars come from ``csrc/gat.cu``.
 """
 from __future__ import annotations
 
-import ctypes as C
 from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Optional

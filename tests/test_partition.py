@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from gmlm_b200.partition import build_local_part, halo_exchange, partition_ranges
 from gmlm_b200 import synth
-from oracle import edge_type_bucket_ref, rgcn_propagate_mean_ref
+from oracle import edge_type_bucket_ref
 
 
 def _free_port():

@@ -3,7 +3,6 @@
 torch symmetric memory, and at what bandwidth?  Not part of the product."""
 import os
 import sys
-import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
