@@ -28,6 +28,7 @@ from .nn import GraphNorm, RGCNConv  # noqa: F401
 from .encoder import GraphEncoder, MultiScaleFusion  # noqa: F401
 from .losses import nt_xent_loss  # noqa: F401
 from .sampling import generate_active_node_mask, weighted_sample_without_replacement  # noqa: F401
+from .dist_norm import partitioned_graph_norm  # noqa: F401
 from .attn import GATConv, GCNConv, LoopGraph, gat_aggregate, get_loop_graph  # noqa: F401
 
 __version__ = "0.1.0"

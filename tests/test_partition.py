@@ -263,3 +263,116 @@ def test_push_offsets_tile_every_owners_staging_area(world):
             seg = staged[off:off + send_splits[p]]
             assert torch.equal(seg, torch.sort(seg).values) and seg.unique().numel() == seg.numel()
             off += send_splits[p]
+
+
+# ----------------------------------------------------------------------------- partitioned GraphNorm (A7 over ranks)
+class _EmulatedGraphNormKernels:
+    """fp64 restatement of the four kernel entry points behind A7, formula by formula as in
+    gmlm_b200/csrc/graphnorm.cu (ONE row count, sums passed in), so that the rank logic of
+    gmlm_b200.dist_norm can be checked on CPU: test infrastructure, like the oracle."""
+
+    @staticmethod
+    def _gelu_grad(n):
+        cdf = 0.5 * (1.0 + torch.erf(n / 2.0 ** 0.5))
+        return cdf + n * torch.exp(-0.5 * n * n) / (2.0 * torch.pi) ** 0.5
+
+    @staticmethod
+    def colstats(x):
+        return x.double().sum(0), (x.double() ** 2).sum(0)
+
+    @staticmethod
+    def fwd(x, colsum, colsq, weight, bias, mean_scale, eps, fuse_gelu):
+        n = x.size(0)
+        mu = colsum / n
+        a = mean_scale.double()
+        var = (colsq / n - mu * mu * (2 * a - a * a)).clamp(min=0)
+        rstd = 1.0 / torch.sqrt(var + eps)
+        y = (x.double() - mu * a) * (weight.double() * rstd) + bias.double()
+        if fuse_gelu:
+            y = torch.nn.functional.gelu(y)
+        return y.to(x.dtype), mu, rstd
+
+    @classmethod
+    def _dn(cls, x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu):
+        oh = (x.double() - mean * mean_scale.double()) * rstd
+        dn = gy.double()
+        if fuse_gelu:
+            dn = dn * cls._gelu_grad(oh * weight.double() + bias.double())
+        return oh, dn
+
+    @classmethod
+    def bwd_stats(cls, x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu):
+        oh, dn = cls._dn(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu)
+        return dn.sum(0), (dn * oh).sum(0)
+
+    @classmethod
+    def bwd_apply(cls, x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, s1, s2, need_gx):
+        n = x.size(0)
+        oh, dn = cls._dn(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu)
+        w, a = weight.double(), mean_scale.double()
+        sum_do = w * rstd * (s1 - s2 * rstd * mean * (1.0 - a))
+        gx = (w * rstd) * (dn - oh * (s2 / n)) - a * sum_do / n
+        return (gx.to(x.dtype) if need_gx else None), s2.clone(), s1.clone(), -mean * sum_do
+
+
+def _gn_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gmlm_b200.dist_norm import partitioned_graph_norm
+        from oracle import GraphNormRef
+        n, c = 157, 12
+        torch.manual_seed(0)                                      # replicated parameters: same draw on every rank
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(n, c, dtype=torch.float64, generator=g) * 2 + 3
+        gout = torch.randn(n, c, dtype=torch.float64, generator=g)
+        cuts = [0, 40, 41, n][: world] + [n]                      # uneven shards, one of a single row
+        lo, hi = cuts[rank], cuts[rank + 1]
+        for fuse_gelu in (False, True):
+            ref = GraphNormRef(c).double()
+            with torch.no_grad():
+                ref.weight.uniform_(0.5, 1.5)
+                ref.bias.uniform_(-0.5, 0.5)
+                ref.mean_scale.uniform_(0.2, 1.2)
+            x64 = x.clone().requires_grad_(True)
+            y_ref = ref(x64)
+            if fuse_gelu:
+                y_ref = torch.nn.functional.gelu(y_ref)
+            y_ref.backward(gout)
+            w = ref.weight.detach().clone().requires_grad_(True)
+            b = ref.bias.detach().clone().requires_grad_(True)
+            ms = ref.mean_scale.detach().clone().requires_grad_(True)
+            xl = x[lo:hi].clone().requires_grad_(True)
+            y = partitioned_graph_norm(xl, w, b, ms, n, ref.eps, fuse_gelu, backend=_EmulatedGraphNormKernels)
+            y.backward(gout[lo:hi])
+            assert torch.allclose(y, y_ref[lo:hi].detach(), rtol=1e-10, atol=1e-12)
+            assert torch.allclose(xl.grad, x64.grad[lo:hi], rtol=1e-9, atol=1e-11)
+            # parameter gradients are the WHOLE-GRAPH gradients on every rank (no further all-reduce)
+            assert torch.allclose(w.grad, ref.weight.grad, rtol=1e-9, atol=1e-11)
+            assert torch.allclose(b.grad, ref.bias.grad, rtol=1e-9, atol=1e-11)
+            assert torch.allclose(ms.grad, ref.mean_scale.grad, rtol=1e-9, atol=1e-11)
+        # the product backend is the CUDA library: CPU tensors are refused (no fallback)
+        with pytest.raises(Exception):
+            partitioned_graph_norm(x[lo:hi].float(), w.float(), b.float(), ms.float(), n)
+        q.put((rank, "ok", None))
+    except Exception:
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_graph_norm_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gn_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in results:
+        assert status == "ok", f"rank {rank}: {info}"
