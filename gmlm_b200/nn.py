@@ -101,6 +101,9 @@ class RGCNConv(nn.Module):
         if x.size(1) != self.in_channels:
             raise _lib.GmlmError(f"RGCNConv: x has {x.size(1)} features, layer expects {self.in_channels}")
         h = rgcn_aggregate(x, graph)                                   # [N, S*Fi], x's dtype
+        if graph.num_src != graph.num_nodes:
+            # destination-row partition: x = [local rows ‖ halo rows]; the root term is over the local rows
+            x = x[: graph.num_nodes]
         w = self.composed_weight()
         live = graph.live_rels
         if len(live) != self.num_relations:

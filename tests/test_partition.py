@@ -376,3 +376,103 @@ def test_partitioned_graph_norm_gloo(world):
         p.join(timeout=60)
     for rank, status, info in results:
         assert status == "ok", f"rank {rank}: {info}"
+
+
+# ----------------------------------------------------------------------------- the whole encoder over ranks
+class _OracleBackedOps:
+    """The three device operations of gmlm_b200.dist_encoder with oracle arithmetic (CPU, fp64): halo exchange
+    with test-side row movers, the per-relation mean + transform of RGCNConvRef on the rank's rectangular edge
+    list (root term on the local rows), GraphNorm+GELU over the partition with the emulated kernels."""
+
+    def __init__(self, part, n_global):
+        self.part, self.n_global = part, n_global
+
+    def exchange(self, x_local):
+        return halo_exchange(x_local, self.part, pack=_cpu_pack, unpack_add=_cpu_unpack_add)
+
+    def conv(self, conv, X):
+        from oracle import rgcn_propagate_mean_ref
+        part = self.part
+        w = conv.composed_weight()
+        out = torch.zeros((part.n_local, conv.out_channels), dtype=X.dtype)
+        for r in range(conv.num_relations):
+            m = part.edge_type == r
+            h = rgcn_propagate_mean_ref(X, part.edge_index[0, m], part.edge_index[1, m], part.n_local)
+            out = out + h @ w[r]
+        return out + X[: part.n_local] @ conv.root + conv.bias
+
+    def norm_gelu(self, gn, y):
+        from gmlm_b200.dist_norm import partitioned_graph_norm
+        return partitioned_graph_norm(y, gn.weight, gn.bias, gn.mean_scale, self.n_global, gn.eps, True,
+                                      backend=_EmulatedGraphNormKernels)
+
+
+def _enc_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from gmlm_b200.dist_encoder import PartitionedGraphEncoder, sync_gradients
+        from gmlm_b200.partition import random_relabel
+        from oracle import EncoderRef
+        n, e, fin, hidden, out_dim = 240, 2600, 10, 4, 6
+        ei = synth.rmat_edges(n, e, seed=21)
+        ei, ranges, _ = random_relabel(ei, n, world)
+        et = edge_type_bucket_ref(ei, n)                              # global out-degree, before partitioning
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(n, fin, dtype=torch.float64, generator=g)
+        gout = torch.randn(n, out_dim, dtype=torch.float64, generator=g)
+        torch.manual_seed(0)                                          # replicated parameters
+        enc_full = EncoderRef(fin, hidden, out_dim, dropout_rate=0.0, use_checkpoint=False).double()
+        with torch.no_grad():
+            for k in range(1, 5):
+                getattr(enc_full, f"gnorm{k}").mean_scale.uniform_(0.5, 1.0)
+                getattr(enc_full, f"rgcn{k}").bias.uniform_(-0.1, 0.1)
+        import copy
+        enc_rank = copy.deepcopy(enc_full)
+        # whole graph, one process
+        x_full = x.clone().requires_grad_(True)
+        fused_full = enc_full(x_full, ei, et)
+        (fused_full * gout).sum().backward()
+        # this rank's rows
+        part = build_local_part(ei, et, ranges, rank)
+        lo, hi = ranges[rank]
+        model = PartitionedGraphEncoder(enc_rank, _OracleBackedOps(part, n))
+        x_local = x[lo:hi].clone().requires_grad_(True)
+        fused = model(x_local)
+        (fused * gout[lo:hi]).sum().backward()
+        sync_gradients(enc_rank)
+        assert torch.allclose(fused, fused_full[lo:hi].detach(), rtol=1e-9, atol=1e-11)
+        assert torch.allclose(x_local.grad, x_full.grad[lo:hi], rtol=1e-8, atol=1e-10)
+        ref_grads = dict(enc_full.named_parameters())
+        checked = 0
+        for name, p in enc_rank.named_parameters():
+            want = ref_grads[name].grad
+            if want is None:
+                assert p.grad is None, name                           # e.g. the dead residual_proj3
+                continue
+            assert p.grad is not None, name
+            assert torch.allclose(p.grad, want, rtol=1e-7, atol=1e-9), (name, float((p.grad - want).abs().max()))
+            checked += 1
+        assert checked >= 4 * 7 + 4 + 9                               # convs, norms, residuals, fusion
+        q.put((rank, "ok", None))
+    except Exception:
+        import traceback
+        q.put((rank, "fail", traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partitioned_encoder_equals_whole_graph_encoder_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_enc_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, status, info in results:
+        assert status == "ok", f"rank {rank}: {info}"
