@@ -6,7 +6,7 @@ by tests/test_partition.py; the real multi-GPU run is tools/check_dist_{norm,enc
 
 These modules were written after the round's GPU budget was spent, so their first execution on hardware is the
 round-end test run: non-strict xfail keeps a surprise there from masking the rest of the suite, and a pass
-shows up as XPASS."""
+shows up as XPASS.  The file name sorts last so that it also RUNS last."""
 import copy
 import os
 import socket
@@ -20,7 +20,7 @@ from gmlm_b200 import synth
 
 from conftest import rel_err
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180),
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread"),
               pytest.mark.xfail(strict=False, reason="first run on hardware (written with the GPU budget spent)")]
 
 
