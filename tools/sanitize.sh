@@ -1,0 +1,15 @@
+#!/usr/bin/env bash
+# compute-sanitizer passes over the kernel tests (run on a GPU box; slow: use the small-shape tests only):
+#   gpurun --timeout 900 -- 'bash tools/sanitize.sh'
+# Writes gpurun_out/sanitize_{memcheck,racecheck,initcheck}.log; exit code != 0 if any tool reports an error.
+set -u
+rc=0
+TESTS="tests/test_gpu_spmm.py tests/test_gpu_modules.py tests/test_gpu_graph.py"
+for tool in memcheck racecheck initcheck; do
+  compute-sanitizer --tool "$tool" --error-exitcode 9 --launch-timeout 0 \
+    python -m pytest $TESTS -x -q -m gpu -k "not bench and not property" \
+    > "gpurun_out/sanitize_${tool}.log" 2>&1 || rc=$?
+  tail -3 "gpurun_out/sanitize_${tool}.log"
+  grep -c "ERROR SUMMARY: 0 errors" "gpurun_out/sanitize_${tool}.log" || true
+done
+exit $rc
