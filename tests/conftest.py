@@ -35,10 +35,22 @@ def cuda_dev(lib_built):
     return torch.device("cuda:0")
 
 
-def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
-    """max |a-b| / max(1, max|b|)-style relative error used for the 1e-5 / 2e-2 gates:
-    norm-wise relative error, the measure that is meaningful for sums with cancellation."""
+def rel_err(a: torch.Tensor, b: torch.Tensor, floor: float = 0.0) -> float:
+    """max |a-b| / max|b|: norm-wise relative error, the measure that is meaningful for sums with
+    cancellation.  ``floor`` bounds the denominator from below for quantities whose exact value is zero
+    (e.g. the gradient of an RGCN bias that feeds GraphNorm with mean_scale = 1: the mean subtraction
+    cancels it, so both sides hold only rounding noise and a pure ratio is meaningless)."""
     a = a.detach().double().cpu()
     b = b.detach().double().cpu()
-    denom = b.abs().max().clamp(min=1e-30)
+    denom = b.abs().max().clamp(min=max(floor, 1e-30))
     return float((a - b).abs().max() / denom)
+
+
+def elementwise_err(a: torch.Tensor, b: torch.Tensor, atol_frac: float = 1e-2) -> float:
+    """Elementwise relative error  max_i |a_i - b_i| / (|b_i| + atol),  atol = atol_frac * rms(b):
+    the stricter companion of ``rel_err`` (north_star's "1e-5 relative" read per element).  The absolute
+    term keeps elements that are tiny only through cancellation from dominating."""
+    a = a.detach().double().cpu()
+    b = b.detach().double().cpu()
+    atol = atol_frac * float(b.pow(2).mean().sqrt().clamp(min=1e-30))
+    return float(((a - b).abs() / (b.abs() + atol)).max())

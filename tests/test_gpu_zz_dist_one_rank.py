@@ -4,9 +4,13 @@ rank (NCCL on one device): with one rank the all-reduces are identities and N_lo
 ``GraphEncoder.get_graph_embeddings``.  The rank logic itself (world 2 and 3, uneven shards) is covered on CPU
 by tests/test_partition.py; the real multi-GPU run is tools/check_dist_{norm,encoder}_multi.py.
 
-These modules were written after the round's GPU budget was spent, so their first execution on hardware is the
-round-end test run: non-strict xfail keeps a surprise there from masking the rest of the suite, and a pass
-shows up as XPASS.  The file name sorts last so that it also RUNS last."""
+The file name sorts last so that it also RUNS last (it initialises a process group).
+
+Round-1 note: this file ran behind a non-strict xfail and the encoder case failed on hardware.  Cause (found in
+round 2, tools/diag_one_rank.py): ``rgcnK.bias`` feeds GraphNorm with ``mean_scale`` = 1, whose mean subtraction
+cancels a bias shift exactly, so the bias gradient is mathematically ZERO and both encoders return ~1e-6 of
+rounding noise there; a ratio of two noises failed the 1e-5 gate.  Every other tensor agreed to 4e-7.  The
+gate now measures parameter-gradient error against the largest gradient of the same layer."""
 import copy
 import os
 import socket
@@ -20,8 +24,7 @@ from gmlm_b200 import synth
 
 from conftest import rel_err
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread"),
-              pytest.mark.xfail(strict=False, reason="first run on hardware (written with the GPU budget spent)")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(180, method="thread")]
 
 
 @pytest.fixture(scope="module")
@@ -88,8 +91,15 @@ def test_partitioned_encoder_one_rank_equals_encoder(cuda_dev, one_rank_group):
     assert rel_err(fused, fused_full) <= 1e-6
     assert rel_err(xl.grad, xf.grad) <= 1e-5
     ref = dict(enc_full.named_parameters())
+    scale = {}                                   # largest gradient magnitude per layer prefix (rgcn1, gnorm1, ...)
+    for name, p in ref.items():
+        if p.grad is not None:
+            k = name.split(".")[0]
+            scale[k] = max(scale.get(k, 0.0), float(p.grad.abs().max()))
     for name, p in enc_rank.named_parameters():
         if ref[name].grad is None:
             assert p.grad is None, name
         else:
-            assert rel_err(p.grad, ref[name].grad) <= 1e-5, name
+            # a gradient that is exactly zero in exact arithmetic (rgcnK.bias under GraphNorm) holds only
+            # rounding noise: measure it against the layer's gradient scale, not against itself
+            assert rel_err(p.grad, ref[name].grad, floor=1e-3 * scale[name.split(".")[0]]) <= 1e-5, name
