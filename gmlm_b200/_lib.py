@@ -36,11 +36,12 @@ SIGNATURES = {
                              _p, _p, _p, _p, _i64, _p]),
     "gmlm_colstats_workspace_bytes": (_sz, [_i64, _i64]),
     "gmlm_colstats": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _sz, _p]),
-    "gmlm_graphnorm_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f32, _int, _p, _i64, _p, _p, _p]),
+    "gmlm_graphnorm_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _p, _p, _p, _f32, _int, _p, _i64, _p, _p, _i64,
+                                  _p]),
     "gmlm_graphnorm_bwd_stats": (_int, [_p, _p, _int, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _int, _p, _p,
                                         _p, _sz, _p]),
     "gmlm_graphnorm_bwd_apply": (_int, [_p, _p, _int, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _p, _int, _p, _p,
-                                        _p, _i64, _p, _p, _p, _p]),
+                                        _p, _i64, _p, _p, _p, _i64, _p]),
     "gmlm_layernorm_max_channels": (_i64, [_int]),
     "gmlm_layernorm_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _f32, _p, _i64, _p, _p, _p]),
     "gmlm_layernorm_bwd_workspace_bytes": (_sz, [_i64, _i64]),

@@ -314,12 +314,13 @@ __global__ void __launch_bounds__(kCta, 2) graphnorm_bwd_apply_kernel(
     const T* __restrict__ x, const T* __restrict__ gy, int64_t num_rows, int64_t C, int64_t ldx, int64_t ldg,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ weight,
     const float* __restrict__ bias, const float* __restrict__ mean_scale, int fuse_gelu,
-    const double* __restrict__ sum_g, const double* __restrict__ sum_go, int tpr, T* __restrict__ gx, int64_t ldgx) {
+    const double* __restrict__ sum_g, const double* __restrict__ sum_go, int64_t stat_rows, int tpr,
+    T* __restrict__ gx, int64_t ldgx) {
   const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr, rpc = kCta / tpr;
   const int64_t c0 = (int64_t(blockIdx.x) * tpr + tx) * VEC;
   if (c0 >= C) return;
   float shift[VEC], rs[VEC], wv[VEC], b[VEC], k1[VEC], k2[VEC], k3[VEC];
-  const double n = double(num_rows);
+  const double n = double(stat_rows);
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const double mu = mean[c0 + k], r = rstd[c0 + k], w = weight[c0 + k], a = mean_scale[c0 + k];
@@ -427,13 +428,14 @@ constexpr int kMaxRowBlocks = 148 * 8;
 // wave of them (each thread strides over the rows), so there is no partial last wave.
 template <auto Kernel>
 int resident_ctas() {
-  static int cached = 0;   // per kernel instantiation; benign race (same value)
-  if (cached == 0) {
+  static int cached[kMaxDevices] = {};   // per kernel instantiation and device; benign race (same value)
+  const int dev = current_device();
+  if (cached[dev] == 0) {
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, Kernel, kCta, 0) != cudaSuccess || occ < 1) occ = 1;
-    cached = std::min(occ * num_sms(), kMaxRowBlocks);
+    cached[dev] = std::min(occ * num_sms(), kMaxRowBlocks);
   }
-  return cached;
+  return cached[dev];
 }
 
 // dispatch helper: calls fn.template operator()<T, VEC>()
@@ -493,15 +495,17 @@ int gmlm_colstats(const void* x, int dtype, int64_t N, int64_t C, int64_t ldx, d
 int gmlm_graphnorm_fwd(const void* x, int dtype, int64_t N, int64_t C, int64_t ldx, const double* colsum,
                        const double* colsq, const float* weight, const float* bias, const float* mean_scale,
                        float eps, int fuse_gelu, void* y, int64_t ldy, float* mean_out, float* rstd_out,
-                       void* stream) {
-  GMLM_REQUIRE(N >= 1 && C >= 0 && ldx >= C && ldy >= C, "graphnorm_fwd: bad sizes");
+                       int64_t stat_rows, void* stream) {
+  if (stat_rows <= 0) stat_rows = N;
+  GMLM_REQUIRE(N >= 0 && stat_rows >= 1 && stat_rows >= N && C >= 0 && ldx >= C && ldy >= C, "graphnorm_fwd: bad sizes");
   if (C == 0) return GMLM_OK;
-  GMLM_REQUIRE(x && y && colsum && colsq && weight && bias && mean_scale && mean_out && rstd_out,
+  GMLM_REQUIRE((N == 0 || (x && y)) && colsum && colsq && weight && bias && mean_scale && mean_out && rstd_out,
                "graphnorm_fwd: null pointer");
   cudaStream_t st = as_stream(stream);
-  graphnorm_prepare_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(colsum, colsq, mean_scale, N, C, eps, mean_out,
-                                                                      rstd_out);
+  graphnorm_prepare_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(colsum, colsq, mean_scale, stat_rows, C, eps,
+                                                                      mean_out, rstd_out);
   GMLM_LAUNCH_CHECK();
+  if (N == 0) return GMLM_OK;
   const bool v = vec_ok(dtype, C, {x, y}, {ldx, ldy});
   return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
     Tile t = make_tile(N, C, VEC, resident_ctas<graphnorm_fwd_kernel<T, VEC>>());
@@ -517,7 +521,7 @@ int gmlm_graphnorm_bwd_stats(const void* x, const void* gy, int dtype, int64_t N
                              int64_t ldg, const float* mean, const float* rstd, const float* weight,
                              const float* bias, const float* mean_scale, int fuse_gelu, double* sum_g,
                              double* sum_go, void* ws, size_t ws_bytes, void* stream) {
-  GMLM_REQUIRE(N >= 1 && C >= 0 && ldx >= C && ldg >= C, "graphnorm_bwd_stats: bad sizes");
+  GMLM_REQUIRE(N >= 0 && C >= 0 && ldx >= C && ldg >= C, "graphnorm_bwd_stats: bad sizes");
   if (C == 0) return GMLM_OK;
   GMLM_REQUIRE(ws && ws_bytes >= partial_bytes(C), "graphnorm_bwd_stats: workspace too small");
   cudaStream_t st = as_stream(stream);
@@ -543,22 +547,24 @@ int gmlm_graphnorm_bwd_apply(const void* x, const void* gy, int dtype, int64_t N
                              int64_t ldg, const float* mean, const float* rstd, const float* weight,
                              const float* bias, const float* mean_scale, int fuse_gelu, const double* sum_g,
                              const double* sum_go, void* gx, int64_t ldgx, float* g_weight, float* g_bias,
-                             float* g_mean_scale, void* stream) {
-  GMLM_REQUIRE(N >= 1 && C >= 0 && ldx >= C && ldg >= C, "graphnorm_bwd_apply: bad sizes");
+                             float* g_mean_scale, int64_t stat_rows, void* stream) {
+  if (stat_rows <= 0) stat_rows = N;
+  GMLM_REQUIRE(N >= 0 && stat_rows >= 1 && stat_rows >= N && C >= 0 && ldx >= C && ldg >= C,
+               "graphnorm_bwd_apply: bad sizes");
   if (C == 0) return GMLM_OK;
   cudaStream_t st = as_stream(stream);
   graphnorm_bwd_params_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(sum_g, sum_go, mean, rstd, weight,
-                                                                         mean_scale, N, C, g_weight, g_bias,
+                                                                         mean_scale, stat_rows, C, g_weight, g_bias,
                                                                          g_mean_scale);
   GMLM_LAUNCH_CHECK();
-  if (gx == nullptr) return GMLM_OK;
+  if (gx == nullptr || N == 0) return GMLM_OK;
   GMLM_REQUIRE(ldgx >= C, "graphnorm_bwd_apply: bad ldgx");
   const bool v = vec_ok(dtype, C, {x, gy, gx}, {ldx, ldg, ldgx});
   return dispatch(dtype, v, [&]<typename T, int VEC>() -> int {
     Tile t = make_tile(N, C, VEC, resident_ctas<graphnorm_bwd_apply_kernel<T, VEC>>());
     graphnorm_bwd_apply_kernel<T, VEC><<<t.grid, kCta, 0, st>>>(
         static_cast<const T*>(x), static_cast<const T*>(gy), N, C, ldx, ldg, mean, rstd, weight, bias, mean_scale,
-        fuse_gelu, sum_g, sum_go, t.tpr, static_cast<T*>(gx), ldgx);
+        fuse_gelu, sum_g, sum_go, stat_rows, t.tpr, static_cast<T*>(gx), ldgx);
     GMLM_LAUNCH_CHECK();
     return GMLM_OK;
   });

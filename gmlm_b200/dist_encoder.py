@@ -80,8 +80,19 @@ class PartitionedGraphEncoder(nn.Module):
 
 def sync_gradients(encoder: nn.Module, group=None) -> None:
     """All-reduce (SUM) the gradients of the replicated parameters after a backward over a node-sum loss.
-    GraphNorm parameters are skipped: their gradients are already whole-graph values on every rank."""
-    for name, p in encoder.named_parameters():
-        if p.grad is None or name.split(".")[0].startswith("gnorm"):
+    GraphNorm parameters are skipped: their gradients are already whole-graph values on every rank.
+    Which parameters take part is agreed collectively first (a parameter that received a gradient on ANY rank is
+    reduced on every rank, a missing local gradient counting as zeros), so that ranks whose backward skipped a
+    parameter cannot leave the others waiting in a collective."""
+    params = [(n, p) for n, p in encoder.named_parameters()
+              if p.requires_grad and not n.split(".")[0].startswith("gnorm")]
+    if not params:
+        return
+    has = torch.tensor([0 if p.grad is None else 1 for _, p in params], dtype=torch.int32, device=params[0][1].device)
+    dist.all_reduce(has, op=dist.ReduceOp.MAX, group=group)
+    for flag, (_, p) in zip(has.tolist(), params):
+        if not flag:
             continue
+        if p.grad is None:
+            p.grad = torch.zeros_like(p)
         dist.all_reduce(p.grad, op=dist.ReduceOp.SUM, group=group)

@@ -152,25 +152,27 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(torch.float32).contiguous()
 
 
-def _graphnorm_fwd(x, weight, bias, mean_scale, eps, fuse_gelu):
+def graphnorm_apply_stats(x, colsum, colsq, weight, bias, mean_scale, eps, fuse_gelu, stat_rows=0):
+    """Normalise pass of A7 given the fp64 column sums; ``stat_rows`` = rows the sums cover (0 = x's rows;
+    the whole-graph count when x holds one rank's rows of a partition)."""
     lib = _lib.load()
     x = _rowmajor(x)
     n, c = x.shape
     dev = x.device
     weight, bias, mean_scale = _f32c(weight), _f32c(bias), _f32c(mean_scale)
-    colsum, colsq = _colstats(x)
     with torch.cuda.device(dev):
         y = torch.empty((n, c), dtype=x.dtype, device=dev)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         rstd = torch.empty(c, dtype=torch.float32, device=dev)
         _lib.check(lib.gmlm_graphnorm_fwd(_ptr(x), _dtype_code(x, "graphnorm"), n, c, _ld(x), _ptr(colsum),
                                           _ptr(colsq), _ptr(weight), _ptr(bias), _ptr(mean_scale), float(eps),
-                                          int(bool(fuse_gelu)), _ptr(y), c, _ptr(mean), _ptr(rstd), _stream(dev)),
-                   "graphnorm_fwd")
+                                          int(bool(fuse_gelu)), _ptr(y), c, _ptr(mean), _ptr(rstd), int(stat_rows),
+                                          _stream(dev)), "graphnorm_fwd")
     return y, mean, rstd
 
 
-def _graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, need_gx):
+def graphnorm_bwd_stats(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu):
+    """Column sums the backward needs (sum dn, sum dn*xhat), fp64, local rows only."""
     lib = _lib.load()
     x = _rowmajor(x)
     gy = _rowmajor(gy)
@@ -179,25 +181,48 @@ def _graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, need_
     n, c = x.shape
     dev = x.device
     weight, bias, mean_scale = _f32c(weight), _f32c(bias), _f32c(mean_scale)
-    dt = _dtype_code(x, "graphnorm_bwd")
     with torch.cuda.device(dev):
         s1 = torch.empty(c, dtype=torch.float64, device=dev)
         s2 = torch.empty(c, dtype=torch.float64, device=dev)
         ws_bytes = lib.gmlm_colstats_workspace_bytes(n, c)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.gmlm_graphnorm_bwd_stats(_ptr(x), _ptr(gy), dt, n, c, _ld(x), _ld(gy), _ptr(mean), _ptr(rstd),
-                                                _ptr(weight), _ptr(bias), _ptr(mean_scale), int(bool(fuse_gelu)),
-                                                _ptr(s1), _ptr(s2), _ptr(ws), ws_bytes, _stream(dev)),
-                   "graphnorm_bwd_stats")
+        _lib.check(lib.gmlm_graphnorm_bwd_stats(_ptr(x), _ptr(gy), _dtype_code(x, "graphnorm_bwd"), n, c, _ld(x),
+                                                _ld(gy), _ptr(mean), _ptr(rstd), _ptr(weight), _ptr(bias),
+                                                _ptr(mean_scale), int(bool(fuse_gelu)), _ptr(s1), _ptr(s2), _ptr(ws),
+                                                ws_bytes, _stream(dev)), "graphnorm_bwd_stats")
+    return s1, s2
+
+
+def graphnorm_bwd_apply(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, s1, s2, need_gx, stat_rows=0):
+    lib = _lib.load()
+    x = _rowmajor(x)
+    gy = _rowmajor(gy)
+    if gy.dtype != x.dtype:
+        gy = gy.to(x.dtype)
+    n, c = x.shape
+    dev = x.device
+    weight, bias, mean_scale = _f32c(weight), _f32c(bias), _f32c(mean_scale)
+    with torch.cuda.device(dev):
         gx = torch.empty((n, c), dtype=x.dtype, device=dev) if need_gx else torch.empty(0, dtype=x.dtype, device=dev)
         gw = torch.empty(c, dtype=torch.float32, device=dev)
         gb = torch.empty(c, dtype=torch.float32, device=dev)
         gms = torch.empty(c, dtype=torch.float32, device=dev)
-        _lib.check(lib.gmlm_graphnorm_bwd_apply(_ptr(x), _ptr(gy), dt, n, c, _ld(x), _ld(gy), _ptr(mean), _ptr(rstd),
-                                                _ptr(weight), _ptr(bias), _ptr(mean_scale), int(bool(fuse_gelu)),
-                                                _ptr(s1), _ptr(s2), _ptr(gx) if need_gx else C.c_void_p(0), c,
-                                                _ptr(gw), _ptr(gb), _ptr(gms), _stream(dev)), "graphnorm_bwd_apply")
+        _lib.check(lib.gmlm_graphnorm_bwd_apply(_ptr(x), _ptr(gy), _dtype_code(x, "graphnorm_bwd"), n, c, _ld(x),
+                                                _ld(gy), _ptr(mean), _ptr(rstd), _ptr(weight), _ptr(bias),
+                                                _ptr(mean_scale), int(bool(fuse_gelu)), _ptr(s1), _ptr(s2),
+                                                _ptr(gx) if need_gx else C.c_void_p(0), c, _ptr(gw), _ptr(gb),
+                                                _ptr(gms), int(stat_rows), _stream(dev)), "graphnorm_bwd_apply")
     return gx, gw, gb, gms
+
+
+def _graphnorm_fwd(x, weight, bias, mean_scale, eps, fuse_gelu):
+    colsum, colsq = _colstats(x)
+    return graphnorm_apply_stats(x, colsum, colsq, weight, bias, mean_scale, eps, fuse_gelu)
+
+
+def _graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, need_gx):
+    s1, s2 = graphnorm_bwd_stats(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu)
+    return graphnorm_bwd_apply(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, s1, s2, need_gx)
 
 
 # ------------------------------------------------------------------------------ A13 LayerNorm

@@ -127,14 +127,17 @@ int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx,
  * stats: colsum[c] = sum_i x[i,c], colsq[c] = sum_i x[i,c]^2 in fp64 (deterministic two-stage).
  * fwd  : mu = colsum/N; o = x - mu*mean_scale; var = E[o^2]; y = weight*o/sqrt(var+eps)+bias,
  *        optionally followed by exact-erf GELU (main.py:274) when fuse_gelu != 0.
- * bwd  : grads for x, weight, bias, mean_scale (through the optional GELU). */
+ * bwd  : grads for x, weight, bias, mean_scale (through the optional GELU).
+ * stat_rows: the row count the sums were taken over (the divisor of the statistics).  0 = num_rows.  A rank of
+ *        a row partition passes the all-reduced WHOLE-GRAPH sums and stat_rows = N_global while num_rows is its
+ *        own (possibly zero) row count; the parameter gradients that come out are then whole-graph values. */
 size_t gmlm_colstats_workspace_bytes(int64_t num_rows, int64_t channels);
 int gmlm_colstats(const void* x, int dtype, int64_t num_rows, int64_t channels, int64_t ldx,
                   double* colsum, double* colsq, void* ws, size_t ws_bytes, void* stream);
 int gmlm_graphnorm_fwd(const void* x, int dtype, int64_t num_rows, int64_t channels, int64_t ldx,
                        const double* colsum, const double* colsq, const float* weight, const float* bias,
                        const float* mean_scale, float eps, int fuse_gelu, void* y, int64_t ldy,
-                       float* mean_out /* [C] */, float* rstd_out /* [C] */, void* stream);
+                       float* mean_out /* [C] */, float* rstd_out /* [C] */, int64_t stat_rows, void* stream);
 int gmlm_graphnorm_bwd_stats(const void* x, const void* gy, int dtype, int64_t num_rows, int64_t channels,
                              int64_t ldx, int64_t ldg, const float* mean, const float* rstd,
                              const float* weight, const float* bias, const float* mean_scale, int fuse_gelu,
@@ -144,7 +147,8 @@ int gmlm_graphnorm_bwd_apply(const void* x, const void* gy, int dtype, int64_t n
                              int64_t ldx, int64_t ldg, const float* mean, const float* rstd,
                              const float* weight, const float* bias, const float* mean_scale, int fuse_gelu,
                              const double* sum_g, const double* sum_go, void* gx, int64_t ldgx,
-                             float* g_weight, float* g_bias, float* g_mean_scale, void* stream);
+                             float* g_weight, float* g_bias, float* g_mean_scale, int64_t stat_rows,
+                             void* stream);
 
 /* ---- A11 soft node masking, soft_masking_gnn_input main.py:92-99 ----
  * fwd: y = x; y[m] = (1-beta)*x[m] + beta*token.   bwd: g_token = beta * sum_{m} gy[m]; gx (optional)

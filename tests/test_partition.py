@@ -268,7 +268,7 @@ def test_push_offsets_tile_every_owners_staging_area(world):
 # ----------------------------------------------------------------------------- partitioned GraphNorm (A7 over ranks)
 class _EmulatedGraphNormKernels:
     """fp64 restatement of the four kernel entry points behind A7, formula by formula as in
-    gmlm_b200/csrc/graphnorm.cu (ONE row count, sums passed in), so that the rank logic of
+    gmlm_b200/csrc/graphnorm.cu (sums and the row count they cover passed in), so that the rank logic of
     gmlm_b200.dist_norm can be checked on CPU: test infrastructure, like the oracle."""
 
     @staticmethod
@@ -281,8 +281,8 @@ class _EmulatedGraphNormKernels:
         return x.double().sum(0), (x.double() ** 2).sum(0)
 
     @staticmethod
-    def fwd(x, colsum, colsq, weight, bias, mean_scale, eps, fuse_gelu):
-        n = x.size(0)
+    def fwd(x, colsum, colsq, weight, bias, mean_scale, eps, fuse_gelu, stat_rows):
+        n = stat_rows or x.size(0)
         mu = colsum / n
         a = mean_scale.double()
         var = (colsq / n - mu * mu * (2 * a - a * a)).clamp(min=0)
@@ -306,8 +306,8 @@ class _EmulatedGraphNormKernels:
         return dn.sum(0), (dn * oh).sum(0)
 
     @classmethod
-    def bwd_apply(cls, x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, s1, s2, need_gx):
-        n = x.size(0)
+    def bwd_apply(cls, x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, s1, s2, need_gx, stat_rows):
+        n = stat_rows or x.size(0)
         oh, dn = cls._dn(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu)
         w, a = weight.double(), mean_scale.double()
         sum_do = w * rstd * (s1 - s2 * rstd * mean * (1.0 - a))
@@ -327,7 +327,7 @@ def _gn_worker(rank, world, port, q):
         g = torch.Generator().manual_seed(4)
         x = torch.randn(n, c, dtype=torch.float64, generator=g) * 2 + 3
         gout = torch.randn(n, c, dtype=torch.float64, generator=g)
-        cuts = [0, 40, 41, n][: world] + [n]                      # uneven shards, one of a single row
+        cuts = [0, 40, 41, 41][: world] + [n]                     # uneven shards: a single row, and (world 4) NO rows
         lo, hi = cuts[rank], cuts[rank + 1]
         for fuse_gelu in (False, True):
             ref = GraphNormRef(c).double()
@@ -363,7 +363,7 @@ def _gn_worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 4])
 def test_partitioned_graph_norm_gloo(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
