@@ -478,6 +478,356 @@ def run_single(args):
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------- our arm, N > 1 GPUs
+FWD_VARIANTS = ("pull", "staged", "tma", "packed")
+BWD_VARIANTS = ("push", "fetch", "fetch_barrier", "pipeline", "plain")
+
+
+def run_partitioned(args):
+    """bench.py --gpus N (N > 1): BASELINE.json configs[4] — the 10M-node / 200M-edge power-law graph,
+    destination-row partitioned (gmlm_b200/partition.py), halo exchange + aggregation forward and backward.
+
+    Transports.  forward: `pull` = one LDG pull kernel then the aggregation; `staged` = K LDG
+    pull stages under the aggregation; `tma` = K stages moved by the bulk-copy engine (cp.async.bulk) from a
+    few single-warp CTAs under the aggregation; `packed` = owner-side pack + copy-engine fetch per (owner,
+    stage).  backward: `push` = owner slices stored into the owners' staging by the aggregation kernel;
+    `fetch` = owner slices aggregated locally and fetched by copy engine behind pairwise signals;
+    `fetch_barrier` = the same behind all-rank barriers; `pipeline`, `plain` = round-1 baselines.
+    `--sweep` times every variant after ONE setup (per-variant ms to stderr and into the JSON line) and then
+    times the full step with the fastest forward and backward."""
+    import torch.distributed as dist
+
+    import gmlm_b200 as G
+    from gmlm_b200 import _lib, synth
+    from gmlm_b200.partition import (PeerHalo, _pack, _unpack_add, build_local_part, cyclic_relabel,
+                                     default_stage_fractions, halo_first_use_stage, partition_ranges,
+                                     random_relabel, restage_part)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world == 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", device_id=dev)
+    try:
+        w = synth.WORKLOADS[args.workload]
+        n = int(w.num_nodes * args.scale)
+        e = int(w.num_edges * args.scale)
+        feat = w.feat
+        dtype = torch.bfloat16 if w.dtype == "bf16" else torch.float32
+        esize = 2 if dtype == torch.bfloat16 else 4
+
+        # every rank generates the same seeded graph (device RNG streams are identical across
+        # identical GPUs) and keeps only its destination range
+        t0 = time.perf_counter()
+        ei = synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
+        et = G.edge_type_from_degree(ei, n)                      # A2 needs the GLOBAL out-degree
+        in_deg = torch.ops.gmlm.degree_i32(ei[1], n)
+        if args.partition == "random":
+            ei, ranges, _ = random_relabel(ei, n, world)         # balanced compute, ingress AND egress
+        elif args.partition == "cyclic":
+            ei, ranges, _ = cyclic_relabel(ei, n, world)
+        else:
+            # cost per node in edge units: fwd writes S (dst,rel) rows, bwd writes 1; each edge is read twice
+            ranges = partition_ranges(in_deg, world, node_cost=2.5)
+        live = sorted(torch.unique(et).tolist())                 # one relation->slot layout for all ranks
+        part = build_local_part(ei, et, ranges, rank)
+        del ei, et, in_deg
+        torch.cuda.empty_cache()
+
+        fwd_list = list(FWD_VARIANTS) if args.sweep else [args.fwd]
+        bwd_list = [b for b in BWD_VARIANTS if b not in ("pipeline", "plain")] if args.sweep else [args.bwd]
+        if args.halo == "nccl":
+            fwd_list, bwd_list = ["nccl"], ["nccl"]
+        if "packed" in fwd_list:
+            # halo rows renumbered (owner, stage of first use, id): contiguous ranges for copy-engine transfers
+            fr = default_stage_fractions(args.packed_stages)
+            part = restage_part(part, halo_first_use_stage(part, live, fr), fr)
+        g = G.RelGraph.build(part.edge_index, part.edge_type, part.n_local, 5, num_src=part.n_src, live_rels=live,
+                             keep_seg=True)
+        torch.cuda.synchronize()
+        t_setup = time.perf_counter() - t0
+        S = g.num_slots
+
+        peer = None
+        if args.halo == "p2p":
+            peer = PeerHalo(part, feat, dtype)
+            peer.build_backward_slices(g)
+            if any(b in ("push", "fetch", "fetch_barrier") for b in bwd_list):
+                peer.build_backward_push(g)
+            if "packed" in fwd_list:
+                peer.build_forward_packed(g)
+            X, gX_buf = peer.X, peer.gX
+        else:
+            X = torch.empty((part.n_src, feat), dtype=dtype, device=dev)
+            gX_buf = None
+            n_send = int(sum(part.send_splits))
+            send_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
+            back_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
+        # persistent buffers: the node features live in the head of the gather matrix X, the halo rows land
+        # straight in its tail (no per-step concat / clone)
+        X[: part.n_local] = synth.make_features(part.n_local, feat, device=dev, seed=42 + rank, dtype=dtype)
+        x_local = X[: part.n_local]
+        gh = synth.make_features(part.n_local * S, feat, device=dev, seed=7 + rank, dtype=dtype)
+        h_buf = torch.empty((part.n_local * S, feat), dtype=dtype, device=dev)
+
+        def _nk(csr):      # kernels of libgmlm_b200.so per aggregation call
+            return 0 if csr is None else 1 + (2 if csr.n_hub else 0)
+
+        staged_cache = {}
+
+        def staged_plan(K):
+            if staged_cache.get("K") != K:
+                peer.build_forward_stages(g, n_stages=K, pull_ctas_overlapped=args.pull_ctas)
+                staged_cache["K"] = K
+                staged_cache["nk"] = sum(_nk(st[0]) + (1 if st[3].numel() else 0) for st in peer.fwd_stages)
+
+        def make_fwd(name):
+            """-> (callable, launches per call, description)"""
+            if name == "nccl":
+                def f():
+                    _pack(x_local, part.send_ids, out=send_buf)
+                    dist.all_to_all_single(X[part.n_local:], send_buf, output_split_sizes=part.recv_splits,
+                                           input_split_sizes=part.send_splits)
+                    return G.spmm(X, g.fwd, _lib.AGG_MEAN, out=h_buf)
+                return f, 1 + _nk(g.fwd), "pack kernel + NCCL all_to_all + aggregation"
+            if name == "pull":
+                def f():
+                    peer.pull_forward()
+                    return G.spmm(X, g.fwd, _lib.AGG_MEAN, out=h_buf)
+                return f, 1 + _nk(g.fwd), "one LDG pull kernel over NVLink peer memory, then the aggregation"
+            if name in ("staged", "tma"):
+                K = args.fwd_stages
+                staged_plan(K)
+                tma = args.tma_ctas if name == "tma" else 0
+
+                def f():
+                    peer.pull_tma_ctas, peer.pull_tma_stage0 = tma, bool(args.tma_stage0) and tma > 0
+                    return peer.forward_staged(out=h_buf)
+                what = (f"{K} halo stages by first use; stage 0 by the LDG pull kernel, later stages " +
+                        (f"by {tma} single-warp bulk-copy (TMA) CTAs" if tma else f"by {args.pull_ctas or 32} LDG CTAs") +
+                        " under the aggregation blocks")
+                return f, staged_cache["nk"], what
+            if name == "packed":
+                def f():
+                    return peer.forward_packed(out=h_buf)
+                return f, sum(_nk(st[0]) for st in peer.packed_stages) + 1, \
+                    f"owner-side pack + copy-engine fetch per (owner, stage), {args.packed_stages} stages"
+            raise ValueError(name)
+
+        def make_bwd(name):
+            if name == "nccl":
+                def f():
+                    gX = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)
+                    dist.all_to_all_single(back_buf, gX[part.n_local:], output_split_sizes=part.send_splits,
+                                           input_split_sizes=part.recv_splits)
+                    gx = gX[: part.n_local]
+                    off = 0
+                    for cnt in part.send_splits:                 # peer order, unique ids per peer
+                        if cnt:
+                            _unpack_add(gx, part.send_ids[off:off + cnt], back_buf[off:off + cnt])
+                        off += cnt
+                    return gx
+                return f, _nk(g.bwd) + world - 1, "aggregation + NCCL all_to_all + scatter-add per peer"
+            sl = _nk(peer.slice_local) + sum(_nk(s_[0]) for s_ in peer.slices)
+            if name == "push":
+                return (lambda: peer.backward_pushed(gh)), sl + 1, \
+                    "owner slices stored into the owners' staging by the aggregation kernel, local reduce"
+            if name == "fetch":
+                return (lambda: peer.backward_fetched(gh, local_last=True, signals=True)), sl + 1, \
+                    "owner slices aggregated locally, fetched by copy engine behind pairwise signals, local rows last, one reduce"
+            if name == "fetch_barrier":
+                return (lambda: peer.backward_fetched(gh, local_last=False, signals=False)), sl + 1, \
+                    "owner slices aggregated locally, fetched by copy engine behind all-rank barriers, one reduce"
+            if name == "pipeline":
+                return (lambda: peer.backward_pipelined(gh)), sl + world - 1, "owner slices pulled by copy engine + scatter-add"
+            if name == "plain":
+                def f():
+                    G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED, out=gX_buf)
+                    return peer.pull_backward()
+                return f, _nk(g.bwd) + 1, "whole transposed aggregation, then one pull-reduce kernel"
+            raise ValueError(name)
+
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def timed(fn, iters, warm=2):
+            """mean ms per call, max over ranks (device time between barriers)."""
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(iters):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            dist.barrier()
+            t = torch.tensor([a.elapsed_time(b) / iters], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        sweep = None
+        if args.sweep:
+            sweep = {"forward_ms": {}, "backward_ms": {}}
+            for name in fwd_list:
+                if name in ("staged", "tma"):
+                    for K in args.sweep_stages:
+                        for c in (args.sweep_tma_ctas if name == "tma" else [0]):
+                            args.fwd_stages, args.tma_ctas = K, c
+                            fn, _, _ = make_fwd(name)
+                            key = f"{name}:K={K}" + (f":ctas={c}" if name == "tma" else "")
+                            sweep["forward_ms"][key] = timed(fn, args.sweep_iters)
+                            if rank == 0:
+                                print(f"[sweep] fwd {key}: {sweep['forward_ms'][key]:.3f} ms", file=sys.stderr, flush=True)
+                else:
+                    fn, _, _ = make_fwd(name)
+                    sweep["forward_ms"][name] = timed(fn, args.sweep_iters)
+                    if rank == 0:
+                        print(f"[sweep] fwd {name}: {sweep['forward_ms'][name]:.3f} ms", file=sys.stderr, flush=True)
+            for name in bwd_list:
+                fn, _, _ = make_bwd(name)
+                sweep["backward_ms"][name] = timed(fn, args.sweep_iters)
+                if rank == 0:
+                    print(f"[sweep] bwd {name}: {sweep['backward_ms'][name]:.3f} ms", file=sys.stderr, flush=True)
+            best_f = min(sweep["forward_ms"], key=sweep["forward_ms"].get)
+            best_b = min(sweep["backward_ms"], key=sweep["backward_ms"].get)
+            parts = best_f.split(":")
+            args.fwd = parts[0]
+            for kv in parts[1:]:
+                k_, v_ = kv.split("=")
+                if k_ == "K":
+                    args.fwd_stages = int(v_)
+                if k_ == "ctas":
+                    args.tma_ctas = int(v_)
+            args.bwd = best_b
+            sweep["chosen"] = {"forward": best_f, "backward": best_b}
+
+        fwd_name = "nccl" if args.halo == "nccl" else args.fwd
+        bwd_name = "nccl" if args.halo == "nccl" else args.bwd
+        fwd_fn, fwd_launches, fwd_what = make_fwd(fwd_name)
+        bwd_fn, bwd_launches, bwd_what = make_bwd(bwd_name)
+        launches_per_step = fwd_launches + bwd_launches
+
+        PH = 2
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(PH + 1)] for _ in range(args.steps)]
+
+        def step(k=None):
+            if k is not None:
+                ev[k][0].record()
+            h = fwd_fn()                       # halo exchange + A5 on [local ‖ halo]
+            if k is not None:
+                ev[k][1].record()
+            gx = bwd_fn()                      # A14 + halo-gradient return
+            if k is not None:
+                ev[k][2].record()
+            return h, gx
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sampler = None
+        if rank == 0:
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+        a.record()
+        for k in range(args.steps):
+            step(k)
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        timeline = None
+        if peer is not None and fwd_name in ("staged", "tma"):   # one extra, untimed step with per-stage events
+            peer.stage_timing = True
+            step()
+            torch.cuda.synchronize()
+            peer.stage_timing = False
+            timeline = {"pull_end_ms": peer.timeline_ms()[0], "block_end_ms": peer.timeline_ms()[1],
+                        "rows_per_stage": peer.fwd_stage_rows}
+            dist.barrier()
+        phases = torch.tensor([statistics.mean(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps))
+                               for i in range(PH)], device=dev, dtype=torch.float64)
+        phases_all = [torch.zeros_like(phases) for _ in range(world)]
+        dist.all_gather(phases_all, phases)
+        ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # device time, max over ranks
+        # ---- e2e: every step each rank copies its node features from pinned host memory and reads a
+        #      scalar of the result back (graph / CSR / halo plan stay resident: the graph is static)
+        x_host = x_local.cpu().pin_memory()
+        res_host = torch.empty(1, dtype=torch.float32).pin_memory()
+        e2e_steps = max(3, min(args.steps, 5))
+
+        def e2e_step():
+            x_local.copy_(x_host, non_blocking=True)
+            _, gx_ = step()
+            res_host.copy_(gx_[:: max(1, part.n_local // 4096)].float().sum().reshape(1), non_blocking=True)
+
+        e2e_step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_ms = torch.tensor([a.elapsed_time(b) / e2e_steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        h2d = torch.tensor([float(x_host.numel() * esize)], device=dev, dtype=torch.float64)
+        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
+        halo_rows = torch.tensor([float(part.n_halo), float(part.edge_index.size(1)), float(part.n_local)],
+                                 device=dev, dtype=torch.float64)
+        halo_all = [torch.zeros_like(halo_rows) for _ in range(world)]
+        dist.all_gather(halo_all, halo_rows)
+        if rank == 0:
+            clocks = sampler.stop()
+            ms_step = float(ms.item())
+            value = e / (ms_step * 1e-3)
+            peak, peak_src = peaks()
+            max_halo = max(float(t[0]) for t in halo_all)
+            max_edges = max(float(t[1]) for t in halo_all)
+            max_rows = max(float(t[2]) for t in halo_all)
+            fwd_b, bwd_b = algorithmic_bytes(int(max_rows), int(max_edges), feat, esize, S)
+            t_hbm = (fwd_b + bwd_b) / (peak * 1e9)
+            t_link = 2 * max_halo * feat * esize / (NVLINK_GBS * 1e9)        # fwd + bwd exchange
+            # compute and exchange can overlap: the bound is the slower of the two, per GPU
+            roof_t = max(t_hbm, t_link)
+            line = {
+                "metric": "message-passing edges/sec fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
+                "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat,
+                           "parallelism": f"dst-row partition x{world} ({args.partition} ownership)",
+                           "halo_forward": fwd_what, "halo_backward": bwd_what,
+                           "l2": "inputs exceed L2", "halo_rows_per_rank": [int(t[0]) for t in halo_all],
+                           "edges_per_rank": [int(t[1]) for t in halo_all],
+                           "rows_per_rank": [int(t[2]) for t in halo_all]},
+                "roofline": {"bound": "nvlink" if t_link > t_hbm else "hbm", "achieved": roof_t / (ms_step * 1e-3),
+                             "peak": 1.0, "unit": "fraction of max(HBM, NVLink) time", "frac": roof_t / (ms_step * 1e-3),
+                             "t_hbm_ms": t_hbm * 1e3, "t_nvlink_ms": t_link * 1e3, "traffic": None,
+                             "peak_source": peak_src + f"; NVLink {NVLINK_GBS} GB/s per direction (B200_PROFILING.md)"},
+                "cpu_baseline": None,
+                "e2e": {"value": e / (float(e2e_ms.item()) * 1e-3), "unit": "edges/s",
+                        "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world,
+                        "ms_per_step": float(e2e_ms.item()),
+                        "note": "each rank copies its node features from pinned host memory every step and reads a "
+                                "scalar back; PCIe-bound"},
+                "gpu_launches": launches_per_step * args.steps,
+                "clocks": clocks, "setup_s": t_setup, "fwd_timeline_rank0": timeline, "sweep": sweep,
+                "phases_ms_per_rank": {"order": ["forward (halo + aggregate)", "backward (aggregate + halo return)"],
+                                       "ranks": [[round(float(v), 3) for v in t] for t in phases_all]},
+            }
+            print(json.dumps(line), flush=True)
+    finally:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -487,17 +837,17 @@ def main():
     ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: halo exchange implementation")
-    ap.add_argument("--no-bwd-pipeline", action="store_true", help="N>1: disable the sliced/pipelined backward")
-    ap.add_argument("--bwd", default="push", choices=["push", "fetch", "pipeline", "plain"],
-                    help="N>1: halo-gradient return (push = remote stores from the aggregation kernel; fetch = "
-                         "copy-engine fetch into staging + one reduce, not yet measured)")
-    ap.add_argument("--fwd", default="pull", choices=["pull", "packed"],
-                    help="N>1: forward halo transport (pull = one SM pull kernel; packed = owner-side pack + "
-                         "copy-engine fetch by (owner, stage), correctness-tested, not yet measured at 8 GPUs)")
-    ap.add_argument("--fwd-stages", type=int, default=1,
-                    help="N>1: halo pull stages overlapped with the aggregation (1 = one pull; measured on 8 GPUs: "
-                         "6 stages 8.52 ms vs 8.55 ms, see DESIGN.md §6)")
-    ap.add_argument("--pull-ctas", type=int, default=0, help="N>1: CTA cap of the overlapped pull kernels (0 = 32 CTAs of 1024 threads)")
+    ap.add_argument("--bwd", default="push", choices=list(BWD_VARIANTS), help="N>1: halo-gradient return (see run_partitioned)")
+    ap.add_argument("--fwd", default="pull", choices=list(FWD_VARIANTS), help="N>1: forward halo transport (see run_partitioned)")
+    ap.add_argument("--fwd-stages", type=int, default=6, help="N>1, --fwd staged|tma: halo stages (by first use)")
+    ap.add_argument("--packed-stages", type=int, default=4, help="N>1, --fwd packed: stages")
+    ap.add_argument("--tma-ctas", type=int, default=32, help="N>1, --fwd tma: single-warp bulk-copy CTAs per overlapped stage")
+    ap.add_argument("--tma-stage0", type=int, default=0, help="N>1, --fwd tma: 1 = stage 0 by bulk copy too (one CTA per SM)")
+    ap.add_argument("--pull-ctas", type=int, default=0, help="N>1, --fwd staged: CTA cap of the overlapped LDG pull kernels (0 = 32 CTAs of 1024 threads)")
+    ap.add_argument("--sweep", action="store_true", help="N>1: time every transport variant after one setup, then the full step with the fastest")
+    ap.add_argument("--sweep-iters", type=int, default=6)
+    ap.add_argument("--sweep-stages", type=int, nargs="+", default=[4, 8])
+    ap.add_argument("--sweep-tma-ctas", type=int, nargs="+", default=[16, 32, 64])
     ap.add_argument("--partition", default="random", choices=["random", "cyclic", "range"],
                     help="N>1: node ownership")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -514,8 +864,7 @@ def main():
         run_reference(args)
         return
     if max(args.gpus, world) > 1:
-        from gmlm_b200.partition import run_partitioned_bench
-        run_partitioned_bench(args)
+        run_partitioned(args)
         return
     run_single(args)
 

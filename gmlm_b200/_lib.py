@@ -28,6 +28,7 @@ SIGNATURES = {
     "gmlm_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "gmlm_csr_build": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, C.POINTER(_i32), _int, _p, _p, _p, _p, _p, _sz, _p]),
     "gmlm_csr_transpose": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "gmlm_dst_plan": (_int, [_p, _p, _i64, _int, _i64, _i64, _p, _p, _p, _p, _p]),
     "gmlm_hub_count": (_int, [_p, _i64, _i32, C.POINTER(_i64), _p, _sz, _p]),
     "gmlm_hub_fill": (_int, [_p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "gmlm_group_plan_size": (_i64, [_i64, _i64, _i64]),
@@ -56,6 +57,7 @@ SIGNATURES = {
     "gmlm_scatter_add_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "gmlm_gather_rows_ptr": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _p]),
     "gmlm_reduce_rows_ptr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i64, _p]),
+    "gmlm_gather_rows_ptr_tma": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _int, _int, _p]),
     "gmlm_soft_mask_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _f32, _p, _i64, _p]),
     "gmlm_soft_mask_bwd_workspace_bytes": (_sz, [_i64, _i64]),
     "gmlm_soft_mask_bwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _f32, _p, _p, _i64, _p, _sz, _p]),

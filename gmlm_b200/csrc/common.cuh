@@ -90,6 +90,8 @@ template <>
 struct Pack<float, 4> {
   float4 v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(reinterpret_cast<const float4*>(p)); }
+  // coherent load (plain ld.global) for operands the same kernel also writes
+  __device__ __forceinline__ void load_rw(const float* p) { v = *reinterpret_cast<const float4*>(p); }
   __device__ __forceinline__ void store(float* p) const { __stcs(reinterpret_cast<float4*>(p), v); }
   __device__ __forceinline__ void unpack(float* f) const { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
   __device__ __forceinline__ void pack(const float* f) { v = make_float4(f[0], f[1], f[2], f[3]); }
@@ -100,6 +102,7 @@ template <>
 struct Pack<float, 1> {
   float v;
   __device__ __forceinline__ void load(const float* p) { v = __ldg(p); }
+  __device__ __forceinline__ void load_rw(const float* p) { v = *p; }
   __device__ __forceinline__ void store(float* p) const { *p = v; }
   __device__ __forceinline__ void unpack(float* f) const { f[0] = v; }
   __device__ __forceinline__ void pack(const float* f) { v = f[0]; }
@@ -110,6 +113,7 @@ template <>
 struct Pack<__nv_bfloat16, 8> {
   uint4 v;
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ __forceinline__ void load_rw(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint4*>(p); }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const { __stcs(reinterpret_cast<uint4*>(p), v); }
   __device__ __forceinline__ void unpack(float* f) const {
     // bf16 -> fp32 is a 16-bit left shift
@@ -133,6 +137,7 @@ template <>
 struct Pack<__nv_bfloat16, 1> {
   __nv_bfloat16 v;
   __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *p; }
+  __device__ __forceinline__ void load_rw(const __nv_bfloat16* p) { v = *p; }
   __device__ __forceinline__ void store(__nv_bfloat16* p) const { *p = v; }
   __device__ __forceinline__ void unpack(float* f) const { f[0] = __bfloat162float(v); }
   __device__ __forceinline__ void pack(const float* f) { v = __float2bfloat16_rn(f[0]); }

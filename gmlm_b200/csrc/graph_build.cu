@@ -37,25 +37,28 @@ inline int grid_for(int64_t n, int per_thread = 1) {
   return int(blocks < cap ? blocks : cap);
 }
 
-// device-side sticky error flag (index out of range)
-__device__ int d_index_error;
+// Index-out-of-range flag: one int PER CALL, carved from the caller's workspace (or stream-allocated), so
+// concurrent builds on different streams / threads / devices cannot see each other's errors.  Kernels
+// take the pointer; nullptr = do not record.
+__device__ __forceinline__ void flag_error(int* flag) {
+  if (flag) *flag = 1;
+}
 
-__global__ void clear_flag_kernel() { d_index_error = 0; }
-
-int read_flag(cudaStream_t st, int* out) {
+int read_flag(const int* d_flag, cudaStream_t st, int* out) {
   int h = 0;
-  GMLM_CUDA_TRY(cudaMemcpyFromSymbolAsync(&h, d_index_error, sizeof(int), 0, cudaMemcpyDeviceToHost, st));
+  GMLM_CUDA_TRY(cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   GMLM_CUDA_TRY(cudaStreamSynchronize(st));
   *out = h;
   return GMLM_OK;
 }
 
 // ------------------------------------------------------------------------ A1
-__global__ void degree_kernel(const int64_t* __restrict__ index, int64_t E, int64_t N, int32_t* __restrict__ deg) {
+__global__ void degree_kernel(const int64_t* __restrict__ index, int64_t E, int64_t N, int32_t* __restrict__ deg,
+                              int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
     int64_t i = index[e];
     if (i >= 0 && i < N) atomicAdd(deg + i, 1);   // integer atomics: order-independent result
-    else d_index_error = 1;
+    else flag_error(err);
   }
 }
 
@@ -68,7 +71,7 @@ __global__ void i32_to_f32_kernel(const int32_t* __restrict__ in, float* __restr
 struct Bounds { int32_t b[8]; int n; };
 
 __global__ void edge_type_kernel(const int64_t* __restrict__ src, int64_t E, const int32_t* __restrict__ deg,
-                                 int64_t N, Bounds bounds, int64_t* __restrict__ out) {
+                                 int64_t N, Bounds bounds, int64_t* __restrict__ out, int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
     int64_t s = src[e];
     int t = 0;
@@ -77,20 +80,20 @@ __global__ void edge_type_kernel(const int64_t* __restrict__ src, int64_t E, con
 #pragma unroll
       for (int k = 0; k < 8; ++k) t += (k < bounds.n && d > bounds.b[k]) ? 1 : 0;
     } else {
-      d_index_error = 1;
+      flag_error(err);
     }
     out[e] = t;
   }
 }
 
 __global__ void rel_hist_kernel(const int64_t* __restrict__ et, int64_t E, int R, unsigned long long* __restrict__ counts) {
+  // values outside [0, R) are simply not counted: the caller compares the total with E
   __shared__ unsigned int sh[64];
   for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
     int64_t t = et[e];
     if (t >= 0 && t < R) atomicAdd(&sh[t], 1u);
-    else d_index_error = 1;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < R; i += blockDim.x)
@@ -104,7 +107,8 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t*
                                  const int64_t* __restrict__ et, int64_t E, int64_t N, int64_t Nsrc, int R,
                                  SlotMap sm, int S,
                                  uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
-                                 int32_t* __restrict__ seg_of_edge, int32_t* __restrict__ counts) {
+                                 int32_t* __restrict__ seg_of_edge, int32_t* __restrict__ counts,
+                                 int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
     int64_t s = src[e], d = dst[e];
     int64_t t = et ? et[e] : 0;
@@ -116,7 +120,7 @@ __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t*
       key = uint32_t(d * S + slot);
       atomicAdd(counts + key, 1);
     } else {
-      d_index_error = 1;
+      flag_error(err);
     }
     keys[e] = key;
     vals[e] = int32_t(e);
@@ -133,7 +137,7 @@ __global__ void gather_col_kernel(const int64_t* __restrict__ src, const int32_t
 // ----------------------------------------------------------------------- A14
 __global__ void make_keys_t_kernel(const int64_t* __restrict__ row_of_edge, int64_t E, int64_t num_rows,
                                    uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
-                                   int32_t* __restrict__ counts) {
+                                   int32_t* __restrict__ counts, int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
     int64_t r = row_of_edge[e];
     uint32_t key = 0;
@@ -141,7 +145,7 @@ __global__ void make_keys_t_kernel(const int64_t* __restrict__ row_of_edge, int6
       key = uint32_t(r);
       atomicAdd(counts + key, 1);
     } else {
-      d_index_error = 1;
+      flag_error(err);
     }
     keys[e] = key;
     vals[e] = int32_t(e);
@@ -160,6 +164,46 @@ __global__ void gather_payload_t_kernel(const int32_t* __restrict__ payload, con
       w_t[i] = 1.0f / float(c);   // IEEE division: equals numpy float32(1)/float32(c)
     } else if (edge_w) {
       w_t[i] = edge_w[e];
+    }
+  }
+}
+
+// --------------------------------------------------- transform-first plan (dst-keyed view of the fwd CSR)
+// For  out[i] = sum_s mean_{e in seg(i,s)} Z[src_e, s]  +  Z[i, S]   (Z = x @ [W_0 | .. | W_{S-1} | root], slab s of
+// row j being row j*(S+1)+s of Z viewed as [N*(S+1), Fo]) the (dst,rel) CSR is re-read as a dst-keyed CSR whose
+// rows are whole destination nodes: the edges of segments i*S .. i*S+S-1 in order, then one self "edge" for the
+// root slab.  col = gathered Z row, w = 1/|segment| (1 for the root slab), dst = destination of every entry (the
+// payload of the transposed plan).  One thread per entry; the segment of an edge is found by binary search.
+__global__ void dst_plan_kernel(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, int64_t N, int S,
+                                int64_t E, int32_t* __restrict__ rowptr_d, int32_t* __restrict__ col_d,
+                                float* __restrict__ w_d, int32_t* __restrict__ dst_d) {
+  const int64_t total = E + N;
+  const int64_t rows = N * S;
+  for (int64_t t = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; t < total + N + 1;
+       t += int64_t(gridDim.x) * blockDim.x) {
+    if (t >= total) {                       // the N+1 row pointers
+      const int64_t i = t - total;
+      rowptr_d[i] = int32_t((i < N ? int64_t(rowptr[i * S]) : E) + i);
+      continue;
+    }
+    if (t < E) {                            // an original edge (position t of the fwd CSR)
+      int64_t lo = 0, hi = rows;            // last segment s with rowptr[s] <= t
+      while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (int64_t(rowptr[mid]) <= t) lo = mid; else hi = mid;
+      }
+      const int64_t seg = lo, i = seg / S, slot = seg - i * S;
+      const int32_t len = rowptr[seg + 1] - rowptr[seg];
+      const int64_t pos = t + i;            // i self entries precede this row
+      col_d[pos] = int32_t(int64_t(col[t]) * (S + 1) + slot);
+      w_d[pos] = 1.0f / float(len);
+      dst_d[pos] = int32_t(i);
+    } else {                                // the self entry of destination i (last in its row)
+      const int64_t i = t - E;
+      const int64_t pos = int64_t(rowptr[(i + 1) * S]) + i;
+      col_d[pos] = int32_t(i * (S + 1) + S);
+      w_d[pos] = 1.0f;
+      dst_d[pos] = int32_t(i);
     }
   }
 }
@@ -267,15 +311,20 @@ int gmlm_degree_i32(const int64_t* index, int64_t E, int64_t N, int32_t* deg, in
   GMLM_REQUIRE(E == 0 || index != nullptr, "degree: null index");
   cudaStream_t st = as_stream(stream);
   if (N == 0) return GMLM_OK;
-  if (check) { clear_flag_kernel<<<1, 1, 0, st>>>(); GMLM_LAUNCH_CHECK(); }
+  int* d_flag = nullptr;
+  if (check) {   // per-call flag from the stream-ordered allocator (this entry point has no workspace argument)
+    GMLM_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void**>(&d_flag), sizeof(int), st));
+    GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  }
   GMLM_CUDA_TRY(cudaMemsetAsync(deg, 0, size_t(N) * sizeof(int32_t), st));
   if (E > 0) {
-    degree_kernel<<<grid_for(E, 4), kThreads, 0, st>>>(index, E, N, deg);
+    degree_kernel<<<grid_for(E, 4), kThreads, 0, st>>>(index, E, N, deg, d_flag);
     GMLM_LAUNCH_CHECK();
   }
   if (check) {
     int flag = 0;
-    int rc = read_flag(st, &flag);
+    int rc = read_flag(d_flag, st, &flag);
+    cudaFreeAsync(d_flag, st);
     if (rc) return rc;
     if (flag) return fail(GMLM_ERR_INDEX, "degree: index out of range [0,%lld)", (long long)N);
   }
@@ -302,7 +351,7 @@ int gmlm_edge_type_bucket(const int64_t* src, int64_t E, const int32_t* deg, int
   for (int k = 0; k < 8; ++k) b.b[k] = k < num_bounds ? bounds_host[k] : 0;
   for (int k = 1; k < num_bounds; ++k) GMLM_REQUIRE(b.b[k] >= b.b[k - 1], "edge_type_bucket: bounds must ascend");
   if (E == 0) return GMLM_OK;
-  edge_type_kernel<<<grid_for(E, 4), kThreads, 0, as_stream(stream)>>>(src, E, deg, N, b, edge_type);
+  edge_type_kernel<<<grid_for(E, 4), kThreads, 0, as_stream(stream)>>>(src, E, deg, N, b, edge_type, nullptr);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }
@@ -325,7 +374,7 @@ size_t gmlm_csr_workspace_bytes(int64_t E, int64_t num_rows) {
   size_t sel = select_temp_bytes(num_rows);
   size_t cub_bytes = t > s ? t : s;
   if (sel > cub_bytes) cub_bytes = sel;
-  // keys_in, keys_out (u32), vals_in (i32) + hub scratch (2 x u64) + alignment slack
+  // keys_in, keys_out (u32), vals_in (i32) + hub scratch (2 x u64) + the per-call error flag + alignment slack
   return cub_bytes + 3 * (size_t(E) * 4 + 256) + 4096;
 }
 
@@ -359,13 +408,13 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
   uint32_t* keys_in = cv.take<uint32_t>(E);
   uint32_t* keys_out = cv.take<uint32_t>(E);
   int32_t* vals_in = cv.take<int32_t>(E);
+  int* d_flag = cv.take<int>(1);
   void* cub_ws = cv.take<char>(0);
   size_t cub_bytes = ws_bytes - cv.used();
 
-  clear_flag_kernel<<<1, 1, 0, st>>>();
-  GMLM_LAUNCH_CHECK();
+  GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   make_keys_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, dst, edge_type, E, N, Nsrc, edge_type ? R : 1, sm, S, keys_in,
-                                                        vals_in, seg_of_edge, rowptr);
+                                                        vals_in, seg_of_edge, rowptr, d_flag);
   GMLM_LAUNCH_CHECK();
   // counts -> exclusive prefix (in place); entry [rows] is 0 on input so rowptr[rows] = E
   size_t need = scan_temp_bytes(rows + 1);
@@ -379,7 +428,7 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
   gather_col_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, perm, E, col);
   GMLM_LAUNCH_CHECK();
   int flag = 0;
-  int rc = read_flag(st, &flag);
+  int rc = read_flag(d_flag, st, &flag);
   if (rc) return rc;
   if (flag) return fail(GMLM_ERR_INDEX, "csr_build: dst outside [0,%lld), src outside [0,%lld) or relation outside [0,%d)",
                         (long long)N, (long long)Nsrc, R);
@@ -402,12 +451,12 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
   uint32_t* keys_in = cv.take<uint32_t>(E);
   uint32_t* keys_out = cv.take<uint32_t>(E);
   int32_t* vals_in = cv.take<int32_t>(E);
+  int* d_flag = cv.take<int>(1);
   void* cub_ws = cv.take<char>(0);
   size_t cub_bytes = ws_bytes - cv.used();
 
-  clear_flag_kernel<<<1, 1, 0, st>>>();
-  GMLM_LAUNCH_CHECK();
-  make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, E, num_rows, keys_in, vals_in, rowptr_t);
+  GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+  make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, E, num_rows, keys_in, vals_in, rowptr_t, d_flag);
   GMLM_LAUNCH_CHECK();
   size_t need = scan_temp_bytes(num_rows + 1);
   GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: scan workspace");
@@ -419,9 +468,21 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
   gather_payload_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(payload, edge_w, fwd_rowptr, perm_t, E, payload_t, w_t);
   GMLM_LAUNCH_CHECK();
   int flag = 0;
-  int rc = read_flag(st, &flag);
+  int rc = read_flag(d_flag, st, &flag);
   if (rc) return rc;
   if (flag) return fail(GMLM_ERR_INDEX, "csr_transpose: row id outside [0,%lld)", (long long)num_rows);
+  return GMLM_OK;
+}
+
+int gmlm_dst_plan(const int32_t* rowptr, const int32_t* col, int64_t N, int S, int64_t E, int64_t Nsrc,
+                  int32_t* rowptr_d, int32_t* col_d, float* w_d, int32_t* dst_d, void* stream) {
+  GMLM_REQUIRE(N >= 0 && S >= 1 && E >= 0 && Nsrc >= N, "dst_plan: bad sizes");
+  GMLM_REQUIRE(E + N < (int64_t(1) << 31) - 1 && Nsrc * (S + 1) < (int64_t(1) << 31) - 1, "dst_plan: int32 limits");
+  GMLM_REQUIRE(rowptr && rowptr_d && (E + N == 0 || (col_d && w_d && dst_d)) && (E == 0 || col), "dst_plan: null pointer");
+  const int64_t threads = E + 2 * N + 1;
+  dst_plan_kernel<<<grid_for(threads, 2), kThreads, 0, as_stream(stream)>>>(rowptr, col, N, S, E, rowptr_d, col_d, w_d,
+                                                                           dst_d);
+  GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }
 

@@ -17,7 +17,7 @@ int tuning_halo_pull_threads();  // threads per CTA of gather_rows_ptr (0 = 256)
 namespace {
 
 template <typename T, int VEC, bool ADD>
-__global__ void __launch_bounds__(256) rows_move_kernel(const T* __restrict__ src, int64_t lds, T* __restrict__ dst,
+__global__ void __launch_bounds__(256) rows_move_kernel(const T* __restrict__ src, int64_t lds, T* dst,
                                                         int64_t ldd, const int64_t* __restrict__ ids, int64_t n,
                                                         int64_t feat, int64_t src_rows) {
   const int64_t packs = (feat + VEC - 1) / VEC;
@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) rows_move_kernel(const T* __restrict__ sr
     if (ADD) {  // dst[id] += src[k]
       Pack<T, VEC> a, b;
       a.load(src + k * lds + f);
-      b.load(dst + id * ldd + f);
+      b.load_rw(dst + id * ldd + f);          // read-modify-write operand: coherent load, not ld.global.nc
       float fa[VEC], fb[VEC];
       a.unpack(fa);
       b.unpack(fb);
@@ -81,11 +81,106 @@ __global__ void __launch_bounds__(1024) gather_ptr_kernel(const T* const* __rest
   }
 }
 
+
+// ------------------------------------------------------------------------------ TMA halo pull
+// out[out_ids[k], :] = *(row_ptrs[k])  with the rows moved by the bulk-copy engine (cp.async.bulk, SASS
+// UBLKCP) instead of by LDG/STG:  peer memory --bulk load--> shared-memory ring --bulk store--> local HBM.
+//
+// Why (measured in round 1): an LDG-driven pull that runs NEXT TO the aggregation kernel is
+// zero-sum.  Its 3 us NVLink requests sit in the same per-SM load queue as the aggregation's 1 us HBM
+// gathers (sprinkled over all SMs it halved the aggregation's throughput), and confined to a few SMs it
+// is capped by what one SM's load path keeps in flight (~24 KB: 260 GB/s from 32 SMs).  Bulk copies do
+// not pass through the LSU / L1 queue and their bytes in flight are bounded by SHARED MEMORY instead:
+// one warp keeps SLOTS-2 batches of 32 rows (16 KB each at 512-byte rows) outstanding, i.e. ~160 KB per
+// SM, so a couple of dozen single-warp CTAs cover the NVLink bandwidth-delay product while the
+// aggregation's CTAs (which use no shared memory) stay resident on the same SMs.
+//
+// One warp per CTA, lane l moves row l of a batch.  Per slot one mbarrier: lane 0 posts the expected
+// byte count, every lane issues its row's bulk load against it, the warp waits for the phase, every
+// lane issues its row's bulk store and commits it to its own bulk group; a slot is refilled two
+// iterations later, after `wait_group.read 1` has shown that the store which read it has drained.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(32, 1) gather_ptr_tma_kernel(const uint64_t* __restrict__ row_ptrs,
+                                                               const int64_t* __restrict__ out_ids, int64_t n,
+                                                               uint32_t row_bytes, uint8_t* __restrict__ out,
+                                                               int64_t ldo_bytes, int slots) {
+  extern __shared__ __align__(128) uint8_t tma_smem[];
+  const int lane = threadIdx.x;
+  const uint32_t slot_bytes = 32u * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_smem + size_t(slots) * slot_bytes);
+  if (lane == 0) {
+    for (int s = 0; s < slots; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t n_batches = (n + 31) / 32;
+  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int depth = slots - 2;                       // batches in flight
+
+  auto issue_load = [&](int64_t it) {
+    const int64_t b = first + it * stride;
+    if (b >= n_batches) return;
+    const int s = int(it % slots);
+    const int64_t k = b * 32 + lane;
+    const int cnt = int(min(int64_t(32), n - b * 32));
+    const uint32_t bar = smem_addr(bars + s);
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(cnt) * row_bytes)
+                   : "memory");
+    __syncwarp();
+    if (lane < cnt) {
+      const uint64_t src = row_ptrs[k];
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_addr(tma_smem + size_t(s) * slot_bytes + size_t(lane) * row_bytes)),
+                   "l"(src), "r"(row_bytes), "r"(bar)
+                   : "memory");
+    }
+  };
+
+  for (int it = 0; it < depth; ++it) issue_load(it);
+  for (int64_t it = 0;; ++it) {
+    const int64_t b = first + it * stride;
+    if (b >= n_batches) break;
+    // the slot refilled now was read by the store of iteration it-2: all but my newest store group are done reading
+    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    __syncwarp();
+    issue_load(it + depth);
+    const int s = int(it % slots);
+    const uint32_t bar = smem_addr(bars + s);
+    const uint32_t parity = uint32_t((it / slots) & 1);
+    uint32_t spins = 0;
+    while (true) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (ok) break;
+      if (++spins > (1u << 26)) __trap();            // a lost transfer traps instead of hanging the GPU
+    }
+    const int64_t k = b * 32 + lane;
+    if (k < n) {
+      const int64_t o = out_ids ? out_ids[k] : k;
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + o * ldo_bytes),
+                   "r"(smem_addr(tma_smem + size_t(s) * slot_bytes + size_t(lane) * row_bytes)), "r"(row_bytes)
+                   : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // every row has landed in `out`
+}
+
 // dst[row_ids[r], :] += sum_{e in [rowptr[r], rowptr[r+1])} *(entry_ptrs[e])[0:feat]
 // fp32 accumulation in entry order (entries of a row are stored in a fixed peer order), one
 // rounding at the end; each destination row is owned by one thread group => no atomics.
 template <typename T, int VEC>
-__global__ void __launch_bounds__(256) reduce_ptr_kernel(T* __restrict__ dst, int64_t ldd,
+__global__ void __launch_bounds__(256) reduce_ptr_kernel(T* dst, int64_t ldd,
                                                          const int64_t* __restrict__ row_ids,
                                                          const int32_t* __restrict__ rowptr,
                                                          const T* const* __restrict__ entry_ptrs, int64_t n_rows,
@@ -98,7 +193,7 @@ __global__ void __launch_bounds__(256) reduce_ptr_kernel(T* __restrict__ dst, in
     const int32_t b = rowptr[r], e = rowptr[r + 1];
     T* d = dst + row_ids[r] * ldd + f;
     Pack<T, VEC> p;
-    p.load(d);
+    p.load_rw(d);                               // read-modify-write operand: coherent load
     float acc[VEC];
     p.unpack(acc);
     int32_t k = b;
@@ -225,6 +320,41 @@ extern "C" int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t 
     reduce_ptr_kernel<__nv_bfloat16, 8><<<unsigned(blocks), 256, 0, st>>>(
         static_cast<__nv_bfloat16*>(dst), ldd, row_ids, rowptr,
         reinterpret_cast<const __nv_bfloat16* const*>(entry_ptrs), n_rows, feat);
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+// TMA variant of gmlm_gather_rows_ptr: `ctas` single-warp CTAs, each with a shared-memory ring of
+// `smem_kb` KiB (0 = 192).  Rows must be 16-byte multiples, 16-byte aligned on both sides, <= 2 KiB.
+extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
+                                        int64_t n, void* out, int64_t ldo, int ctas, int smem_kb, void* stream) {
+  GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "gather_rows_ptr_tma: dtype must be GMLM_F32 or GMLM_BF16");
+  const int esz = dtype == GMLM_F32 ? 4 : 2;
+  const int64_t row_bytes = feat * esz;
+  GMLM_REQUIRE(n >= 0 && feat >= 0 && ldo >= feat, "gather_rows_ptr_tma: bad sizes");
+  GMLM_REQUIRE(row_bytes % 16 == 0 && (ldo * esz) % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+               "gather_rows_ptr_tma: rows must be 16-byte multiples and 16-byte aligned");
+  if (n == 0 || feat == 0) return GMLM_OK;
+  GMLM_REQUIRE(row_ptrs && out, "gather_rows_ptr_tma: null pointer");
+  if (smem_kb <= 0) smem_kb = 192;
+  GMLM_REQUIRE(smem_kb <= 224, "gather_rows_ptr_tma: at most 224 KiB of shared memory per CTA");
+  const int64_t slot_bytes = 32 * row_bytes;
+  const int slots = int(std::min<int64_t>(64, (int64_t(smem_kb) * 1024 - 64 * 8) / slot_bytes));
+  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (<= 2 KiB at 192 KiB)");
+  const size_t smem = size_t(slots) * slot_bytes + size_t(slots) * 8;
+  if (ctas <= 0) ctas = num_sms();
+  const int64_t n_batches = (n + 31) / 32;
+  if (ctas > n_batches) ctas = int(n_batches);
+  auto kern = gather_ptr_tma_kernel<0>;
+  static size_t configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (configured[dev] < smem) {
+    GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    configured[dev] = 224 * 1024;
+  }
+  kern<<<unsigned(ctas), 32, smem, as_stream(stream)>>>(reinterpret_cast<const uint64_t*>(row_ptrs), out_ids, n,
+                                                        uint32_t(row_bytes), static_cast<uint8_t*>(out),
+                                                        ldo * esz, slots);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }

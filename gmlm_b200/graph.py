@@ -195,6 +195,7 @@ class RelGraph:
     num_src: int = -1              # source rows; > num_nodes for a partition with halo rows
     seg_of_edge: Optional[torch.Tensor] = None   # int32 [E] forward segment of each ORIGINAL edge (kept on request)
     _keepalive: list = field(default_factory=list, repr=False)
+    _dst_plan: Optional[tuple] = field(default=None, repr=False)
 
     def __post_init__(self):
         if self.num_src < 0:
@@ -203,6 +204,33 @@ class RelGraph:
     @property
     def num_slots(self) -> int:
         return len(self.live_rels)
+
+    def dst_plan(self):
+        """(fwd, bwd) CSR pair of the TRANSFORM-FIRST formulation (``gmlm_dst_plan``, include/gmlm_b200.h), built
+        on first use and kept with the graph:
+
+          fwd: rows = destination nodes; entries gather rows of Z = x @ [W_0|..|W_{S-1}|root] viewed as
+               [num_src*(S+1), Fo] (col = src*(S+1)+slot, w = 1/|segment|; last entry = the node's own root slab)
+          bwd: rows = (src, slot) pairs, i.e. the rows of dZ; entries gather rows of grad_out [N, Fo]."""
+        if self._dst_plan is not None:
+            return self._dst_plan
+        lib = _lib.load()
+        fwd = self.fwd
+        dev = fwd.rowptr.device
+        n, S, E = self.num_nodes, self.num_slots, self.num_edges
+        with torch.cuda.device(dev):
+            rowptr_d = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            col_d = torch.empty(E + n, dtype=torch.int32, device=dev)
+            w_d = torch.empty(E + n, dtype=torch.float32, device=dev)
+            dst_d = torch.empty(E + n, dtype=torch.int32, device=dev)
+            _lib.check(lib.gmlm_dst_plan(_ptr(fwd.rowptr), _ptr(fwd.col), n, S, E, self.num_src, _ptr(rowptr_d),
+                                         _ptr(col_d), _ptr(w_d), _ptr(dst_d), _stream(dev)), "dst_plan")
+        f = CSR(rowptr=rowptr_d, col=col_d, num_rows=n, w=w_d, hub_thresh=fwd.hub_thresh)
+        f.plan_hubs()
+        f.plan_groups()
+        b = transpose_csr(col_d.long(), dst_d, self.num_src * (S + 1), edge_w=w_d, hub_thresh=fwd.hub_thresh)
+        self._dst_plan = (f, b)
+        return self._dst_plan
 
     @staticmethod
     def build(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int, num_relations: int,

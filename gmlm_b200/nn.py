@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .graph import RelGraph, get_rel_graph
-from .ops import graph_norm, rgcn_aggregate, rgcn_transform, rgcn_transform_ok
+from .ops import graph_norm, rgcn_aggregate, rgcn_transform, rgcn_transform_first, rgcn_transform_ok
 
 
 def glorot_(t: Optional[torch.Tensor]):
@@ -45,6 +45,7 @@ class RGCNConv(nn.Module):
         super().__init__()
         self.out_dtype = out_dtype  # None = upstream behaviour (default dtype); bf16 for the bandwidth study
         self.use_tcgen05 = True     # bf16 activations: dense transform on the tcgen05 GEMM (else cuBLAS)
+        self.transform_first = None  # None = by the byte-count model below; True / False force the formulation
         if num_blocks is not None:
             raise NotImplementedError("gmlm_b200.RGCNConv: block-diagonal decomposition is not on the reference "
                                       "path (main.py uses num_bases=30)")
@@ -89,6 +90,21 @@ class RGCNConv(nn.Module):
                                                                 self.out_channels)
         return w
 
+    def _use_transform_first(self, graph: RelGraph) -> bool:
+        """Bytes moved per formulation (element counts; index traffic is the same order in both):
+          aggregate-first : gather E*Fi, write + re-read H = 2*N*S*Fi
+          transform-first : write + re-read Z = 2*Nsrc*(S+1)*Fo, gather (E+N)*Fo
+        Transform-first wins for layers that narrow (the 256 -> 64 input layer of the bandwidth study, the
+        1703 -> 512 input layer on Cornell-shaped data); widening layers keep aggregate-first."""
+        if self.root is None:
+            return False
+        if self.transform_first is not None:
+            return bool(self.transform_first)
+        S, fi, fo = graph.num_slots, self.in_channels, self.out_channels
+        agg_first = graph.num_edges * fi + 2 * graph.num_nodes * S * fi
+        tr_first = 2 * graph.num_src * (S + 1) * fo + (graph.num_edges + graph.num_nodes) * fo
+        return tr_first < 0.8 * agg_first
+
     def forward(self, x: torch.Tensor, edge_index, edge_type: Optional[torch.Tensor] = None) -> torch.Tensor:
         if isinstance(edge_index, RelGraph):
             graph = edge_index
@@ -100,14 +116,17 @@ class RGCNConv(nn.Module):
             raise NotImplementedError("gmlm_b200.RGCNConv: integer node-id inputs are not on the reference path")
         if x.size(1) != self.in_channels:
             raise _lib.GmlmError(f"RGCNConv: x has {x.size(1)} features, layer expects {self.in_channels}")
-        h = rgcn_aggregate(x, graph)                                   # [N, S*Fi], x's dtype
-        if graph.num_src != graph.num_nodes:
-            # destination-row partition: x = [local rows ‖ halo rows]; the root term is over the local rows
-            x = x[: graph.num_nodes]
         w = self.composed_weight()
         live = graph.live_rels
         if len(live) != self.num_relations:
             w = w.index_select(0, torch.as_tensor(live, device=w.device))
+        if self._use_transform_first(graph):
+            # narrowing layer: Z = x @ [W_r | root] first, then gather Fo-wide slabs; H is never materialised
+            return rgcn_transform_first(x, graph, w, self.root, self.bias, self.out_dtype or torch.get_default_dtype())
+        h = rgcn_aggregate(x, graph)                                   # [N, S*Fi], x's dtype
+        if graph.num_src != graph.num_nodes:
+            # destination-row partition: x = [local rows ‖ halo rows]; the root term is over the local rows
+            x = x[: graph.num_nodes]
         w = w.reshape(len(live) * self.in_channels, self.out_channels)
         # upstream accumulates into `out = torch.zeros(N, Fo)` of the default dtype (fp32) while the
         # matmuls run in the operand dtype, or in the autocast dtype under torch.amp.autocast

@@ -399,6 +399,104 @@ class _RGCNTransform(torch.autograd.Function):
         return dh, dx, dw, droot, dbias, None
 
 
+def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """a @ b with an fp32 result for a parameter gradient (a reduction over up to millions of rows must not be
+    rounded to 8 mantissa bits before it reaches the fp32 parameter)."""
+    if a.dtype == torch.float32:
+        return a @ b
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return (a @ b).float()
+
+
+def linear_nt_ok(x: torch.Tensor, n_out: int) -> bool:
+    """Shapes ``linear_nt`` runs on the tcgen05 GEMM: bf16 CUDA activations, K a multiple of 64, N of 32."""
+    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and x.size(1) % 64 == 0 and x.size(1) > 0
+            and n_out % 32 == 0 and n_out > 0)
+
+
+class _LinearNT(torch.autograd.Function):
+    """y = x @ wt.T + bias on the tcgen05 GEMM (bf16 operands, fp32 accumulation).  Backward: dx on the same
+    kernel when its shape fits (K = n_out a multiple of 64), weight gradient as an fp32 reduction."""
+
+    @staticmethod
+    def forward(ctx, x, wt, bias, out_dtype):
+        wtb = wt.detach().to(torch.bfloat16).contiguous()                 # [N_out, K]
+        y = gemm_nt(x, wtb, bias=bias, out_dtype=out_dtype)
+        ctx.save_for_backward(x, wtb)
+        ctx.dtypes = (wt.dtype, None if bias is None else bias.dtype)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, wtb = ctx.saved_tensors
+        gb = g.to(torch.bfloat16).contiguous()
+        dx = dwt = dbias = None
+        if ctx.needs_input_grad[0]:
+            if wtb.size(0) % 64 == 0 and wtb.size(1) % 32 == 0:
+                dx = gemm_nt(gb, wtb.t().contiguous())                     # [M, N_out] x [K, N_out]^T
+            else:
+                dx = gb @ wtb
+        if ctx.needs_input_grad[1]:
+            dwt = _mm_f32(gb.t(), x).to(ctx.dtypes[0])
+        if ctx.needs_input_grad[2]:
+            dbias = torch.ops.gmlm.colstats(gb)[0].to(ctx.dtypes[1])       # one pass, fp64 accumulate, deterministic
+        return dx, dwt, dbias, None
+
+
+def linear_nt(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
+              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``F.linear(x, wt, bias)`` for the bf16 pipeline (``linear_nt_ok``) on the tcgen05 GEMM."""
+    return _LinearNT.apply(x, wt, bias, out_dtype or x.dtype)
+
+
+class _PlanAggregate(torch.autograd.Function):
+    """out = weighted gather-reduce of ``rows`` over ``fwd``; backward = the same over ``bwd`` (its transpose)."""
+
+    @staticmethod
+    def forward(ctx, rows, fwd: CSR, bwd: CSR):
+        ctx.bwd = bwd
+        ctx.in_dtype = rows.dtype
+        return spmm(rows, fwd, _lib.AGG_WEIGHTED)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        if g.dtype != ctx.in_dtype:
+            g = g.to(ctx.in_dtype)
+        return spmm(g, ctx.bwd, _lib.AGG_WEIGHTED), None, None
+
+
+def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, w_live: torch.Tensor, root: torch.Tensor,
+                         bias: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+    """RGCNConv as TRANSFORM-then-aggregate (A5+A6 fused by linearity of the mean; include/gmlm_b200.h
+    ``gmlm_dst_plan``):  Z = x @ [W_0 | .. | W_{S-1} | root] (+ bias on the root slab),
+    out[i] = sum_e w_e Z[src_e, slot_e] + Z[i, S].  The [N, S*Fi] matrix H of the aggregate-first form is never
+    materialised and the gather moves Fo-wide rows instead of Fi-wide ones.
+
+    x [num_src, Fi]; w_live [S, Fi, Fo] (composed weights of the populated relations); root [Fi, Fo]."""
+    _require_cuda(x, "x")
+    S, fi, fo = w_live.shape
+    if S != graph.num_slots or x.size(0) != graph.num_src or x.size(1) != fi:
+        raise _lib.GmlmError("rgcn_transform_first: shape mismatch")
+    fplan, bplan = graph.dst_plan()
+    wcat_t = torch.cat([w_live.permute(0, 2, 1).reshape(S * fo, fi), root.t()], dim=0)     # [(S+1)*Fo, Fi]
+    bias_cat = None
+    if bias is not None:
+        bias_cat = torch.cat([bias.new_zeros(S * fo), bias])
+    if linear_nt_ok(x, (S + 1) * fo) and not torch.is_autocast_enabled("cuda"):
+        z = linear_nt(x, wcat_t, bias_cat)
+    else:
+        z = torch.nn.functional.linear(x, wcat_t if torch.is_autocast_enabled("cuda") else wcat_t.to(x.dtype),
+                                       None if bias_cat is None else
+                                       (bias_cat if torch.is_autocast_enabled("cuda") else bias_cat.to(x.dtype)))
+        if z.dtype not in _DT:
+            z = z.float()                                   # autocast produced fp16: the kernels take fp32 / bf16
+    out = _PlanAggregate.apply(z.view(graph.num_src * (S + 1), fo), fplan, bplan)
+    return out if out.dtype == out_dtype else out.to(out_dtype)
+
+
 def rgcn_transform_ok(h: torch.Tensor, x: torch.Tensor, fo: int) -> bool:
     """Shapes the tcgen05 path covers: bf16 activations, K blocks of 64, Fo a multiple of 64."""
     return (h.is_cuda and h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and h.size(1) % 64 == 0

@@ -584,30 +584,45 @@ class PeerHalo:
                    "reduce_rows_ptr")
         return gx
 
-    def backward_fetched(self, gh: torch.Tensor) -> torch.Tensor:
+    def backward_fetched(self, gh: torch.Tensor, local_last: bool = True, signals: bool = True) -> torch.Tensor:
         """Variant of ``backward_pushed`` whose halo gradients travel by copy engine instead of by the
         aggregation kernel's remote stores (measured ~450 GB/s, which bounds the pushed slices): every owner
-        slice is aggregated into my own gX tail at HBM speed; after a barrier its owner fetches it with ONE
-        contiguous device-to-device copy into its staging area while the next slice is being aggregated;
-        one local reduce at the end (same plan, same fixed order per row as the pushed variant).
-        NOT YET MEASURED (written at the end of round 1 with the GPU budget spent): `bench.py --bwd fetch`."""
+        slice is aggregated into my own gX tail at HBM speed; its owner then fetches it with ONE contiguous
+        device-to-device copy into its staging area while the next slice is being aggregated; one local reduce
+        at the end (same plan, same fixed order per row as the pushed variant => bit-equal to it).
+
+        ``local_last``: aggregate the local rows AFTER the owner slices on the main stream, so that the last
+        owner slice's transfer is hidden under them instead of being exposed in front of the reduce.
+        ``signals``: pairwise symmetric-memory signals (producer -> owner, on the copy stream) instead of an
+        all-rank barrier after every slice: the main stream never waits for another rank inside the loop."""
         from . import _lib
         from .ops import spmm
         lib = _liblib()
         main = torch.cuda.current_stream()
-        n_local = self.part.n_local
+        part = self.part
+        world, rank = part.world, part.rank
+        n_local = part.n_local
         gx = self.gX[:n_local]
         if not hasattr(self, "copy_stream"):
             self.copy_stream = torch.cuda.Stream(device=gx.device)
         self.hg.barrier()                                    # peers have fetched last step's slices from my gX tail
-        start = torch.cuda.Event()
-        start.record(main)
-        self.comm_stream.wait_event(start)
-        with torch.cuda.stream(self.comm_stream):
-            spmm(gh, self.slice_local, _lib.AGG_WEIGHTED, out=gx)
-        for (csr, a, b, pull), dst in zip(self.slices, self.fetch_dst):
+        if not local_last:
+            start = torch.cuda.Event()
+            start.record(main)
+            self.comm_stream.wait_event(start)
+            with torch.cuda.stream(self.comm_stream):
+                spmm(gh, self.slice_local, _lib.AGG_WEIGHTED, out=gx)
+        for k, ((csr, a, b, pull), dst) in enumerate(zip(self.slices, self.fetch_dst), start=1):
+            owner, src_rank = (rank + k) % world, (rank - k) % world
             if csr is not None:
                 spmm(gh, csr, _lib.AGG_WEIGHTED, out=self.gX[a:b])
+            if signals:
+                self.hg.put_signal(owner, 1)                 # my slice for `owner` is complete (release)
+                with torch.cuda.stream(self.copy_stream):
+                    self.hg.wait_signal(src_rank, 1)         # the slice `src_rank` computed for me is complete
+                    if pull is not None and dst is not None:
+                        dst.copy_(pull[0], non_blocking=True)
+                continue
             self.hg.barrier()                                # every rank has finished this step's slice
             ev = torch.cuda.Event()
             ev.record(main)
@@ -615,7 +630,10 @@ class PeerHalo:
                 with torch.cuda.stream(self.copy_stream):
                     self.copy_stream.wait_event(ev)
                     dst.copy_(pull[0], non_blocking=True)    # contiguous remote rows over NVLink (copy engine)
-        main.wait_stream(self.comm_stream)
+        if local_last:
+            spmm(gh, self.slice_local, _lib.AGG_WEIGHTED, out=gx)
+        else:
+            main.wait_stream(self.comm_stream)
         main.wait_stream(self.copy_stream)
         n_rows = int(self.push_rows.numel())
         if n_rows:
@@ -673,6 +691,10 @@ class PeerHalo:
         # sprinkled over every SM they halved the aggregation's throughput (8 GPUs, 148 x 256 threads)
         self.pull_ctas_overlapped = int(pull_ctas_overlapped) or 32
         self.fwd_stage_rows = [int(st[3].numel()) for st in self.fwd_stages]
+        # transport of the overlapped stages (k >= 1): 0 = the LDG pull kernel confined to `pull_ctas_overlapped`
+        # CTAs; > 0 = that many single-warp bulk-copy (TMA) CTAs, which do not share the aggregation's load queues
+        self.pull_tma_ctas = int(getattr(self, "pull_tma_ctas", 0))
+        self.pull_tma_stage0 = bool(getattr(self, "pull_tma_stage0", False))
         return self
 
     def forward_staged(self, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -696,7 +718,13 @@ class PeerHalo:
         with torch.cuda.stream(self.pull_stream):
             for k, (_, _, _, ptrs, outs) in enumerate(self.fwd_stages):
                 cnt = int(ptrs.numel())
-                if cnt:
+                if cnt and self.pull_tma_ctas > 0 and (k > 0 or self.pull_tma_stage0):
+                    # bulk-copy engine transport: stage 0 has the GPU to itself (one CTA per SM), later stages
+                    # run under an aggregation kernel from a few single-warp CTAs
+                    _check(lib.gmlm_gather_rows_ptr_tma(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
+                                                        self.feat, 0 if k == 0 else self.pull_tma_ctas, 0,
+                                                        _st(tail.device)), "gather_rows_ptr_tma")
+                elif cnt:
                     # stage 0 has the GPU to itself; later stages share it with an aggregation kernel
                     lib.gmlm_set_tuning(b"halo_pull_ctas", 0 if k == 0 else self.pull_ctas_overlapped)
                     lib.gmlm_set_tuning(b"halo_pull_threads", 0 if k == 0 else 1024)
@@ -845,287 +873,3 @@ def _st(dev):
 def _dt(dtype):
     from . import _lib
     return {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[dtype]
-
-
-# ----------------------------------------------------------------------------- multi-GPU bench
-def run_partitioned_bench(args):
-    """bench.py --gpus N (N > 1): BASELINE.json configs[4] — the 10M-node / 200M-edge power-law
-    graph, destination-row partitioned, halo exchange + aggregation forward and backward."""
-    import json
-    import os
-    import statistics
-    import sys
-    import time
-
-    import gmlm_b200 as G
-    from gmlm_b200 import _lib, synth
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
-    if world == 1:
-        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    dev = torch.device(f"cuda:{local_rank}")
-    torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", device_id=dev)
-    try:
-        w = synth.WORKLOADS[args.workload]
-        n = int(w.num_nodes * args.scale)
-        e = int(w.num_edges * args.scale)
-        feat = w.feat
-        dtype = torch.bfloat16 if w.dtype == "bf16" else torch.float32
-        esize = 2 if dtype == torch.bfloat16 else 4
-
-        # every rank generates the same seeded graph (device RNG streams are identical across
-        # identical GPUs) and keeps only its destination range
-        t0 = time.perf_counter()
-        ei = synth.make_graph(w, device=dev, num_nodes=n, num_edges=e)
-        et = G.edge_type_from_degree(ei, n)                      # A2 needs the GLOBAL out-degree
-        in_deg = torch.ops.gmlm.degree_i32(ei[1], n)
-        pmode = getattr(args, "partition", "random")
-        if pmode == "random":
-            ei, ranges, _ = random_relabel(ei, n, world)         # balanced compute, ingress AND egress
-        elif pmode == "cyclic":
-            ei, ranges, _ = cyclic_relabel(ei, n, world)
-        else:
-            # cost per node in edge units: fwd writes S (dst,rel) rows, bwd writes 1; each edge is read twice
-            ranges = partition_ranges(in_deg, world, node_cost=2.5)
-        live = sorted(torch.unique(et).tolist())                 # one relation->slot layout for all ranks
-        part = build_local_part(ei, et, ranges, rank)
-        del ei, et, in_deg
-        torch.cuda.empty_cache()
-        fwd_mode = getattr(args, "fwd", "pull")
-        if fwd_mode == "packed" and getattr(args, "halo", "p2p") == "p2p":
-            # halo rows renumbered (owner, stage of first use, id): contiguous ranges for copy-engine transfers
-            k_req = int(getattr(args, "fwd_stages", 1))
-            fr = default_stage_fractions(k_req if k_req > 1 else 4)
-            part = restage_part(part, halo_first_use_stage(part, live, fr), fr)
-        g = G.RelGraph.build(part.edge_index, part.edge_type, part.n_local, 5, num_src=part.n_src, live_rels=live,
-                             keep_seg=True)
-        torch.cuda.synchronize()
-        t_setup = time.perf_counter() - t0
-        S = g.num_slots
-        # persistent buffers: the node features live in the head of the gather matrix X, the halo
-        # rows land straight in its tail (no per-step concat / clone)
-        halo_mode = getattr(args, "halo", "p2p")
-        peer = None
-        if halo_mode == "p2p":
-            try:
-                peer = PeerHalo(part, feat, dtype)
-            except Exception as ex:  # symmetric memory unavailable on this box: use the NCCL exchange
-                if rank == 0:
-                    print(f"[bench] peer-memory halo unavailable ({ex!r}); using NCCL all_to_all", file=sys.stderr)
-                halo_mode = "nccl"
-        ok = torch.tensor([1 if peer is not None else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if int(ok.item()) == 0:
-            peer, halo_mode = None, "nccl"
-        bwd_mode = getattr(args, "bwd", "push") if peer is not None else "plain"
-        if getattr(args, "no_bwd_pipeline", False) and peer is not None:
-            bwd_mode = "plain"
-        pipelined = bwd_mode in ("push", "pipeline", "fetch")
-        if pipelined:
-            peer.build_backward_slices(g)
-        if bwd_mode in ("push", "fetch"):
-            peer.build_backward_push(g)
-        fwd_stages = int(getattr(args, "fwd_stages", 1)) if peer is not None else 0
-        packed = peer is not None and fwd_mode == "packed" and part.recv_stage_counts is not None
-        if packed:
-            peer.build_forward_packed(g)
-            fwd_stages = 0
-            h_buf = torch.empty((part.n_local * S, feat), dtype=dtype, device=dev)
-        if fwd_stages > 1:
-            peer.build_forward_stages(g, n_stages=fwd_stages, pull_ctas_overlapped=int(getattr(args, "pull_ctas", 0)))
-            h_buf = torch.empty((part.n_local * S, feat), dtype=dtype, device=dev)
-        if peer is not None:
-            X, gX_buf = peer.X, peer.gX
-        else:
-            X = torch.empty((part.n_src, feat), dtype=dtype, device=dev)
-            gX_buf = None
-        X[: part.n_local] = synth.make_features(part.n_local, feat, device=dev, seed=42 + rank, dtype=dtype)
-        x_local = X[: part.n_local]
-        gh = synth.make_features(part.n_local * S, feat, device=dev, seed=7 + rank, dtype=dtype)
-        n_send = int(sum(part.send_splits))
-        if peer is None:
-            send_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
-            back_buf = torch.empty((n_send, feat), dtype=dtype, device=dev)
-        # kernels of libgmlm_b200.so per step (symmetric-memory barriers and copies are not counted)
-        def _nk(csr):
-            return 0 if csr is None else 1 + (2 if csr.n_hub else 0)
-        if packed:
-            launches_per_step = sum(_nk(st[0]) for st in peer.packed_stages) + 1
-        elif peer is not None and fwd_stages > 1:
-            launches_per_step = sum(_nk(st[0]) + (1 if st[3].numel() else 0) for st in peer.fwd_stages)
-        else:
-            launches_per_step = _nk(g.fwd) + 1
-        if bwd_mode in ("push", "fetch"):
-            launches_per_step += _nk(peer.slice_local) + sum(_nk(sl[0]) for sl in peer.slices) + 1
-        elif bwd_mode == "pipeline":
-            launches_per_step += _nk(peer.slice_local) + sum(_nk(sl[0]) + 1 for sl in peer.slices)
-        else:
-            launches_per_step += _nk(g.bwd) + 1
-        PH = 5
-        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(PH + 1)] for _ in range(args.steps)]
-
-        def step(k=None):
-            rec = (lambda i: ev[k][i].record()) if k is not None else (lambda i: None)
-            rec(0)
-            if packed:
-                rec(1)
-                rec(2)
-                h = peer.forward_packed(out=h_buf)        # owners pack, copy engines fetch under the aggregation
-            elif peer is not None and fwd_stages > 1:
-                rec(1)
-                rec(2)
-                h = peer.forward_staged(out=h_buf)        # halo pulled stage by stage under the aggregation
-            elif peer is not None:
-                rec(1)
-                peer.pull_forward()                                                  # rows read over NVLink peer memory
-            else:
-                _pack(x_local, part.send_ids, out=send_buf)                          # pack (gmlm_gather_rows)
-                rec(1)
-                dist.all_to_all_single(X[part.n_local:], send_buf, output_split_sizes=part.recv_splits,
-                                       input_split_sizes=part.send_splits)           # halo rows via NCCL
-            if not (packed or (peer is not None and fwd_stages > 1)):
-                rec(2)
-                h = G.spmm(X, g.fwd, _lib.AGG_MEAN)                                  # A5 on [local ‖ halo]
-            rec(3)
-            if peer is not None and pipelined:
-                if bwd_mode == "push":
-                    gx = peer.backward_pushed(gh)     # A14 slice by slice, written straight into the owners' staging
-                elif bwd_mode == "fetch":
-                    gx = peer.backward_fetched(gh)    # A14 slice by slice, owners fetch by copy engine, one reduce
-                else:
-                    gx = peer.backward_pipelined(gh)  # A14 slice by slice, owners pull while the next slice runs
-                rec(4)
-                rec(5)
-                return h, gx
-            gX = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED, out=gX_buf)                    # A14: grads for local AND halo rows
-            rec(4)
-            if peer is not None:
-                gx = peer.pull_backward()                                            # owners pull-add their halo grads
-            else:
-                dist.all_to_all_single(back_buf, gX[part.n_local:], output_split_sizes=part.send_splits,
-                                       input_split_sizes=part.recv_splits)
-                gx = gX[: part.n_local]
-                off = 0
-                for cnt in part.send_splits:                                         # peer order, unique ids per peer
-                    if cnt:
-                        _unpack_add(gx, part.send_ids[off:off + cnt], back_buf[off:off + cnt])
-                    off += cnt
-            rec(5)
-            return h, gx
-
-        for _ in range(args.warmup):
-            step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        sampler = None
-        if rank == 0:
-            from bench import ClockSampler
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-        a.record()
-        for k in range(args.steps):
-            step(k)
-        b.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        timeline = None
-        if peer is not None and fwd_stages > 1:            # one extra, untimed step with per-stage events
-            peer.stage_timing = True
-            step()
-            torch.cuda.synchronize()
-            peer.stage_timing = False
-            timeline = {"pull_end_ms": peer.timeline_ms()[0], "block_end_ms": peer.timeline_ms()[1],
-                        "rows_per_stage": peer.fwd_stage_rows}
-            dist.barrier()
-        phases = torch.tensor([statistics.mean(ev[k][i].elapsed_time(ev[k][i + 1]) for k in range(args.steps))
-                               for i in range(PH)], device=dev, dtype=torch.float64)
-        phases_all = [torch.zeros_like(phases) for _ in range(world)]
-        dist.all_gather(phases_all, phases)
-        ms = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)               # device time, max over ranks
-        # ---- e2e: every step each rank copies its node features from pinned host memory and reads a
-        #      scalar of the result back (graph / CSR / halo plan stay resident: the graph is static)
-        x_host = x_local.cpu().pin_memory()
-        res_host = torch.empty(1, dtype=torch.float32).pin_memory()
-        e2e_steps = max(3, min(args.steps, 5))
-
-        def e2e_step():
-            x_local.copy_(x_host, non_blocking=True)
-            _, gx_ = step()
-            res_host.copy_(gx_[:: max(1, part.n_local // 4096)].float().sum().reshape(1), non_blocking=True)
-
-        e2e_step()
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(e2e_steps):
-            e2e_step()
-        b.record()
-        torch.cuda.synchronize()
-        dist.barrier()
-        e2e_ms = torch.tensor([a.elapsed_time(b) / e2e_steps], device=dev, dtype=torch.float64)
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-        h2d = torch.tensor([float(x_host.numel() * esize)], device=dev, dtype=torch.float64)
-        dist.all_reduce(h2d, op=dist.ReduceOp.SUM)
-        halo_rows = torch.tensor([float(part.n_halo), float(part.edge_index.size(1)), float(part.n_local)],
-                                 device=dev, dtype=torch.float64)
-        halo_all = [torch.zeros_like(halo_rows) for _ in range(world)]
-        dist.all_gather(halo_all, halo_rows)
-        if rank == 0:
-            clocks = sampler.stop()
-            from bench import NVLINK_GBS, algorithmic_bytes, peaks
-            ms_step = float(ms.item())
-            value = e / (ms_step * 1e-3)
-            peak, peak_src = peaks()
-            max_halo = max(float(t[0]) for t in halo_all)
-            max_edges = max(float(t[1]) for t in halo_all)
-            max_rows = max(float(t[2]) for t in halo_all)
-            fwd_b, bwd_b = algorithmic_bytes(int(max_rows), int(max_edges), feat, esize, S)
-            t_hbm = (fwd_b + bwd_b) / (peak * 1e9)
-            t_link = 2 * max_halo * feat * esize / (NVLINK_GBS * 1e9)        # fwd + bwd exchange
-            roof_t = max(t_hbm, t_link)
-            line = {
-                "metric": "message-passing edges/sec fwd+bwd", "value": value, "unit": "edges/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": w.dtype, "data": "synthetic",
-                "config": {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat,
-                           "parallelism": f"dst-row partition x{world} ({getattr(args, 'partition', 'random')} ownership), "
-                                          "halo exchange: " + (
-                               ("NVLink peer memory; forward: " +
-                                ("owner-side pack + copy-engine fetch by (owner, stage) under the aggregation" if packed
-                                 else f"{fwd_stages}-stage pull under the aggregation" if fwd_stages > 1
-                                 else "one pull kernel") +
-                                "; backward: " + {"push": "owner slices stored into the owners' staging by the aggregation "
-                                                          "kernel, local reduce", "pipeline": "owner slices pulled by copy engine",
-                                                  "fetch": "owner slices fetched by copy engine into staging, one local reduce",
-                                                  "plain": "pull-reduce kernel"}[bwd_mode])
-                               if peer is not None else "NCCL all_to_all"),
-                           "l2": "inputs exceed L2", "halo_rows_per_rank": [int(t[0]) for t in halo_all],
-                           "edges_per_rank": [int(t[1]) for t in halo_all],
-                           "rows_per_rank": [int(t[2]) for t in halo_all]},
-                "roofline": {"bound": "nvlink" if t_link > t_hbm else "hbm", "achieved": roof_t / (ms_step * 1e-3),
-                             "peak": 1.0, "unit": "fraction of max(HBM, NVLink) time", "frac": roof_t / (ms_step * 1e-3),
-                             "t_hbm_ms": t_hbm * 1e3, "t_nvlink_ms": t_link * 1e3, "traffic": None,
-                             "peak_source": peak_src + f"; NVLink {NVLINK_GBS} GB/s per direction (B200_PROFILING.md)"},
-                "cpu_baseline": None,
-                "e2e": {"value": e / (float(e2e_ms.item()) * 1e-3), "unit": "edges/s",
-                        "h2d_bytes_per_step": int(h2d.item()), "d2h_bytes_per_step": 4 * world,
-                        "ms_per_step": float(e2e_ms.item()),
-                        "note": "each rank copies its node features from pinned host memory every step and reads a "
-                                "scalar back; PCIe-bound"},
-                "gpu_launches": launches_per_step * args.steps,
-                "clocks": clocks, "setup_s": t_setup, "fwd_timeline_rank0": timeline,
-                "phases_ms_per_rank": {"order": ["pack", "all_to_all_fwd", "aggregate_fwd", "aggregate_bwd",
-                                                 "all_to_all_bwd+scatter"],
-                                       "ranks": [[round(float(v), 3) for v in t] for t in phases_all]},
-            }
-            print(json.dumps(line), flush=True)
-    finally:
-        dist.destroy_process_group()

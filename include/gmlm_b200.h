@@ -90,6 +90,18 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
                        int32_t* rowptr_t, int32_t* payload_t, float* w_t, int32_t* perm_t,
                        void* ws, size_t ws_bytes, void* stream);
 
+/* ---- transform-first plan (A5+A6 for layers whose output is narrower than their input) ----
+ * [PyG] RGCNConv computes sum_r mean_r(x) @ W_r + x @ root (main.py:272); because the mean is linear this equals
+ * sum_r mean_r(x @ W_r) + (x @ root), so when (S+1)*Fo < S*Fi the dense transform Z = x @ [W_0|..|W_{S-1}|root]
+ * runs FIRST and the aggregation gathers Fo-wide slabs of Z; H [N, S*Fi] is never materialised.  This call
+ * re-reads the (dst,rel) CSR as a dst-keyed CSR over the rows of Z viewed as [num_src*(S+1), Fo]:
+ *   row i        = the edges of segments i*S .. i*S+S-1 in CSR order, then one self entry for the root slab
+ *   col_d        = src*(S+1) + slot   (self entry: i*(S+1) + S)
+ *   w_d          = 1/|segment|        (self entry: 1)         dst_d = i  (payload for gmlm_csr_transpose)
+ * Sizes: rowptr_d [N+1], col_d / w_d / dst_d [E+N]. */
+int gmlm_dst_plan(const int32_t* rowptr, const int32_t* col, int64_t num_dst, int num_slots, int64_t num_edges,
+                  int64_t num_src, int32_t* rowptr_d, int32_t* col_d, float* w_d, int32_t* dst_d, void* stream);
+
 /* ---- hub plan: rows longer than `thresh` are split into chunks of `thresh` edges so that the
  *      aggregation stays balanced AND deterministic on power-law graphs ----
  * count: counts_host[0] = #hub rows, counts_host[1] = #chunks (synchronises).
@@ -222,6 +234,11 @@ int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* out_ids, in
                          int64_t n, void* out, int64_t ldo, void* stream);
 int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t ldd, const int64_t* row_ids,
                          const int32_t* rowptr, const void* const* entry_ptrs, int64_t n_rows, void* stream);
+/* gather_rows_ptr moved by the bulk-copy engine (cp.async.bulk: peer memory -> shared-memory ring -> local HBM)
+ * from `ctas` single-warp CTAs (0 = one per SM) with `smem_kb` KiB of ring each (0 = 192): the transport that
+ * can run UNDER an aggregation kernel without sharing its load queues.  Rows <= 2 KiB. */
+int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
+                             int64_t n, void* out, int64_t ldo, int ctas, int smem_kb, void* stream);
 
 #ifdef __cplusplus
 }

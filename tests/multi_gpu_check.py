@@ -176,6 +176,14 @@ def main():
                     h_st = peer.forward_staged().view(part.n_local, S * feat)
                     assert torch.equal(h_st, h_full.detach()[lo:hi]), f"staged forward ({stages}) differs"
             assert sum(peer.fwd_stage_rows) == part.n_halo
+            # the same stages moved by the bulk-copy engine (cp.async.bulk over NVLink peer memory)
+            peer.build_forward_stages(g, n_stages=3)
+            for ctas, st0 in ((4, False), (9, True)):
+                peer.pull_tma_ctas, peer.pull_tma_stage0 = ctas, st0
+                for _ in range(2):
+                    h_st = peer.forward_staged().view(part.n_local, S * feat)
+                    assert torch.equal(h_st, h_full.detach()[lo:hi]), f"TMA-staged forward ({ctas}, {st0}) differs"
+            peer.pull_tma_ctas, peer.pull_tma_stage0 = 0, False
             # pushed backward (owner slices written into the owners' staging areas by the aggregation kernel)
             peer.build_backward_push(g)
             q1 = peer.backward_pushed(ghl).clone()
@@ -186,9 +194,12 @@ def main():
             assert e_push <= tol, e_push
             assert rel(q1, p1) <= tol
             # fetched backward (owner slices travel by copy engine into the same staging plan): bit-equal to pushed
-            f1 = peer.backward_fetched(ghl).clone()
-            torch.cuda.synchronize()
-            assert torch.equal(f1, q1), "fetched and pushed backward differ"
+            for kw in (dict(local_last=True, signals=True), dict(local_last=False, signals=False),
+                       dict(local_last=True, signals=False), dict(local_last=False, signals=True)):
+                for _ in range(2):
+                    f1 = peer.backward_fetched(ghl, **kw).clone()
+                    torch.cuda.synchronize()
+                    assert torch.equal(f1, q1), f"fetched ({kw}) and pushed backward differ"
             print(f"[rank {rank}] {dtype}: staged fwd ok (rows per stage {peer.fwd_stage_rows}), pushed grad err {e_push:.2e}",
                   flush=True)
             # packed forward on a restaged part (owners pack, peers fetch contiguous (owner, stage) ranges with
