@@ -325,7 +325,7 @@ extern "C" int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t 
 }
 
 // TMA variant of gmlm_gather_rows_ptr: `ctas` single-warp CTAs, each with a shared-memory ring of
-// `smem_kb` KiB (0 = 192).  Rows must be 16-byte multiples, 16-byte aligned on both sides, <= 2 KiB.
+// `smem_kb` KiB (0 = 200).  Rows must be 16-byte multiples, 16-byte aligned on both sides, <= 2 KiB.
 extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
                                         int64_t n, void* out, int64_t ldo, int ctas, int smem_kb, void* stream) {
   GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "gather_rows_ptr_tma: dtype must be GMLM_F32 or GMLM_BF16");
@@ -336,11 +336,11 @@ extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64
                "gather_rows_ptr_tma: rows must be 16-byte multiples and 16-byte aligned");
   if (n == 0 || feat == 0) return GMLM_OK;
   GMLM_REQUIRE(row_ptrs && out, "gather_rows_ptr_tma: null pointer");
-  if (smem_kb <= 0) smem_kb = 192;
+  if (smem_kb <= 0) smem_kb = 200;
   GMLM_REQUIRE(smem_kb <= 224, "gather_rows_ptr_tma: at most 224 KiB of shared memory per CTA");
   const int64_t slot_bytes = 32 * row_bytes;
   const int slots = int(std::min<int64_t>(64, (int64_t(smem_kb) * 1024 - 64 * 8) / slot_bytes));
-  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (<= 2 KiB at 192 KiB)");
+  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (<= 2 KiB at 200 KiB)");
   const size_t smem = size_t(slots) * slot_bytes + size_t(slots) * 8;
   if (ctas <= 0) ctas = num_sms();
   const int64_t n_batches = (n + 31) / 32;

@@ -235,7 +235,7 @@ int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* out_ids, in
 int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t ldd, const int64_t* row_ids,
                          const int32_t* rowptr, const void* const* entry_ptrs, int64_t n_rows, void* stream);
 /* gather_rows_ptr moved by the bulk-copy engine (cp.async.bulk: peer memory -> shared-memory ring -> local HBM)
- * from `ctas` single-warp CTAs (0 = one per SM) with `smem_kb` KiB of ring each (0 = 192): the transport that
+ * from `ctas` single-warp CTAs (0 = one per SM) with `smem_kb` KiB of ring each (0 = 200): the transport that
  * can run UNDER an aggregation kernel without sharing its load queues.  Rows <= 2 KiB. */
 int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
                              int64_t n, void* out, int64_t ldo, int ctas, int smem_kb, void* stream);

