@@ -87,6 +87,11 @@ def load():
         fn.restype = res
         fn.argtypes = args
     _lib = lib
+    import os
+    for key in ("spmm_variant", "spmm_unroll"):          # A/B switches for measurements (development)
+        val = os.environ.get("GMLM_" + key.upper())
+        if val is not None:
+            lib.gmlm_set_tuning(key.encode(), int(val))
     return lib
 
 
