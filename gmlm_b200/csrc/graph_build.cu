@@ -17,7 +17,7 @@ char* err_buf() {
   return buf;
 }
 
-static int g_spmm_variant = 2;   // 0 = one row per walk, 1 = flat walk (registers), 2 = flat walk with cp.async FIFOs
+static int g_spmm_variant = 1;   // 0 = one row per walk, 1 = flat walk over runs of rows (default)
 static int g_spmm_unroll = 0;
 int tuning_spmm_variant() { return g_spmm_variant; }
 int tuning_spmm_unroll() { return g_spmm_unroll; }

@@ -337,298 +337,14 @@ __global__ void __launch_bounds__(256, MINB) chunk_kernel(const ChunkParams p) {
 }
 
 
-// ================================================================== cp.async FIFO variants
-// ncu on the round-1 kernels (profiles/r1_spmm_ncu.md): 7-16 warps stalled on the long scoreboard per
-// issued instruction, DRAM 53-61 % busy, issue slots 35-49 % -- the gather is bound by how many row loads
-// an SM keeps in flight (U = 4 x 512 B per warp in registers: 64 KB per SM), not by HBM or by issue.
-// These variants move the in-flight rows out of the register file: every lane owns a private FIFO of R
-// 16-byte slots in shared memory (`cp.async.cg`, SASS LDGSTS: global -> shared without a register), keeps
-// D = R-1 row loads outstanding at all times (a rolling window, not batches of U) and consumes the oldest
-// with one LDS.  A lane only ever reads the bytes it copied itself, so `cp.async.wait_group` (per thread) is
-// the only synchronisation.  8 warps x 16 slots x 512 B = 64 KB per CTA, 3 CTAs per SM: 192 KB of gathered
-// rows in flight per SM, three times the register version.  Summation order is unchanged (CSR order).
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-template <typename T, int VEC>
-__device__ __forceinline__ void lds_pack(Pack<T, VEC>& v, uint32_t addr) {
-  static_assert(sizeof(v.v) == 16, "FIFO slots are 16-byte packs");
-  uint32_t a, b, c, d;
-  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(addr) : "memory");
-  uint4 u = make_uint4(a, b, c, d);
-  v.v = *reinterpret_cast<decltype(v.v)*>(&u);
-}
-
-// The edge stream of one lane group: 32-edge index batches in registers (IPL indices per lane), a rolling
-// window of D outstanding row copies.  `Consume` is called once per edge, in CSR order.
-template <typename T, int VEC, int CH, int LPR, int R, bool WEIGHTED>
-struct EdgeStream {
-  static constexpr int D = R - 1;
-  static constexpr int IPL = 32 / LPR;
-  static_assert(D >= 1 && D < 32, "prefetch distance must stay inside two index batches");
-  const T* xf;
-  uint32_t row_bytes;
-  const int32_t* col;
-  const float* wp;
-  int64_t wst;
-  unsigned gmask;
-  int gl;
-  uint32_t fifo;          // this lane's slot 0, chunk 0 (shared-memory address)
-  bool fvalid[CH];
-
-  __device__ __forceinline__ void load_idx(int base, int e1, int (&c)[IPL]) const {
-#pragma unroll
-    for (int q = 0; q < IPL; ++q) {
-      const int idx = base + gl * IPL + q;
-      c[q] = idx < e1 ? ld_stream(col + idx) : 0;
-    }
-  }
-  __device__ __forceinline__ void load_w(int base, int e1, float (&w)[IPL]) const {
-#pragma unroll
-    for (int q = 0; q < IPL; ++q) {
-      const int idx = base + gl * IPL + q;
-      w[q] = idx < e1 ? ld_stream(wp + int64_t(idx) * wst) : 0.f;
-    }
-  }
-  template <int K>   // K = position inside the 32-edge batch
-  __device__ __forceinline__ int bcast_i(const int (&c)[IPL]) const { return __shfl_sync(gmask, c[K % IPL], K / IPL, LPR); }
-  template <int K>
-  __device__ __forceinline__ float bcast_f(const float (&w)[IPL]) const { return __shfl_sync(gmask, w[K % IPL], K / IPL, LPR); }
-
-  template <int SLOT>
-  __device__ __forceinline__ void issue(int c, bool on) const {
-    if (on) {
-      const T* rowp = row_ptr(xf, c, row_bytes);
-#pragma unroll
-      for (int ch = 0; ch < CH; ++ch)
-        if (fvalid[ch]) cp_async16(fifo + uint32_t(SLOT * CH + ch) * 512u, rowp + ch * LPR * VEC);
-    }
-    cp_async_commit();     // always: group counting stays position-based
-  }
-  template <int SLOT>
-  __device__ __forceinline__ void take(float wgt, float (&acc)[CH][VEC]) const {
-    cp_async_wait<D - 1>();
-    Pack<T, VEC> v[CH];
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
-      if (fvalid[ch]) lds_pack<T, VEC>(v[ch], fifo + uint32_t(SLOT * CH + ch) * 512u);
-    bool fv[CH];
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch) fv[ch] = fvalid[ch];
-    add_pack<T, VEC, CH>(v, fv, wgt, WEIGHTED, acc);
-  }
-
-  // walk edges [e0, e1): for every edge i call pre(i) (row bookkeeping; may shrink e1), then accumulate it.
-  // Steps of one 32-edge batch are unrolled so that FIFO slots and index lanes are compile-time constants.
-  template <typename Pre>
-  __device__ __forceinline__ void run(int e0, int& e1, float (&acc)[CH][VEC], Pre&& pre) const {
-    int col_cur[IPL], col_next[IPL];
-    float w_cur[IPL];
-    load_idx(e0, e1, col_cur);
-    load_idx(e0 + 32, e1, col_next);
-    prologue<0>(e0, e1, col_cur);
-    for (int base = e0; base < e1; base += 32) {
-      if (WEIGHTED) load_w(base, e1, w_cur);
-      steps<0>(base, e1, col_cur, col_next, w_cur, acc, pre);
-#pragma unroll
-      for (int q = 0; q < IPL; ++q) col_cur[q] = col_next[q];
-      load_idx(base + 64, e1, col_next);
-    }
-    cp_async_wait<0>();    // abandoned prefetches (after a shrink of e1) must not land in a reused slot
-  }
-  template <int J>
-  __device__ __forceinline__ void prologue(int e0, int e1, const int (&col_cur)[IPL]) const {
-    if constexpr (J < D) {
-      issue<J % R>(bcast_i<J>(col_cur), e0 + J < e1);
-      prologue<J + 1>(e0, e1, col_cur);
-    }
-  }
-  template <int U, typename Pre>
-  __device__ __forceinline__ void steps(int base, int& e1, const int (&col_cur)[IPL], const int (&col_next)[IPL],
-                                        const float (&w_cur)[IPL], float (&acc)[CH][VEC], Pre& pre) const {
-    if constexpr (U < 32) {
-      const int i = base + U;
-      float wgt = 1.f;
-      if (WEIGHTED) wgt = bcast_f<U>(w_cur);
-      // the edge that enters the window now (D ahead): its index sits in this batch or in the next one
-      constexpr int K = (U + D) % 32;
-      const int cj = (U + D < 32) ? bcast_i<K>(col_cur) : bcast_i<K>(col_next);
-      if (i < e1) {
-        pre(i);                            // may flush rows, may set e1 = i (stop in front of a hub row)
-        if (i < e1) take<U % R>(wgt, acc);
-      }
-      issue<(U + D) % R>(cj, i + D < e1);   // refills the slot consumed one step ago
-      steps<U + 1>(base, e1, col_cur, col_next, w_cur, acc, pre);
-    }
-  }
-};
-
-template <typename T, int VEC, int CH, int LPR>
-__device__ __forceinline__ void store_row(T* dst, float (&acc)[CH][VEC], const bool (&fvalid)[CH], float scale, bool empty) {
-  if (empty) {
-#pragma unroll
-    for (int ch = 0; ch < CH; ++ch)
-      if (fvalid[ch]) { Pack<T, VEC> z; z.zero(); z.store(dst + ch * LPR * VEC); }
-    return;
-  }
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch) {
-    if (fvalid[ch]) {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[ch][k] *= scale;
-      Pack<T, VEC> o;
-      o.pack(acc[ch]);
-      o.store(dst + ch * LPR * VEC);
-    }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-  }
-}
-
-// rows kernel, FIFO version: a group streams ALL the edges of its row range [r_lo, r_hi) as one flat
-// sequence (not 32 rows at a time: the median (dst,rel) row is empty and a 32-row run holds ~50 edges, too
-// short to fill a pipeline), flushing the accumulator whenever the cursor crosses a row end.  The group
-// plan cuts at hub rows (a hub row is alone in its group and is skipped here: the chunk kernel owns it); a
-// plan without those cuts still works: the stream stops in front of a hub row and restarts behind it.
-template <typename T, int VEC, int CH, int LPR, int R, int NT, int MINB, bool WEIGHTED>
-__global__ void __launch_bounds__(NT, MINB) rows_fifo_kernel(const RowsParams p) {
-  extern __shared__ __align__(16) uint8_t fifo_smem[];
-  constexpr int GROUPS = 32 / LPR;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPR;
-  const int g = lane / LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
-  const int64_t group_id = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + g;
-  if (group_id >= p.n_groups) return;
-  const int r_lo = __ldg(p.grp_row + group_id);
-  const int r_hi = __ldg(p.grp_row + group_id + 1);
-
-  const int64_t slab_stride = p.slab_stride ? p.slab_stride : int64_t(LPR) * VEC * CH;
-  const int64_t slab_width = p.slab_width ? p.slab_width : slab_stride;
-  const int64_t f0 = int64_t(blockIdx.y) * slab_stride + gl * VEC;
-  bool fvalid[CH];
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch)
-    fvalid[ch] = (gl * VEC + ch * LPR * VEC < slab_width) && (f0 + ch * LPR * VEC < p.feat);
-
-  EdgeStream<T, VEC, CH, LPR, R, WEIGHTED> es;
-  es.xf = static_cast<const T*>(p.x) + f0;
-  es.row_bytes = uint32_t(p.ldx) * uint32_t(sizeof(T));
-  es.col = p.col;
-  es.wp = WEIGHTED ? p.w + (p.w_stride > 1 ? int64_t(blockIdx.y) : 0) : nullptr;
-  es.wst = p.w_stride;
-  es.gmask = gmask;
-  es.gl = gl;
-  es.fifo = smem_u32(fifo_smem) + (uint32_t(threadIdx.x >> 5) * uint32_t(R * CH * 32) + uint32_t(lane)) * 16u;
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch) es.fvalid[ch] = fvalid[ch];
-  T* __restrict__ outf = static_cast<T*>(p.out) + f0;
-  const int64_t ldo = p.ldo;
-  const int32_t hub_thresh = p.hub_thresh;
-  const bool mean = p.mean != 0;
-
-  float acc[CH][VEC];
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-
-  int r = r_lo;
-  while (r < r_hi) {
-    // row extents in blocks of LPR rows: lane gl holds the END of row blk0 + gl
-    int blk0 = r;
-    int my_end = __ldg(p.rowptr + min(blk0 + gl, r_hi - 1) + 1);
-    int cur = r;
-    int cur_beg = __ldg(p.rowptr + r);
-    int cur_end = __shfl_sync(gmask, my_end, 0, LPR);
-    if (cur_end - cur_beg > hub_thresh) { ++r; continue; }       // a hub row: written by the chunk kernel
-    int e1 = __ldg(p.rowptr + r_hi);
-    bool hub_ahead = false;
-    auto flush = [&]() {
-      const int len = cur_end - cur_beg;
-      const float scale = (mean && len > 1) ? 1.0f / float(len) : 1.0f;
-      store_row<T, VEC, CH, LPR>(outf + int64_t(cur) * ldo, acc, fvalid, scale, len == 0);
-      cur_beg = cur_end;
-      ++cur;
-      if (cur < r_hi) {
-        if (cur - blk0 == LPR) {
-          blk0 = cur;
-          my_end = __ldg(p.rowptr + min(blk0 + gl, r_hi - 1) + 1);
-        }
-        cur_end = __shfl_sync(gmask, my_end, cur - blk0, LPR);
-      }
-    };
-    es.run(cur_beg, e1, acc, [&](int i) {
-      while (i >= cur_end) flush();                   // crossed one (or several empty) row ends
-      if (cur_end - cur_beg > hub_thresh) {           // the row this edge opens is a hub: stop in front of it
-        e1 = i;
-        hub_ahead = true;
-      }
-    });
-    if (hub_ahead) {
-      r = cur + 1;                                    // rows before `cur` are flushed; skip the hub row
-      continue;
-    }
-    while (cur < r_hi) flush();                       // last row with edges, then trailing empty rows
-    r = r_hi;
-  }
-}
-
-// chunk kernel, FIFO version: one group per hub chunk, fp32 partial sums.
-template <typename T, int VEC, int CH, int LPR, int R, int NT, int MINB, bool WEIGHTED>
-__global__ void __launch_bounds__(NT, MINB) chunk_fifo_kernel(const ChunkParams p) {
-  extern __shared__ __align__(16) uint8_t fifo_smem[];
-  constexpr int GROUPS = 32 / LPR;
-  const int lane = threadIdx.x & 31;
-  const int gl = lane % LPR;
-  const int g = lane / LPR;
-  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (g * LPR));
-  const int64_t c_id = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + g;
-  if (c_id >= p.n_chunks) return;
-  const int64_t slab_stride = p.slab_stride ? p.slab_stride : int64_t(LPR) * VEC * CH;
-  const int64_t slab_width = p.slab_width ? p.slab_width : slab_stride;
-  const int64_t f0 = int64_t(blockIdx.y) * slab_stride + gl * VEC;
-  bool fvalid[CH];
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch)
-    fvalid[ch] = (gl * VEC + ch * LPR * VEC < slab_width) && (f0 + ch * LPR * VEC < p.feat);
-  EdgeStream<T, VEC, CH, LPR, R, WEIGHTED> es;
-  es.xf = static_cast<const T*>(p.x) + f0;
-  es.row_bytes = uint32_t(p.ldx) * uint32_t(sizeof(T));
-  es.col = p.col;
-  es.wp = WEIGHTED ? p.w + (p.w_stride > 1 ? int64_t(blockIdx.y) : 0) : nullptr;
-  es.wst = p.w_stride;
-  es.gmask = gmask;
-  es.gl = gl;
-  es.fifo = smem_u32(fifo_smem) + (uint32_t(threadIdx.x >> 5) * uint32_t(R * CH * 32) + uint32_t(lane)) * 16u;
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch) es.fvalid[ch] = fvalid[ch];
-  float acc[CH][VEC];
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch)
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
-  int e1 = __ldg(p.chunk_end + c_id);
-  es.run(__ldg(p.chunk_beg + c_id), e1, acc, [](int) {});
-  float* __restrict__ dst = p.out + c_id * p.feat + f0;
-#pragma unroll
-  for (int ch = 0; ch < CH; ++ch) {
-    if (fvalid[ch]) {
-      if constexpr (VEC == 8) {
-        reinterpret_cast<float4*>(dst + ch * LPR * VEC)[0] = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
-        reinterpret_cast<float4*>(dst + ch * LPR * VEC)[1] = make_float4(acc[ch][4], acc[ch][5], acc[ch][6], acc[ch][7]);
-      } else {
-        reinterpret_cast<float4*>(dst + ch * LPR * VEC)[0] = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
-      }
-    }
-  }
-}
+// NOTE (round 2, measured): a cp.async (LDGSTS) variant of these kernels -- every lane owning a private
+// 32-slot FIFO in shared memory so that 186 KB of gathered rows per SM are in flight instead of 64 KB -- is
+// bit-exact but 3.4x SLOWER on B200 (C5: 112.7 ms/step against 33.4; profiles/r2_spmm_cp_async_fifo_ab.jsonl):
+// LDGSTS.128 issues at ~24 cycles per 512-byte row per SM (~21 B/clk/SM), a third of what LDG.128 sustains.
+// The kernels above are bound by the bytes one SM's load path keeps outstanding (long-scoreboard stalls, DRAM
+// 53-61 % busy); the copy path that is NOT bounded that way is the bulk-copy engine, whose per-row issue cost
+// (one UBLKCP per row from uniform registers, ~75 cycles) is measured in profiles/r2_row_gather_tma_vs_ldg.log.
+// The FIFO kernels are in the history (commit "Experiment: cp.async ... FIFO variants").
 
 // final in-order reduction of the hub partials: `tpr` threads per hub row, each thread owns the
 // features f = t, t+tpr, ...; chunk partials are loaded 8 at a time (independent loads) and added
@@ -685,7 +401,6 @@ struct Job {
   bool do_rows;
   bool do_chunks;
   int unroll;  // 0 = default
-  bool fifo;   // cp.async FIFO kernels (spmm_variant 2, the default)
 };
 
 template <typename T, int VEC, int CH, int LPR, int U, int MINB>
@@ -723,82 +438,11 @@ int launch_geo(Job& job, cudaStream_t st) {
   return GMLM_OK;
 }
 
-// FIFO kernels: R ring slots per lane, NT/32 warps per CTA -> (NT/32) * R * CH * 512 B of dynamic shared memory
-template <typename T, int VEC, int CH, int LPR, int R, int NT, int MINB>
-int launch_fifo(Job& job, cudaStream_t st) {
-  constexpr int GROUPS = 32 / LPR;
-  constexpr size_t smem = size_t(NT / 32) * R * CH * 512;
-  const int64_t groups_per_cta = int64_t(NT / 32) * GROUPS;
-  const int64_t slab = int64_t(LPR) * VEC * CH;
-  static bool configured[kMaxDevices][4] = {};
-  const int dev = current_device();
-  auto configure = [&](auto kern, int which) -> int {
-    if (!configured[dev][which]) {
-      GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-      GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      configured[dev][which] = true;
-    }
-    return GMLM_OK;
-  };
-  if (job.do_rows) {
-    RowsParams& p = job.rows;
-    const int64_t gx = (p.n_groups + groups_per_cta - 1) / groups_per_cta;
-    const int64_t sstride = p.slab_stride ? p.slab_stride : slab;
-    const int64_t gy = (p.feat + sstride - 1) / sstride;
-    GMLM_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large");
-    if (gx > 0) {
-      dim3 grid((unsigned)gx, (unsigned)gy);
-      if (job.weighted) {
-        auto k = rows_fifo_kernel<T, VEC, CH, LPR, R, NT, MINB, true>;
-        if (int rc = configure(k, 0)) return rc;
-        k<<<grid, NT, smem, st>>>(p);
-      } else {
-        auto k = rows_fifo_kernel<T, VEC, CH, LPR, R, NT, MINB, false>;
-        if (int rc = configure(k, 1)) return rc;
-        k<<<grid, NT, smem, st>>>(p);
-      }
-      GMLM_LAUNCH_CHECK();
-    }
-  }
-  if (job.do_chunks) {
-    ChunkParams& q = job.chunks;
-    const int64_t gx = (q.n_chunks + groups_per_cta - 1) / groups_per_cta;
-    const int64_t sstride = q.slab_stride ? q.slab_stride : slab;
-    const int64_t gy = (q.feat + sstride - 1) / sstride;
-    GMLM_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large");
-    if (gx > 0) {
-      dim3 grid((unsigned)gx, (unsigned)gy);
-      if (job.weighted) {
-        auto k = chunk_fifo_kernel<T, VEC, CH, LPR, R, NT, MINB, true>;
-        if (int rc = configure(k, 2)) return rc;
-        k<<<grid, NT, smem, st>>>(q);
-      } else {
-        auto k = chunk_fifo_kernel<T, VEC, CH, LPR, R, NT, MINB, false>;
-        if (int rc = configure(k, 3)) return rc;
-        k<<<grid, NT, smem, st>>>(q);
-      }
-      GMLM_LAUNCH_CHECK();
-    }
-  }
-  return GMLM_OK;
-}
-
 template <typename T, int VEC>
 int launch_vec(Job& job, cudaStream_t st) {
   const int64_t width = job.rows.slab_width ? job.rows.slab_width : job.rows.feat;
   const int64_t nvec = (width + VEC - 1) / VEC;
   if (job.rows.slab_width) GMLM_REQUIRE(nvec <= 128, "spmm: per-head width above 128 packs is not supported");
-  if constexpr (VEC * sizeof(T) == 16) {
-    // cp.async FIFO kernels: 16-byte packs, a cost-balanced group plan, rows up to 64 packs (1 KiB)
-    if (job.fifo && job.rows.grp_row != nullptr && nvec <= 64) {
-      // 4 warps x 32 slots x 512 B = 64 KB per CTA, 3 CTAs per SM: 12 warps keep 186 KB of rows in flight,
-      // and 168 registers per thread leave the 32-step unrolled walk without spills
-      if (nvec <= 8) return launch_fifo<T, VEC, 1, 8, 32, 128, 3>(job, st);
-      if (nvec <= 16) return launch_fifo<T, VEC, 1, 16, 32, 128, 3>(job, st);
-      if (nvec <= 32) return launch_fifo<T, VEC, 1, 32, 32, 128, 3>(job, st);
-      return launch_fifo<T, VEC, 2, 32, 16, 128, 3>(job, st);
-    }
-  }
   if (nvec <= 8) return launch_geo<T, VEC, 1, 8, 8, 3>(job, st);
   if (nvec <= 16) return launch_geo<T, VEC, 1, 16, 8, 3>(job, st);
   if (nvec <= 32) {
@@ -866,7 +510,6 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   job.do_rows = true;
   job.do_chunks = n_hub > 0;
   job.unroll = tuning_spmm_unroll();
-  job.fifo = tuning_spmm_variant() >= 2;
   RowsParams& p = job.rows;
   p.x = x; p.ldx = ldx; p.feat = feat;
   p.rowptr = rowptr; p.col = col; p.w = w; p.num_rows = num_rows;

@@ -82,14 +82,6 @@ class CSR:
             self.grp_row = torch.empty(self.n_groups + 1, dtype=torch.int32, device=dev)
             _lib.check(lib.gmlm_group_plan(_ptr(self.rowptr), self.num_rows, self.nnz, q, _ptr(self.grp_row),
                                            _stream(dev)), "group_plan")
-            if self.n_hub:
-                # cut at the hub rows too: a hub row (owned by the chunk kernel) then sits alone in its group, and
-                # every other group is a hub-free stretch whose edges form ONE contiguous range -- what the
-                # streaming (cp.async FIFO) rows kernel walks without stopping
-                hub = self.hub_row
-                cuts = torch.unique(torch.cat([self.grp_row, hub, hub + 1]))      # sorted, duplicates removed
-                self.grp_row = cuts.to(torch.int32).contiguous()
-                self.n_groups = int(self.grp_row.numel()) - 1
         return self
 
     def plan_hubs(self, thresh: Optional[int] = None):
