@@ -94,22 +94,29 @@ __global__ void __launch_bounds__(1024) gather_ptr_kernel(const T* const* __rest
 // one warp keeps SLOTS-2 batches of 32 rows (16 KB each at 512-byte rows) outstanding, i.e. ~160 KB per
 // SM, so a couple of dozen single-warp CTAs cover the NVLink bandwidth-delay product while the
 // aggregation's CTAs (which use no shared memory) stay resident on the same SMs.
+// Measured on one B200 (profiles/r2_row_gather_tma_vs_ldg.log): ONE warp moves 12.3 M rows/s whatever the row
+// width or ring size (6.3 GB/s at 512-byte rows) -- UBLKCP takes its operands from uniform registers, so the
+// 32 lanes of a batch are issued one after the other (~75 cycles per bulk op) -- and the rate scales linearly
+// with the number of warps (296 single-warp CTAs: 1.8 TB/s).  Hence several warps per CTA, each with its own
+// ring, and ~120 warps for an NVLink's worth of 512-byte rows.
 //
-// One warp per CTA, lane l moves row l of a batch.  Per slot one mbarrier: lane 0 posts the expected
+// Every warp works alone; lane l moves row l of a batch.  Per slot one mbarrier: lane 0 posts the expected
 // byte count, every lane issues its row's bulk load against it, the warp waits for the phase, every
 // lane issues its row's bulk store and commits it to its own bulk group; a slot is refilled two
 // iterations later, after `wait_group.read 1` has shown that the store which read it has drained.
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
 
 template <int UNUSED = 0>
-__global__ void __launch_bounds__(32, 1) gather_ptr_tma_kernel(const uint64_t* __restrict__ row_ptrs,
-                                                               const int64_t* __restrict__ out_ids, int64_t n,
-                                                               uint32_t row_bytes, uint8_t* __restrict__ out,
-                                                               int64_t ldo_bytes, int slots) {
-  extern __shared__ __align__(128) uint8_t tma_smem[];
-  const int lane = threadIdx.x;
+__global__ void __launch_bounds__(256, 1) gather_ptr_tma_kernel(const uint64_t* __restrict__ row_ptrs,
+                                                                const int64_t* __restrict__ out_ids, int64_t n,
+                                                                uint32_t row_bytes, uint8_t* __restrict__ out,
+                                                                int64_t ldo_bytes, int slots) {
+  extern __shared__ __align__(128) uint8_t tma_smem_all[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const uint32_t slot_bytes = 32u * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_smem + size_t(slots) * slot_bytes);
+  uint8_t* tma_smem = tma_smem_all + size_t(warp) * slots * slot_bytes;              // this warp's ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_smem_all + size_t(nwarps) * slots * slot_bytes) + warp * slots;
   if (lane == 0) {
     for (int s = 0; s < slots; ++s)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + s)));
@@ -117,7 +124,7 @@ __global__ void __launch_bounds__(32, 1) gather_ptr_tma_kernel(const uint64_t* _
   }
   __syncwarp();
   const int64_t n_batches = (n + 31) / 32;
-  const int64_t first = blockIdx.x, stride = gridDim.x;
+  const int64_t first = int64_t(blockIdx.x) * nwarps + warp, stride = int64_t(gridDim.x) * nwarps;
   const int depth = slots - 2;                       // batches in flight
 
   auto issue_load = [&](int64_t it) {
@@ -324,10 +331,12 @@ extern "C" int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t 
   return GMLM_OK;
 }
 
-// TMA variant of gmlm_gather_rows_ptr: `ctas` single-warp CTAs, each with a shared-memory ring of
-// `smem_kb` KiB (0 = 200).  Rows must be 16-byte multiples, 16-byte aligned on both sides, <= 2 KiB.
+// TMA variant of gmlm_gather_rows_ptr: `ctas` CTAs (0 = one per SM) of `warps` warps (0 = 3, at most 8), each
+// warp with its own ring inside the CTA's `smem_kb` KiB (0 = 200) of shared memory.  Rows must be 16-byte
+// multiples, 16-byte aligned on both sides, and at least three 32-row batches per warp must fit the ring.
 extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
-                                        int64_t n, void* out, int64_t ldo, int ctas, int smem_kb, void* stream) {
+                                        int64_t n, void* out, int64_t ldo, int ctas, int warps, int smem_kb,
+                                        void* stream) {
   GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "gather_rows_ptr_tma: dtype must be GMLM_F32 or GMLM_BF16");
   const int esz = dtype == GMLM_F32 ? 4 : 2;
   const int64_t row_bytes = feat * esz;
@@ -338,23 +347,29 @@ extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64
   GMLM_REQUIRE(row_ptrs && out, "gather_rows_ptr_tma: null pointer");
   if (smem_kb <= 0) smem_kb = 200;
   GMLM_REQUIRE(smem_kb <= 224, "gather_rows_ptr_tma: at most 224 KiB of shared memory per CTA");
+  GMLM_REQUIRE(warps >= 0 && warps <= 8, "gather_rows_ptr_tma: 0..8 warps per CTA");
   const int64_t slot_bytes = 32 * row_bytes;
-  const int slots = int(std::min<int64_t>(64, (int64_t(smem_kb) * 1024 - 64 * 8) / slot_bytes));
-  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (<= 2 KiB at 200 KiB)");
-  const size_t smem = size_t(slots) * slot_bytes + size_t(slots) * 8;
+  const int64_t budget = int64_t(smem_kb) * 1024 - 8 * 64 * 8;
+  if (warps == 0) {                       // as many warps (up to 3) as still get a four-slot ring each
+    warps = 3;
+    while (warps > 1 && budget / (warps * slot_bytes) < 4) --warps;
+  }
+  const int slots = int(std::min<int64_t>(64, budget / (warps * slot_bytes)));
+  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (three 32-row batches per warp)");
+  const size_t smem = size_t(warps) * slots * slot_bytes + size_t(warps) * slots * 8;
   if (ctas <= 0) ctas = num_sms();
   const int64_t n_batches = (n + 31) / 32;
-  if (ctas > n_batches) ctas = int(n_batches);
+  if (int64_t(ctas) * warps > n_batches) ctas = int((n_batches + warps - 1) / warps);
   auto kern = gather_ptr_tma_kernel<0>;
-  static size_t configured[kMaxDevices] = {};
+  static bool configured[kMaxDevices] = {};
   const int dev = current_device();
-  if (configured[dev] < smem) {
+  if (!configured[dev]) {
     GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    configured[dev] = 224 * 1024;
+    configured[dev] = true;
   }
-  kern<<<unsigned(ctas), 32, smem, as_stream(stream)>>>(reinterpret_cast<const uint64_t*>(row_ptrs), out_ids, n,
-                                                        uint32_t(row_bytes), static_cast<uint8_t*>(out),
-                                                        ldo * esz, slots);
+  kern<<<unsigned(ctas), 32 * warps, smem, as_stream(stream)>>>(reinterpret_cast<const uint64_t*>(row_ptrs), out_ids, n,
+                                                               uint32_t(row_bytes), static_cast<uint8_t*>(out),
+                                                               ldo * esz, slots);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }

@@ -722,7 +722,7 @@ class PeerHalo:
                     # bulk-copy engine transport: stage 0 has the GPU to itself (one CTA per SM), later stages
                     # run under an aggregation kernel from a few single-warp CTAs
                     _check(lib.gmlm_gather_rows_ptr_tma(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
-                                                        self.feat, 0 if k == 0 else self.pull_tma_ctas, 0,
+                                                        self.feat, 0 if k == 0 else self.pull_tma_ctas, 0, 0,
                                                         _st(tail.device)), "gather_rows_ptr_tma")
                 elif cnt:
                     # stage 0 has the GPU to itself; later stages share it with an aggregation kernel

@@ -235,10 +235,11 @@ int gmlm_gather_rows_ptr(const void* const* row_ptrs, const int64_t* out_ids, in
 int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t ldd, const int64_t* row_ids,
                          const int32_t* rowptr, const void* const* entry_ptrs, int64_t n_rows, void* stream);
 /* gather_rows_ptr moved by the bulk-copy engine (cp.async.bulk: peer memory -> shared-memory ring -> local HBM)
- * from `ctas` single-warp CTAs (0 = one per SM) with `smem_kb` KiB of ring each (0 = 200): the transport that
- * can run UNDER an aggregation kernel without sharing its load queues.  Rows <= 2 KiB. */
+ * from `ctas` CTAs (0 = one per SM) of `warps` warps (0 = up to 3; each warp runs its own ring and moves
+ * ~12 M rows/s) sharing `smem_kb` KiB (0 = 200): the transport that can run UNDER an aggregation kernel without
+ * sharing its load queues.  Three 32-row batches per warp must fit the ring (rows <= 2 KiB with one warp). */
 int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
-                             int64_t n, void* out, int64_t ldo, int ctas, int smem_kb, void* stream);
+                             int64_t n, void* out, int64_t ldo, int ctas, int warps, int smem_kb, void* stream);
 
 #ifdef __cplusplus
 }
