@@ -11,7 +11,7 @@ from pathlib import Path
 _LIB_PATH = Path(__file__).resolve().parent / "libgmlm_b200.so"
 _lib = None
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 AGG_SUM, AGG_MEAN, AGG_WEIGHTED = 0, 1, 2
 
 _p, _i64, _i32, _int, _f32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_int, C.c_float, C.c_size_t
@@ -49,6 +49,8 @@ SIGNATURES = {
     "gmlm_layernorm_bwd": (_int, [_p, _p, _int, _i64, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _sz, _p]),
     "gmlm_gemm_nt_bf16": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int,
                                  _p]),
+    "gmlm_gemm_nt": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int,
+                            _p]),
     "gmlm_gcn_edge_weights": (_int, [_p, _p, _i64, _p, _p, _p]),
     "gmlm_gat_alpha_fwd": (_int, [_p, _p, _i64, _p, _p, _int, _f32, _p, _p]),
     "gmlm_gat_alpha_bwd": (_int, [_p, _p, _i64, _p, _i64, _p, _i64, _int, _int, _int, _p, _p, _p, _f32, _p, _p, _p]),

@@ -3,20 +3,21 @@
 //
 //   forward : out = [H | x] · [W_live ; root]   (one GEMM instead of upstream's R+1 matmuls + adds,
 //             [PyG] RGCNConv.forward called main.py:272,285,298,308); the two A sources are two TMA
-//             descriptors, so H and x are never concatenated in memory.
-//   backward: [dH | dx_root] = g · [W_live ; root]^T, written through two output pointers so that
-//             dH lands contiguous for the transposed aggregation.
+//             descriptors, so H and x are never concatenated in memory.  Transform-first layers:
+//             Z = x · [W_0 | .. | W_{S-1} | root] with the bias on the root slab.
+//   backward: [dH | dx_root] = g · [W_live ; root]^T, written through two output maps so that dH lands
+//             contiguous for the transposed aggregation;  dx = dZ · [W | root]^T.
 //
-// bf16 operands, fp32 accumulation in TMEM, bf16 or fp32 output.  Both operands are K-major.
-// Structure (one CTA per 128 x BLOCK_N tile, 6 warps):
-//   warp 0   : TMA producer — cp.async.bulk.tensor 2-D tiles (128B swizzle) into a STAGES-deep ring,
-//              mbarrier expect_tx / complete_tx
-//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue (UMMA 128 x BLOCK_N x 16, cta_group::1),
-//              tcgen05.commit releases smem stages and finally signals the epilogue
-//   warps 2-5: epilogue — tcgen05.ld (32 lanes x 32 columns), + bias, convert, 128-bit row stores
-// The shapes of this path are tall and skinny (M = #nodes, N = 64..512, K = 320..1280): the kernel
-// is bound by streaming A from HBM, which the TMA ring keeps in flight; B (<= 160 KB) lives in L2.
+// bf16 or fp16 operands (fp16 = what torch.amp.autocast feeds the reference's matmuls, main.py:446,543), fp32
+// accumulation in TMEM, bf16 or fp32 output.  Both operands are K-major.  Persistent, warp-specialised kernel
+// (one CTA per SM, 6 warps): see gemm_nt_kernel.  The shapes of this path are tall and skinny (M = #nodes,
+// N = 64..1280, K = 64..1280): the kernel is bound by streaming A / writing C, which the TMA ring and the
+// double-buffered accumulator keep overlapped; B (<= 160 KB) lives in L2.
 #include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 
@@ -72,9 +73,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;                       // SWIZZLE_128B
   return d;
 }
-// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M x N
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+// kind::f16 instruction descriptor: D = F32 (bit 4), A / B element format in bits [7,10) / [10,13) (F16 = 0,
+// BF16 = 1), both operands K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t make_idesc(int m, int n, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
 }
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -87,7 +89,23 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+struct GemmParams {
+  int M, N, K, K1;        // K1: columns served by the first A descriptor (multiple of BLOCK_K)
+  int N1;                 // output columns [0,N1) go to C1, [N1,N) to C2 (multiple of BLOCK_N, or N)
+  const float* bias;      // [N] or nullptr
+  uint32_t idesc_formats; // a/b element format bits of the instruction descriptor (F16 = 0, BF16 = 1)
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -97,50 +115,72 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-struct GemmParams {
-  int M, N, K, K1;        // K1: columns served by the first A descriptor (multiple of BLOCK_K)
-  int N1;                 // output columns [0,N1) go to C1, [N1,N) to C2 (multiple of BLOCK_N, or N)
-  const float* bias;      // [N] or nullptr
-  void* C1;
-  int64_t ldc1;
-  void* C2;
-  int64_t ldc2;
-};
+constexpr int stages_for(int block_n) { return block_n >= 256 ? 3 : (block_n >= 128 ? 5 : (block_n >= 64 ? 6 : 8)); }
+constexpr uint32_t tmem_cols_for(int block_n) {
+  return 2 * block_n <= 32 ? 32u : (2 * block_n <= 64 ? 64u : (2 * block_n <= 128 ? 128u : (2 * block_n <= 256 ? 256u : 512u)));
+}
+constexpr int kStagingBytes = 4 * 2 * 32 * 128;     // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+template <int BLOCK_N>
+constexpr size_t smem_bytes_for() {
+  return size_t(stages_for(BLOCK_N)) * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + kStagingBytes +
+         2 * BLOCK_N * sizeof(float) + (2 * stages_for(BLOCK_N) + 4) * 8 + 16 + 1024;
+}
 
-template <int BLOCK_N, int STAGES, typename OutT>
-__global__ void __launch_bounds__(kThreads) gemm_nt_kernel(const __grid_constant__ CUtensorMap tma_a1,
-                                                           const __grid_constant__ CUtensorMap tma_a2,
-                                                           const __grid_constant__ CUtensorMap tma_b,
-                                                           const GemmParams p) {
+// PERSISTENT kernel: every CTA (one per SM) walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the
+// 128 x BLOCK_N output grid (N tiles of one M block adjacent in t, so the CTAs that run together share their A
+// tile through L2).  Three pipelines run concurrently inside a CTA:
+//   TMA ring (warp 0)       full/empty mbarriers over STAGES operand stages, k-block counter running across tiles
+//   accumulators (warp 1)   TWO TMEM buffers of BLOCK_N fp32 columns: the MMAs of tile i+1 run while the epilogue
+//                           drains tile i (tmem_full / tmem_empty mbarriers)
+//   epilogue (warps 2-5)    tcgen05.ld -> + bias -> convert -> 128-byte-swizzled staging rows in shared memory ->
+//                           TMA store (cp.async.bulk.tensor, clips the M tail), double-buffered per warp
+// The round-1 kernel ran one tile per CTA with one accumulator: on the backward shape (K = 64: ONE k-block per
+// tile) load latency, MMA and a 64 KB epilogue were serialised per tile (3.3 ms against 0.88 ms for cuBLAS).
+template <int BLOCK_N, typename OutT>
+__global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_constant__ CUtensorMap tma_a1,
+                                                              const __grid_constant__ CUtensorMap tma_a2,
+                                                              const __grid_constant__ CUtensorMap tma_b,
+                                                              const __grid_constant__ CUtensorMap tma_c1,
+                                                              const __grid_constant__ CUtensorMap tma_c2,
+                                                              const GemmParams p) {
+  constexpr int STAGES = stages_for(BLOCK_N);
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  constexpr uint32_t TMEM_COLS = tmem_cols_for(BLOCK_N);
+  constexpr int CHUNK = 128 / int(sizeof(OutT));          // output columns per 128-byte staging row
+  constexpr int N_CHUNKS = BLOCK_N / CHUNK;
+  static_assert(BLOCK_N % CHUNK == 0, "tile width must be a multiple of one staging row");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint8_t* smem_b = smem_a + STAGES * A_BYTES;
+  uint8_t* staging = smem_b + STAGES * B_BYTES;                       // 1024-aligned: A_BYTES, B_BYTES are
+  float* bias_s = reinterpret_cast<float*>(staging + kStagingBytes);  // [2][BLOCK_N]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BLOCK_M;
-  const int n0 = blockIdx.y * BLOCK_N;
   const int num_kb = p.K / BLOCK_K;
+  const int n_tiles = p.N / BLOCK_N;
+  const int total_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * n_tiles;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(full + s), 1);
       mbar_init(smem_u32(empty + s), 1);
     }
-    mbar_init(smem_u32(tmem_full), 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(tmem_full + b), 1);
+      mbar_init(smem_u32(tmem_empty + b), 4);     // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -157,87 +197,131 @@ __global__ void __launch_bounds__(kThreads) gemm_nt_kernel(const __grid_constant
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(empty + s), ph ^ 1);
-        mbar_expect_tx(smem_u32(full + s), A_BYTES + B_BYTES);
-        const int k0 = kb * BLOCK_K;
-        if (k0 < p.K1) tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a1, smem_u32(full + s), k0, m0);
-        else tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a2, smem_u32(full + s), k0 - p.K1, m0);
-        tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tma_b, smem_u32(full + s), k0, n0);
+      uint32_t kc = 0;                                   // k-blocks issued so far, across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int m0 = (t / n_tiles) * BLOCK_M;
+        const int n0 = (t % n_tiles) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1;
+          mbar_wait(smem_u32(empty + s), ph ^ 1);
+          mbar_expect_tx(smem_u32(full + s), A_BYTES + B_BYTES);
+          const int k0 = kb * BLOCK_K;
+          if (k0 < p.K1) tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a1, smem_u32(full + s), k0, m0);
+          else tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a2, smem_u32(full + s), k0 - p.K1, m0);
+          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tma_b, smem_u32(full + s), k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer (single thread)
-      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(smem_u32(full + s), ph);
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, p.idesc_formats);
+      uint32_t kc = 0, it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        const uint32_t buf = it & 1, aph = (it >> 1) & 1;
+        mbar_wait(smem_u32(tmem_empty + buf), aph ^ 1);   // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_BYTES));
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_BYTES));
+        const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          const int s = kc % STAGES;
+          const uint32_t ph = (kc / STAGES) & 1;
+          mbar_wait(smem_u32(full + s), ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advancing 16 bf16 along K inside the swizzle atom = +32 bytes = +2 in the address field
-          umma(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advancing 16 elements along K inside the swizzle atom = +32 bytes = +2 in the address field
+            umma(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(empty + s));      // frees the smem stage once these MMAs have read it
         }
-        umma_commit(smem_u32(empty + s));      // frees the smem stage once these MMAs have read it
+        umma_commit(smem_u32(tmem_full + buf));  // accumulator complete
       }
-      umma_commit(smem_u32(tmem_full));        // accumulator complete
     }
   } else {
-    // ---------------- epilogue: warp w owns TMEM lanes [32*(w%4), 32*(w%4)+32) = 32 output rows.
-    // TMEM -> registers (one row per lane) -> shared memory (the drained pipeline stages, padded
-    // rows: conflict-free 16-byte writes) -> global with fully coalesced 128-bit row segments.
+    // ---------------- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = 32 output rows of the tile.
     const int quad = warp & 3;
-    mbar_wait(smem_u32(tmem_full), 0);
-    tc_fence_after();
-    constexpr int ROW_BYTES = BLOCK_N * int(sizeof(OutT));
-    constexpr int STRIDE = ROW_BYTES + 16;                 // odd multiple of 16 bytes
-    uint8_t* stage = smem + quad * 32 * STRIDE;            // K loop is over: the operand ring is free
-    uint8_t* my_row = stage + lane * STRIDE;
+    const int et = int(threadIdx.x) - 64;                  // 0..127 among the epilogue threads
+    uint8_t* stg = staging + quad * (2 * 32 * 128);
+    uint32_t it = 0, sp = 0;                               // tile counter, staging-buffer toggle
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const int m0 = (t / n_tiles) * BLOCK_M;
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      const uint32_t buf = it & 1, aph = (it >> 1) & 1;
+      float* bs = bias_s + buf * BLOCK_N;
+      if (p.bias) {
+        for (int c = et; c < BLOCK_N; c += 128) bs[c] = __ldg(p.bias + n0 + c);
+      }
+      // all four warps have finished tile it-1 here, hence every read of bias_s[buf] from tile it-2
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(smem_u32(tmem_full + buf), aph);
+      tc_fence_after();
+      const bool second = n0 >= p.N1;
+      const CUtensorMap* cmap = second ? &tma_c2 : &tma_c1;
+      const int ccol0 = second ? n0 - p.N1 : n0;
+      const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16) + buf * BLOCK_N;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
-      float v[32];
+      for (int ch = 0; ch < N_CHUNKS; ++ch, sp ^= 1) {
+        uint8_t* sb = stg + sp * (32 * 128);
+        // the TMA store issued from this buffer two chunks ago must have finished READING it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        float v[CHUNK];
+        {
+          uint32_t r0[32];
+          tmem_ld32_nowait(t_lane + uint32_t(ch * CHUNK), r0);
+          if constexpr (CHUNK == 64) {
+            uint32_t r1[32];
+            tmem_ld32_nowait(t_lane + uint32_t(ch * CHUNK + 32), r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        v[j] = __uint_as_float(r[j]);
-        if (p.bias) v[j] += __ldg(p.bias + n0 + c0 + j);
-      }
-      if constexpr (sizeof(OutT) == 2) {
+            for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(r0[j]); v[32 + j] = __uint_as_float(r1[j]); }
+          } else {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          Pack<__nv_bfloat16, 8> o;
-          o.pack(v + j);
-          *reinterpret_cast<uint4*>(my_row + (c0 + j) * 2) = o.v;
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
+          }
         }
-      } else {
+        if (ch == N_CHUNKS - 1) {                          // accumulator fully read: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
+        }
+        if (p.bias) {
+          const float4* b4 = reinterpret_cast<const float4*>(bs + ch * CHUNK);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(my_row + (c0 + j) * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < CHUNK / 4; ++j) {
+            const float4 bb = b4[j];                       // same address in every lane: a broadcast
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+        }
+        // one 128-byte row per lane; 16-byte chunk j goes to position j ^ (row & 7): the SWIZZLE_128B pattern of
+        // the output tensor map, and conflict-free for these per-lane-row writes
+        uint8_t* my_row = sb + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 val;
+          if constexpr (sizeof(OutT) == 2) {
+            Pack<__nv_bfloat16, 8> o;
+            o.pack(v + 8 * j);
+            val = o.v;
+          } else {
+            val = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                             __float_as_uint(v[4 * j + 3]));
+          }
+          *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 4)) = val;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(cmap, smem_u32(sb), ccol0 + ch * CHUNK, m0 + quad * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
       }
     }
-    __syncwarp();
-    const bool second = n0 >= p.N1;
-    uint8_t* cbase = second ? static_cast<uint8_t*>(p.C2) + int64_t(n0 - p.N1) * sizeof(OutT)
-                            : static_cast<uint8_t*>(p.C1) + int64_t(n0) * sizeof(OutT);
-    const int64_t ldc_bytes = (second ? p.ldc2 : p.ldc1) * int64_t(sizeof(OutT));
-    constexpr int CHUNKS = ROW_BYTES / 16;                 // 16-byte chunks per output row
-    const int row0 = m0 + quad * 32;
-#pragma unroll 4
-    for (int idx = lane; idx < 32 * CHUNKS; idx += 32) {
-      const int rr = idx / CHUNKS;
-      const int cc = idx - rr * CHUNKS;
-      if (row0 + rr < p.M) {
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + rr * STRIDE + cc * 16);
-        __stcs(reinterpret_cast<uint4*>(cbase + int64_t(row0 + rr) * ldc_bytes + cc * 16), val);
-      }
-    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all rows have left shared memory
   }
   tc_fence_before();
   __syncthreads();
@@ -264,33 +348,73 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// row-major [rows, cols] bf16 matrix with leading dimension ld (elements); box = 64 cols x box_rows
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// Tensor maps are pure functions of (address, shape, pitch, box, element type): they are cached, so that a
+// training loop that calls the same layer with the allocator handing back the same buffers pays for the
+// driver's encode once (round 1 encoded three maps on every call).
+struct MapKey {
+  const void* base;
+  int64_t rows, cols, ld;
+  int box_rows, box_cols, dtype, dev;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
+           box_cols == o.box_cols && dtype == o.dtype && dev == o.dev;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = reinterpret_cast<uintptr_t>(k.base);
+    auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+    mix(uint64_t(k.rows)); mix(uint64_t(k.cols)); mix(uint64_t(k.ld));
+    mix(uint64_t(k.box_rows) << 32 | uint32_t(k.box_cols)); mix(uint64_t(k.dtype) << 8 | uint32_t(k.dev));
+    return size_t(h);
+  }
+};
+std::mutex g_map_mutex;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+
+// row-major [rows, cols] matrix with leading dimension ld (elements); box = box_cols x box_rows, 128-byte swizzle
+// (box_cols * element size must be 128 bytes)
+int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
+            int dtype) {
+  const MapKey key{base, rows, cols, ld, box_rows, box_cols, dtype, current_device()};
+  {
+    std::lock_guard<std::mutex> lock(g_map_mutex);
+    auto it = g_map_cache.find(key);
+    if (it != g_map_cache.end()) { *out = it->second; return GMLM_OK; }
+  }
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(GMLM_ERR_CUDA, "gemm: cuTensorMapEncodeTiled is not available from the driver");
+  const int esz = dtype == GMLM_F32 ? 4 : 2;
+  const CUtensorMapDataType dt = dtype == GMLM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                 : dtype == GMLM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
-  cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
-  cuuint32_t box[2] = {cuuint32_t(BLOCK_K), cuuint32_t(box_rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * esz};
+  cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GMLM_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed with code %d", int(r));
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  if (g_map_cache.size() > 4096) g_map_cache.clear();
+  g_map_cache.emplace(key, *out);
   return GMLM_OK;
 }
 
 template <int BLOCK_N, typename OutT>
-int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
-  constexpr int STAGES = 4;   // BLOCK_N <= 64: 2 CTAs/SM (prologue/epilogue of one overlap the K loop of the other)
-  constexpr size_t smem = size_t(STAGES) * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + (2 * STAGES + 2) * 8 + 1024;
-  auto kern = gemm_nt_kernel<BLOCK_N, STAGES, OutT>;
-  static bool configured = false;
-  if (!configured) {
+int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c1,
+           const CUtensorMap& c2, const GemmParams& p, cudaStream_t st) {
+  constexpr size_t smem = smem_bytes_for<BLOCK_N>();
+  static_assert(smem <= 227 * 1024, "tile configuration exceeds the shared memory of one SM");
+  auto kern = gemm_nt_kernel<BLOCK_N, OutT>;
+  static bool configured[kMaxDevices] = {};          // per device: the opt-in is a per-device function attribute
+  const int dev = current_device();
+  if (!configured[dev]) {
     GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-    configured = true;
+    configured[dev] = true;
   }
-  dim3 grid((p.M + BLOCK_M - 1) / BLOCK_M, p.N / BLOCK_N);
-  kern<<<grid, kThreads, smem, st>>>(a1, a2, b, p);
+  const int64_t tiles = int64_t((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BLOCK_N);
+  const unsigned grid = unsigned(std::min<int64_t>(tiles, num_sms()));     // persistent: one CTA per SM
+  kern<<<grid, kThreads, smem, st>>>(a1, a2, b, c1, c2, p);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }
@@ -300,55 +424,68 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, c
 
 using namespace gmlm;
 
-extern "C" int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
-                                 const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1,
-                                 int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int out_dtype, void* stream) {
+extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                            const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1,
+                            int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype,
+                            void* stream) {
   const int64_t K = K1 + K2;
   GMLM_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "gemm: bad sizes");
   GMLM_REQUIRE(M < (int64_t(1) << 31) && N <= 65535 * 256 && K < (int64_t(1) << 31), "gemm: sizes exceed int32");
   GMLM_REQUIRE(K1 % BLOCK_K == 0 && K2 % BLOCK_K == 0, "gemm: K1 and K2 must be multiples of 64");
-  GMLM_REQUIRE(N % 32 == 0, "gemm: N must be a multiple of 32");
+  GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16, "gemm: operands must be GMLM_BF16 or GMLM_F16");
   GMLM_REQUIRE(out_dtype == GMLM_F32 || out_dtype == GMLM_BF16, "gemm: out_dtype must be GMLM_F32 or GMLM_BF16");
+  const int min_n = out_dtype == GMLM_F32 ? 32 : 64;     // one 128-byte staging row of the epilogue
+  GMLM_REQUIRE(N % min_n == 0, "gemm: N must be a multiple of 32 (fp32 output) / 64 (bf16 output)");
   GMLM_REQUIRE(A1 && B && C1 && (K2 == 0 || A2), "gemm: null pointer");
   GMLM_REQUIRE(lda1 >= K1 && (K2 == 0 || lda2 >= K2) && ldb >= K, "gemm: bad leading dimensions");
   GMLM_REQUIRE(lda1 % 8 == 0 && (K2 == 0 || lda2 % 8 == 0) && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8");
+  GMLM_REQUIRE((reinterpret_cast<uintptr_t>(A1) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
+                   (K2 == 0 || (reinterpret_cast<uintptr_t>(A2) & 15) == 0),
+               "gemm: operands must be 16-byte aligned");
   if (M == 0) return GMLM_OK;
   int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
   if (N1 <= 0 || N1 >= N) { N1 = N; C2 = C1; ldc2 = ldc1; }
   else {
     GMLM_REQUIRE(C2 != nullptr, "gemm: second output missing");
-    while (bn > 32 && N1 % bn != 0) bn >>= 1;
+    while (bn > min_n && N1 % bn != 0) bn >>= 1;
     GMLM_REQUIRE(N1 % bn == 0 && (N - N1) % bn == 0, "gemm: N1 must split N on a tile boundary");
   }
   const int esz = out_dtype == GMLM_F32 ? 4 : 2;
   GMLM_REQUIRE((reinterpret_cast<uintptr_t>(C1) & 15) == 0 && (reinterpret_cast<uintptr_t>(C2) & 15) == 0 &&
                    (ldc1 * esz) % 16 == 0 && (ldc2 * esz) % 16 == 0,
                "gemm: outputs must be 16-byte aligned");
-  // cuTensorMapEncodeTiled is a driver entry point: it needs a current context on THIS thread.
-  // Autograd worker threads may not have one bound yet in this library's runtime instance, so
-  // bind the device that owns the operands.
+  // cuTensorMapEncodeTiled is a driver entry point: it needs a current context on THIS thread (autograd worker
+  // threads may not have touched the runtime of this library yet).  The caller's current device is the device of
+  // the operands (the torch layer guards it); it is neither changed nor queried per call.
   {
-    cudaPointerAttributes attr;
-    GMLM_CUDA_TRY(cudaPointerGetAttributes(&attr, A1));
-    GMLM_REQUIRE(attr.type == cudaMemoryTypeDevice, "gemm: A1 is not device memory");
-    GMLM_CUDA_TRY(cudaSetDevice(attr.device));
-    GMLM_CUDA_TRY(cudaFree(nullptr));
+    static thread_local bool ctx_ready[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!ctx_ready[dev]) {
+      GMLM_CUDA_TRY(cudaFree(nullptr));
+      ctx_ready[dev] = true;
+    }
   }
-  CUtensorMap ma1, ma2, mb;
-  int rc = make_map(&ma1, A1, M, K1, lda1, BLOCK_M);
+  CUtensorMap ma1, ma2, mb, mc1, mc2;
+  int rc = get_map(&ma1, A1, M, K1, lda1, BLOCK_M, BLOCK_K, in_dtype);
   if (rc) return rc;
-  rc = K2 ? make_map(&ma2, A2, M, K2, lda2, BLOCK_M) : make_map(&ma2, A1, M, K1, lda1, BLOCK_M);
+  rc = K2 ? get_map(&ma2, A2, M, K2, lda2, BLOCK_M, BLOCK_K, in_dtype) : (ma2 = ma1, GMLM_OK);
   if (rc) return rc;
-  rc = make_map(&mb, B, N, K, ldb, bn);
+  rc = get_map(&mb, B, N, K, ldb, bn, BLOCK_K, in_dtype);
+  if (rc) return rc;
+  const int chunk = 128 / esz;
+  rc = get_map(&mc1, C1, M, N1, ldc1, 32, chunk, out_dtype);
+  if (rc) return rc;
+  rc = N1 < N ? get_map(&mc2, C2, M, N - N1, ldc2, 32, chunk, out_dtype) : (mc2 = mc1, GMLM_OK);
   if (rc) return rc;
   GemmParams p;
   p.M = int(M); p.N = int(N); p.K = int(K); p.K1 = int(K1); p.N1 = int(N1);
-  p.bias = bias; p.C1 = C1; p.ldc1 = ldc1; p.C2 = C2; p.ldc2 = ldc2;
+  p.bias = bias;
+  p.idesc_formats = in_dtype == GMLM_BF16 ? 1u : 0u;
   cudaStream_t st = as_stream(stream);
-#define GMLM_GEMM_CASE(BN)                                                                        \
-  case BN:                                                                                        \
-    return out_dtype == GMLM_F32 ? launch<BN, float>(ma1, ma2, mb, p, st)                         \
-                                 : launch<BN, __nv_bfloat16>(ma1, ma2, mb, p, st);
+#define GMLM_GEMM_CASE(BN)                                                                                  \
+  case BN:                                                                                                  \
+    return out_dtype == GMLM_F32 ? launch<BN, float>(ma1, ma2, mb, mc1, mc2, p, st)                         \
+                                 : launch<(BN < 64 ? 64 : BN), __nv_bfloat16>(ma1, ma2, mb, mc1, mc2, p, st);
   switch (bn) {
     GMLM_GEMM_CASE(256)
     GMLM_GEMM_CASE(128)
@@ -357,4 +494,11 @@ extern "C" int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const
   }
 #undef GMLM_GEMM_CASE
   return fail(GMLM_ERR_INVALID, "gemm: unsupported tile");
+}
+
+extern "C" int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                                 const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1,
+                                 int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int out_dtype, void* stream) {
+  return gmlm_gemm_nt(A1, lda1, K1, A2, lda2, K2, B, ldb, bias, M, N, C1, ldc1, N1, C2, ldc2, GMLM_BF16, out_dtype,
+                      stream);
 }

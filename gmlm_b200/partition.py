@@ -735,14 +735,28 @@ class PeerHalo:
                 events.append(ev)
             lib.gmlm_set_tuning(b"halo_pull_ctas", 0)
             lib.gmlm_set_tuning(b"halo_pull_threads", 0)
-        for (csr, r0, r1, _, _), ev in zip(self.fwd_stages, events):
-            main.wait_event(ev)
+        # the blocks depend on their halo stage, not on each other (disjoint output rows): alternate them over two
+        # streams so that the tail of block k (partial last wave of its rows / chunk / final kernels) is filled
+        # by the start of block k+1 -- measured on 2 GPUs, 4 serial blocks cost 12 % over one whole aggregation
+        if not hasattr(self, "agg_streams"):
+            self.agg_streams = [torch.cuda.Stream(device=self.X.device), torch.cuda.Stream(device=self.X.device)]
+        two = bool(getattr(self, "overlap_blocks", True)) and not timing and len(self.fwd_stages) > 1
+        if two:
+            for st in self.agg_streams:
+                st.wait_event(ready)
+        for k, ((csr, r0, r1, _, _), ev) in enumerate(zip(self.fwd_stages, events)):
+            st = self.agg_streams[k % 2] if two else main
+            st.wait_event(ev)
             if csr is not None:
-                spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
+                with torch.cuda.stream(st):
+                    spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
             if timing:
                 d = torch.cuda.Event(enable_timing=True)
                 d.record(main)
                 agg_done.append(d)
+        if two:
+            for st in self.agg_streams:
+                main.wait_stream(st)
         self.hx.barrier()                                   # every rank is done reading
         if timing:
             self.last_timeline = (ready, events, agg_done)
@@ -829,10 +843,21 @@ class PeerHalo:
                 ev = torch.cuda.Event()
                 ev.record(self.copy_stream)
                 events.append(ev)
-        for (csr, r0, r1, _), ev in zip(self.packed_stages, events):
-            main.wait_event(ev)
+        if not hasattr(self, "agg_streams"):
+            self.agg_streams = [torch.cuda.Stream(device=self.X.device), torch.cuda.Stream(device=self.X.device)]
+        two = bool(getattr(self, "overlap_blocks", True)) and len(self.packed_stages) > 1
+        if two:                                                             # blocks alternate over two streams: see
+            for st in self.agg_streams:                                     # forward_staged
+                st.wait_event(ready)
+        for k, ((csr, r0, r1, _), ev) in enumerate(zip(self.packed_stages, events)):
+            st = self.agg_streams[k % 2] if two else main
+            st.wait_event(ev)
             if csr is not None:
-                spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
+                with torch.cuda.stream(st):
+                    spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
+        if two:
+            for st in self.agg_streams:
+                main.wait_stream(st)
         self.hp.barrier()                                                   # every peer has fetched its rows
         return out
 

@@ -33,6 +33,7 @@ extern "C" {
 /* element types of dense feature matrices */
 #define GMLM_F32 0
 #define GMLM_BF16 1
+#define GMLM_F16 2   /* GEMM operands only (torch.amp.autocast's matmul dtype) */
 
 /* aggregation modes of gmlm_spmm_csr */
 #define GMLM_AGG_SUM 0      /* out[r] = sum_e x[col[e]]                       */
@@ -194,6 +195,11 @@ int gmlm_layernorm_bwd(const void* x, const void* gy, int dtype, int64_t num_row
 int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                       const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
                       int64_t N1, void* C2, int64_t ldc2, int out_dtype, void* stream);
+/* the same with the operand type given: in_dtype = GMLM_BF16 or GMLM_F16 (fp16 is what torch.amp.autocast feeds
+ * the reference's matmuls, main.py:446,543); N multiple of 32 for fp32 output, of 64 for bf16 output */
+int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
+                 const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
+                 int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream);
 
 /* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference): per-edge scalars
  *      of the GCN symmetric normalisation and the GAT edge-softmax on a dst-keyed CSR.  The

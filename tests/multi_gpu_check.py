@@ -49,7 +49,7 @@ def check_dist_norm(rank, world, dev):
     lo, hi = cuts[rank], cuts[rank + 1]
     for dtype, tol in ((torch.float32, 2e-5), (torch.bfloat16, 2e-2)):
         for fuse in (False, True):
-            xf = x.to(dtype).requires_grad_(True)
+            xf = x.to(dtype).clone().requires_grad_(True)      # clone: .to() of the same dtype would alias x
             norm.zero_grad()
             y_full = norm(xf, fuse_gelu=fuse)
             y_full.backward(gout.to(dtype))
@@ -58,7 +58,7 @@ def check_dist_norm(rank, world, dev):
             w = norm.weight.detach().clone().requires_grad_(True)
             b = norm.bias.detach().clone().requires_grad_(True)
             ms = norm.mean_scale.detach().clone().requires_grad_(True)
-            xl = x[lo:hi].to(dtype).requires_grad_(True)
+            xl = x[lo:hi].to(dtype).clone().requires_grad_(True)
             y = G.partitioned_graph_norm(xl, w, b, ms, n, norm.eps, fuse)
             y.backward(gout[lo:hi].to(dtype))
             errs = (rel(y, want[0][lo:hi]), rel(xl.grad, want[1][lo:hi]), rel(w.grad, want[2]), rel(b.grad, want[3]),

@@ -34,8 +34,9 @@ def test_gather_rows_ptr_matches_indexing(cuda_dev, dtype, feat, n, impl):
         rc = lib.gmlm_gather_rows_ptr(_ptr(ptrs), _ptr(out_ids), code, feat, n, _ptr(out), feat, _stream(cuda_dev))
     else:
         ctas, warps = {"tma1": (1, 0), "tma7": (7, 0), "tma_all": (0, 0), "tma_1warp": (5, 1), "tma_8warps": (3, 8)}[impl]
-        if warps == 8 and feat * src.element_size() > 256:
-            warps = 2                                                 # 8 rings of wide rows do not fit one CTA
+        row_bytes = feat * src.element_size()
+        if warps == 8 and row_bytes > 256:
+            warps = 2 if row_bytes <= 1024 else 1                     # 8 rings of wide rows do not fit one CTA
         rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), _ptr(out_ids), code, feat, n, _ptr(out), feat, ctas, warps, 0,
                                           _stream(cuda_dev))
     _lib.check(rc, "gather_rows_ptr")
