@@ -411,9 +411,9 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def linear_nt_ok(x: torch.Tensor, n_out: int) -> bool:
-    """Shapes ``linear_nt`` runs on the tcgen05 GEMM: bf16 CUDA activations, K a multiple of 64, N of 32."""
+    """Shapes ``linear_nt`` runs on the tcgen05 GEMM: bf16 CUDA activations, K and N multiples of 64."""
     return (x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and x.size(1) % 64 == 0 and x.size(1) > 0
-            and n_out % 32 == 0 and n_out > 0)
+            and n_out % 64 == 0 and n_out > 0)
 
 
 class _LinearNT(torch.autograd.Function):
@@ -434,7 +434,7 @@ class _LinearNT(torch.autograd.Function):
         gb = g.to(torch.bfloat16).contiguous()
         dx = dwt = dbias = None
         if ctx.needs_input_grad[0]:
-            if wtb.size(0) % 64 == 0 and wtb.size(1) % 32 == 0:
+            if wtb.size(0) % 64 == 0 and wtb.size(1) % 64 == 0:
                 dx = gemm_nt(gb, wtb.t().contiguous())                     # [M, N_out] x [K, N_out]^T
             else:
                 dx = gb @ wtb

@@ -22,7 +22,8 @@ def t(fn, it=10):
 
 dev = torch.device("cuda:0")
 for (m, n, k1, k2) in [(2_000_000, 64, 1024, 256), (2_000_000, 128, 256, 64), (2_000_000, 256, 512, 128),
-                       (2_000_000, 1024 + 256, 64, 0)]:
+                       (2_000_000, 1024 + 256, 64, 0), (2_000_000, 320, 256, 0), (2_000_000, 256, 320, 0),
+                       (2_000_000, 768, 960, 0)]:
     a1 = torch.randn(m, k1, device=dev).bfloat16()
     a2 = torch.randn(m, k2, device=dev).bfloat16() if k2 else None
     b = torch.randn(n, k1 + k2, device=dev).bfloat16()
