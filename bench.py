@@ -537,7 +537,7 @@ def run_partitioned(args):
         del ei, et, in_deg
         torch.cuda.empty_cache()
 
-        fwd_list = list(FWD_VARIANTS) if args.sweep else [args.fwd]
+        fwd_list = (args.sweep_fwd or list(FWD_VARIANTS)) if args.sweep else [args.fwd]
         bwd_list = [b for b in BWD_VARIANTS if b not in ("pipeline", "plain")] if args.sweep else [args.bwd]
         if args.halo == "nccl":
             fwd_list, bwd_list = ["nccl"], ["nccl"]
@@ -579,9 +579,12 @@ def run_partitioned(args):
         staged_cache = {}
 
         def staged_plan(K):
+            K = (K, args.stage_fractions)
             if staged_cache.get("K") != K:
-                peer.build_forward_stages(g, n_stages=K, pull_ctas_overlapped=args.pull_ctas)
-                staged_cache["K"] = K
+                K = K[0]
+                peer.build_forward_stages(g, n_stages=K, pull_ctas_overlapped=args.pull_ctas,
+                                          fractions=default_stage_fractions(K, args.stage_fractions))
+                staged_cache["K"] = (K, args.stage_fractions)
                 staged_cache["nk"] = sum(_nk(st[0]) + (1 if st[3].numel() else 0) for st in peer.fwd_stages)
 
         def make_fwd(name):
@@ -602,13 +605,15 @@ def run_partitioned(args):
                 K = args.fwd_stages
                 staged_plan(K)
                 tma = args.tma_ctas if name == "tma" else 0
+                st0 = bool(args.tma_stage0) and tma > 0
 
                 def f():
-                    peer.pull_tma_ctas, peer.pull_tma_stage0 = tma, bool(args.tma_stage0) and tma > 0
+                    peer.pull_tma_ctas, peer.pull_tma_stage0 = tma, st0
                     return peer.forward_staged(out=h_buf)
-                what = (f"{K} halo stages by first use; stage 0 by the LDG pull kernel, later stages " +
-                        (f"by {tma} single-warp bulk-copy (TMA) CTAs" if tma else f"by {args.pull_ctas or 32} LDG CTAs") +
-                        " under the aggregation blocks")
+                what = (f"{K} halo stages by first use (block sizes '{args.stage_fractions}'); stage 0 by " +
+                        ("bulk-copy (TMA) CTAs on every SM" if st0 else "the LDG pull kernel") + ", later stages " +
+                        (f"by {tma} bulk-copy (TMA) CTAs of 3 warps" if tma else f"by {args.pull_ctas or 32} LDG CTAs") +
+                        " under the aggregation blocks (two streams)")
                 return f, staged_cache["nk"], what
             if name == "packed":
                 def f():
@@ -676,12 +681,15 @@ def run_partitioned(args):
                 if name in ("staged", "tma"):
                     for K in args.sweep_stages:
                         for c in (args.sweep_tma_ctas if name == "tma" else [0]):
-                            args.fwd_stages, args.tma_ctas = K, c
-                            fn, _, _ = make_fwd(name)
-                            key = f"{name}:K={K}" + (f":ctas={c}" if name == "tma" else "")
-                            sweep["forward_ms"][key] = timed(fn, args.sweep_iters)
-                            if rank == 0:
-                                print(f"[sweep] fwd {key}: {sweep['forward_ms'][key]:.3f} ms", file=sys.stderr, flush=True)
+                            for fr in args.sweep_fractions:
+                                for s0 in (args.sweep_stage0 if name == "tma" else [0]):
+                                    args.fwd_stages, args.tma_ctas, args.stage_fractions, args.tma_stage0 = K, c, fr, s0
+                                    fn, _, _ = make_fwd(name)
+                                    key = f"{name}:K={K}:fr={fr}" + (f":ctas={c}:s0={s0}" if name == "tma" else "")
+                                    sweep["forward_ms"][key] = timed(fn, args.sweep_iters)
+                                    if rank == 0:
+                                        print(f"[sweep] fwd {key}: {sweep['forward_ms'][key]:.3f} ms", file=sys.stderr,
+                                              flush=True)
                 else:
                     fn, _, _ = make_fwd(name)
                     sweep["forward_ms"][name] = timed(fn, args.sweep_iters)
@@ -702,6 +710,10 @@ def run_partitioned(args):
                     args.fwd_stages = int(v_)
                 if k_ == "ctas":
                     args.tma_ctas = int(v_)
+                if k_ == "fr":
+                    args.stage_fractions = v_
+                if k_ == "s0":
+                    args.tma_stage0 = int(v_)
             args.bwd = best_b
             sweep["chosen"] = {"forward": best_f, "backward": best_b}
 
@@ -848,6 +860,11 @@ def main():
     ap.add_argument("--sweep-iters", type=int, default=6)
     ap.add_argument("--sweep-stages", type=int, nargs="+", default=[4, 8])
     ap.add_argument("--sweep-tma-ctas", type=int, nargs="+", default=[16, 32, 64])
+    ap.add_argument("--sweep-fractions", nargs="+", default=["fib"])
+    ap.add_argument("--sweep-stage0", type=int, nargs="+", default=[0])
+    ap.add_argument("--sweep-fwd", nargs="+", default=None, help="restrict the forward variants of --sweep")
+    ap.add_argument("--stage-fractions", default="fib", choices=["fib", "lin", "flat"],
+                    help="N>1, --fwd staged|tma: relative sizes of the aggregation blocks")
     ap.add_argument("--partition", default="random", choices=["random", "cyclic", "range"],
                     help="N>1: node ownership")
     ap.add_argument("--no-cpu-baseline", action="store_true")

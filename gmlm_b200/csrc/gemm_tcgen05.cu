@@ -27,7 +27,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-9: epilogue
+constexpr int kEpiWarps = 8;
 constexpr uint32_t kSpinLimit = 1u << 28;   // a lost barrier traps instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
@@ -117,11 +118,16 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr));
 }
 
-constexpr int stages_for(int block_n) { return block_n >= 256 ? 3 : (block_n >= 128 ? 5 : (block_n >= 64 ? 6 : 8)); }
+constexpr int stages_for(int block_n) { return block_n >= 256 ? 3 : (block_n >= 128 ? 4 : (block_n >= 64 ? 6 : 7)); }
 constexpr uint32_t tmem_cols_for(int block_n) {
   return 2 * block_n <= 32 ? 32u : (2 * block_n <= 64 ? 64u : (2 * block_n <= 128 ? 128u : (2 * block_n <= 256 ? 256u : 512u)));
 }
-constexpr int kStagingBytes = 4 * 2 * 32 * 128;     // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+constexpr int kStagingBytes = kEpiWarps * 2 * 32 * 128;   // 8 epilogue warps x 2 buffers x (32 rows x 128 B)
+// output columns per staging row: a full 128-byte swizzle row when the tile width allows it, else 64 bytes
+template <int BLOCK_N, typename OutT>
+constexpr int chunk_cols() {
+  return BLOCK_N % (128 / int(sizeof(OutT))) == 0 ? 128 / int(sizeof(OutT)) : 64 / int(sizeof(OutT));
+}
 template <int BLOCK_N>
 constexpr size_t smem_bytes_for() {
   return size_t(stages_for(BLOCK_N)) * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + kStagingBytes +
@@ -134,8 +140,9 @@ constexpr size_t smem_bytes_for() {
 //   TMA ring (warp 0)       full/empty mbarriers over STAGES operand stages, k-block counter running across tiles
 //   accumulators (warp 1)   TWO TMEM buffers of BLOCK_N fp32 columns: the MMAs of tile i+1 run while the epilogue
 //                           drains tile i (tmem_full / tmem_empty mbarriers)
-//   epilogue (warps 2-5)    tcgen05.ld -> + bias -> convert -> 128-byte-swizzled staging rows in shared memory ->
-//                           TMA store (cp.async.bulk.tensor, clips the M tail), double-buffered per warp
+//   epilogue (warps 2-9)    tcgen05.ld -> + bias -> convert -> swizzled staging rows in shared memory -> TMA store
+//                           (cp.async.bulk.tensor, clips the M tail), double-buffered per warp; two warps per TMEM
+//                           lane quarter split the column chunks (the epilogue, not the MMA, paces K <= 128 shapes)
 // The round-1 kernel ran one tile per CTA with one accumulator: on the backward shape (K = 64: ONE k-block per
 // tile) load latency, MMA and a 64 KB epilogue were serialised per tile (3.3 ms against 0.88 ms for cuBLAS).
 template <int BLOCK_N, typename OutT>
@@ -149,9 +156,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
   constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
   constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr uint32_t TMEM_COLS = tmem_cols_for(BLOCK_N);
-  constexpr int CHUNK = 128 / int(sizeof(OutT));          // output columns per 128-byte staging row
+  constexpr int CHUNK = chunk_cols<BLOCK_N, OutT>();      // output columns per staging row (128 or 64 bytes)
+  constexpr int ROWB = CHUNK * int(sizeof(OutT));
   constexpr int N_CHUNKS = BLOCK_N / CHUNK;
-  static_assert(BLOCK_N % CHUNK == 0, "tile width must be a multiple of one staging row");
+  static_assert(BLOCK_N % CHUNK == 0 && (ROWB == 128 || ROWB == 64) && (CHUNK == 32 || CHUNK == 64),
+                "tile width must be a multiple of one staging row");
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment for the 128B-swizzled tiles
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -179,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(tmem_full + b), 1);
-      mbar_init(smem_u32(tmem_empty + b), 4);     // one arrival per epilogue warp
+      mbar_init(smem_u32(tmem_empty + b), kEpiWarps);     // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -241,10 +250,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
       }
     }
   } else {
-    // ---------------- epilogue: warp w owns TMEM lanes [32*(w%4), +32) = 32 output rows of the tile.
+    // ---------------- epilogue: warp w may read TMEM lanes [32*(w%4), +32) = 32 output rows of the tile; the two
+    // warps that share a lane quarter take the even / the odd column chunks.
     const int quad = warp & 3;
-    const int et = int(threadIdx.x) - 64;                  // 0..127 among the epilogue threads
-    uint8_t* stg = staging + quad * (2 * 32 * 128);
+    const int half = (warp - 2) >> 2;
+    const int et = int(threadIdx.x) - 64;                  // 0..255 among the epilogue threads
+    uint8_t* stg = staging + (warp - 2) * (2 * 32 * 128);
+    constexpr int LAST0 = ((N_CHUNKS - 1) / 2) * 2;        // last chunk of the even warp
+    constexpr int LAST1 = N_CHUNKS >= 2 ? ((N_CHUNKS - 2) / 2) * 2 + 1 : -1;
+    const int my_last = half == 0 ? LAST0 : LAST1;
     uint32_t it = 0, sp = 0;                               // tile counter, staging-buffer toggle
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int m0 = (t / n_tiles) * BLOCK_M;
@@ -252,18 +266,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
       const uint32_t buf = it & 1, aph = (it >> 1) & 1;
       float* bs = bias_s + buf * BLOCK_N;
       if (p.bias) {
-        for (int c = et; c < BLOCK_N; c += 128) bs[c] = __ldg(p.bias + n0 + c);
+        for (int c = et; c < BLOCK_N; c += 32 * kEpiWarps) bs[c] = __ldg(p.bias + n0 + c);
       }
-      // all four warps have finished tile it-1 here, hence every read of bias_s[buf] from tile it-2
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      // every epilogue warp has finished tile it-1 here, hence every read of bias_s[buf] from tile it-2
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(smem_u32(tmem_full + buf), aph);
       tc_fence_after();
+      if (my_last < 0) {                                   // nothing to read (one-chunk tiles): stay in step
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
+        continue;
+      }
       const bool second = n0 >= p.N1;
       const CUtensorMap* cmap = second ? &tma_c2 : &tma_c1;
       const int ccol0 = second ? n0 - p.N1 : n0;
       const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16) + buf * BLOCK_N;
 #pragma unroll 1
-      for (int ch = 0; ch < N_CHUNKS; ++ch, sp ^= 1) {
+      for (int ch = half; ch < N_CHUNKS; ch += 2, sp ^= 1) {
         uint8_t* sb = stg + sp * (32 * 128);
         // the TMA store issued from this buffer two chunks ago must have finished READING it
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -284,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]);
           }
         }
-        if (ch == N_CHUNKS - 1) {                          // accumulator fully read: hand the TMEM buffer back
+        if (ch == my_last) {                               // my share of the accumulator is read: hand it back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
@@ -297,21 +317,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
             v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
           }
         }
-        // one 128-byte row per lane; 16-byte chunk j goes to position j ^ (row & 7): the SWIZZLE_128B pattern of
-        // the output tensor map, and conflict-free for these per-lane-row writes
-        uint8_t* my_row = sb + lane * 128;
+        // one staging row per lane; its 16-byte chunk j goes to position j ^ (row & 7) (128-byte rows) or
+        // j ^ ((row >> 1) & 3) (64-byte rows): the SWIZZLE_128B / SWIZZLE_64B pattern of the output tensor map
+        // (byte-address bits [4,7) ^= bits [7,10), resp. [4,6) ^= [7,9)), conflict-free for per-lane-row writes
+        uint8_t* my_row = sb + lane * ROWB;
+        constexpr int EPC = 16 / int(sizeof(OutT));        // elements per 16-byte chunk
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < ROWB / 16; ++j) {
           uint4 val;
           if constexpr (sizeof(OutT) == 2) {
             Pack<__nv_bfloat16, 8> o;
-            o.pack(v + 8 * j);
+            o.pack(v + EPC * j);
             val = o.v;
           } else {
             val = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
                              __float_as_uint(v[4 * j + 3]));
           }
-          *reinterpret_cast<uint4*>(my_row + ((j ^ (lane & 7)) << 4)) = val;
+          const int pos = ROWB == 128 ? (j ^ (lane & 7)) : (j ^ ((lane >> 1) & 3));
+          *reinterpret_cast<uint4*>(my_row + (pos << 4)) = val;
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
         __syncwarp();
@@ -354,7 +377,7 @@ EncodeTiledFn encode_fn() {
 struct MapKey {
   const void* base;
   int64_t rows, cols, ld;
-  int box_rows, box_cols, dtype, dev;
+  int box_rows, box_cols, dtype, dev;   // the swizzle mode follows from box_cols * element size (128 or 64 bytes)
   bool operator==(const MapKey& o) const {
     return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
            box_cols == o.box_cols && dtype == o.dtype && dev == o.dev;
@@ -372,8 +395,8 @@ struct MapKeyHash {
 std::mutex g_map_mutex;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 
-// row-major [rows, cols] matrix with leading dimension ld (elements); box = box_cols x box_rows, 128-byte swizzle
-// (box_cols * element size must be 128 bytes)
+// row-major [rows, cols] matrix with leading dimension ld (elements); box = box_cols x box_rows; box_cols * element
+// size is 128 bytes (SWIZZLE_128B) or 64 bytes (SWIZZLE_64B)
 int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
             int dtype) {
   const MapKey key{base, rows, cols, ld, box_rows, box_cols, dtype, current_device()};
@@ -391,8 +414,9 @@ int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int6
   cuuint64_t strides[1] = {cuuint64_t(ld) * esz};
   cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GMLM_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed with code %d", int(r));
   std::lock_guard<std::mutex> lock(g_map_mutex);
   if (g_map_cache.size() > 4096) g_map_cache.clear();
@@ -434,8 +458,8 @@ extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void
   GMLM_REQUIRE(K1 % BLOCK_K == 0 && K2 % BLOCK_K == 0, "gemm: K1 and K2 must be multiples of 64");
   GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16, "gemm: operands must be GMLM_BF16 or GMLM_F16");
   GMLM_REQUIRE(out_dtype == GMLM_F32 || out_dtype == GMLM_BF16, "gemm: out_dtype must be GMLM_F32 or GMLM_BF16");
-  const int min_n = out_dtype == GMLM_F32 ? 32 : 64;     // one 128-byte staging row of the epilogue
-  GMLM_REQUIRE(N % min_n == 0, "gemm: N must be a multiple of 32 (fp32 output) / 64 (bf16 output)");
+  const int min_n = 32;
+  GMLM_REQUIRE(N % min_n == 0, "gemm: N must be a multiple of 32");
   GMLM_REQUIRE(A1 && B && C1 && (K2 == 0 || A2), "gemm: null pointer");
   GMLM_REQUIRE(lda1 >= K1 && (K2 == 0 || lda2 >= K2) && ldb >= K, "gemm: bad leading dimensions");
   GMLM_REQUIRE(lda1 % 8 == 0 && (K2 == 0 || lda2 % 8 == 0) && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8");
@@ -444,8 +468,12 @@ extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void
                "gemm: operands must be 16-byte aligned");
   if (M == 0) return GMLM_OK;
   int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
-  if (N1 <= 0 || N1 >= N) { N1 = N; C2 = C1; ldc2 = ldc1; }
-  else {
+  if (N1 <= 0 || N1 >= N) {
+    N1 = N; C2 = C1; ldc2 = ldc1;
+    // 160-wide tiles for N = 320, 640, ... ((S+1) * Fo of the transform-first layers): two passes over A through L2
+    // instead of five with 64-wide tiles (measured: 64-wide tiles made that shape L2-bandwidth-bound)
+    if (N % 256 != 0 && N % 160 == 0) bn = 160;
+  } else {
     GMLM_REQUIRE(C2 != nullptr, "gemm: second output missing");
     while (bn > min_n && N1 % bn != 0) bn >>= 1;
     GMLM_REQUIRE(N1 % bn == 0 && (N - N1) % bn == 0, "gemm: N1 must split N on a tile boundary");
@@ -472,7 +500,7 @@ extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void
   if (rc) return rc;
   rc = get_map(&mb, B, N, K, ldb, bn, BLOCK_K, in_dtype);
   if (rc) return rc;
-  const int chunk = 128 / esz;
+  const int chunk = bn % (128 / esz) == 0 ? 128 / esz : 64 / esz;      // chunk_cols<BLOCK_N, OutT>()
   rc = get_map(&mc1, C1, M, N1, ldc1, 32, chunk, out_dtype);
   if (rc) return rc;
   rc = N1 < N ? get_map(&mc2, C2, M, N - N1, ldc2, 32, chunk, out_dtype) : (mc2 = mc1, GMLM_OK);
@@ -485,9 +513,10 @@ extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void
 #define GMLM_GEMM_CASE(BN)                                                                                  \
   case BN:                                                                                                  \
     return out_dtype == GMLM_F32 ? launch<BN, float>(ma1, ma2, mb, mc1, mc2, p, st)                         \
-                                 : launch<(BN < 64 ? 64 : BN), __nv_bfloat16>(ma1, ma2, mb, mc1, mc2, p, st);
+                                 : launch<BN, __nv_bfloat16>(ma1, ma2, mb, mc1, mc2, p, st);
   switch (bn) {
     GMLM_GEMM_CASE(256)
+    GMLM_GEMM_CASE(160)
     GMLM_GEMM_CASE(128)
     GMLM_GEMM_CASE(64)
     GMLM_GEMM_CASE(32)

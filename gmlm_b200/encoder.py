@@ -25,7 +25,8 @@ from torch.utils.checkpoint import checkpoint
 
 from .graph import _tensor_key, get_rel_graph
 from .nn import GraphNorm, RGCNConv
-from .ops import edge_type_from_degree, layer_norm, layer_norm_ok, soft_masking_gnn_input
+from .ops import (edge_type_from_degree, layer_norm, layer_norm_ok, linear_nt, linear_nt_ok,
+                  soft_masking_gnn_input)
 
 
 class MultiScaleFusion(nn.Module):
@@ -48,7 +49,10 @@ class MultiScaleFusion(nn.Module):
         weight = torch.cat([w[i] * p.weight for i, p in enumerate(self.projections)], dim=1)
         bias = sum(w[i] * p.bias for i, p in enumerate(self.projections))
         xs = torch.cat([e if autocast else e.to(dt) for e in embeddings_list], dim=1)
-        fused = F.linear(xs, weight, bias)
+        if not autocast and linear_nt_ok(xs, weight.size(0)):
+            fused = linear_nt(xs, weight, bias)                      # bf16 pipeline: the tcgen05 GEMM (csrc/gemm_tcgen05.cu)
+        else:
+            fused = F.linear(xs, weight, bias)
         ln = self.layer_norm
         if autocast:                      # torch.autocast runs layer_norm in fp32
             fused = fused.float()
@@ -114,6 +118,8 @@ class GraphEncoder(nn.Module):
         return self._block(k)(x, graph)
 
     def _lin(self, lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+        if not torch.is_autocast_enabled("cuda") and linear_nt_ok(x, lin.out_features):
+            return linear_nt(x, lin.weight, lin.bias)                # bf16 pipeline: the tcgen05 GEMM
         if torch.is_autocast_enabled("cuda") or x.dtype == lin.weight.dtype:
             return lin(x)
         return F.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype))

@@ -132,10 +132,17 @@ class RGCNConv(nn.Module):
         # matmuls run in the operand dtype, or in the autocast dtype under torch.amp.autocast
         autocast = torch.is_autocast_enabled("cuda")
         out_dtype = self.out_dtype or torch.get_default_dtype()
-        if (self.use_tcgen05 and not autocast and self.root is not None and out_dtype in (torch.float32, torch.bfloat16)
-                and rgcn_transform_ok(h, x, self.out_channels)):
-            # bf16 pipeline: one tcgen05 GEMM over [h | x] with the bias in its epilogue
-            return rgcn_transform(h, x, w, self.root, self.bias, out_dtype)
+        if self.use_tcgen05 and self.root is not None and out_dtype in (torch.float32, torch.bfloat16):
+            if not autocast and rgcn_transform_ok(h, x, self.out_channels):
+                # bf16 pipeline: one tcgen05 GEMM over [h | x] with the bias in its epilogue
+                return rgcn_transform(h, x, w, self.root, self.bias, out_dtype)
+            if autocast:
+                # torch.amp.autocast (main.py:446,543): the matmuls run in the autocast dtype (fp16 by default) and
+                # accumulate into the fp32 `out`; here h and x are cast once and ONE tcgen05 GEMM writes fp32
+                op = torch.get_autocast_dtype("cuda")
+                if rgcn_transform_ok(h, x, self.out_channels, op):
+                    with torch.amp.autocast("cuda", enabled=False):
+                        return rgcn_transform(h, x, w, self.root, self.bias, out_dtype, op)
 
         def mm(a, b):
             return torch.matmul(a, b) if autocast else torch.matmul(a, b.to(a.dtype))

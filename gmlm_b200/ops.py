@@ -330,14 +330,14 @@ _LIB.impl("soft_mask_bwd", _soft_mask_bwd, "CUDA")
 # ------------------------------------------------------------------------------ A6 dense transform (tcgen05)
 def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
             out_dtype: Optional[torch.dtype] = None, split: int = 0):
-    """``[a1 | a2] @ b.T + bias`` on the tcgen05 tensor cores (bf16 in, fp32 accumulate).
+    """``[a1 | a2] @ b.T + bias`` on the tcgen05 tensor cores (bf16 or fp16 in, fp32 accumulate).
 
-    a1 [M,K1], a2 [M,K2] (optional), b [N,K1+K2], all bf16 with unit inner stride; returns C [M,N],
-    or (C[:, :split], C[:, split:]) as two contiguous tensors when ``split`` > 0."""
+    a1 [M,K1], a2 [M,K2] (optional), b [N,K1+K2], all bf16 (or all fp16) with unit inner stride; returns C [M,N]
+    (bf16 or fp32), or (C[:, :split], C[:, split:]) as two contiguous tensors when ``split`` > 0."""
     lib = _lib.load()
     _require_cuda(a1, "a1")
-    if a1.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or (a2 is not None and a2.dtype != torch.bfloat16):
-        raise _lib.GmlmError("gemm_nt: operands must be bfloat16")
+    if a1.dtype not in (torch.bfloat16, torch.float16) or b.dtype != a1.dtype or (a2 is not None and a2.dtype != a1.dtype):
+        raise _lib.GmlmError("gemm_nt: operands must all be bfloat16 or all be float16")
     a1, b = _rowmajor(a1), _rowmajor(b)
     a2 = _rowmajor(a2) if a2 is not None else None
     m, k1 = a1.shape
@@ -346,8 +346,11 @@ def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = No
     if b.size(1) != k1 + k2 or (a2 is not None and a2.size(0) != m):
         raise _lib.GmlmError(f"gemm_nt: shape mismatch a1 {tuple(a1.shape)} a2 {None if a2 is None else tuple(a2.shape)} "
                              f"b {tuple(b.shape)}")
-    out_dtype = out_dtype or torch.bfloat16
+    out_dtype = out_dtype or (torch.bfloat16 if a1.dtype == torch.bfloat16 else torch.float32)
+    if out_dtype not in _DT:
+        raise _lib.GmlmError("gemm_nt: output must be float32 or bfloat16")
     code = _DT[out_dtype]
+    in_code = _lib.BF16 if a1.dtype == torch.bfloat16 else _lib.F16
     dev = a1.device
     bias32 = bias.detach().float().contiguous() if bias is not None else None
     with torch.cuda.device(dev):
@@ -358,45 +361,62 @@ def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = No
             split = 0
             c1 = torch.empty((m, n), dtype=out_dtype, device=dev)
             c2 = None
-        _lib.check(lib.gmlm_gemm_nt_bf16(_ptr(a1), _ld(a1), k1, _ptr(a2), _ld(a2) if a2 is not None else 0, k2,
-                                         _ptr(b), _ld(b), _ptr(bias32), m, n, _ptr(c1), c1.size(1), split,
-                                         _ptr(c2), c2.size(1) if c2 is not None else 0, code, _stream(dev)),
-                   "gemm_nt_bf16")
+        _lib.check(lib.gmlm_gemm_nt(_ptr(a1), _ld(a1), k1, _ptr(a2), _ld(a2) if a2 is not None else 0, k2,
+                                    _ptr(b), _ld(b), _ptr(bias32), m, n, _ptr(c1), c1.size(1), split,
+                                    _ptr(c2), c2.size(1) if c2 is not None else 0, in_code, code, _stream(dev)),
+                   "gemm_nt")
     return (c1, c2) if c2 is not None else c1
 
 
 class _RGCNTransform(torch.autograd.Function):
-    """out = [h | x] @ [w ; root] + bias as ONE tcgen05 GEMM (A6; measured 0.80 ms vs 1.01 ms for the
-    two cuBLAS calls at M=2M, K=1280, N=64 — 103 % of the measured HBM copy peak).  Backward GEMMs
-    are plain library shapes and stay on cuBLAS: dh = g w^T and dx = g root^T are output-write-bound
-    (measured cuBLAS 0.88 ms vs 3.3 ms for this kernel at N=1280, K=64), dW = h^T g and
-    droot = x^T g are 2M-deep reductions."""
+    """out = [h | x] @ [w ; root] + bias as ONE tcgen05 GEMM (A6; 0.81 ms vs 1.03 ms for the two cuBLAS calls at
+    M=2M, K=1280, N=64).  Backward: [dh | dx] = g @ [w ; root]^T is one more launch of the same persistent kernel,
+    its two outputs written through two tensor maps so that dh lands contiguous for the transposed aggregation;
+    dW = h^T g and droot = x^T g are reductions over all nodes and are produced in fp32.
+
+    ``op_dtype`` is the operand type of the GEMMs: bf16 for the bf16 pipeline, fp16 under ``torch.amp.autocast``
+    (what the reference's matmuls run in, main.py:446,543); h and x are cast once and saved in that type."""
 
     @staticmethod
-    def forward(ctx, h, x, w, root, bias, out_dtype):
-        wc = torch.cat([w, root], dim=0).to(torch.bfloat16)            # [K1+K2, Fo]
-        out = gemm_nt(h, wc.t().contiguous(), bias=bias, a2=x, out_dtype=out_dtype)
-        ctx.save_for_backward(h, x, wc)
+    def forward(ctx, h, x, w, root, bias, out_dtype, op_dtype):
+        hq = h if h.dtype == op_dtype else h.to(op_dtype)
+        xq = x if x.dtype == op_dtype else x.to(op_dtype)
+        wc = torch.cat([w, root], dim=0).detach().to(op_dtype)          # [K1+K2, Fo]
+        out = gemm_nt(hq, wc.t().contiguous(), bias=bias, a2=xq, out_dtype=out_dtype)
+        ctx.save_for_backward(hq, xq, wc)
         ctx.k1 = h.size(1)
-        ctx.dtypes = (w.dtype, root.dtype, None if bias is None else bias.dtype)
+        ctx.dtypes = (w.dtype, root.dtype, None if bias is None else bias.dtype, h.dtype, x.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g):
         h, x, wc = ctx.saved_tensors
-        gb = g.to(torch.bfloat16).contiguous()
+        k1, k2 = ctx.k1, x.size(1)
+        gb = g.to(wc.dtype).contiguous()
+        fo = gb.size(1)
         dh = dx = dw = droot = dbias = None
-        if ctx.needs_input_grad[0]:
-            dh = gb @ wc[: ctx.k1].t()                                 # [M,K1]
-        if ctx.needs_input_grad[1]:
-            dx = gb @ wc[ctx.k1:].t()                                  # [M,K2]
+        need_h, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_h or need_x:
+            out_dt = torch.bfloat16 if ctx.dtypes[3] == torch.bfloat16 else torch.float32
+            if fo % 64 == 0 and k1 % 32 == 0 and k2 % 32 == 0 and ctx.dtypes[3] == ctx.dtypes[4]:
+                if need_h and need_x:
+                    dh, dx = gemm_nt(gb, wc, out_dtype=out_dt, split=k1)      # [M, Fo] x [K1+K2, Fo]^T
+                elif need_h:
+                    dh = gemm_nt(gb, wc[:k1], out_dtype=out_dt)
+                else:
+                    dx = gemm_nt(gb, wc[k1:], out_dtype=out_dt)
+            else:
+                if need_h:
+                    dh = (gb @ wc[:k1].t()).to(ctx.dtypes[3])
+                if need_x:
+                    dx = (gb @ wc[k1:].t()).to(ctx.dtypes[4])
         if ctx.needs_input_grad[2]:
-            dw = (h.t() @ gb).to(ctx.dtypes[0])
+            dw = _mm_f32(h.t(), gb).to(ctx.dtypes[0])
         if ctx.needs_input_grad[3]:
-            droot = (x.t() @ gb).to(ctx.dtypes[1])
+            droot = _mm_f32(x.t(), gb).to(ctx.dtypes[1])
         if ctx.needs_input_grad[4]:
-            dbias = torch.ops.gmlm.colstats(gb)[0].to(ctx.dtypes[2])   # one pass, fp64 accumulate, deterministic
-        return dh, dx, dw, droot, dbias, None
+            dbias = torch.ops.gmlm.colstats(gb.float() if gb.dtype == torch.float16 else gb)[0].to(ctx.dtypes[2])
+        return dh, dx, dw, droot, dbias, None, None
 
 
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -411,9 +431,9 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 def linear_nt_ok(x: torch.Tensor, n_out: int) -> bool:
-    """Shapes ``linear_nt`` runs on the tcgen05 GEMM: bf16 CUDA activations, K and N multiples of 64."""
+    """Shapes ``linear_nt`` runs on the tcgen05 GEMM: bf16 CUDA activations, K a multiple of 64, N of 32."""
     return (x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and x.size(1) % 64 == 0 and x.size(1) > 0
-            and n_out % 64 == 0 and n_out > 0)
+            and n_out % 32 == 0 and n_out > 0)
 
 
 class _LinearNT(torch.autograd.Function):
@@ -434,7 +454,7 @@ class _LinearNT(torch.autograd.Function):
         gb = g.to(torch.bfloat16).contiguous()
         dx = dwt = dbias = None
         if ctx.needs_input_grad[0]:
-            if wtb.size(0) % 64 == 0 and wtb.size(1) % 64 == 0:
+            if wtb.size(0) % 64 == 0 and wtb.size(1) % 32 == 0:
                 dx = gemm_nt(gb, wtb.t().contiguous())                     # [M, N_out] x [K, N_out]^T
             else:
                 dx = gb @ wtb
@@ -497,14 +517,18 @@ def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, w_live: torch.Tensor,
     return out if out.dtype == out_dtype else out.to(out_dtype)
 
 
-def rgcn_transform_ok(h: torch.Tensor, x: torch.Tensor, fo: int) -> bool:
-    """Shapes the tcgen05 path covers: bf16 activations, K blocks of 64, Fo a multiple of 64."""
-    return (h.is_cuda and h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and h.size(1) % 64 == 0
-            and x.size(1) % 64 == 0 and fo % 64 == 0 and h.size(1) > 0)
+def rgcn_transform_ok(h: torch.Tensor, x: torch.Tensor, fo: int, op_dtype: Optional[torch.dtype] = None) -> bool:
+    """Shapes the tcgen05 path covers: K blocks of 64, Fo a multiple of 32; activations bf16 (bf16 pipeline) or
+    anything castable when an explicit fp16 / bf16 operand type is given (autocast)."""
+    if not (h.is_cuda and h.size(1) % 64 == 0 and x.size(1) % 64 == 0 and fo % 32 == 0 and h.size(1) > 0):
+        return False
+    if op_dtype is None:
+        return h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
+    return op_dtype in (torch.bfloat16, torch.float16)
 
 
-def rgcn_transform(h, x, w, root, bias, out_dtype) -> torch.Tensor:
-    return _RGCNTransform.apply(h, x, w, root, bias, out_dtype)
+def rgcn_transform(h, x, w, root, bias, out_dtype, op_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    return _RGCNTransform.apply(h, x, w, root, bias, out_dtype, op_dtype or h.dtype)
 
 
 # ------------------------------------------------------------------------------ halo pack / unpack

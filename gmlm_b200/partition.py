@@ -215,13 +215,20 @@ def halo_exchange(x_local: torch.Tensor, part: LocalPart, group=None, *, pack=No
 
 
 
-def default_stage_fractions(n_stages: int) -> List[float]:
-    """Relative block sizes of the staged forward: 1, 2, 3, 5, 8, 13, ... (the first pull is the only exposed
-    one, so the first block is small; the late blocks are big because most of the halo has arrived by then)."""
+def default_stage_fractions(n_stages: int, kind: str = "fib") -> List[float]:
+    """Relative block sizes of the staged forward.  ``fib``: 1, 2, 3, 5, 8, 13, ... (the first pull is the only
+    exposed one, so the first block is small; the late blocks are big because most of the halo has arrived by
+    then).  ``lin``: 1, 2, 3, 4, ... (a smaller last block: less compute left when the last stage lands -- for
+    transports whose pull chain is about as long as the aggregation).  ``flat``: equal blocks."""
+    n = max(1, n_stages)
+    if kind == "lin":
+        return [float(i + 1) for i in range(n)]
+    if kind == "flat":
+        return [1.0] * n
     fr = [1.0, 2.0]
-    while len(fr) < n_stages:
+    while len(fr) < n:
         fr.append(fr[-1] + fr[-2])
-    return fr[:max(1, n_stages)]
+    return fr[:n]
 
 
 def stage_row_cuts(rowptr: torch.Tensor, fractions) -> Tuple[List[int], torch.Tensor]:
