@@ -607,12 +607,15 @@ def run_partitioned(args):
                 tma = args.tma_ctas if name == "tma" else 0
                 st0 = bool(args.tma_stage0) and tma > 0
 
+                shape = tuple(args.tma_shape)
+
                 def f():
-                    peer.pull_tma_ctas, peer.pull_tma_stage0 = tma, st0
+                    peer.pull_tma_ctas, peer.pull_tma_stage0, peer.pull_tma_shape = tma, st0, shape
                     return peer.forward_staged(out=h_buf)
                 what = (f"{K} halo stages by first use (block sizes '{args.stage_fractions}'); stage 0 by " +
                         ("bulk-copy (TMA) CTAs on every SM" if st0 else "the LDG pull kernel") + ", later stages " +
-                        (f"by {tma} bulk-copy (TMA) CTAs of 3 warps" if tma else f"by {args.pull_ctas or 32} LDG CTAs") +
+                        (f"by {tma} bulk-copy (TMA) CTAs (warps, ring KiB, rows per batch = {shape}; 0 = default)" if tma
+                         else f"by {args.pull_ctas or 32} LDG CTAs") +
                         " under the aggregation blocks (two streams)")
                 return f, staged_cache["nk"], what
             if name == "packed":
@@ -683,18 +686,34 @@ def run_partitioned(args):
                         for c in (args.sweep_tma_ctas if name == "tma" else [0]):
                             for fr in args.sweep_fractions:
                                 for s0 in (args.sweep_stage0 if name == "tma" else [0]):
-                                    args.fwd_stages, args.tma_ctas, args.stage_fractions, args.tma_stage0 = K, c, fr, s0
-                                    fn, _, _ = make_fwd(name)
-                                    key = f"{name}:K={K}:fr={fr}" + (f":ctas={c}:s0={s0}" if name == "tma" else "")
-                                    sweep["forward_ms"][key] = timed(fn, args.sweep_iters)
-                                    if rank == 0:
-                                        print(f"[sweep] fwd {key}: {sweep['forward_ms'][key]:.3f} ms", file=sys.stderr,
-                                              flush=True)
+                                    for shp in (args.sweep_tma_shapes if name == "tma" else ["0,0,0"]):
+                                        args.fwd_stages, args.tma_ctas, args.stage_fractions, args.tma_stage0 = K, c, fr, s0
+                                        args.tma_shape = [int(v) for v in shp.split(",")]
+                                        fn, _, _ = make_fwd(name)
+                                        key = f"{name}:K={K}:fr={fr}" + (f":ctas={c}:s0={s0}:shape={shp}" if name == "tma" else "")
+                                        sweep["forward_ms"][key] = timed(fn, args.sweep_iters)
+                                        if rank == 0:
+                                            print(f"[sweep] fwd {key}: {sweep['forward_ms'][key]:.3f} ms", file=sys.stderr,
+                                                  flush=True)
                 else:
                     fn, _, _ = make_fwd(name)
                     sweep["forward_ms"][name] = timed(fn, args.sweep_iters)
                     if rank == 0:
                         print(f"[sweep] fwd {name}: {sweep['forward_ms'][name]:.3f} ms", file=sys.stderr, flush=True)
+            if peer is not None and "tma" in fwd_list:
+                # decomposition of the staged forward (measurement only): the pull chain alone, the blocks alone,
+                # the blocks alone on ONE stream, and one whole-CSR aggregation
+                sweep["decomposition_ms"] = {}
+                fn, _, _ = make_fwd("tma")                     # the last swept configuration
+                for tag, skip, ov in (("pulls_only", "agg", True), ("blocks_only_two_streams", "pull", True),
+                                      ("blocks_only_one_stream", "pull", False)):
+                    peer.debug_skip, peer.overlap_blocks = skip, ov
+                    sweep["decomposition_ms"][tag] = timed(fn, args.sweep_iters)
+                peer.debug_skip, peer.overlap_blocks = "", True
+                sweep["decomposition_ms"]["whole_aggregation"] = timed(
+                    lambda: G.spmm(X, g.fwd, _lib.AGG_MEAN, out=h_buf), args.sweep_iters)
+                if rank == 0:
+                    print(f"[sweep] decomposition {sweep['decomposition_ms']}", file=sys.stderr, flush=True)
             for name in bwd_list:
                 fn, _, _ = make_bwd(name)
                 sweep["backward_ms"][name] = timed(fn, args.sweep_iters)
@@ -714,6 +733,8 @@ def run_partitioned(args):
                     args.stage_fractions = v_
                 if k_ == "s0":
                     args.tma_stage0 = int(v_)
+                if k_ == "shape":
+                    args.tma_shape = [int(v) for v in v_.split(",")]
             args.bwd = best_b
             sweep["chosen"] = {"forward": best_f, "backward": best_b}
 
@@ -849,11 +870,12 @@ def main():
     ap.add_argument("--workload", default=None, choices=["c2", "c3", "c4", "c5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"], help="N>1: halo exchange implementation")
-    ap.add_argument("--bwd", default="push", choices=list(BWD_VARIANTS), help="N>1: halo-gradient return (see run_partitioned)")
-    ap.add_argument("--fwd", default="pull", choices=list(FWD_VARIANTS), help="N>1: forward halo transport (see run_partitioned)")
+    # defaults = the fastest variants of the round-2 sweeps on 8 GPUs (profiles/r2_scale_sweeps.md)
+    ap.add_argument("--bwd", default="fetch", choices=list(BWD_VARIANTS), help="N>1: halo-gradient return (see run_partitioned)")
+    ap.add_argument("--fwd", default="tma", choices=list(FWD_VARIANTS), help="N>1: forward halo transport (see run_partitioned)")
     ap.add_argument("--fwd-stages", type=int, default=6, help="N>1, --fwd staged|tma: halo stages (by first use)")
     ap.add_argument("--packed-stages", type=int, default=4, help="N>1, --fwd packed: stages")
-    ap.add_argument("--tma-ctas", type=int, default=32, help="N>1, --fwd tma: single-warp bulk-copy CTAs per overlapped stage")
+    ap.add_argument("--tma-ctas", type=int, default=64, help="N>1, --fwd tma: bulk-copy CTAs per overlapped stage")
     ap.add_argument("--tma-stage0", type=int, default=0, help="N>1, --fwd tma: 1 = stage 0 by bulk copy too (one CTA per SM)")
     ap.add_argument("--pull-ctas", type=int, default=0, help="N>1, --fwd staged: CTA cap of the overlapped LDG pull kernels (0 = 32 CTAs of 1024 threads)")
     ap.add_argument("--sweep", action="store_true", help="N>1: time every transport variant after one setup, then the full step with the fastest")
@@ -861,9 +883,12 @@ def main():
     ap.add_argument("--sweep-stages", type=int, nargs="+", default=[4, 8])
     ap.add_argument("--sweep-tma-ctas", type=int, nargs="+", default=[16, 32, 64])
     ap.add_argument("--sweep-fractions", nargs="+", default=["fib"])
+    ap.add_argument("--sweep-tma-shapes", nargs="+", default=["0,0,0"], help="warps,ringKiB,rowsPerBatch per variant")
+    ap.add_argument("--tma-shape", type=int, nargs=3, default=[0, 0, 0],
+                    help="N>1, --fwd tma: warps per CTA, ring KiB per CTA, rows per batch of the overlapped pull (0 = default)")
     ap.add_argument("--sweep-stage0", type=int, nargs="+", default=[0])
     ap.add_argument("--sweep-fwd", nargs="+", default=None, help="restrict the forward variants of --sweep")
-    ap.add_argument("--stage-fractions", default="fib", choices=["fib", "lin", "flat"],
+    ap.add_argument("--stage-fractions", default="lin", choices=["fib", "lin", "flat"],
                     help="N>1, --fwd staged|tma: relative sizes of the aggregation blocks")
     ap.add_argument("--partition", default="random", choices=["random", "cyclic", "range"],
                     help="N>1: node ownership")

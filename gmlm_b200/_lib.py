@@ -59,7 +59,7 @@ SIGNATURES = {
     "gmlm_scatter_add_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "gmlm_gather_rows_ptr": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _p]),
     "gmlm_reduce_rows_ptr": (_int, [_p, _int, _i64, _i64, _p, _p, _p, _i64, _p]),
-    "gmlm_gather_rows_ptr_tma": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _int, _int, _int, _p]),
+    "gmlm_gather_rows_ptr_tma": (_int, [_p, _p, _int, _i64, _i64, _p, _i64, _int, _int, _int, _int, _p]),
     "gmlm_soft_mask_fwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _p, _f32, _p, _i64, _p]),
     "gmlm_soft_mask_bwd_workspace_bytes": (_sz, [_i64, _i64]),
     "gmlm_soft_mask_bwd": (_int, [_p, _int, _i64, _i64, _i64, _p, _f32, _p, _p, _i64, _p, _sz, _p]),

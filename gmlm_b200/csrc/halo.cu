@@ -110,11 +110,13 @@ template <int UNUSED = 0>
 __global__ void __launch_bounds__(256, 1) gather_ptr_tma_kernel(const uint64_t* __restrict__ row_ptrs,
                                                                 const int64_t* __restrict__ out_ids, int64_t n,
                                                                 uint32_t row_bytes, uint8_t* __restrict__ out,
-                                                                int64_t ldo_bytes, int slots) {
+                                                                int64_t ldo_bytes, int slots, int rb) {
+  // rb = rows per batch (32, 16 or 8: lanes >= rb idle) -- small batches keep the ring, and with it the bite this
+  // kernel takes out of the SM's unified L1 / shared memory, small when it runs under an aggregation kernel
   extern __shared__ __align__(128) uint8_t tma_smem_all[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  const uint32_t slot_bytes = 32u * row_bytes;
+  const uint32_t slot_bytes = uint32_t(rb) * row_bytes;
   uint8_t* tma_smem = tma_smem_all + size_t(warp) * slots * slot_bytes;              // this warp's ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(tma_smem_all + size_t(nwarps) * slots * slot_bytes) + warp * slots;
   if (lane == 0) {
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(256, 1) gather_ptr_tma_kernel(const uint64_t* 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  const int64_t n_batches = (n + 31) / 32;
+  const int64_t n_batches = (n + rb - 1) / rb;
   const int64_t first = int64_t(blockIdx.x) * nwarps + warp, stride = int64_t(gridDim.x) * nwarps;
   const int depth = slots - 2;                       // batches in flight
 
@@ -131,8 +133,8 @@ __global__ void __launch_bounds__(256, 1) gather_ptr_tma_kernel(const uint64_t* 
     const int64_t b = first + it * stride;
     if (b >= n_batches) return;
     const int s = int(it % slots);
-    const int64_t k = b * 32 + lane;
-    const int cnt = int(min(int64_t(32), n - b * 32));
+    const int64_t k = b * rb + lane;
+    const int cnt = int(min(int64_t(rb), n - b * rb));
     const uint32_t bar = smem_addr(bars + s);
     if (lane == 0)
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(cnt) * row_bytes)
@@ -171,8 +173,8 @@ __global__ void __launch_bounds__(256, 1) gather_ptr_tma_kernel(const uint64_t* 
       if (ok) break;
       if (++spins > (1u << 26)) __trap();            // a lost transfer traps instead of hanging the GPU
     }
-    const int64_t k = b * 32 + lane;
-    if (k < n) {
+    const int64_t k = b * rb + lane;
+    if (lane < rb && k < n) {
       const int64_t o = out_ids ? out_ids[k] : k;
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + o * ldo_bytes),
                    "r"(smem_addr(tma_smem + size_t(s) * slot_bytes + size_t(lane) * row_bytes)), "r"(row_bytes)
@@ -332,11 +334,12 @@ extern "C" int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t 
 }
 
 // TMA variant of gmlm_gather_rows_ptr: `ctas` CTAs (0 = one per SM) of `warps` warps (0 = 3, at most 8), each
-// warp with its own ring inside the CTA's `smem_kb` KiB (0 = 200) of shared memory.  Rows must be 16-byte
-// multiples, 16-byte aligned on both sides, and at least three 32-row batches per warp must fit the ring.
+// warp with its own ring of `rows_per_batch`-row batches (0 = 32; 16, 8) inside the CTA's `smem_kb` KiB (0 = 200) of
+// shared memory.  Rows must be 16-byte multiples, 16-byte aligned on both sides, and at least three batches per
+// warp must fit the ring.
 extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
                                         int64_t n, void* out, int64_t ldo, int ctas, int warps, int smem_kb,
-                                        void* stream) {
+                                        int rows_per_batch, void* stream) {
   GMLM_REQUIRE(dtype == GMLM_F32 || dtype == GMLM_BF16, "gather_rows_ptr_tma: dtype must be GMLM_F32 or GMLM_BF16");
   const int esz = dtype == GMLM_F32 ? 4 : 2;
   const int64_t row_bytes = feat * esz;
@@ -348,17 +351,19 @@ extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64
   if (smem_kb <= 0) smem_kb = 200;
   GMLM_REQUIRE(smem_kb <= 224, "gather_rows_ptr_tma: at most 224 KiB of shared memory per CTA");
   GMLM_REQUIRE(warps >= 0 && warps <= 8, "gather_rows_ptr_tma: 0..8 warps per CTA");
-  const int64_t slot_bytes = 32 * row_bytes;
+  const int rb = rows_per_batch <= 0 ? 32 : rows_per_batch;
+  GMLM_REQUIRE(rb == 32 || rb == 16 || rb == 8, "gather_rows_ptr_tma: rows_per_batch must be 32, 16 or 8");
+  const int64_t slot_bytes = rb * row_bytes;
   const int64_t budget = int64_t(smem_kb) * 1024 - 8 * 64 * 8;
   if (warps == 0) {                       // as many warps (up to 3) as still get a four-slot ring each
     warps = 3;
     while (warps > 1 && budget / (warps * slot_bytes) < 4) --warps;
   }
   const int slots = int(std::min<int64_t>(64, budget / (warps * slot_bytes)));
-  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (three 32-row batches per warp)");
+  GMLM_REQUIRE(slots >= 3, "gather_rows_ptr_tma: rows too wide for the shared-memory ring (three batches per warp)");
   const size_t smem = size_t(warps) * slots * slot_bytes + size_t(warps) * slots * 8;
   if (ctas <= 0) ctas = num_sms();
-  const int64_t n_batches = (n + 31) / 32;
+  const int64_t n_batches = (n + rb - 1) / rb;
   if (int64_t(ctas) * warps > n_batches) ctas = int((n_batches + warps - 1) / warps);
   auto kern = gather_ptr_tma_kernel<0>;
   static bool configured[kMaxDevices] = {};
@@ -369,7 +374,7 @@ extern "C" int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64
   }
   kern<<<unsigned(ctas), 32 * warps, smem, as_stream(stream)>>>(reinterpret_cast<const uint64_t*>(row_ptrs), out_ids, n,
                                                                uint32_t(row_bytes), static_cast<uint8_t*>(out),
-                                                               ldo * esz, slots);
+                                                               ldo * esz, slots, rb);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }

@@ -722,15 +722,21 @@ class PeerHalo:
         ready.record(main)
         self.pull_stream.wait_event(ready)
         events, agg_done = [], []
+        dbg = getattr(self, "debug_skip", "")               # measurement only: "pull" / "agg" leaves that half out
         with torch.cuda.stream(self.pull_stream):
             for k, (_, _, _, ptrs, outs) in enumerate(self.fwd_stages):
-                cnt = int(ptrs.numel())
+                cnt = int(ptrs.numel()) if dbg != "pull" else 0
                 if cnt and self.pull_tma_ctas > 0 and (k > 0 or self.pull_tma_stage0):
                     # bulk-copy engine transport: stage 0 has the GPU to itself (one CTA per SM), later stages
                     # run under an aggregation kernel from a few single-warp CTAs
-                    _check(lib.gmlm_gather_rows_ptr_tma(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
-                                                        self.feat, 0 if k == 0 else self.pull_tma_ctas, 0, 0,
-                                                        _st(tail.device)), "gather_rows_ptr_tma")
+                    warps, kb, rb = getattr(self, "pull_tma_shape", (0, 0, 0))      # (warps, ring KiB, rows per batch)
+                    if k == 0:
+                        _check(lib.gmlm_gather_rows_ptr_tma(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
+                                                            self.feat, 0, 0, 0, 0, _st(tail.device)), "gather_rows_ptr_tma")
+                    else:
+                        _check(lib.gmlm_gather_rows_ptr_tma(_p(ptrs), _p(outs), _dt(self.dtype), self.feat, cnt, _p(tail),
+                                                            self.feat, self.pull_tma_ctas, warps, kb, rb,
+                                                            _st(tail.device)), "gather_rows_ptr_tma")
                 elif cnt:
                     # stage 0 has the GPU to itself; later stages share it with an aggregation kernel
                     lib.gmlm_set_tuning(b"halo_pull_ctas", 0 if k == 0 else self.pull_ctas_overlapped)
@@ -754,7 +760,7 @@ class PeerHalo:
         for k, ((csr, r0, r1, _, _), ev) in enumerate(zip(self.fwd_stages, events)):
             st = self.agg_streams[k % 2] if two else main
             st.wait_event(ev)
-            if csr is not None:
+            if csr is not None and dbg != "agg":
                 with torch.cuda.stream(st):
                     spmm(self.X, csr, _lib.AGG_MEAN, out=out[r0:r1])
             if timing:

@@ -243,9 +243,11 @@ int gmlm_reduce_rows_ptr(void* dst, int dtype, int64_t feat, int64_t ldd, const 
 /* gather_rows_ptr moved by the bulk-copy engine (cp.async.bulk: peer memory -> shared-memory ring -> local HBM)
  * from `ctas` CTAs (0 = one per SM) of `warps` warps (0 = up to 3; each warp runs its own ring and moves
  * ~12 M rows/s) sharing `smem_kb` KiB (0 = 200): the transport that can run UNDER an aggregation kernel without
- * sharing its load queues.  Three 32-row batches per warp must fit the ring (rows <= 2 KiB with one warp). */
+ * sharing its load queues.  Batches are `rows_per_batch` rows (0 = 32; 16 or 8 keep the ring -- and the bite out of
+ * the SM's unified L1 / shared memory -- small); three batches per warp must fit the ring. */
 int gmlm_gather_rows_ptr_tma(const void* const* row_ptrs, const int64_t* out_ids, int dtype, int64_t feat,
-                             int64_t n, void* out, int64_t ldo, int ctas, int warps, int smem_kb, void* stream);
+                             int64_t n, void* out, int64_t ldo, int ctas, int warps, int smem_kb,
+                             int rows_per_batch, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ def _row_ptrs(src, ids):
 @pytest.mark.parametrize("dtype,feat", [(torch.bfloat16, 256), (torch.bfloat16, 64), (torch.float32, 256),
                                         (torch.float32, 20), (torch.bfloat16, 1024)])
 @pytest.mark.parametrize("n", [1, 31, 32, 33, 5000])
-@pytest.mark.parametrize("impl", ["ldg", "tma1", "tma7", "tma_all", "tma_1warp", "tma_8warps"])
+@pytest.mark.parametrize("impl", ["ldg", "tma1", "tma7", "tma_all", "tma_1warp", "tma_8warps", "tma_rb16", "tma_rb8"])
 def test_gather_rows_ptr_matches_indexing(cuda_dev, dtype, feat, n, impl):
     lib = _lib.load()
     g = torch.Generator(device="cpu").manual_seed(n * 131 + feat)
@@ -33,11 +33,14 @@ def test_gather_rows_ptr_matches_indexing(cuda_dev, dtype, feat, n, impl):
     if impl == "ldg":
         rc = lib.gmlm_gather_rows_ptr(_ptr(ptrs), _ptr(out_ids), code, feat, n, _ptr(out), feat, _stream(cuda_dev))
     else:
-        ctas, warps = {"tma1": (1, 0), "tma7": (7, 0), "tma_all": (0, 0), "tma_1warp": (5, 1), "tma_8warps": (3, 8)}[impl]
+        ctas, warps, kb, rb = {"tma1": (1, 0, 0, 0), "tma7": (7, 0, 0, 0), "tma_all": (0, 0, 0, 0), "tma_1warp": (5, 1, 0, 0),
+                               "tma_8warps": (3, 8, 0, 0), "tma_rb16": (9, 2, 100, 16), "tma_rb8": (4, 2, 64, 8)}[impl]
         row_bytes = feat * src.element_size()
         if warps == 8 and row_bytes > 256:
             warps = 2 if row_bytes <= 1024 else 1                     # 8 rings of wide rows do not fit one CTA
-        rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), _ptr(out_ids), code, feat, n, _ptr(out), feat, ctas, warps, 0,
+        if rb and row_bytes > 512:
+            kb = 200                                                  # wide rows need the full ring
+        rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), _ptr(out_ids), code, feat, n, _ptr(out), feat, ctas, warps, kb, rb,
                                           _stream(cuda_dev))
     _lib.check(rc, "gather_rows_ptr")
     want = torch.full_like(out, -7.0)
@@ -53,7 +56,7 @@ def test_gather_rows_ptr_tma_small_ring_and_identity_destinations(cuda_dev):
     ids = torch.randint(0, 30_000, (n,), device=cuda_dev)
     out = torch.empty((n, feat), device=cuda_dev, dtype=torch.bfloat16)
     ptrs = _row_ptrs(src, ids)
-    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), C.c_void_p(0), _lib.BF16, feat, n, _ptr(out), feat, 3, 1, 29,
+    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), C.c_void_p(0), _lib.BF16, feat, n, _ptr(out), feat, 3, 1, 29, 0,
                                       _stream(cuda_dev))
     _lib.check(rc, "gather_rows_ptr_tma")
     assert torch.equal(out, src[ids])
@@ -65,7 +68,7 @@ def test_gather_rows_ptr_tma_rejects_wide_rows(cuda_dev):
     ids = torch.arange(4, device=cuda_dev)
     out = torch.empty_like(src)
     ptrs = _row_ptrs(src, ids)
-    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), C.c_void_p(0), _lib.F32, 4096, 4, _ptr(out), 4096, 0, 0, 0,
+    rc = lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), C.c_void_p(0), _lib.F32, 4096, 4, _ptr(out), 4096, 0, 0, 0, 0,
                                       _stream(cuda_dev))
     assert rc != 0
 

@@ -31,11 +31,11 @@ for feat in (256, 64):
     print(f"feat {feat}: LDG gather        {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s (read+write)")
     for ctas in (16, 32, 74, 148):
         for warps in (1, 2, 3, 4, 6, 8):
-            if lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), None, _lib.BF16, feat, n, _ptr(out), feat, ctas, warps, 0,
+            if lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), None, _lib.BF16, feat, n, _ptr(out), feat, ctas, warps, 0, 0,
                                             _stream(dev)):
                 continue                                            # ring too small for that many warps
             ms = timeit(lambda: _lib.check(lib.gmlm_gather_rows_ptr_tma(_ptr(ptrs), None, _lib.BF16, feat, n, _ptr(out), feat,
-                                                                        ctas, warps, 0, _stream(dev))))
+                                                                        ctas, warps, 0, 0, _stream(dev))))
             print(f"feat {feat}: TMA ctas={ctas:3d} warps={warps}  {ms:.3f} ms  {nbytes / ms / 1e6:.0f} GB/s  "
                   f"({nbytes / 2 / ms / 1e6 / ctas:.1f} GB/s gathered per CTA)")
     assert torch.equal(out, src[ids])
