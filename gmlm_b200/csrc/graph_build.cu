@@ -100,6 +100,25 @@ __global__ void rel_hist_kernel(const int64_t* __restrict__ et, int64_t E, int R
     if (sh[i]) atomicAdd(counts + i, (unsigned long long)sh[i]);
 }
 
+// ---------------------------------------------------------------- content key of an index tensor
+// out[0] = sum_i x_i * (2i+1),  out[1] = sum_i (x_i ^ (x_i >> 17)) * (i * 0x9E3779B97F4A7C15 + 1)   (mod 2^64).
+// Position-weighted, so permutations change it; integer atomics, so the result does not depend on the order of
+// the additions.  Used to recognise a graph whose edge tensors were re-created with the same contents (the
+// reference builds a fresh edge_type tensor on every call, main.py:255) without rebuilding its CSR.
+__global__ void checksum_kernel(const uint64_t* __restrict__ x, int64_t n, unsigned long long* __restrict__ out) {
+  unsigned long long a = 0, b = 0;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
+    const unsigned long long v = x[i];
+    a += v * (2ull * (unsigned long long)i + 1ull);
+    b += (v ^ (v >> 17)) * ((unsigned long long)i * 0x9E3779B97F4A7C15ull + 1ull);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out, a); atomicAdd(out + 1, b); }
+}
+
 // ------------------------------------------------------------------------ A3
 struct SlotMap { int32_t slot[64]; };
 
@@ -353,6 +372,18 @@ int gmlm_edge_type_bucket(const int64_t* src, int64_t E, const int32_t* deg, int
   if (E == 0) return GMLM_OK;
   edge_type_kernel<<<grid_for(E, 4), kThreads, 0, as_stream(stream)>>>(src, E, deg, N, b, edge_type, nullptr);
   GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
+int gmlm_checksum_i64(const int64_t* x, int64_t n, uint64_t* out2, void* stream) {
+  GMLM_REQUIRE(n >= 0 && out2 != nullptr && (n == 0 || x != nullptr), "checksum: bad arguments");
+  cudaStream_t st = as_stream(stream);
+  GMLM_CUDA_TRY(cudaMemsetAsync(out2, 0, 2 * sizeof(uint64_t), st));
+  if (n > 0) {
+    checksum_kernel<<<grid_for(n, 8), kThreads, 0, st>>>(reinterpret_cast<const uint64_t*>(x), n,
+                                                         reinterpret_cast<unsigned long long*>(out2));
+    GMLM_LAUNCH_CHECK();
+  }
   return GMLM_OK;
 }
 

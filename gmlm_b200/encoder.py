@@ -65,7 +65,9 @@ _ET_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 
 
 def cached_edge_type(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
-    """Degree-bucket relation ids for ``edge_index`` (main.py:253-267), computed once per graph."""
+    """Degree-bucket relation ids for ``edge_index`` (main.py:253-267), computed once per graph.  Keyed on the
+    identity of ``edge_index`` (the reference passes the same ``data.edge_index`` every call); the SAME tensor is
+    returned on a hit, so the graph cache behind it hits on identity as well."""
     key = (_tensor_key(edge_index), int(num_nodes))
     hit = _ET_CACHE.get(key)
     if hit is not None:

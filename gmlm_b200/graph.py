@@ -284,12 +284,21 @@ class RelGraph:
 
 
 # ------------------------------------------------------------------------------ cache
-# The reference rebuilds its per-relation edge lists on every conv call.  Here the structure
-# is built once per (edge_index, edge_type) pair.  Entries hold strong references to the key
-# tensors so their storage cannot be recycled under a stale key; `_version` catches in-place
-# edits.  Read-only after construction (checkpoint recompute / autograd threads only read).
-_CACHE: "OrderedDict[tuple, RelGraph]" = OrderedDict()
+# The reference rebuilds its per-relation edge lists on every conv call.  Here the structure is built once
+# per graph.  Two keys:
+#   * identity  (data_ptr, _version, shape, ...) of the two tensors: the fast path, no device work;
+#   * content   (shape, dtype, device, two 64-bit position-weighted checksums per tensor, `gmlm_checksum_i64`):
+#     what makes the advertised one-line import swap hit -- the reference builds a FRESH edge_type tensor on
+#     every get_graph_embeddings call (main.py:255), so identity alone would rebuild the CSR (two radix sorts,
+#     four host syncs) per layer call.  A content lookup costs one pass over the indices and one host read.
+# Entries hold strong references to the tensors of their FIRST key so that storage cannot be recycled under a
+# stale identity key; `_version` catches in-place edits.  Graphs are read-only after construction (checkpoint
+# recompute / autograd threads only read).
+_CACHE: "OrderedDict[tuple, RelGraph]" = OrderedDict()           # content key -> graph
+_ALIAS: "OrderedDict[tuple, tuple]" = OrderedDict()              # identity key -> (content key, keepalive tensors)
 _CACHE_SIZE = int(os.environ.get("GMLM_GRAPH_CACHE", "4"))
+_ALIAS_SIZE = 64
+cache_stats = {"identity_hits": 0, "content_hits": 0, "builds": 0}
 
 
 def _tensor_key(t: Optional[torch.Tensor]):
@@ -298,20 +307,45 @@ def _tensor_key(t: Optional[torch.Tensor]):
     return (t.data_ptr(), t._version, tuple(t.shape), tuple(t.stride()), t.dtype, str(t.device))
 
 
+def _content_key(t: Optional[torch.Tensor]):
+    if t is None:
+        return None
+    lib = _lib.load()
+    x = t if (t.dtype == torch.int64 and t.is_contiguous()) else t.long().contiguous()
+    with torch.cuda.device(x.device):
+        out = torch.empty(2, dtype=torch.int64, device=x.device)
+        _lib.check(lib.gmlm_checksum_i64(_ptr(x), x.numel(), _ptr(out), _stream(x.device)), "checksum")
+    a, b = out.tolist()                                           # one host read
+    return (tuple(t.shape), str(t.device), a, b)
+
+
 def get_rel_graph(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int,
                   num_relations: int) -> RelGraph:
-    key = (_tensor_key(edge_index), _tensor_key(edge_type), int(num_nodes), int(num_relations))
-    g = _CACHE.get(key)
-    if g is not None:
-        _CACHE.move_to_end(key)
-        return g
-    g = RelGraph.build(edge_index, edge_type, num_nodes, num_relations)
-    g._keepalive = [edge_index, edge_type]
-    _CACHE[key] = g
-    while len(_CACHE) > _CACHE_SIZE:
-        _CACHE.popitem(last=False)
+    ikey = (_tensor_key(edge_index), _tensor_key(edge_type), int(num_nodes), int(num_relations))
+    hit = _ALIAS.get(ikey)
+    if hit is not None and hit[0] in _CACHE:
+        _ALIAS.move_to_end(ikey)
+        _CACHE.move_to_end(hit[0])
+        cache_stats["identity_hits"] += 1
+        return _CACHE[hit[0]]
+    _require_cuda(edge_index, "edge_index")
+    ckey = (_content_key(edge_index), _content_key(edge_type), int(num_nodes), int(num_relations))
+    g = _CACHE.get(ckey)
+    if g is None:
+        g = RelGraph.build(edge_index, edge_type, num_nodes, num_relations)
+        _CACHE[ckey] = g
+        cache_stats["builds"] += 1
+        while len(_CACHE) > _CACHE_SIZE:
+            _CACHE.popitem(last=False)
+    else:
+        _CACHE.move_to_end(ckey)
+        cache_stats["content_hits"] += 1
+    _ALIAS[ikey] = (ckey, (edge_index, edge_type))              # keep the key tensors alive with the alias
+    while len(_ALIAS) > _ALIAS_SIZE:
+        _ALIAS.popitem(last=False)
     return g
 
 
 def clear_graph_cache():
     _CACHE.clear()
+    _ALIAS.clear()

@@ -65,6 +65,11 @@ int gmlm_edge_type_bucket(const int64_t* src, int64_t num_edges, const int32_t* 
 int gmlm_relation_histogram(const int64_t* edge_type, int64_t num_edges, int num_relations,
                             int64_t* counts /* [num_relations] */, void* stream);
 
+/* ---- content key of an int64 index tensor (graph cache: the reference re-creates edge_type on every call,
+ *      main.py:255, so tensor identity cannot key the cached CSR) ----
+ * out2[0], out2[1] = two position-weighted 64-bit sums of x[0..n) (order-independent integer atomics). */
+int gmlm_checksum_i64(const int64_t* x, int64_t n, uint64_t* out2, void* stream);
+
 /* ---- A3  (dst,rel)-keyed CSR: replaces the per-relation boolean-mask compaction inside
  *          [PyG] RGCNConv.forward (called main.py:272,285,298,308) ----
  * Segment id s = dst*num_slots + slot_of_rel_host[edge_type[e]]  (edge_type may be NULL: slot 0).

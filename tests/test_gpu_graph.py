@@ -110,16 +110,44 @@ def test_csr_rejects_bad_indices(cuda_dev):
         G.RelGraph.build(ei, torch.tensor([0, 1, 7]).to(cuda_dev), 5, 5)   # relation 7 out of range
 
 
-def test_graph_cache_identity(cuda_dev):
+def test_graph_cache_identity_and_content(cuda_dev):
+    """Identity is the fast path; CONTENT is what the one-line import swap needs: the reference re-creates its
+    edge_type tensor on every call (main.py:255), which must not rebuild the CSR."""
+    from gmlm_b200 import graph as gg
+    G.clear_graph_cache()
     n, ei = GRAPHS["cornell"]
     ei = ei.to(cuda_dev)
     et = G.edge_type_from_degree(ei, n)
     a = G.get_rel_graph(ei, et, n, 5)
+    before = dict(gg.cache_stats)
     b = G.get_rel_graph(ei, et, n, 5)
-    assert a is b
-    et2 = et.clone()
-    c = G.get_rel_graph(ei, et2, n, 5)
-    assert c is not a
-    et2[0] = (et2[0] + 1) % 4          # in-place edit bumps _version -> new key
+    assert a is b and gg.cache_stats["identity_hits"] == before["identity_hits"] + 1
+    et2 = et.clone()                   # same contents, new tensor: no rebuild
+    c = G.get_rel_graph(ei.clone(), et2, n, 5)
+    assert c is a and gg.cache_stats["content_hits"] == before["content_hits"] + 1
+    assert gg.cache_stats["builds"] == before["builds"]
+    et2[0] = (et2[0] + 1) % 4          # in-place edit bumps _version AND changes the contents -> new graph
     d = G.get_rel_graph(ei, et2, n, 5)
-    assert d is not c
+    assert d is not a and gg.cache_stats["builds"] == before["builds"] + 1
+    perm = torch.randperm(ei.size(1), device=cuda_dev)            # same multiset of edges, different order:
+    e = G.get_rel_graph(ei[:, perm].contiguous(), et[perm].contiguous(), n, 5)   # a different CSR edge order
+    assert e is not a
+
+
+def test_reference_style_calls_build_the_csr_once(cuda_dev):
+    """What main.py:250-267 does under the import swap: a fresh edge_type per get_graph_embeddings call and four
+    conv calls with it.  One CSR build in total."""
+    from gmlm_b200 import graph as gg
+    G.clear_graph_cache()
+    n, ei = GRAPHS["star_hub"]
+    ei = ei.to(cuda_dev)
+    conv = G.RGCNConv(16, 8, 5, 30).to(cuda_dev)
+    x = torch.randn(n, 16, device=cuda_dev)
+    builds0 = gg.cache_stats["builds"]
+    outs = []
+    for _ in range(3):
+        et = G.edge_type_from_degree(ei, n)      # fresh tensor every call, as the reference's loop produces
+        for _ in range(4):
+            outs.append(conv(x, ei, et))
+    assert gg.cache_stats["builds"] == builds0 + 1
+    assert all(torch.equal(o, outs[0]) for o in outs)
