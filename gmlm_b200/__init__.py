@@ -30,6 +30,6 @@ from .losses import nt_xent_loss  # noqa: F401
 from .sampling import generate_active_node_mask, weighted_sample_without_replacement  # noqa: F401
 from .dist_norm import partitioned_graph_norm  # noqa: F401
 from .dist_encoder import CudaPartitionOps, PartitionedGraphEncoder, sync_gradients  # noqa: F401
-from .attn import GATConv, GCNConv, LoopGraph, gat_aggregate, get_loop_graph  # noqa: F401
+from .attn import GATConv, GCNConv, LoopGraph, gat_aggregate, gat_dropout_mask, get_loop_graph  # noqa: F401
 
 __version__ = "0.1.0"

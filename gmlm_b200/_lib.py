@@ -53,8 +53,12 @@ SIGNATURES = {
     "gmlm_gemm_nt": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int,
                             _p]),
     "gmlm_gcn_edge_weights": (_int, [_p, _p, _i64, _p, _p, _p]),
-    "gmlm_gat_alpha_fwd": (_int, [_p, _p, _i64, _p, _p, _int, _f32, _p, _p]),
-    "gmlm_gat_alpha_bwd": (_int, [_p, _p, _i64, _p, _i64, _p, _i64, _int, _int, _int, _p, _p, _p, _f32, _p, _p, _p]),
+    "gmlm_gat_workspace_bytes": (_sz, [_i64, _int, _int]),
+    "gmlm_gat_fused_fwd": (_int, [_p, _p, _i64, _p, _int, _i64, _p, _p, _int, _int, _f32, _f32, C.c_uint64, _i32, _i64, _i64,
+                                  _p, _p, _p, _p, _p, _sz, _p, _i64, _p, _p, _p]),
+    "gmlm_gat_bwd_edges": (_int, [_p, _p, _i64, _p, _int, _i64, _p, _i64, _p, _p, _p, _p, _p, _int, _int, _f32, _f32,
+                                  C.c_uint64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p, _p, _p, _p]),
+    "gmlm_gat_dropout_mask": (_int, [C.c_uint64, _i64, _f32, _p, _p]),
     "gmlm_segment_sum_f32": (_int, [_p, _p, _p, _i64, _int, _p, _p]),
     "gmlm_gather_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),
     "gmlm_scatter_add_rows": (_int, [_p, _int, _i64, _i64, _p, _i64, _p, _i64, _p]),

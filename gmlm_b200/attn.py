@@ -4,9 +4,10 @@ They have **no counterpart in /root/reference** (it uses only RGCNConv); semanti
 ``GCNConv`` / ``GATConv`` defaults as restated in ``oracle/pyg_ref.py`` ("parity unpinned").
 
 Both run on one dst-keyed CSR with self-loops normalised the upstream way (existing self-loops
-removed, one loop per node appended) and reuse the aggregation kernel ``gmlm_spmm_csr`` in
-weighted mode — scalar weights for GCN, one weight column per head for GAT — forward on the
-CSR, backward on its transpose.  The per-edge scalars come from ``csrc/gat.cu``.
+removed, one loop per node appended).  GCN reuses the aggregation kernel ``gmlm_spmm_csr`` in weighted
+mode with per-edge scalars from ``csrc/gat.cu``.  GAT is ``csrc/gat_fused.cu``: the forward is ONE pass
+(online softmax, the score computed where the source row is gathered, alpha never stored), the backward
+one edge pass over the same CSR plus two gathers over its transpose; long rows use the hub plan.
 """
 from __future__ import annotations
 
@@ -119,67 +120,101 @@ class GCNConv(nn.Module):
 
 
 # ------------------------------------------------------------------------------ GAT (A9)
+def _hub_args(csr: CSR):
+    return (csr.hub_thresh, csr.n_hub, csr.n_chunks, _ptr(csr.hub_row), _ptr(csr.hub_chunk_ptr), _ptr(csr.chunk_beg),
+            _ptr(csr.chunk_end))
+
+
 class _GATAggregate(torch.autograd.Function):
+    """Fused edge-softmax aggregation (csrc/gat_fused.cu): one pass, online softmax, alpha never stored."""
+
     @staticmethod
-    def forward(ctx, z, a_src, a_dst, graph: LoopGraph, slope: float):
+    def forward(ctx, z, a_src, a_dst, graph: LoopGraph, slope: float, p_drop: float, seed: int):
         lib = _lib.load()
         z = _rowmajor(z)
-        n, heads = a_src.shape
+        n, heads = a_dst.shape
+        head_dim = z.size(1) // heads
         dev = z.device
+        fwd = graph.fwd
         a_src32, a_dst32 = a_src.detach().float().contiguous(), a_dst.detach().float().contiguous()
         with torch.cuda.device(dev):
-            alpha = torch.empty((graph.fwd.nnz, heads), dtype=torch.float32, device=dev)
-            _lib.check(lib.gmlm_gat_alpha_fwd(_ptr(graph.fwd.rowptr), _ptr(graph.fwd.col), graph.num_nodes,
-                                              _ptr(a_src32), _ptr(a_dst32), heads, float(slope), _ptr(alpha),
-                                              _stream(dev)), "gat_alpha_fwd")
-        out = spmm(z, _with_w(graph.fwd, alpha), _lib.AGG_WEIGHTED)
-        ctx.graph, ctx.slope = graph, float(slope)
-        ctx.save_for_backward(z, a_src32, a_dst32, alpha)
+            out = torch.empty((n, heads * head_dim), dtype=z.dtype, device=dev)
+            m = torch.empty((n, heads), dtype=torch.float32, device=dev)
+            l = torch.empty((n, heads), dtype=torch.float32, device=dev)
+            ws_bytes = lib.gmlm_gat_workspace_bytes(fwd.n_chunks, heads, head_dim) if fwd.n_hub else 0
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            _lib.check(lib.gmlm_gat_fused_fwd(_ptr(fwd.rowptr), _ptr(fwd.col), n, _ptr(z), _dtype_code(z, "gat"), _ld(z),
+                                              _ptr(a_src32), _ptr(a_dst32), heads, head_dim, float(slope), float(p_drop),
+                                              int(seed), *_hub_args(fwd), _ptr(ws), ws_bytes, _ptr(out),
+                                              heads * head_dim, _ptr(m), _ptr(l), _stream(dev)), "gat_fused_fwd")
+        ctx.graph, ctx.slope, ctx.p_drop, ctx.seed = graph, float(slope), float(p_drop), int(seed)
+        ctx.save_for_backward(z, a_src32, a_dst32, m, l, out)
         ctx.in_dtypes = (a_src.dtype, a_dst.dtype)
         return out
 
     @staticmethod
     def backward(ctx, g):
         lib = _lib.load()
-        z, a_src, a_dst, alpha = ctx.saved_tensors
+        z, a_src, a_dst, m, l, out = ctx.saved_tensors
         graph: LoopGraph = ctx.graph
+        fwd = graph.fwd
         g = _rowmajor(g)
         if g.dtype != z.dtype:
             g = g.to(z.dtype)
-        n, heads = a_src.shape
+        n, heads = a_dst.shape
         head_dim = z.size(1) // heads
         dev = z.device
+        # t[i,h] = <g[i,h,:], out[i,h,:]> = sum_e alpha_e keep_e d_alpha_e (no pass over the edges needed)
+        t = (g.view(n, heads, head_dim).float() * out.view(n, heads, head_dim).float()).sum(-1).contiguous()
         with torch.cuda.device(dev):
-            d_score = torch.empty_like(alpha)
+            alpha_eff = torch.empty((fwd.nnz, heads), dtype=torch.float32, device=dev)
+            d_score = torch.empty((fwd.nnz, heads), dtype=torch.float32, device=dev)
             da_dst = torch.empty((n, heads), dtype=torch.float32, device=dev)
-            _lib.check(lib.gmlm_gat_alpha_bwd(_ptr(graph.fwd.rowptr), _ptr(graph.fwd.col), n, _ptr(z), _ld(z), _ptr(g),
-                                              _ld(g), _dtype_code(z, "gat_alpha_bwd"), heads, head_dim, _ptr(a_src),
-                                              _ptr(a_dst), _ptr(alpha), ctx.slope, _ptr(d_score), _ptr(da_dst),
-                                              _stream(dev)), "gat_alpha_bwd")
-            da_src = torch.empty((n, heads), dtype=torch.float32, device=dev)
-            _lib.check(lib.gmlm_segment_sum_f32(_ptr(d_score), _ptr(graph.t2f), _ptr(graph.bwd.rowptr), n, heads,
-                                                _ptr(da_src), _stream(dev)), "segment_sum")
-        dz = spmm(g, _with_w(graph.bwd, alpha[graph.t2f].contiguous()), _lib.AGG_WEIGHTED)
-        return dz, da_src.to(ctx.in_dtypes[0]), da_dst.to(ctx.in_dtypes[1]), None, None
+            ws_bytes = lib.gmlm_gat_workspace_bytes(fwd.n_chunks, heads, head_dim) if fwd.n_hub else 0
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+            _lib.check(lib.gmlm_gat_bwd_edges(_ptr(fwd.rowptr), _ptr(fwd.col), n, _ptr(z), _dtype_code(z, "gat"), _ld(z),
+                                              _ptr(g), _ld(g), _ptr(a_src), _ptr(a_dst), _ptr(m), _ptr(l), _ptr(t), heads,
+                                              head_dim, ctx.slope, ctx.p_drop, ctx.seed, *_hub_args(fwd), _ptr(ws),
+                                              ws_bytes, _ptr(alpha_eff), _ptr(d_score), _ptr(da_dst), _stream(dev)),
+                       "gat_bwd_edges")
+            da_src = torch.empty((a_src.size(0), heads), dtype=torch.float32, device=dev)
+            _lib.check(lib.gmlm_segment_sum_f32(_ptr(d_score), _ptr(graph.t2f), _ptr(graph.bwd.rowptr), a_src.size(0),
+                                                heads, _ptr(da_src), _stream(dev)), "segment_sum")
+        dz = spmm(g, _with_w(graph.bwd, alpha_eff[graph.t2f].contiguous()), _lib.AGG_WEIGHTED)
+        return dz, da_src.to(ctx.in_dtypes[0]), da_dst.to(ctx.in_dtypes[1]), None, None, None, None
 
 
-def gat_aggregate(z, a_src, a_dst, graph: LoopGraph, negative_slope: float = 0.2) -> torch.Tensor:
-    """``out[i,h,:] = sum_j softmax_j(leaky_relu(a_src[j,h] + a_dst[i,h])) * z[j,h,:]`` over the in-edges."""
+def gat_aggregate(z, a_src, a_dst, graph: LoopGraph, negative_slope: float = 0.2, dropout: float = 0.0,
+                  seed: int = 0) -> torch.Tensor:
+    """``out[i,h,:] = sum_j softmax_j(leaky_relu(a_src[j,h] + a_dst[i,h])) * z[j,h,:]`` over the in-edges, with
+    optional attention dropout (keep mask = counter-based hash of (seed, edge, head): see ``gat_dropout_mask``)."""
     _require_cuda(z, "z")
-    return _GATAggregate.apply(z, a_src, a_dst, graph, negative_slope)
+    return _GATAggregate.apply(z, a_src, a_dst, graph, negative_slope, dropout, seed)
+
+
+def gat_dropout_mask(seed: int, num_edges: int, heads: int, p_drop: float, device) -> torch.Tensor:
+    """bool [num_edges, heads] keep mask of the fused kernels, edges in forward-CSR order (tests / inspection)."""
+    lib = _lib.load()
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        keep = torch.empty(num_edges * heads, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_gat_dropout_mask(int(seed), keep.numel(), float(p_drop), _ptr(keep), _stream(dev)),
+                   "gat_dropout_mask")
+    return keep.view(num_edges, heads).bool()
 
 
 class GATConv(nn.Module):
-    """Upstream ``GATConv`` defaults (self-loops, LeakyReLU 0.2, concat heads, bias; attention
-    dropout is not implemented — the upstream default is 0).  Row A9 / BASELINE configs[2]."""
+    """Upstream ``GATConv`` defaults (self-loops, LeakyReLU 0.2, concat heads, bias, attention dropout in training
+    mode).  Row A9 / BASELINE configs[2].  The edge-softmax and the aggregation are ONE kernel pass."""
 
     def __init__(self, in_channels: int, out_channels: int, heads: int = 1, concat: bool = True,
                  negative_slope: float = 0.2, dropout: float = 0.0, bias: bool = True):
         super().__init__()
-        if dropout != 0.0:
-            raise NotImplementedError("gmlm_b200.GATConv: attention dropout is not implemented (upstream default 0)")
+        if not 0.0 <= dropout < 1.0:
+            raise ValueError("gmlm_b200.GATConv: dropout must be in [0, 1)")
         self.in_channels, self.out_channels, self.heads, self.concat = in_channels, out_channels, heads, concat
         self.negative_slope = negative_slope
+        self.dropout = dropout
         self.lin = nn.Linear(in_channels, heads * out_channels, bias=False)
         self.att_src = nn.Parameter(torch.empty(1, heads, out_channels))
         self.att_dst = nn.Parameter(torch.empty(1, heads, out_channels))
@@ -196,14 +231,18 @@ class GATConv(nn.Module):
         if self.bias is not None:
             nn.init.zeros_(self.bias)
 
-    def forward(self, x: torch.Tensor, edge_index) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, edge_index, dropout_seed: Optional[int] = None) -> torch.Tensor:
         n, h, c = x.size(0), self.heads, self.out_channels
         graph = edge_index if isinstance(edge_index, LoopGraph) else get_loop_graph(edge_index, n)
         z = self.lin(x)
         zv = z.view(n, h, c)
         a_src = (zv * self.att_src).sum(-1)
         a_dst = (zv * self.att_dst).sum(-1)
-        out = gat_aggregate(z, a_src, a_dst, graph, self.negative_slope)
+        p = self.dropout if self.training else 0.0
+        seed = 0
+        if p > 0.0:                      # one draw from torch's CPU generator per call (reproducible under manual_seed)
+            seed = int(dropout_seed) if dropout_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
+        out = gat_aggregate(z, a_src, a_dst, graph, self.negative_slope, p, seed)
         if not self.concat:
             out = out.view(n, h, c).mean(dim=1)
         return out + self.bias if self.bias is not None else out

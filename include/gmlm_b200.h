@@ -206,24 +206,42 @@ int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64
                  const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
                  int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream);
 
-/* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference): per-edge scalars
- *      of the GCN symmetric normalisation and the GAT edge-softmax on a dst-keyed CSR.  The
- *      feature aggregation itself is gmlm_spmm_csr in weighted mode (w_heads = 1 / = heads). ----
- * gcn_edge_weights: w[e] = deg[col[e]]^-1/2 * deg[row]^-1/2, deg = CSR row length (self-loops included)
- * gat_alpha_fwd   : alpha[e,h] = softmax over row(e) of leaky_relu(a_src[col[e],h] + a_dst[row,h])  (+1e-16)
- * gat_alpha_bwd   : d_score[e,h] = d/d(raw score); da_dst[r,h] = sum over row r of d_score
- * segment_sum_f32 : out[r,h] = sum_{i in row r} vals[idx[i],h]  (idx NULL = identity) */
+/* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference: semantics = upstream GCNConv /
+ *      GATConv defaults, restated in oracle/pyg_ref.py) on a dst-keyed CSR with upstream's self-loop handling ----
+ * gcn_edge_weights: w[e] = deg[col[e]]^-1/2 * deg[row]^-1/2, deg = CSR row length (self-loops included); the GCN
+ *                   aggregation itself is gmlm_spmm_csr in weighted mode.
+ * segment_sum_f32 : out[r,h] = sum_{i in row r} vals[idx[i],h]  (idx NULL = identity; one warp per row)
+ *
+ * gat_fused_fwd   : out[i,h,:] = sum_{e->i} alpha[e,h] z[col[e],h,:],  alpha = softmax over the in-edges of i of
+ *                   leaky_relu(a_src[col[e],h] + a_dst[i,h]) (+1e-16 in the denominator, as upstream), optional
+ *                   attention dropout on alpha.  ONE pass with an online softmax: the score is computed where the
+ *                   source row is gathered and alpha is never materialised; m_out / l_out [rows, H] keep each row's
+ *                   maximum and normaliser for the backward.  Rows longer than hub_thresh use the CSR's hub plan
+ *                   (chunk partials merged by the split-softmax identity, chunk order => deterministic).
+ * gat_bwd_edges   : per edge alpha_eff[e,h] (alpha * keep / (1-p): the weights of the transposed aggregation of g),
+ *                   d_score[e,h] (gradient of the raw score) and da_dst[i,h] = sum_e d_score;  t[i,h] must hold
+ *                   <g[i,h,:], out[i,h,:]>.  da_src and dz are gathers over the transposed CSR (segment_sum_f32,
+ *                   gmlm_spmm_csr with one weight column per head).
+ * gat_dropout_mask: keep[i] of the counter-based hash both kernels use (index = CSR position * H + head). */
 int gmlm_gcn_edge_weights(const int32_t* rowptr, const int32_t* col, int64_t num_rows, float* dis_ws /* [rows] */,
                           float* w /* [nnz] */, void* stream);
-int gmlm_gat_alpha_fwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, const float* a_src,
-                       const float* a_dst, int heads, float negative_slope, float* alpha /* [nnz,heads] */,
-                       void* stream);
-int gmlm_gat_alpha_bwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, const void* z, int64_t ldz,
-                       const void* g, int64_t ldg, int dtype, int heads, int head_dim, const float* a_src,
-                       const float* a_dst, const float* alpha, float negative_slope, float* d_score /* [nnz,heads] */,
-                       float* da_dst /* [rows,heads] */, void* stream);
-int gmlm_segment_sum_f32(const float* vals, const int64_t* idx, const int32_t* rowptr, int64_t num_rows, int heads,
-                         float* out, void* stream);
+int gmlm_segment_sum_f32(const float* vals, const int64_t* idx, const int32_t* rowptr, int64_t num_rows,
+                         int heads, float* out, void* stream);
+size_t gmlm_gat_workspace_bytes(int64_t n_chunks, int heads, int head_dim);
+int gmlm_gat_fused_fwd(const int32_t* rowptr, const int32_t* col, int64_t num_rows, const void* z, int dtype,
+                       int64_t ldz, const float* a_src, const float* a_dst, int heads, int head_dim,
+                       float negative_slope, float p_drop, uint64_t seed, int32_t hub_thresh, int64_t n_hub,
+                       int64_t n_chunks, const int32_t* hub_row, const int32_t* hub_chunk_ptr,
+                       const int32_t* chunk_beg, const int32_t* chunk_end, void* ws, size_t ws_bytes,
+                       void* out, int64_t ldo, float* m_out, float* l_out, void* stream);
+int gmlm_gat_bwd_edges(const int32_t* rowptr, const int32_t* col, int64_t num_rows, const void* z, int dtype,
+                       int64_t ldz, const void* g, int64_t ldg, const float* a_src, const float* a_dst,
+                       const float* m_in, const float* l_in, const float* t_in, int heads, int head_dim,
+                       float negative_slope, float p_drop, uint64_t seed, int32_t hub_thresh, int64_t n_hub,
+                       int64_t n_chunks, const int32_t* hub_row, const int32_t* hub_chunk_ptr,
+                       const int32_t* chunk_beg, const int32_t* chunk_end, void* ws, size_t ws_bytes,
+                       float* alpha_eff, float* d_score, float* da_dst, void* stream);
+int gmlm_gat_dropout_mask(uint64_t seed, int64_t n, float p_drop, uint8_t* keep, void* stream);
 
 /* ---- halo pack / unpack for the destination-row partition (the reference has no
  *      multi-GPU path) ----

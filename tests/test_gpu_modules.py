@@ -376,3 +376,106 @@ def test_mask_sampler_on_cuda(cuda_dev):
     k = max(1, int(0.3 * int(train_mask.sum())))
     assert m.dtype == torch.bool and int(m.sum()) == k
     assert bool(train_mask[m].all()) and bool((w[m] > 0).all())
+
+
+def _gat_reference_csr(graph, z, a_s, a_d, slope, keep=None, p=0.0):
+    """fp64 restatement of the GAT aggregation in forward-CSR order (edge k of the CSR), optional keep mask."""
+    rowptr, col = graph.fwd.rowptr.cpu().long(), graph.fwd.col.cpu().long()
+    n, heads = a_d.shape
+    c = z.size(1) // heads
+    z64 = z.detach().double().cpu().view(-1, heads, c)
+    dst = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    e = torch.nn.functional.leaky_relu(a_s.double().cpu()[col] + a_d.double().cpu()[dst], slope)
+    emax = torch.full((n, heads), float("-inf"), dtype=torch.float64).scatter_reduce(
+        0, dst.unsqueeze(-1).expand_as(e), e, reduce="amax", include_self=True)
+    ex = (e - emax[dst]).exp()
+    den = torch.zeros((n, heads), dtype=torch.float64).index_add_(0, dst, ex) + 1e-16
+    alpha = ex / den[dst]
+    if keep is not None:
+        alpha = alpha * keep.cpu().double() / (1.0 - p)
+    out = torch.zeros((n, heads, c), dtype=torch.float64).index_add_(0, dst, alpha.unsqueeze(-1) * z64[col])
+    return out.view(n, heads * c)
+
+
+def test_gat_hub_rows_split_softmax_matches_reference_and_is_deterministic(cuda_dev):
+    """A star-shaped graph: destination 7 has thousands of in-edges, so the row is cut into chunks whose partial
+    (max, normaliser, accumulator) triples are merged by the split-softmax identity; forward AND backward."""
+    from gmlm_b200.attn import LoopGraph
+    n, e, heads, c = 600, 30000, 4, 16
+    g = torch.Generator().manual_seed(5)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.where(torch.rand(e, generator=g) < 0.6, torch.tensor(7), torch.randint(0, n, (e,), generator=g))
+    ei = torch.stack([src, dst]).to(cuda_dev)
+    graph = LoopGraph.build(ei, n, hub_thresh=64)
+    assert graph.fwd.n_hub >= 1 and graph.fwd.n_chunks > graph.fwd.n_hub
+    z = torch.randn(n, heads * c, generator=g).to(cuda_dev).requires_grad_(True)
+    a_s = (torch.randn(n, heads, generator=g) * 3).to(cuda_dev).requires_grad_(True)     # wide score range
+    a_d = (torch.randn(n, heads, generator=g) * 3).to(cuda_dev).requires_grad_(True)
+    gout = torch.randn(n, heads * c, generator=g).to(cuda_dev)
+    out = G.gat_aggregate(z, a_s, a_d, graph)
+    out.backward(gout)
+    z64 = z.detach().double().cpu().requires_grad_(True)
+    as64, ad64 = a_s.detach().double().cpu().requires_grad_(True), a_d.detach().double().cpu().requires_grad_(True)
+    # autograd through the fp64 restatement (edge list = the CSR)
+    rowptr, col = graph.fwd.rowptr.cpu().long(), graph.fwd.col.cpu().long()
+    dstv = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    sc = torch.nn.functional.leaky_relu(as64[col] + ad64[dstv], 0.2)
+    emax = torch.full((n, heads), float("-inf"), dtype=torch.float64).scatter_reduce(
+        0, dstv.unsqueeze(-1).expand_as(sc), sc.detach(), reduce="amax", include_self=True)
+    ex = (sc - emax[dstv]).exp()
+    alpha = ex / (torch.zeros((n, heads), dtype=torch.float64).index_add_(0, dstv, ex) + 1e-16)[dstv]
+    ref = torch.zeros((n, heads, c), dtype=torch.float64).index_add_(0, dstv, alpha.unsqueeze(-1) * z64.view(n, heads, c)[col])
+    ref = ref.view(n, heads * c)
+    ref.backward(gout.double().cpu())
+    assert rel_err(out, ref) <= FP32_TOL
+    assert rel_err(z.grad, z64.grad) <= 2e-5
+    assert rel_err(a_s.grad, as64.grad) <= 2e-5 and rel_err(a_d.grad, ad64.grad) <= 2e-5
+    out2 = G.gat_aggregate(z.detach(), a_s.detach(), a_d.detach(), graph)
+    assert torch.equal(out.detach(), out2)                       # no atomics: bit-identical run to run
+
+
+def test_gat_attention_dropout_uses_the_hash_mask(cuda_dev):
+    """Training-mode attention dropout (upstream: F.dropout on alpha).  The keep mask is a counter-based hash of
+    (seed, CSR position, head); with that mask the output equals the reference exactly, the kept fraction is
+    1 - p, eval mode ignores dropout and a fixed seed reproduces the call."""
+    from gmlm_b200.attn import gat_dropout_mask
+    n, e, heads, c, p = 1500, 20000, 8, 16, 0.4
+    ei = synth.rmat_edges(n, e, seed=9).to(cuda_dev)
+    graph = G.get_loop_graph(ei, n)
+    gen = torch.Generator().manual_seed(2)
+    z = torch.randn(n, heads * c, generator=gen).to(cuda_dev)
+    a_s, a_d = torch.randn(n, heads, generator=gen).to(cuda_dev), torch.randn(n, heads, generator=gen).to(cuda_dev)
+    seed = 123456789
+    keep = gat_dropout_mask(seed, graph.fwd.nnz, heads, p, cuda_dev)
+    assert abs(float(keep.float().mean()) - (1 - p)) < 0.01
+    out = G.gat_aggregate(z, a_s, a_d, graph, 0.2, p, seed)
+    ref = _gat_reference_csr(graph, z, a_s, a_d, 0.2, keep=keep, p=p)
+    assert rel_err(out, ref) <= FP32_TOL
+    assert torch.equal(out, G.gat_aggregate(z, a_s, a_d, graph, 0.2, p, seed))
+    assert not torch.equal(out, G.gat_aggregate(z, a_s, a_d, graph, 0.2, p, seed + 1))
+    # gradient through the dropped attention: finite differences are noisy, so compare with autograd of the reference
+    zg = z.clone().requires_grad_(True)
+    og = G.gat_aggregate(zg, a_s, a_d, graph, 0.2, p, seed)
+    og.sum().backward()
+    rowptr, col = graph.fwd.rowptr.cpu().long(), graph.fwd.col.cpu().long()
+    # d(sum out)/dz[j,h,:] = sum over out-edges of j of alpha_eff  (broadcast over the head's channels)
+    dstv = torch.repeat_interleave(torch.arange(n), rowptr[1:] - rowptr[:-1])
+    sc = torch.nn.functional.leaky_relu(a_s.double().cpu()[col] + a_d.double().cpu()[dstv], 0.2)
+    emax = torch.full((n, heads), float("-inf"), dtype=torch.float64).scatter_reduce(
+        0, dstv.unsqueeze(-1).expand_as(sc), sc, reduce="amax", include_self=True)
+    ex = (sc - emax[dstv]).exp()
+    alpha = ex / (torch.zeros((n, heads), dtype=torch.float64).index_add_(0, dstv, ex) + 1e-16)[dstv]
+    alpha = alpha * keep.cpu().double() / (1 - p)
+    want = torch.zeros((n, heads), dtype=torch.float64).index_add_(0, col, alpha)
+    assert rel_err(zg.grad.view(n, heads, c)[:, :, 0], want) <= 2e-5
+    mod = G.GATConv(32, c, heads=heads, dropout=p).to(cuda_dev)
+    x = torch.randn(n, 32, device=cuda_dev)
+    mod.eval()
+    assert torch.equal(mod(x, ei), mod(x, ei))                   # eval: dropout off
+    mod.train()
+    torch.manual_seed(0)
+    y1 = mod(x, ei)
+    torch.manual_seed(0)
+    y2 = mod(x, ei)
+    assert torch.equal(y1, y2) and not torch.equal(y1, mod(x, ei))
+
