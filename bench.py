@@ -297,6 +297,8 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
             "frac": fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
             "algorithmic_bytes": fwd_b, "ms": fwd_ms}
     if traffic:
+        roof["traffic_source"] = ("stored ncu figure (dram__bytes_read.sum + dram__bytes_write.sum of the same kernels on "
+                                  "this workload, profiles/traffic.json), NOT measured in this run")
         roof["dram_gbs"] = traffic / (fwd_ms * 1e-3) / 1e9
         roof["note"] = ("achieved counts ALGORITHMIC bytes (SURVEY §8d: no credit for cache hits); on this power-law "
                         "graph the 126 MB L2 serves the hub source rows, so DRAM traffic (ncu, `traffic`) is well below "
@@ -453,6 +455,97 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
     return line
 
 
+# ----------------------------------------------------------------------------- the reference's own dataset shapes
+def measure_small(args, key: str, with_stock: bool):
+    """BASELINE.json configs[1] / configs[2]: the GNN encoder of main.py:250-320 with the shipped widths
+    (hidden_channels = 512) on a Roman-empire- / Amazon-ratings-shaped graph, forward + backward under
+    torch.amp.autocast exactly as the reference's training loops call it (main.py:446,543); configs[2] adds a
+    GATConv(300 -> 8 x 64) layer (the edge-softmax variant north_star names).  These graphs fit in L2, so the
+    figure is TIME (an encoder pass; a contrastive pre-training epoch runs two, main.py:447-448), not HBM
+    fraction.  `stock_torch_on_gpu` = the oracle modules (index_select / index_add_ / scatter ops, what
+    torch_geometric executes) on the same B200, same inputs -- part of the baseline leg."""
+    import gmlm_b200 as G
+    from gmlm_b200 import synth
+
+    dev = torch.device("cuda:0")
+    w = synth.WORKLOADS[key]
+    n, e, feat = w.num_nodes, w.num_edges, w.feat
+    ei = synth.make_graph(w, device=dev)
+    x = synth.make_features(n, feat, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timeit(fn, warm=3, iters=10):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    out = {"workload": w.title, "num_nodes": n, "num_edges": e, "feat": feat, "hidden_channels": w.hidden}
+    torch.manual_seed(0)
+    enc = G.GraphEncoder(feat, w.hidden, 768, dropout_rate=0.0).to(dev)
+    xg = x.detach().requires_grad_(True)
+
+    def enc_step(m=enc):
+        with torch.amp.autocast("cuda"):
+            y = m.get_graph_embeddings(xg, ei)
+        y.backward(torch.ones_like(y))
+        xg.grad = None
+
+    ms = timeit(enc_step)
+    out["encoder_ms_fwd_bwd"] = ms
+    out["pretrain_epoch_encoder_ms"] = 2 * ms
+    out["encoder_edges_per_s"] = 4 * e / (ms * 1e-3)
+    gat = None
+    if key == "c3":
+        gat = G.GATConv(feat, 64, heads=8).to(dev)
+
+        def gat_step(m=gat):
+            y = m(xg, ei)
+            y.backward(torch.ones_like(y))
+            xg.grad = None
+
+        out["gat_layer_ms_fwd_bwd"] = timeit(gat_step)
+        out["gat_layer_what"] = "GATConv(300 -> 8 heads x 64): fused one-pass edge-softmax aggregation, fp32"
+    if with_stock:
+        try:
+            from oracle import EncoderRef, GATConvRef
+            torch.manual_seed(0)
+            ref = EncoderRef(feat, w.hidden, 768, dropout_rate=0.0, use_checkpoint=False).to(dev)
+
+            def ref_step():
+                with torch.amp.autocast("cuda"):
+                    y = ref(xg, ei)
+                y.backward(torch.ones_like(y))
+                xg.grad = None
+
+            stock = {"encoder_ms_fwd_bwd": timeit(ref_step, warm=2, iters=5),
+                     "what": "oracle EncoderRef (vectorised edge typing + per-relation index_select/index_add_ "
+                             "RGCN, stock GraphNorm ops) on the same B200 under autocast; the reference's own "
+                             "per-edge Python typing loop is NOT included (it alone costs seconds per call)"}
+            if gat is not None:
+                gref = GATConvRef(feat, 64, heads=8).to(dev)
+
+                def gref_step():
+                    y = gref(xg, ei)
+                    y.backward(torch.ones_like(y))
+                    xg.grad = None
+
+                stock["gat_layer_ms_fwd_bwd"] = timeit(gref_step, warm=2, iters=5)
+            out["stock_torch_on_gpu"] = stock
+            del ref
+        except Exception as ex:
+            out["stock_torch_on_gpu"] = {"error": repr(ex)[:200]}
+    del enc
+    G.clear_graph_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_single(args):
     """N=1.  Default: BASELINE.json configs[4]'s graph (10M nodes / 200M edges) whole on one GPU — the
     denominator of the 1/2/4/8-GPU scaling the metric names — followed by configs[3] (2M / 40M, the
@@ -475,6 +568,13 @@ def run_single(args):
         line["cpu_baseline"] = {"value": eps, "unit": "edges/s", "cores": cores, "kind": "port",
                                 "sample": f"R-MAT {args.cpu_sample_nodes} nodes / {args.cpu_sample_edges} edges, F=256 "
                                           f"fp32, fwd+bwd, oracle port of torch_geometric propagate, {cms:.0f} ms/step"}
+    if not args.no_small:
+        # BASELINE.json configs[1] / configs[2]: encoder (and GAT layer) time on the reference's own dataset shapes
+        for key in ("c2", "c3"):
+            try:
+                line[key] = measure_small(args, key, with_stock=not args.no_cpu_baseline)
+            except Exception as ex:      # context legs never hide the headline
+                line[key] = {"error": repr(ex)[:300]}
     print(json.dumps(line), flush=True)
 
 
@@ -895,6 +995,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="N=1 default run: skip the configs[3] roofline-study leg")
     ap.add_argument("--no-layer", action="store_true")
+    ap.add_argument("--no-small", action="store_true", help="N=1 default run: skip the configs[1]/[2] (C2/C3) legs")
     ap.add_argument("--cpu-sample-nodes", type=int, default=100_000)
     ap.add_argument("--cpu-sample-edges", type=int, default=2_000_000)
     args = ap.parse_args()

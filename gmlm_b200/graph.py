@@ -120,33 +120,16 @@ def build_csr(row: torch.Tensor, col: torch.Tensor, num_rows: int, num_cols: int
     ``row``/``col``/``rel`` are int64 edge arrays (as in ``edge_index`` / ``edge_type``).
     Returns ``(CSR, seg_of_edge or None)``.  ``row`` is validated against ``num_rows`` and ``col``
     against ``num_cols`` (one host sync)."""
-    lib = _lib.load()
     _require_cuda(row, "edge_index")
-    dev = row.device
-    E = int(row.numel())
-    row = row.contiguous()
-    col = col.contiguous()
-    if rel is not None:
-        rel = rel.contiguous()
-        if rel.dtype != torch.int64:
-            rel = rel.long()
+    if rel is not None and rel.dtype != torch.int64:
+        rel = rel.long()
     rows_total = num_rows * num_slots
-    with torch.cuda.device(dev):
-        rowptr = torch.empty(rows_total + 1, dtype=torch.int32, device=dev)
-        colv = torch.empty(E, dtype=torch.int32, device=dev)
-        perm = torch.empty(E, dtype=torch.int32, device=dev)
-        seg = torch.empty(E, dtype=torch.int32, device=dev) if want_seg_of_edge else None
-        ws_bytes = lib.gmlm_csr_workspace_bytes(max(E, 1), rows_total)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        slots = None
-        if rel is not None:
-            slot_list = slot_of_rel if slot_of_rel is not None else list(range(num_relations))
-            slots = (C.c_int32 * num_relations)(*slot_list)
-        # csr_build keys on `dst`; here the CSR row plays that role and `col` is the gathered id
-        _lib.check(lib.gmlm_csr_build(_ptr(col), _ptr(row), _ptr(rel), E, num_rows, num_cols, num_relations, slots,
-                                      num_slots,
-                                      _ptr(rowptr), _ptr(colv), _ptr(perm), _ptr(seg), _ptr(ws), ws_bytes,
-                                      _stream(dev)), "csr_build")
+    slot_list = list(slot_of_rel) if slot_of_rel is not None else list(range(num_relations))
+    from . import ops  # noqa: F401  (registers torch.ops.gmlm.*)
+    rowptr, colv, perm, seg = torch.ops.gmlm.csr_build(row, col, rel, int(num_rows), int(num_cols), int(num_relations),
+                                                       [int(v) for v in slot_list], int(num_slots))
+    if not want_seg_of_edge:
+        seg = None
     csr = CSR(rowptr=rowptr, col=colv, num_rows=rows_total, perm=perm)
     csr.plan_hubs(hub_thresh)
     csr.plan_groups(quantum)

@@ -2,12 +2,13 @@
 allocator, launch on the current stream, autograd registration.
 
 Registered ops (``torch.ops.gmlm.*``, CUDA only — calling them with CPU tensors raises from
-the dispatcher; there is no fallback):
+the dispatcher; there is no fallback), every one with a fake (meta) implementation:
 
-    degree_i32, edge_type_bucket, spmm_csr, colstats, graphnorm_fwd, graphnorm_bwd,
-    layernorm_fwd, layernorm_bwd, soft_mask_fwd, soft_mask_bwd
+    degree_i32, edge_type_bucket, csr_build, spmm_csr, colstats, gemm_nt, graphnorm_bwd, layernorm_bwd, soft_mask_bwd
+    rgcn_aggregate, plan_aggregate, graphnorm_fwd, layernorm_fwd, soft_mask_fwd      <- differentiable
+                                                       (torch.library.register_autograd: backward = the ops above)
 
-Autograd wrappers used by the modules in ``gmlm_b200.nn``:
+Thin functional wrappers used by the modules in ``gmlm_b200.nn``:
 
     rgcn_aggregate(x, graph)            A5 forward / A14 backward
     graph_norm(x, weight, bias, mean_scale, eps, fuse_gelu)   A7
@@ -62,6 +63,12 @@ _LIB.define("layernorm_bwd(Tensor x, Tensor gy, Tensor mean, Tensor rstd, Tensor
             "-> (Tensor, Tensor, Tensor)")
 _LIB.define("soft_mask_fwd(Tensor x, Tensor mask, Tensor token, float beta) -> Tensor")
 _LIB.define("soft_mask_bwd(Tensor gy, Tensor mask, float beta, bool need_gx) -> (Tensor, Tensor)")
+# differentiable ops (autograd registered below with torch.library.register_autograd)
+_LIB.define("rgcn_aggregate(Tensor x, Tensor?[] fwd, Tensor?[] bwd, int[] meta) -> Tensor")
+_LIB.define("plan_aggregate(Tensor rows, Tensor?[] fwd, Tensor?[] bwd, int[] meta) -> Tensor")
+_LIB.define("gemm_nt(Tensor a1, Tensor b, Tensor? bias, Tensor? a2, ScalarType out_dtype) -> Tensor")
+_LIB.define("csr_build(Tensor row, Tensor col, Tensor? rel, int num_rows, int num_cols, int num_relations, "
+            "int[] slot_of_rel, int num_slots) -> (Tensor, Tensor, Tensor, Tensor)")
 
 
 # ------------------------------------------------------------------------------ A1 / A2
@@ -327,6 +334,227 @@ _LIB.impl("soft_mask_fwd", _soft_mask_fwd, "CUDA")
 _LIB.impl("soft_mask_bwd", _soft_mask_bwd, "CUDA")
 
 
+# ------------------------------------------------------------------------------ differentiable custom ops
+# torch.ops.gmlm.{rgcn_aggregate, plan_aggregate, graphnorm_fwd, layernorm_fwd, soft_mask_fwd} carry their
+# backward (torch.library.register_autograd) and a fake implementation (register_fake), so they can be called,
+# traced and differentiated as ordinary torch operators; the thin functions further down only validate arguments.
+def csr_pack(csr: CSR):
+    """CSR -> (Tensor?[8], [num_rows, hub_thresh]): rowptr, col, w, grp_row, hub_row, hub_chunk_ptr, chunk_beg, chunk_end."""
+    return ([csr.rowptr, csr.col, csr.w, csr.grp_row, csr.hub_row, csr.hub_chunk_ptr, csr.chunk_beg, csr.chunk_end],
+            [int(csr.num_rows), int(csr.hub_thresh)])
+
+
+def _spmm_list(x, c, rows, thresh, mode):
+    return _spmm_csr(x, c[0], c[1], c[2] if mode == _lib.AGG_WEIGHTED else None, rows, mode, c[3], thresh, c[4], c[5],
+                     c[6], c[7])
+
+
+def _rgcn_aggregate_impl(x, fwd, bwd, meta):
+    rows_f, thresh_f, _, _, n_nodes, n_slots = meta
+    h = _spmm_list(x, fwd, rows_f, thresh_f, _lib.AGG_MEAN)                 # [N*S, F]
+    return h.view(n_nodes, n_slots * x.size(1))
+
+
+def _plan_aggregate_impl(rows, fwd, bwd, meta):
+    return _spmm_list(rows, fwd, meta[0], meta[1], _lib.AGG_WEIGHTED)
+
+
+def _gemm_nt_op(a1, b, bias, a2, out_dtype):
+    return gemm_nt(a1, b, bias=bias, a2=a2, out_dtype=out_dtype)
+
+
+def _csr_build_op(row, col, rel, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
+    """(rowptr int32 [num_rows*num_slots+1], col int32 [E], perm int32 [E], seg_of_edge int32 [E]) of the CSR keyed
+    on ``row*num_slots + slot_of_rel[rel]`` (stable: original edge order inside a segment); A3."""
+    lib = _lib.load()
+    dev = row.device
+    E = int(row.numel())
+    row, col = row.contiguous(), col.contiguous()
+    rel = rel.contiguous() if rel is not None else None
+    rows_total = num_rows * num_slots
+    with torch.cuda.device(dev):
+        rowptr = torch.empty(rows_total + 1, dtype=torch.int32, device=dev)
+        colv = torch.empty(E, dtype=torch.int32, device=dev)
+        perm = torch.empty(E, dtype=torch.int32, device=dev)
+        seg = torch.empty(E, dtype=torch.int32, device=dev)
+        ws_bytes = lib.gmlm_csr_workspace_bytes(max(E, 1), rows_total)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        slots = (C.c_int32 * max(num_relations, 1))(*[int(v) for v in slot_of_rel]) if rel is not None else None
+        # csr_build keys on `dst`; here the CSR row plays that role and `col` is the gathered id
+        _lib.check(lib.gmlm_csr_build(_ptr(col), _ptr(row), _ptr(rel), E, num_rows, num_cols, num_relations, slots,
+                                      num_slots, _ptr(rowptr), _ptr(colv), _ptr(perm), _ptr(seg), _ptr(ws), ws_bytes,
+                                      _stream(dev)), "csr_build")
+    return rowptr, colv, perm, seg
+
+
+_LIB.impl("rgcn_aggregate", _rgcn_aggregate_impl, "CUDA")
+_LIB.impl("plan_aggregate", _plan_aggregate_impl, "CUDA")
+_LIB.impl("gemm_nt", _gemm_nt_op, "CUDA")
+_LIB.impl("csr_build", _csr_build_op, "CUDA")
+
+
+# ---- fake (meta) implementations: shapes and dtypes only
+@torch.library.register_fake("gmlm::degree_i32")
+def _(index, num_nodes):
+    return index.new_empty((num_nodes,), dtype=torch.int32)
+
+
+@torch.library.register_fake("gmlm::edge_type_bucket")
+def _(src, deg, bounds):
+    return src.new_empty((src.numel(),), dtype=torch.int64)
+
+
+@torch.library.register_fake("gmlm::spmm_csr")
+def _(x, rowptr, col, w, num_rows, mode, grp_row, hub_thresh, hub_row, hub_chunk_ptr, chunk_beg, chunk_end):
+    return x.new_empty((num_rows, x.size(1)))
+
+
+@torch.library.register_fake("gmlm::colstats")
+def _(x):
+    return x.new_empty((x.size(1),), dtype=torch.float64), x.new_empty((x.size(1),), dtype=torch.float64)
+
+
+@torch.library.register_fake("gmlm::graphnorm_fwd")
+def _(x, weight, bias, mean_scale, eps, fuse_gelu):
+    c = x.size(1)
+    return torch.empty_like(x), x.new_empty((c,), dtype=torch.float32), x.new_empty((c,), dtype=torch.float32)
+
+
+@torch.library.register_fake("gmlm::graphnorm_bwd")
+def _(x, gy, mean, rstd, weight, bias, mean_scale, fuse_gelu, need_gx):
+    c = x.size(1)
+    f = lambda: x.new_empty((c,), dtype=torch.float32)   # noqa: E731
+    return (torch.empty_like(x) if need_gx else x.new_empty((0,))), f(), f(), f()
+
+
+@torch.library.register_fake("gmlm::layernorm_fwd")
+def _(x, weight, bias, eps):
+    n = x.size(0)
+    return torch.empty_like(x), x.new_empty((n,), dtype=torch.float32), x.new_empty((n,), dtype=torch.float32)
+
+
+@torch.library.register_fake("gmlm::layernorm_bwd")
+def _(x, gy, mean, rstd, weight, need_gx):
+    c = x.size(1)
+    return ((torch.empty_like(x) if need_gx else x.new_empty((0,))), x.new_empty((c,), dtype=torch.float32),
+            x.new_empty((c,), dtype=torch.float32))
+
+
+@torch.library.register_fake("gmlm::soft_mask_fwd")
+def _(x, mask, token, beta):
+    return torch.empty_like(x)
+
+
+@torch.library.register_fake("gmlm::soft_mask_bwd")
+def _(gy, mask, beta, need_gx):
+    return gy.new_empty((gy.size(1),), dtype=torch.float32), (torch.empty_like(gy) if need_gx else gy.new_empty((0,)))
+
+
+@torch.library.register_fake("gmlm::rgcn_aggregate")
+def _(x, fwd, bwd, meta):
+    return x.new_empty((meta[4], meta[5] * x.size(1)))
+
+
+@torch.library.register_fake("gmlm::plan_aggregate")
+def _(rows, fwd, bwd, meta):
+    return rows.new_empty((meta[0], rows.size(1)))
+
+
+@torch.library.register_fake("gmlm::gemm_nt")
+def _(a1, b, bias, a2, out_dtype):
+    return a1.new_empty((a1.size(0), b.size(0)), dtype=out_dtype)
+
+
+@torch.library.register_fake("gmlm::csr_build")
+def _(row, col, rel, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
+    e = row.numel()
+    i32 = lambda k: row.new_empty((k,), dtype=torch.int32)   # noqa: E731
+    return i32(num_rows * num_slots + 1), i32(e), i32(e), i32(e)
+
+
+# ---- autograd formulas
+def _rgcn_aggregate_setup(ctx, inputs, output):
+    x, fwd, bwd, meta = inputs
+    ctx.bwd, ctx.meta, ctx.x_dtype = bwd, meta, x.dtype
+
+
+def _rgcn_aggregate_backward(ctx, gh):
+    _, _, rows_b, thresh_b, n_nodes, n_slots = ctx.meta
+    gh = gh.contiguous()
+    if gh.dtype != ctx.x_dtype:
+        gh = gh.to(ctx.x_dtype)
+    feat = gh.size(1) // n_slots
+    b = ctx.bwd
+    gx = torch.ops.gmlm.spmm_csr(gh.view(n_nodes * n_slots, feat), b[0], b[1], b[2], rows_b, _lib.AGG_WEIGHTED, b[3],
+                                 thresh_b, b[4], b[5], b[6], b[7])            # A14: gather on the transposed CSR
+    return gx, None, None, None
+
+
+def _plan_aggregate_setup(ctx, inputs, output):
+    rows, fwd, bwd, meta = inputs
+    ctx.bwd, ctx.meta, ctx.in_dtype = bwd, meta, rows.dtype
+
+
+def _plan_aggregate_backward(ctx, g):
+    g = g.contiguous()
+    if g.dtype != ctx.in_dtype:
+        g = g.to(ctx.in_dtype)
+    b = ctx.bwd
+    return (torch.ops.gmlm.spmm_csr(g, b[0], b[1], b[2], ctx.meta[2], _lib.AGG_WEIGHTED, b[3], ctx.meta[3], b[4], b[5],
+                                    b[6], b[7]), None, None, None)
+
+
+def _graphnorm_setup(ctx, inputs, output):
+    x, weight, bias, mean_scale, eps, fuse_gelu = inputs
+    _, mean, rstd = output
+    ctx.save_for_backward(x, mean, rstd, weight, bias, mean_scale)
+    ctx.fuse_gelu = bool(fuse_gelu)
+
+
+def _graphnorm_backward(ctx, gy, g_mean, g_rstd):
+    x, mean, rstd, weight, bias, mean_scale = ctx.saved_tensors
+    gx, gw, gb, gms = torch.ops.gmlm.graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, ctx.fuse_gelu,
+                                                   ctx.needs_input_grad[0])
+    return (gx if ctx.needs_input_grad[0] else None,
+            gw.to(weight.dtype) if ctx.needs_input_grad[1] else None,
+            gb.to(bias.dtype) if ctx.needs_input_grad[2] else None,
+            gms.to(mean_scale.dtype) if ctx.needs_input_grad[3] else None, None, None)
+
+
+def _layernorm_setup(ctx, inputs, output):
+    x, weight, bias, eps = inputs
+    _, mean, rstd = output
+    ctx.save_for_backward(x, mean, rstd, weight)
+    ctx.bias_dtype = bias.dtype
+
+
+def _layernorm_backward(ctx, gy, g_mean, g_rstd):
+    x, mean, rstd, weight = ctx.saved_tensors
+    gx, gw, gb = torch.ops.gmlm.layernorm_bwd(x, gy, mean, rstd, weight, ctx.needs_input_grad[0])
+    return (gx if ctx.needs_input_grad[0] else None, gw.to(weight.dtype) if ctx.needs_input_grad[1] else None,
+            gb.to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None, None)
+
+
+def _soft_mask_setup(ctx, inputs, output):
+    x, mask, token, beta = inputs
+    ctx.save_for_backward(mask)
+    ctx.beta, ctx.token_shape, ctx.token_dtype = float(beta), token.shape, token.dtype
+
+
+def _soft_mask_backward(ctx, gy):
+    (mask,) = ctx.saved_tensors
+    g_token, gx = torch.ops.gmlm.soft_mask_bwd(gy, mask, ctx.beta, ctx.needs_input_grad[0])
+    return (gx if ctx.needs_input_grad[0] else None, None,
+            g_token.view(ctx.token_shape).to(ctx.token_dtype) if ctx.needs_input_grad[2] else None, None)
+
+
+torch.library.register_autograd("gmlm::rgcn_aggregate", _rgcn_aggregate_backward, setup_context=_rgcn_aggregate_setup)
+torch.library.register_autograd("gmlm::plan_aggregate", _plan_aggregate_backward, setup_context=_plan_aggregate_setup)
+torch.library.register_autograd("gmlm::graphnorm_fwd", _graphnorm_backward, setup_context=_graphnorm_setup)
+torch.library.register_autograd("gmlm::layernorm_fwd", _layernorm_backward, setup_context=_layernorm_setup)
+torch.library.register_autograd("gmlm::soft_mask_fwd", _soft_mask_backward, setup_context=_soft_mask_setup)
+
+
 # ------------------------------------------------------------------------------ A6 dense transform (tcgen05)
 def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
             out_dtype: Optional[torch.dtype] = None, split: int = 0):
@@ -471,23 +699,6 @@ def linear_nt(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = 
     return _LinearNT.apply(x, wt, bias, out_dtype or x.dtype)
 
 
-class _PlanAggregate(torch.autograd.Function):
-    """out = weighted gather-reduce of ``rows`` over ``fwd``; backward = the same over ``bwd`` (its transpose)."""
-
-    @staticmethod
-    def forward(ctx, rows, fwd: CSR, bwd: CSR):
-        ctx.bwd = bwd
-        ctx.in_dtype = rows.dtype
-        return spmm(rows, fwd, _lib.AGG_WEIGHTED)
-
-    @staticmethod
-    def backward(ctx, g):
-        g = g.contiguous()
-        if g.dtype != ctx.in_dtype:
-            g = g.to(ctx.in_dtype)
-        return spmm(g, ctx.bwd, _lib.AGG_WEIGHTED), None, None
-
-
 def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, w_live: torch.Tensor, root: torch.Tensor,
                          bias: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
     """RGCNConv as TRANSFORM-then-aggregate (A5+A6 fused by linearity of the mean; include/gmlm_b200.h
@@ -513,7 +724,9 @@ def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, w_live: torch.Tensor,
                                        (bias_cat if torch.is_autocast_enabled("cuda") else bias_cat.to(x.dtype)))
         if z.dtype not in _DT:
             z = z.float()                                   # autocast produced fp16: the kernels take fp32 / bf16
-    out = _PlanAggregate.apply(z.view(graph.num_src * (S + 1), fo), fplan, bplan)
+    fl, fm = csr_pack(fplan)
+    bl, bm = csr_pack(bplan)
+    out = torch.ops.gmlm.plan_aggregate(z.view(graph.num_src * (S + 1), fo), fl, bl, fm + bm)
     return out if out.dtype == out_dtype else out.to(out_dtype)
 
 
@@ -582,73 +795,20 @@ def edge_type_from_degree(edge_index: torch.Tensor, num_nodes: int, bounds: Sequ
     return torch.ops.gmlm.edge_type_bucket(src, deg, list(bounds))
 
 
-class _RGCNAggregate(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, graph: RelGraph):
-        ctx.graph = graph
-        ctx.x_dtype = x.dtype
-        h = spmm(x, graph.fwd, _lib.AGG_MEAN)              # [N*S, F]
-        return h.view(graph.num_nodes, graph.num_slots * x.size(1))
-
-    @staticmethod
-    def backward(ctx, gh):
-        g: RelGraph = ctx.graph
-        gh = gh.contiguous()
-        if gh.dtype != ctx.x_dtype:
-            gh = gh.to(ctx.x_dtype)
-        feat = gh.size(1) // g.num_slots
-        gx = spmm(gh.view(g.num_nodes * g.num_slots, feat), g.bwd, _lib.AGG_WEIGHTED)   # [N, F]
-        return gx, None
-
-
 def rgcn_aggregate(x: torch.Tensor, graph: RelGraph) -> torch.Tensor:
     """Per-(dst, relation) mean of source rows: ``[N, F] -> [N, S*F]`` (S = populated relations).
     Forward = A5, backward = A14 (gather on the transposed CSR with 1/count folded in)."""
     _require_cuda(x, "x")
     if x.size(0) != graph.num_src:
         raise _lib.GmlmError(f"x has {x.size(0)} rows, graph has {graph.num_src} source nodes")
-    return _RGCNAggregate.apply(x, graph)
-
-
-class _GraphNorm(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, mean_scale, eps, fuse_gelu):
-        y, mean, rstd = torch.ops.gmlm.graphnorm_fwd(x, weight, bias, mean_scale, float(eps), bool(fuse_gelu))
-        ctx.save_for_backward(x, mean, rstd, weight, bias, mean_scale)
-        ctx.fuse_gelu = bool(fuse_gelu)
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, mean, rstd, weight, bias, mean_scale = ctx.saved_tensors
-        gx, gw, gb, gms = torch.ops.gmlm.graphnorm_bwd(x, gy, mean, rstd, weight, bias, mean_scale, ctx.fuse_gelu,
-                                                       ctx.needs_input_grad[0])
-        return (gx if ctx.needs_input_grad[0] else None,
-                gw.to(weight.dtype) if ctx.needs_input_grad[1] else None,
-                gb.to(bias.dtype) if ctx.needs_input_grad[2] else None,
-                gms.to(mean_scale.dtype) if ctx.needs_input_grad[3] else None, None, None)
+    fl, fm = csr_pack(graph.fwd)
+    bl, bm = csr_pack(graph.bwd)
+    return torch.ops.gmlm.rgcn_aggregate(x, fl, bl, fm + bm + [int(graph.num_nodes), int(graph.num_slots)])
 
 
 def graph_norm(x, weight, bias, mean_scale, eps: float = 1e-5, fuse_gelu: bool = False) -> torch.Tensor:
     _require_cuda(x, "x")
-    return _GraphNorm.apply(x, weight, bias, mean_scale, eps, fuse_gelu)
-
-
-class _LayerNorm(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, weight, bias, eps):
-        y, mean, rstd = torch.ops.gmlm.layernorm_fwd(x, weight, bias, float(eps))
-        ctx.save_for_backward(x, mean, rstd, weight)
-        ctx.bias_dtype = bias.dtype
-        return y
-
-    @staticmethod
-    def backward(ctx, gy):
-        x, mean, rstd, weight = ctx.saved_tensors
-        gx, gw, gb = torch.ops.gmlm.layernorm_bwd(x, gy, mean, rstd, weight, ctx.needs_input_grad[0])
-        return (gx if ctx.needs_input_grad[0] else None,
-                gw.to(weight.dtype) if ctx.needs_input_grad[1] else None,
-                gb.to(ctx.bias_dtype) if ctx.needs_input_grad[2] else None, None)
+    return torch.ops.gmlm.graphnorm_fwd(x, weight, bias, mean_scale, float(eps), bool(fuse_gelu))[0]
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
@@ -658,24 +818,7 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
     _require_cuda(x, "x")
     if not layer_norm_ok(x):
         raise _lib.GmlmError(f"layer_norm: unsupported input {tuple(x.shape)} {x.dtype} (see layer_norm_ok)")
-    return _LayerNorm.apply(x, weight, bias, eps)
-
-
-class _SoftMask(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x, mask, token, beta):
-        ctx.save_for_backward(mask)
-        ctx.beta = float(beta)
-        ctx.token_shape = token.shape
-        ctx.token_dtype = token.dtype
-        return torch.ops.gmlm.soft_mask_fwd(x, mask, token, float(beta))
-
-    @staticmethod
-    def backward(ctx, gy):
-        (mask,) = ctx.saved_tensors
-        g_token, gx = torch.ops.gmlm.soft_mask_bwd(gy, mask, ctx.beta, ctx.needs_input_grad[0])
-        return (gx if ctx.needs_input_grad[0] else None, None,
-                g_token.view(ctx.token_shape).to(ctx.token_dtype) if ctx.needs_input_grad[2] else None, None)
+    return torch.ops.gmlm.layernorm_fwd(x, weight, bias, float(eps))[0]
 
 
 def soft_masking_gnn_input(x: torch.Tensor, gnn_perturb_mask: torch.Tensor, mask_token_embed: torch.Tensor,
@@ -683,4 +826,4 @@ def soft_masking_gnn_input(x: torch.Tensor, gnn_perturb_mask: torch.Tensor, mask
     """Drop-in for ``soft_masking_gnn_input`` (``/root/reference/main.py:92-99``): one fused pass,
     no clone + boolean-index round trip and no ``.any()`` host sync."""
     _require_cuda(x, "x")
-    return _SoftMask.apply(x, gnn_perturb_mask, mask_token_embed, beta)
+    return torch.ops.gmlm.soft_mask_fwd(x, gnn_perturb_mask, mask_token_embed, float(beta))

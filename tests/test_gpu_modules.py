@@ -309,8 +309,10 @@ def test_gat_conv_matches_oracle(cuda_dev, n, e, fi, c, heads, concat):
     y.backward(gout.to(cuda_dev))
     assert rel_err(y, y_ref) <= FP32_TOL
     assert rel_err(xg.grad, x64.grad) <= 2e-5
+    # the floor covers gradients that are exactly zero in exact arithmetic (a node whose only in-edge is its
+    # self-loop has alpha = 1: d_score = alpha (d_alpha - t) cancels to rounding noise ~1e-8, not to 0.0)
     for name in ("att_src", "att_dst", "bias"):
-        assert rel_err(getattr(mod, name).grad, getattr(ref, name).grad) <= 2e-5, name
+        assert rel_err(getattr(mod, name).grad, getattr(ref, name).grad, floor=1e-2) <= 2e-5, name
     assert rel_err(mod.lin.weight.grad, ref.lin.weight.grad) <= 2e-5
 
 
