@@ -64,8 +64,13 @@ _LIB.define("layernorm_bwd(Tensor x, Tensor gy, Tensor mean, Tensor rstd, Tensor
 _LIB.define("soft_mask_fwd(Tensor x, Tensor mask, Tensor token, float beta) -> Tensor")
 _LIB.define("soft_mask_bwd(Tensor gy, Tensor mask, float beta, bool need_gx) -> (Tensor, Tensor)")
 # differentiable ops (autograd registered below with torch.library.register_autograd)
-_LIB.define("rgcn_aggregate(Tensor x, Tensor?[] fwd, Tensor?[] bwd, int[] meta) -> Tensor")
-_LIB.define("plan_aggregate(Tensor rows, Tensor?[] fwd, Tensor?[] bwd, int[] meta) -> Tensor")
+# a CSR travels as eight (optional) tensors: rowptr, col, w, grp_row, hub_row, hub_chunk_ptr, chunk_beg, chunk_end
+_CSR_ARGS = ("Tensor {p}rowptr, Tensor {p}col, Tensor? {p}w, Tensor? {p}grp, Tensor? {p}hub_row, "
+             "Tensor? {p}hub_chunk_ptr, Tensor? {p}chunk_beg, Tensor? {p}chunk_end")
+_LIB.define("rgcn_aggregate(Tensor x, " + _CSR_ARGS.format(p="f_") + ", " + _CSR_ARGS.format(p="b_") +
+            ", int[] meta) -> Tensor")
+_LIB.define("plan_aggregate(Tensor rows, " + _CSR_ARGS.format(p="f_") + ", " + _CSR_ARGS.format(p="b_") +
+            ", int[] meta) -> Tensor")
 _LIB.define("gemm_nt(Tensor a1, Tensor b, Tensor? bias, Tensor? a2, ScalarType out_dtype) -> Tensor")
 _LIB.define("csr_build(Tensor row, Tensor col, Tensor? rel, int num_rows, int num_cols, int num_relations, "
             "int[] slot_of_rel, int num_slots) -> (Tensor, Tensor, Tensor, Tensor)")
@@ -349,13 +354,15 @@ def _spmm_list(x, c, rows, thresh, mode):
                      c[6], c[7])
 
 
-def _rgcn_aggregate_impl(x, fwd, bwd, meta):
+def _rgcn_aggregate_impl(x, *a):
+    fwd, meta = a[0:8], a[16]
     rows_f, thresh_f, _, _, n_nodes, n_slots = meta
     h = _spmm_list(x, fwd, rows_f, thresh_f, _lib.AGG_MEAN)                 # [N*S, F]
     return h.view(n_nodes, n_slots * x.size(1))
 
 
-def _plan_aggregate_impl(rows, fwd, bwd, meta):
+def _plan_aggregate_impl(rows, *a):
+    fwd, meta = a[0:8], a[16]
     return _spmm_list(rows, fwd, meta[0], meta[1], _lib.AGG_WEIGHTED)
 
 
@@ -451,13 +458,14 @@ def _(gy, mask, beta, need_gx):
 
 
 @torch.library.register_fake("gmlm::rgcn_aggregate")
-def _(x, fwd, bwd, meta):
+def _(x, *a):
+    meta = a[16]
     return x.new_empty((meta[4], meta[5] * x.size(1)))
 
 
 @torch.library.register_fake("gmlm::plan_aggregate")
-def _(rows, fwd, bwd, meta):
-    return rows.new_empty((meta[0], rows.size(1)))
+def _(rows, *a):
+    return rows.new_empty((a[16][0], rows.size(1)))
 
 
 @torch.library.register_fake("gmlm::gemm_nt")
@@ -474,8 +482,8 @@ def _(row, col, rel, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
 
 # ---- autograd formulas
 def _rgcn_aggregate_setup(ctx, inputs, output):
-    x, fwd, bwd, meta = inputs
-    ctx.bwd, ctx.meta, ctx.x_dtype = bwd, meta, x.dtype
+    x = inputs[0]
+    ctx.bwd, ctx.meta, ctx.x_dtype = inputs[9:17], inputs[17], x.dtype
 
 
 def _rgcn_aggregate_backward(ctx, gh):
@@ -487,12 +495,11 @@ def _rgcn_aggregate_backward(ctx, gh):
     b = ctx.bwd
     gx = torch.ops.gmlm.spmm_csr(gh.view(n_nodes * n_slots, feat), b[0], b[1], b[2], rows_b, _lib.AGG_WEIGHTED, b[3],
                                  thresh_b, b[4], b[5], b[6], b[7])            # A14: gather on the transposed CSR
-    return gx, None, None, None
+    return (gx,) + (None,) * 17
 
 
 def _plan_aggregate_setup(ctx, inputs, output):
-    rows, fwd, bwd, meta = inputs
-    ctx.bwd, ctx.meta, ctx.in_dtype = bwd, meta, rows.dtype
+    ctx.bwd, ctx.meta, ctx.in_dtype = inputs[9:17], inputs[17], inputs[0].dtype
 
 
 def _plan_aggregate_backward(ctx, g):
@@ -501,7 +508,7 @@ def _plan_aggregate_backward(ctx, g):
         g = g.to(ctx.in_dtype)
     b = ctx.bwd
     return (torch.ops.gmlm.spmm_csr(g, b[0], b[1], b[2], ctx.meta[2], _lib.AGG_WEIGHTED, b[3], ctx.meta[3], b[4], b[5],
-                                    b[6], b[7]), None, None, None)
+                                    b[6], b[7]),) + (None,) * 17
 
 
 def _graphnorm_setup(ctx, inputs, output):
@@ -726,7 +733,7 @@ def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, w_live: torch.Tensor,
             z = z.float()                                   # autocast produced fp16: the kernels take fp32 / bf16
     fl, fm = csr_pack(fplan)
     bl, bm = csr_pack(bplan)
-    out = torch.ops.gmlm.plan_aggregate(z.view(graph.num_src * (S + 1), fo), fl, bl, fm + bm)
+    out = torch.ops.gmlm.plan_aggregate(z.view(graph.num_src * (S + 1), fo), *fl, *bl, fm + bm)
     return out if out.dtype == out_dtype else out.to(out_dtype)
 
 
@@ -803,7 +810,7 @@ def rgcn_aggregate(x: torch.Tensor, graph: RelGraph) -> torch.Tensor:
         raise _lib.GmlmError(f"x has {x.size(0)} rows, graph has {graph.num_src} source nodes")
     fl, fm = csr_pack(graph.fwd)
     bl, bm = csr_pack(graph.bwd)
-    return torch.ops.gmlm.rgcn_aggregate(x, fl, bl, fm + bm + [int(graph.num_nodes), int(graph.num_slots)])
+    return torch.ops.gmlm.rgcn_aggregate(x, *fl, *bl, fm + bm + [int(graph.num_nodes), int(graph.num_slots)])
 
 
 def graph_norm(x, weight, bias, mean_scale, eps: float = 1e-5, fuse_gelu: bool = False) -> torch.Tensor:

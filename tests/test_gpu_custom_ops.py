@@ -32,16 +32,16 @@ def test_opcheck_rgcn_aggregate_and_plan_aggregate(cuda_dev):
     x = torch.randn(n, 32, device=cuda_dev, requires_grad=True)
     fl, fm = csr_pack(g.fwd)
     bl, bm = csr_pack(g.bwd)
-    torch.library.opcheck(torch.ops.gmlm.rgcn_aggregate.default, (x, fl, bl, fm + bm + [n, g.num_slots]),
+    torch.library.opcheck(torch.ops.gmlm.rgcn_aggregate.default, (x, *fl, *bl, fm + bm + [n, g.num_slots]),
                           test_utils=CHECKS)
     fp, bp = g.dst_plan()
     z = torch.randn(n * (g.num_slots + 1), 16, device=cuda_dev, requires_grad=True)
     fl2, fm2 = csr_pack(fp)
     bl2, bm2 = csr_pack(bp)
-    torch.library.opcheck(torch.ops.gmlm.plan_aggregate.default, (z, fl2, bl2, fm2 + bm2), test_utils=CHECKS)
+    torch.library.opcheck(torch.ops.gmlm.plan_aggregate.default, (z, *fl2, *bl2, fm2 + bm2), test_utils=CHECKS)
     # and the gradient itself: d/dx of sum(h * G) is the transposed aggregation
     gh = torch.randn(n, g.num_slots * 32, device=cuda_dev)
-    h = torch.ops.gmlm.rgcn_aggregate(x, fl, bl, fm + bm + [n, g.num_slots])
+    h = torch.ops.gmlm.rgcn_aggregate(x, *fl, *bl, fm + bm + [n, g.num_slots])
     (gx,) = torch.autograd.grad((h * gh).sum(), x)
     want = G.spmm(gh.view(n * g.num_slots, 32), g.bwd, _lib.AGG_WEIGHTED)
     assert torch.equal(gx, want)
