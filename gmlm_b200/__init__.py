@@ -31,5 +31,7 @@ from .sampling import generate_active_node_mask, weighted_sample_without_replace
 from .dist_norm import partitioned_graph_norm  # noqa: F401
 from .dist_encoder import CudaPartitionOps, PartitionedGraphEncoder, sync_gradients  # noqa: F401
 from .attn import GATConv, GCNConv, LoopGraph, gat_aggregate, gat_dropout_mask, get_loop_graph  # noqa: F401
+from .ingest import (augment_graph, build_dropped_graph, edge_dropout_mask, load_npz_graph, load_rel_graph,  # noqa: F401
+                     save_rel_graph)
 
 __version__ = "0.1.0"

@@ -22,13 +22,15 @@ SIGNATURES = {
     "gmlm_last_error": (C.c_char_p, []),
     "gmlm_set_tuning": (_int, [C.c_char_p, _int]),
     "gmlm_degree_i32": (_int, [_p, _i64, _i64, _p, _int, _p]),
+    "gmlm_degree_i32_masked": (_int, [_p, _p, _i64, _i64, _p, _int, _p]),
     "gmlm_degree_f32": (_int, [_p, _i64, _i64, _p, _p, _int, _p]),
     "gmlm_edge_type_bucket": (_int, [_p, _i64, _p, _i64, C.POINTER(_i32), _int, _p, _p]),
     "gmlm_checksum_i64": (_int, [_p, _i64, _p, _p]),
-    "gmlm_relation_histogram": (_int, [_p, _i64, _int, _p, _p]),
+    "gmlm_relation_histogram": (_int, [_p, _p, _i64, _int, _p, _p]),
     "gmlm_csr_workspace_bytes": (_sz, [_i64, _i64]),
-    "gmlm_csr_build": (_int, [_p, _p, _p, _i64, _i64, _i64, _int, C.POINTER(_i32), _int, _p, _p, _p, _p, _p, _sz, _p]),
-    "gmlm_csr_transpose": (_int, [_p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "gmlm_csr_build": (_int, [_p, _p, _p, _p, _i64, _i64, _i64, _int, C.POINTER(_i32), _int, _p, _p, _p, _p,
+                              C.POINTER(_i64), _p, _sz, _p]),
+    "gmlm_csr_transpose": (_int, [_p, _p, _p, _p, _p, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "gmlm_dst_plan": (_int, [_p, _p, _i64, _int, _i64, _i64, _p, _p, _p, _p, _p]),
     "gmlm_hub_count": (_int, [_p, _i64, _i32, C.POINTER(_i64), _p, _sz, _p]),
     "gmlm_hub_fill": (_int, [_p, _i64, _i32, _i64, _i64, _p, _p, _p, _p, _p, _sz, _p]),

@@ -53,9 +53,10 @@ int read_flag(const int* d_flag, cudaStream_t st, int* out) {
 }
 
 // ------------------------------------------------------------------------ A1
-__global__ void degree_kernel(const int64_t* __restrict__ index, int64_t E, int64_t N, int32_t* __restrict__ deg,
-                              int* __restrict__ err) {
+__global__ void degree_kernel(const int64_t* __restrict__ index, const uint8_t* __restrict__ keep, int64_t E, int64_t N,
+                              int32_t* __restrict__ deg, int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    if (keep && !keep[e]) continue;               // edge dropout (main.py:832-837) fused into the histogram
     int64_t i = index[e];
     if (i >= 0 && i < N) atomicAdd(deg + i, 1);   // integer atomics: order-independent result
     else flag_error(err);
@@ -86,12 +87,14 @@ __global__ void edge_type_kernel(const int64_t* __restrict__ src, int64_t E, con
   }
 }
 
-__global__ void rel_hist_kernel(const int64_t* __restrict__ et, int64_t E, int R, unsigned long long* __restrict__ counts) {
+__global__ void rel_hist_kernel(const int64_t* __restrict__ et, const uint8_t* __restrict__ keep, int64_t E, int R,
+                                unsigned long long* __restrict__ counts) {
   // values outside [0, R) are simply not counted: the caller compares the total with E
   __shared__ unsigned int sh[64];
   for (int i = threadIdx.x; i < 64; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    if (keep && !keep[e]) continue;
     int64_t t = et[e];
     if (t >= 0 && t < R) atomicAdd(&sh[t], 1u);
   }
@@ -122,13 +125,21 @@ __global__ void checksum_kernel(const uint64_t* __restrict__ x, int64_t n, unsig
 // ------------------------------------------------------------------------ A3
 struct SlotMap { int32_t slot[64]; };
 
+// A dropped edge (keep[e] == 0: the reference's `augment_graph` edge dropout, main.py:832-837) gets the sentinel
+// key N*S: it is not counted, sorts behind every kept edge, and rowptr[N*S] ends up as the number of kept edges.
 __global__ void make_keys_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                                 const int64_t* __restrict__ et, int64_t E, int64_t N, int64_t Nsrc, int R,
-                                 SlotMap sm, int S,
+                                 const int64_t* __restrict__ et, const uint8_t* __restrict__ keep, int64_t E, int64_t N,
+                                 int64_t Nsrc, int R, SlotMap sm, int S,
                                  uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
                                  int32_t* __restrict__ seg_of_edge, int32_t* __restrict__ counts,
                                  int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    if (keep && !keep[e]) {
+      keys[e] = uint32_t(N * S);
+      vals[e] = int32_t(e);
+      if (seg_of_edge) seg_of_edge[e] = int32_t(N * S);
+      continue;
+    }
     int64_t s = src[e], d = dst[e];
     int64_t t = et ? et[e] : 0;
     bool ok = s >= 0 && s < Nsrc && d >= 0 && d < N && t >= 0 && t < R;
@@ -154,10 +165,11 @@ __global__ void gather_col_kernel(const int64_t* __restrict__ src, const int32_t
 }
 
 // ----------------------------------------------------------------------- A14
-__global__ void make_keys_t_kernel(const int64_t* __restrict__ row_of_edge, int64_t E, int64_t num_rows,
-                                   uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
+__global__ void make_keys_t_kernel(const int64_t* __restrict__ row_of_edge, const uint8_t* __restrict__ keep, int64_t E,
+                                   int64_t num_rows, uint32_t* __restrict__ keys, int32_t* __restrict__ vals,
                                    int32_t* __restrict__ counts, int* __restrict__ err) {
   for (int64_t e = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; e < E; e += int64_t(gridDim.x) * blockDim.x) {
+    if (keep && !keep[e]) { keys[e] = uint32_t(num_rows); vals[e] = int32_t(e); continue; }   // dropped: sentinel key
     int64_t r = row_of_edge[e];
     uint32_t key = 0;
     if (r >= 0 && r < num_rows) {
@@ -173,9 +185,11 @@ __global__ void make_keys_t_kernel(const int64_t* __restrict__ row_of_edge, int6
 
 __global__ void gather_payload_t_kernel(const int32_t* __restrict__ payload, const float* __restrict__ edge_w,
                                         const int32_t* __restrict__ fwd_rowptr, const int32_t* __restrict__ perm_t,
-                                        int64_t E, int32_t* __restrict__ payload_t, float* __restrict__ w_t) {
+                                        const uint8_t* __restrict__ keep, int64_t E, int32_t* __restrict__ payload_t,
+                                        float* __restrict__ w_t) {
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < E; i += int64_t(gridDim.x) * blockDim.x) {
     int32_t e = perm_t[i];
+    if (keep && !keep[e]) { payload_t[i] = 0; if (w_t) w_t[i] = 0.f; continue; }   // dropped edges: the unused tail
     int32_t p = payload[e];
     payload_t[i] = p;
     if (fwd_rowptr) {
@@ -326,6 +340,11 @@ int gmlm_set_tuning(const char* key, int value) {
 }
 
 int gmlm_degree_i32(const int64_t* index, int64_t E, int64_t N, int32_t* deg, int check, void* stream) {
+  return gmlm_degree_i32_masked(index, nullptr, E, N, deg, check, stream);
+}
+
+int gmlm_degree_i32_masked(const int64_t* index, const uint8_t* keep, int64_t E, int64_t N, int32_t* deg, int check,
+                           void* stream) {
   GMLM_REQUIRE(E >= 0 && N >= 0, "degree: negative size");
   GMLM_REQUIRE(E == 0 || index != nullptr, "degree: null index");
   cudaStream_t st = as_stream(stream);
@@ -337,7 +356,7 @@ int gmlm_degree_i32(const int64_t* index, int64_t E, int64_t N, int32_t* deg, in
   }
   GMLM_CUDA_TRY(cudaMemsetAsync(deg, 0, size_t(N) * sizeof(int32_t), st));
   if (E > 0) {
-    degree_kernel<<<grid_for(E, 4), kThreads, 0, st>>>(index, E, N, deg, d_flag);
+    degree_kernel<<<grid_for(E, 4), kThreads, 0, st>>>(index, keep, E, N, deg, d_flag);
     GMLM_LAUNCH_CHECK();
   }
   if (check) {
@@ -387,12 +406,14 @@ int gmlm_checksum_i64(const int64_t* x, int64_t n, uint64_t* out2, void* stream)
   return GMLM_OK;
 }
 
-int gmlm_relation_histogram(const int64_t* edge_type, int64_t E, int R, int64_t* counts, void* stream) {
+int gmlm_relation_histogram(const int64_t* edge_type, const uint8_t* keep, int64_t E, int R, int64_t* counts,
+                            void* stream) {
   GMLM_REQUIRE(R >= 1 && R <= 64, "relation_histogram: 1..64 relations supported");
   cudaStream_t st = as_stream(stream);
   GMLM_CUDA_TRY(cudaMemsetAsync(counts, 0, size_t(R) * sizeof(int64_t), st));
   if (E > 0) {
-    rel_hist_kernel<<<grid_for(E, 8), kThreads, 0, st>>>(edge_type, E, R, reinterpret_cast<unsigned long long*>(counts));
+    rel_hist_kernel<<<grid_for(E, 8), kThreads, 0, st>>>(edge_type, keep, E, R,
+                                                         reinterpret_cast<unsigned long long*>(counts));
     GMLM_LAUNCH_CHECK();
   }
   return GMLM_OK;
@@ -409,9 +430,9 @@ size_t gmlm_csr_workspace_bytes(int64_t E, int64_t num_rows) {
   return cub_bytes + 3 * (size_t(E) * 4 + 256) + 4096;
 }
 
-int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, int64_t E, int64_t N,
-                   int64_t Nsrc, int R, const int32_t* slot_of_rel_host, int S, int32_t* rowptr, int32_t* col, int32_t* perm,
-                   int32_t* seg_of_edge, void* ws, size_t ws_bytes, void* stream) {
+int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, const uint8_t* keep, int64_t E,
+                   int64_t N, int64_t Nsrc, int R, const int32_t* slot_of_rel_host, int S, int32_t* rowptr, int32_t* col,
+                   int32_t* perm, int32_t* seg_of_edge, int64_t* nnz_host, void* ws, size_t ws_bytes, void* stream) {
   GMLM_REQUIRE(E >= 0 && N >= 0 && Nsrc >= 0 && R >= 1 && R <= 64 && S >= 1 && S <= R, "csr_build: bad sizes");
   GMLM_REQUIRE(Nsrc < (int64_t(1) << 31) - 1, "csr_build: num_src must fit int32");
   GMLM_REQUIRE(E < (int64_t(1) << 31) - 1, "csr_build: more than 2^31-2 edges needs a 64-bit CSR");
@@ -432,6 +453,7 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
     }
   }
   GMLM_CUDA_TRY(cudaMemsetAsync(rowptr, 0, size_t(rows + 1) * sizeof(int32_t), st));
+  if (nnz_host) *nnz_host = 0;
   if (E == 0) return GMLM_OK;
   GMLM_REQUIRE(src && dst && col && perm, "csr_build: null pointer");
 
@@ -444,8 +466,8 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
   size_t cub_bytes = ws_bytes - cv.used();
 
   GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-  make_keys_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, dst, edge_type, E, N, Nsrc, edge_type ? R : 1, sm, S, keys_in,
-                                                        vals_in, seg_of_edge, rowptr, d_flag);
+  make_keys_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, dst, edge_type, keep, E, N, Nsrc, edge_type ? R : 1, sm, S,
+                                                        keys_in, vals_in, seg_of_edge, rowptr, d_flag);
   GMLM_LAUNCH_CHECK();
   // counts -> exclusive prefix (in place); entry [rows] is 0 on input so rowptr[rows] = E
   size_t need = scan_temp_bytes(rows + 1);
@@ -455,19 +477,22 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
   GMLM_REQUIRE(need <= cub_bytes, "csr_build: sort workspace");
   // LSD radix sort is stable: equal (dst,slot) keys keep the original edge order
   GMLM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, need, keys_in, keys_out, vals_in, perm, int(E), 0,
-                                                bits_for(uint64_t(rows)), st));
+                                                bits_for(uint64_t(rows) + (keep ? 1 : 0)), st));
   gather_col_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, perm, E, col);
   GMLM_LAUNCH_CHECK();
   int flag = 0;
-  int rc = read_flag(d_flag, st, &flag);
+  int32_t kept = int32_t(E);
+  if (nnz_host) GMLM_CUDA_TRY(cudaMemcpyAsync(&kept, rowptr + rows, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  int rc = read_flag(d_flag, st, &flag);       // synchronises the stream: `kept` has arrived too
   if (rc) return rc;
+  if (nnz_host) *nnz_host = kept;
   if (flag) return fail(GMLM_ERR_INDEX, "csr_build: dst outside [0,%lld), src outside [0,%lld) or relation outside [0,%d)",
                         (long long)N, (long long)Nsrc, R);
   return GMLM_OK;
 }
 
 int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const float* edge_w,
-                       const int32_t* fwd_rowptr, int64_t E, int64_t num_rows, int32_t* rowptr_t,
+                       const int32_t* fwd_rowptr, const uint8_t* keep, int64_t E, int64_t num_rows, int32_t* rowptr_t,
                        int32_t* payload_t, float* w_t, int32_t* perm_t, void* ws, size_t ws_bytes, void* stream) {
   GMLM_REQUIRE(E >= 0 && num_rows >= 0, "csr_transpose: bad sizes");
   GMLM_REQUIRE(E < (int64_t(1) << 31) - 1 && num_rows < (int64_t(1) << 31) - 1, "csr_transpose: int32 limits");
@@ -487,7 +512,8 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
   size_t cub_bytes = ws_bytes - cv.used();
 
   GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
-  make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, E, num_rows, keys_in, vals_in, rowptr_t, d_flag);
+  make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, keep, E, num_rows, keys_in, vals_in, rowptr_t,
+                                                          d_flag);
   GMLM_LAUNCH_CHECK();
   size_t need = scan_temp_bytes(num_rows + 1);
   GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: scan workspace");
@@ -495,8 +521,9 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
   need = sort_temp_bytes(E);
   GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: sort workspace");
   GMLM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, need, keys_in, keys_out, vals_in, perm_t, int(E), 0,
-                                                bits_for(uint64_t(num_rows)), st));
-  gather_payload_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(payload, edge_w, fwd_rowptr, perm_t, E, payload_t, w_t);
+                                                bits_for(uint64_t(num_rows) + (keep ? 1 : 0)), st));
+  gather_payload_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(payload, edge_w, fwd_rowptr, perm_t, keep, E, payload_t,
+                                                               w_t);
   GMLM_LAUNCH_CHECK();
   int flag = 0;
   int rc = read_flag(d_flag, st, &flag);

@@ -114,20 +114,24 @@ def build_csr(row: torch.Tensor, col: torch.Tensor, num_rows: int, num_cols: int
               rel: Optional[torch.Tensor] = None, num_relations: int = 1,
               slot_of_rel: Optional[List[int]] = None, num_slots: int = 1,
               want_seg_of_edge: bool = False, hub_thresh: Optional[int] = None,
-              quantum: Optional[int] = None):
+              quantum: Optional[int] = None, keep: Optional[torch.Tensor] = None):
     """CSR with segments ``row*num_slots + slot_of_rel[rel]`` and gather index ``col``.
 
     ``row``/``col``/``rel`` are int64 edge arrays (as in ``edge_index`` / ``edge_type``).
     Returns ``(CSR, seg_of_edge or None)``.  ``row`` is validated against ``num_rows`` and ``col``
-    against ``num_cols`` (one host sync)."""
+    against ``num_cols`` (one host sync).  ``keep`` (bool [E], optional): edge-dropout mask fused into the
+    build (N3) -- the result equals the CSR of ``edge_index[:, keep]``."""
     _require_cuda(row, "edge_index")
     if rel is not None and rel.dtype != torch.int64:
         rel = rel.long()
     rows_total = num_rows * num_slots
     slot_list = list(slot_of_rel) if slot_of_rel is not None else list(range(num_relations))
     from . import ops  # noqa: F401  (registers torch.ops.gmlm.*)
-    rowptr, colv, perm, seg = torch.ops.gmlm.csr_build(row, col, rel, int(num_rows), int(num_cols), int(num_relations),
-                                                       [int(v) for v in slot_list], int(num_slots))
+    rowptr, colv, perm, seg = torch.ops.gmlm.csr_build(row, col, rel, keep, int(num_rows), int(num_cols),
+                                                       int(num_relations), [int(v) for v in slot_list], int(num_slots))
+    if keep is not None:
+        nnz = int(rowptr[-1].item())                 # kept edges; the dropped ones sorted behind them
+        colv, perm = colv[:nnz], perm[:nnz]
     if not want_seg_of_edge:
         seg = None
     csr = CSR(rowptr=rowptr, col=colv, num_rows=rows_total, perm=perm)
@@ -138,9 +142,11 @@ def build_csr(row: torch.Tensor, col: torch.Tensor, num_rows: int, num_cols: int
 
 def transpose_csr(row_of_edge: torch.Tensor, payload: torch.Tensor, num_rows: int, *,
                   fwd_rowptr: Optional[torch.Tensor] = None, edge_w: Optional[torch.Tensor] = None,
-                  hub_thresh: Optional[int] = None, quantum: Optional[int] = None) -> CSR:
+                  hub_thresh: Optional[int] = None, quantum: Optional[int] = None,
+                  keep: Optional[torch.Tensor] = None) -> CSR:
     """CSR over ``row_of_edge`` (int64 [E]) whose gather index is ``payload`` (int32 [E], e.g. the
-    forward segment of each edge); weights are 1/|fwd segment| or ``edge_w`` permuted."""
+    forward segment of each edge); weights are 1/|fwd segment| or ``edge_w`` permuted.  ``keep``: as in
+    ``build_csr``."""
     lib = _lib.load()
     dev = row_of_edge.device
     E = int(row_of_edge.numel())
@@ -153,9 +159,16 @@ def transpose_csr(row_of_edge: torch.Tensor, payload: torch.Tensor, num_rows: in
         w_t = torch.empty(E, dtype=torch.float32, device=dev) if has_w else None
         ws_bytes = lib.gmlm_csr_workspace_bytes(max(E, 1), num_rows)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.gmlm_csr_transpose(_ptr(row_of_edge), _ptr(payload), _ptr(edge_w), _ptr(fwd_rowptr), E,
-                                          num_rows, _ptr(rowptr_t), _ptr(payload_t), _ptr(w_t), _ptr(perm_t),
-                                          _ptr(ws), ws_bytes, _stream(dev)), "csr_transpose")
+        keep_u8 = None
+        if keep is not None:
+            keep_u8 = keep.contiguous().view(torch.uint8) if keep.dtype == torch.bool else (keep != 0).view(torch.uint8)
+        _lib.check(lib.gmlm_csr_transpose(_ptr(row_of_edge), _ptr(payload), _ptr(edge_w), _ptr(fwd_rowptr),
+                                          _ptr(keep_u8), E, num_rows, _ptr(rowptr_t), _ptr(payload_t), _ptr(w_t),
+                                          _ptr(perm_t), _ptr(ws), ws_bytes, _stream(dev)), "csr_transpose")
+    if keep is not None:
+        nnz = int(rowptr_t[-1].item())
+        payload_t, perm_t = payload_t[:nnz], perm_t[:nnz]
+        w_t = w_t[:nnz] if w_t is not None else None
     csr = CSR(rowptr=rowptr_t, col=payload_t, num_rows=num_rows, w=w_t, perm=perm_t)
     csr.plan_hubs(hub_thresh)
     csr.plan_groups(quantum)
@@ -218,10 +231,14 @@ class RelGraph:
     @staticmethod
     def build(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int, num_relations: int,
               hub_thresh: Optional[int] = None, quantum: Optional[int] = None, num_src: Optional[int] = None,
-              live_rels: Optional[List[int]] = None, keep_seg: bool = False) -> "RelGraph":
+              live_rels: Optional[List[int]] = None, keep_seg: bool = False,
+              keep_mask: Optional[torch.Tensor] = None) -> "RelGraph":
         """``num_src`` > ``num_nodes`` builds the rectangular CSR of a destination-row partition
         (columns = local rows followed by halo rows).  ``live_rels`` pins the relation->slot
-        layout (ranks of a partition must agree on it); default = the populated relations."""
+        layout (ranks of a partition must agree on it); default = the populated relations.
+        ``keep_mask`` (bool [E]): the reference's edge dropout (``augment_graph``, main.py:832-837) fused into the
+        build -- same graph as ``RelGraph.build(edge_index[:, keep_mask], edge_type[keep_mask], ...)`` without
+        materialising the filtered edge list."""
         lib = _lib.load()
         n_src = num_nodes if num_src is None else int(num_src)
         _require_cuda(edge_index, "edge_index")
@@ -241,7 +258,11 @@ class RelGraph:
             edge_type = edge_type.long().contiguous()
             with torch.cuda.device(dev):
                 counts = torch.empty(num_relations, dtype=torch.int64, device=dev)
-                _lib.check(lib.gmlm_relation_histogram(_ptr(edge_type), E, num_relations, _ptr(counts),
+                keep_u8 = None
+                if keep_mask is not None:
+                    keep_u8 = (keep_mask.contiguous().view(torch.uint8) if keep_mask.dtype == torch.bool
+                               else (keep_mask != 0).view(torch.uint8))
+                _lib.check(lib.gmlm_relation_histogram(_ptr(edge_type), _ptr(keep_u8), E, num_relations, _ptr(counts),
                                                        _stream(dev)), "relation_histogram")
             counts_h = counts.cpu().tolist()
             live = [r for r, c in enumerate(counts_h) if c > 0]
@@ -249,7 +270,8 @@ class RelGraph:
                 if not set(live) <= set(live_rels):
                     raise _lib.GmlmError(f"live_rels {live_rels} does not cover the populated relations {live}")
                 live = sorted(live_rels)
-            if sum(counts_h) != E:
+            n_kept = E if keep_mask is None else int(keep_mask.sum().item())
+            if sum(counts_h) != n_kept:
                 raise _lib.GmlmError(f"edge_type has values outside [0, {num_relations})")
             if not live:
                 live = [0]
@@ -260,8 +282,10 @@ class RelGraph:
             slot_of_rel[0] = 0
         fwd, seg = build_csr(dst, src, num_nodes, n_src, rel=edge_type, num_relations=num_relations,
                              slot_of_rel=slot_of_rel, num_slots=len(live), want_seg_of_edge=True,
-                             hub_thresh=hub_thresh, quantum=quantum)
-        bwd = transpose_csr(src, seg, n_src, fwd_rowptr=fwd.rowptr, hub_thresh=hub_thresh, quantum=quantum)
+                             hub_thresh=hub_thresh, quantum=quantum, keep=keep_mask)
+        bwd = transpose_csr(src, seg, n_src, fwd_rowptr=fwd.rowptr, hub_thresh=hub_thresh, quantum=quantum,
+                            keep=keep_mask)
+        E = fwd.nnz                                    # kept edges
         return RelGraph(num_nodes=num_nodes, num_edges=E, num_relations=num_relations, live_rels=live, fwd=fwd,
                         bwd=bwd, num_src=n_src, seg_of_edge=seg if keep_seg else None)
 

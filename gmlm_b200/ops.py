@@ -72,7 +72,7 @@ _LIB.define("rgcn_aggregate(Tensor x, " + _CSR_ARGS.format(p="f_") + ", " + _CSR
 _LIB.define("plan_aggregate(Tensor rows, " + _CSR_ARGS.format(p="f_") + ", " + _CSR_ARGS.format(p="b_") +
             ", int[] meta) -> Tensor")
 _LIB.define("gemm_nt(Tensor a1, Tensor b, Tensor? bias, Tensor? a2, ScalarType out_dtype) -> Tensor")
-_LIB.define("csr_build(Tensor row, Tensor col, Tensor? rel, int num_rows, int num_cols, int num_relations, "
+_LIB.define("csr_build(Tensor row, Tensor col, Tensor? rel, Tensor? keep, int num_rows, int num_cols, int num_relations, "
             "int[] slot_of_rel, int num_slots) -> (Tensor, Tensor, Tensor, Tensor)")
 
 
@@ -370,9 +370,11 @@ def _gemm_nt_op(a1, b, bias, a2, out_dtype):
     return gemm_nt(a1, b, bias=bias, a2=a2, out_dtype=out_dtype)
 
 
-def _csr_build_op(row, col, rel, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
+def _csr_build_op(row, col, rel, keep, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
     """(rowptr int32 [num_rows*num_slots+1], col int32 [E], perm int32 [E], seg_of_edge int32 [E]) of the CSR keyed
-    on ``row*num_slots + slot_of_rel[rel]`` (stable: original edge order inside a segment); A3."""
+    on ``row*num_slots + slot_of_rel[rel]`` (stable: original edge order inside a segment); A3.  ``keep`` (uint8 /
+    bool [E], optional) is an edge-dropout mask fused into the build: only the first rowptr[-1] entries of col / perm
+    are then the CSR."""
     lib = _lib.load()
     dev = row.device
     E = int(row.numel())
@@ -387,10 +389,13 @@ def _csr_build_op(row, col, rel, num_rows, num_cols, num_relations, slot_of_rel,
         ws_bytes = lib.gmlm_csr_workspace_bytes(max(E, 1), rows_total)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         slots = (C.c_int32 * max(num_relations, 1))(*[int(v) for v in slot_of_rel]) if rel is not None else None
+        keep_u8 = _mask_u8(keep, E) if keep is not None else None
+        nnz = C.c_int64(0)
         # csr_build keys on `dst`; here the CSR row plays that role and `col` is the gathered id
-        _lib.check(lib.gmlm_csr_build(_ptr(col), _ptr(row), _ptr(rel), E, num_rows, num_cols, num_relations, slots,
-                                      num_slots, _ptr(rowptr), _ptr(colv), _ptr(perm), _ptr(seg), _ptr(ws), ws_bytes,
-                                      _stream(dev)), "csr_build")
+        _lib.check(lib.gmlm_csr_build(_ptr(col), _ptr(row), _ptr(rel), _ptr(keep_u8), E, num_rows, num_cols,
+                                      num_relations, slots, num_slots, _ptr(rowptr), _ptr(colv), _ptr(perm), _ptr(seg),
+                                      C.byref(nnz) if keep is not None else None, _ptr(ws), ws_bytes, _stream(dev)),
+                   "csr_build")
     return rowptr, colv, perm, seg
 
 
@@ -474,7 +479,7 @@ def _(a1, b, bias, a2, out_dtype):
 
 
 @torch.library.register_fake("gmlm::csr_build")
-def _(row, col, rel, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
+def _(row, col, rel, keep, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
     e = row.numel()
     i32 = lambda k: row.new_empty((k,), dtype=torch.int32)   # noqa: E731
     return i32(num_rows * num_slots + 1), i32(e), i32(e), i32(e)

@@ -53,6 +53,10 @@ int gmlm_set_tuning(const char* key, int value);
  * `check_host_sync` != 0 (costs one stream synchronisation). */
 int gmlm_degree_i32(const int64_t* index, int64_t num_edges, int64_t num_nodes, int32_t* deg,
                     int check_host_sync, void* stream);
+/* the same over the edges with keep[e] != 0 only (N3: the reference's 10 % edge dropout `augment_graph`,
+ * main.py:832-837, fused into the histogram instead of materialising a filtered edge_index; keep NULL = all) */
+int gmlm_degree_i32_masked(const int64_t* index, const uint8_t* keep, int64_t num_edges, int64_t num_nodes,
+                           int32_t* deg, int check_host_sync, void* stream);
 int gmlm_degree_f32(const int64_t* index, int64_t num_edges, int64_t num_nodes, float* deg,
                     int32_t* deg_i32_ws /* [num_nodes] scratch */, int check_host_sync, void* stream);
 
@@ -62,8 +66,8 @@ int gmlm_edge_type_bucket(const int64_t* src, int64_t num_edges, const int32_t* 
                           const int32_t* bounds_host, int num_bounds, int64_t* edge_type, void* stream);
 
 /* per-relation edge counts (host decides which relations are populated) */
-int gmlm_relation_histogram(const int64_t* edge_type, int64_t num_edges, int num_relations,
-                            int64_t* counts /* [num_relations] */, void* stream);
+int gmlm_relation_histogram(const int64_t* edge_type, const uint8_t* keep /* NULL = all edges */, int64_t num_edges,
+                            int num_relations, int64_t* counts /* [num_relations] */, void* stream);
 
 /* ---- content key of an int64 index tensor (graph cache: the reference re-creates edge_type on every call,
  *      main.py:255, so tensor identity cannot key the cached CSR) ----
@@ -80,10 +84,14 @@ int gmlm_checksum_i64(const int64_t* x, int64_t n, uint64_t* out2, void* stream)
  *   seg_of_edge int32[E] (segment of ORIGINAL edge e; may be NULL).
  * Synchronises the stream once to report GMLM_ERR_INDEX. */
 size_t gmlm_csr_workspace_bytes(int64_t num_edges, int64_t num_rows);
-int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, int64_t num_edges,
-                   int64_t num_dst, int64_t num_src, int num_relations, const int32_t* slot_of_rel_host,
-                   int num_slots,
-                   int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* seg_of_edge,
+/* keep (N3, optional): uint8 [num_edges] edge-dropout mask (main.py:832-837 `augment_graph`) fused into the build: a
+ * dropped edge is not counted and sorts behind every kept edge, so rowptr[num_dst*num_slots] = *nnz_host = the
+ * number of kept edges and only the first nnz entries of col / perm are the CSR (seg_of_edge of a dropped edge is
+ * num_dst*num_slots).  Equal, array for array, to building from edge_index[:, keep]. */
+int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, const uint8_t* keep,
+                   int64_t num_edges, int64_t num_dst, int64_t num_src, int num_relations,
+                   const int32_t* slot_of_rel_host, int num_slots,
+                   int32_t* rowptr, int32_t* col, int32_t* perm, int32_t* seg_of_edge, int64_t* nnz_host,
                    void* ws, size_t ws_bytes, void* stream);
 
 /* ---- A14 transposed CSR for the backward gather (autograd of index_select/scatter_add in
@@ -92,7 +100,8 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
  * if fwd_rowptr != NULL: w_t[i] = 1 / (fwd_rowptr[p+1]-fwd_rowptr[p]) with p = payload_t[i]
  * (the mean divisor folded in); else if edge_w != NULL: w_t[i] = edge_w[perm_t[i]]; else w_t untouched. */
 int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const float* edge_w,
-                       const int32_t* fwd_rowptr, int64_t num_edges, int64_t num_rows,
+                       const int32_t* fwd_rowptr, const uint8_t* keep /* as in csr_build; NULL = all */,
+                       int64_t num_edges, int64_t num_rows,
                        int32_t* rowptr_t, int32_t* payload_t, float* w_t, int32_t* perm_t,
                        void* ws, size_t ws_bytes, void* stream);
 

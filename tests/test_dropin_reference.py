@@ -255,3 +255,44 @@ def test_batched_nt_xent_property(ref_main_on_oracle):
             assert got.grad_fn is None
 
     check()
+
+
+# ----------------------------------------------------------------------------- N3: ingest (main.py:780-837)
+def _write_npz(path, n=57, e=300, f=9, classes=4, seed=0):
+    import numpy as np
+    rng = np.random.RandomState(seed)
+    np.savez(path, node_features=rng.randn(n, f).astype(np.float32), edges=rng.randint(0, n, size=(2, e)),
+             node_labels=rng.randint(0, classes, size=n), node_texts=np.array([f"text {i}" for i in range(n)], dtype=object),
+             label_texts=np.array([f"label {c}" for c in range(classes)], dtype=object),
+             train_masks=rng.rand(n) < 0.5, val_masks=rng.rand(n) < 0.3, test_masks=rng.rand(n) < 0.2)
+
+
+def test_load_npz_graph_equals_the_reference_loader(ref_main, tmp_path):
+    """gmlm_b200.load_npz_graph vs the reference's own load_npz_dataset on the same file, both split modes."""
+    from gmlm_b200.ingest import load_npz_graph
+    p = str(tmp_path / "toy.npz")
+    _write_npz(p)
+    for ratios in (None, (0.48, 0.32, 0.20), (0.5, 0.25, 0.25)):
+        want, wf, wc = ref_main.load_npz_dataset("toy", p, split_ratios=ratios)
+        got, gf, gc = load_npz_graph(p, split_ratios=ratios)
+        assert (gf, gc) == (wf, wc)
+        for k in ("x", "edge_index", "y", "train_mask", "val_mask", "test_mask"):
+            a, b = getattr(got, k), getattr(want, k)
+            assert a.dtype == b.dtype and torch.equal(a, b), k
+        assert got.node_texts == want.node_texts and got.label_texts == want.label_texts
+
+
+def test_augment_graph_keeps_the_same_edges_as_the_reference_under_a_seed(ref_main, tmp_path):
+    from gmlm_b200.ingest import augment_graph, edge_dropout_mask, load_npz_graph
+    p = str(tmp_path / "toy.npz")
+    _write_npz(p, e=5000)
+    want, _, _ = ref_main.load_npz_dataset("toy", p)
+    got, _, _ = load_npz_graph(p)
+    torch.manual_seed(7)
+    want = ref_main.augment_graph(want, edge_dropout_p=0.1)
+    torch.manual_seed(7)
+    keep = edge_dropout_mask(got.edge_index.size(1), 0.1)
+    torch.manual_seed(7)
+    got = augment_graph(got, edge_dropout_p=0.1)
+    assert torch.equal(got.edge_index, want.edge_index)
+    assert int(keep.sum()) == want.edge_index.size(1) and 0.85 < keep.float().mean() < 0.95
