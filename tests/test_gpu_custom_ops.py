@@ -66,7 +66,7 @@ def test_opcheck_gemm_and_csr_build(cuda_dev):
     torch.library.opcheck(torch.ops.gmlm.gemm_nt.default, (a, bm, bias, None, torch.float32),
                           test_utils=("test_schema", "test_faketensor"))
     n, ei, et, g = _graph(cuda_dev)
-    args = (ei[1].contiguous(), ei[0].contiguous(), et, n, n, 5, [0, 1, 2, 3, -1], 4)
+    args = (ei[1].contiguous(), ei[0].contiguous(), et, None, n, n, 5, [0, 1, 2, 3, -1], 4)
     torch.library.opcheck(torch.ops.gmlm.csr_build.default, args, test_utils=("test_schema", "test_faketensor"))
     rowptr, col, perm, seg = torch.ops.gmlm.csr_build(*args)
     assert int(rowptr[-1]) == ei.size(1) and torch.equal(col, ei[0][perm.long()].int())
