@@ -377,10 +377,10 @@ EncodeTiledFn encode_fn() {
 struct MapKey {
   const void* base;
   int64_t rows, cols, ld;
-  int box_rows, box_cols, dtype, dev;   // the swizzle mode follows from box_cols * element size (128 or 64 bytes)
+  int box_rows, box_cols, dtype, dev, swizzle;   // swizzle: 128 / 64 (bytes) or 0 = none
   bool operator==(const MapKey& o) const {
     return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows &&
-           box_cols == o.box_cols && dtype == o.dtype && dev == o.dev;
+           box_cols == o.box_cols && dtype == o.dtype && dev == o.dev && swizzle == o.swizzle;
   }
 };
 struct MapKeyHash {
@@ -389,6 +389,7 @@ struct MapKeyHash {
     auto mix = [&](uint64_t v) { h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
     mix(uint64_t(k.rows)); mix(uint64_t(k.cols)); mix(uint64_t(k.ld));
     mix(uint64_t(k.box_rows) << 32 | uint32_t(k.box_cols)); mix(uint64_t(k.dtype) << 8 | uint32_t(k.dev));
+    mix(uint64_t(k.swizzle));
     return size_t(h);
   }
 };
@@ -398,8 +399,12 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
 // row-major [rows, cols] matrix with leading dimension ld (elements); box = box_cols x box_rows; box_cols * element
 // size is 128 bytes (SWIZZLE_128B) or 64 bytes (SWIZZLE_64B)
 int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols,
-            int dtype) {
-  const MapKey key{base, rows, cols, ld, box_rows, box_cols, dtype, current_device()};
+            int dtype, int swizzle = -1) {
+  {
+    const int e = dtype == GMLM_F32 ? 4 : 2;
+    if (swizzle < 0) swizzle = box_cols * e == 128 ? 128 : 64;
+  }
+  const MapKey key{base, rows, cols, ld, box_rows, box_cols, dtype, current_device(), swizzle};
   {
     std::lock_guard<std::mutex> lock(g_map_mutex);
     auto it = g_map_cache.find(key);
@@ -414,7 +419,8 @@ int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int6
   cuuint64_t strides[1] = {cuuint64_t(ld) * esz};
   cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = box_cols * esz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  const CUtensorMapSwizzle sw = swizzle == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(GMLM_ERR_CUDA, "gemm: cuTensorMapEncodeTiled failed with code %d", int(r));
@@ -444,6 +450,18 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, c
 }
 
 }  // namespace
+
+// row-gather tensor map for the aggregation kernels (spmm.cu): [rows, cols] matrix, box = one whole row, no swizzle
+// (the box shape `tile::gather4` takes: four arbitrary rows per bulk-tensor op; probed in tools/probes/)
+int row_gather_map(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int dtype) {
+  static thread_local bool ctx_ready[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!ctx_ready[dev]) {
+    GMLM_CUDA_TRY(cudaFree(nullptr));
+    ctx_ready[dev] = true;
+  }
+  return get_map(static_cast<CUtensorMap*>(out_map), base, rows, cols, ld, 1, int(cols), dtype, 0);
+}
 }  // namespace gmlm
 
 using namespace gmlm;

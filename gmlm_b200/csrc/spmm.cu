@@ -25,10 +25,15 @@
 //     hub_thresh edges, one group per chunk, fp32 partials, then an in-order final sum.
 //   * Determinism: fp32 accumulation strictly in CSR order (stable-sorted = original edge
 //     order), fixed chunking, no atomics: bit-identical run to run.
+#include <cuda.h>
+
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace gmlm {
 
+int row_gather_map(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int dtype);  // gemm_tcgen05.cu
 int tuning_spmm_variant();
 int tuning_spmm_unroll();
 
@@ -346,6 +351,180 @@ __global__ void __launch_bounds__(256, MINB) chunk_kernel(const ChunkParams p) {
 // (one UBLKCP per row from uniform registers, ~75 cycles) is measured in profiles/r2_row_gather_tma_vs_ldg.log.
 // The FIFO kernels are in the history (commit "Experiment: cp.async ... FIFO variants").
 
+
+// ================================================================== bulk-copy (TMA) hub-chunk kernel
+// The chunk kernel above keeps U = 4 row loads per warp in registers; what bounds it is the bytes one SM's load
+// path keeps outstanding (ncu: 15.8 warps stalled on the long scoreboard per issued instruction, DRAM 53 % busy).
+// Here the rows of a chunk are staged by the bulk-copy engine instead: every warp owns a ring of SLOTS batches of
+// TB rows in shared memory; lane l issues `cp.async.bulk.shared.global` for row l of a batch against the batch's
+// mbarrier, the whole warp then reads its 16-byte packs back with LDS and accumulates in CSR order (bit-identical
+// to the register kernel).  Bytes in flight are bounded by shared memory (NW warps x (SLOTS-1) batches x TB rows),
+// not by the load queues: the path measured at 95 % of the copy peak for a plain row gather
+// (profiles/r2_row_gather_tma_vs_ldg.log).  Rows must be exactly CH x 512 bytes (F = 256 bf16 / 128 fp32: CH = 1).
+constexpr int kTmaRows = 16;     // rows per batch
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+
+// PERSISTENT: one CTA per SM, every warp streams the batches of its chunks (chunk c -> warp c mod #warps) back to
+// back, the issue cursor running SLOTS-1 batches ahead of the consume cursor ACROSS chunk boundaries, so the ring
+// never drains (one chunk per warp and CTA left start-up and tail bubbles with one resident CTA per SM).
+template <typename T, int VEC, int CH, int NW, int SLOTS, bool WEIGHTED>
+__global__ void __launch_bounds__(NW * 32, 1) chunk_tma_kernel(const __grid_constant__ CUtensorMap xmap,
+                                                               const ChunkParams p) {
+  extern __shared__ __align__(128) uint8_t tma_ring[];
+  constexpr uint32_t ROW_BYTES = 512u * CH;
+  constexpr uint32_t SLOT_BYTES = kTmaRows * ROW_BYTES;
+  constexpr int D = SLOTS - 1;                     // batches in flight
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* ring = tma_ring + size_t(warp) * SLOTS * SLOT_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tma_ring + size_t(NW) * SLOTS * SLOT_BYTES) + warp * SLOTS;
+  if (lane == 0) {
+    for (int s = 0; s < SLOTS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bars + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const int64_t first = int64_t(blockIdx.x) * NW + warp, stride = int64_t(gridDim.x) * NW;
+
+  struct Cursor {            // a position in this warp's batch stream
+    int64_t c;               // chunk id
+    int b, nb, beg, end;     // batch inside the chunk, #batches, edge range
+  };
+  auto open_chunk = [&](Cursor& k, int64_t c) {
+    k.c = c;
+    k.b = 0;
+    if (c < p.n_chunks) {
+      k.beg = __ldg(p.chunk_beg + c);
+      k.end = __ldg(p.chunk_end + c);
+      k.nb = (k.end - k.beg + kTmaRows - 1) / kTmaRows;
+    } else {
+      k.beg = k.end = k.nb = 0;
+    }
+  };
+  auto advance = [&](Cursor& k) {
+    if (++k.b >= k.nb) open_chunk(k, k.c + stride);
+  };
+  auto load_col = [&](const Cursor& k) -> int {
+    const int idx = k.beg + k.b * kTmaRows + lane;
+    return (k.c < p.n_chunks && lane < kTmaRows && idx < k.end) ? ld_stream(p.col + idx) : 0;
+  };
+  // `tile::gather4`: ONE bulk-tensor op fetches four arbitrary rows (2 KB): the per-op cost of the copy engine
+  // (about one op per 18 cycles per SM whatever its size) capped single-row bulk copies at the LDG rate
+  auto issue = [&](const Cursor& k, uint32_t g, int my_col) {
+    if (k.c >= p.n_chunks) return;
+    const int s = int(g % SLOTS);
+    const int n = min(kTmaRows, k.end - (k.beg + k.b * kTmaRows));
+    const uint32_t bar = smem_u32(bars + s);
+    const int n_ops = (n + 3) >> 2;
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(uint32_t(n_ops) * 4u * ROW_BYTES)
+                   : "memory");
+    __syncwarp();
+    const int q = (lane & 3) * 4;                     // op `lane` takes rows 4*lane .. 4*lane+3 of the batch
+    const int r0 = __shfl_sync(0xffffffffu, my_col, q), r1 = __shfl_sync(0xffffffffu, my_col, q + 1);
+    const int r2 = __shfl_sync(0xffffffffu, my_col, q + 2), r3 = __shfl_sync(0xffffffffu, my_col, q + 3);
+    if (lane < n_ops) {                               // rows past the chunk end hold index 0: fetched, never read
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.tile::gather4.mbarrier::complete_tx::bytes"
+          " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(smem_u32(ring + size_t(s) * SLOT_BYTES + size_t(lane) * 4 * ROW_BYTES)),
+          "l"(reinterpret_cast<uint64_t>(&xmap)), "r"(bar), "r"(0), "r"(r0), "r"(r1), "r"(r2), "r"(r3)
+          : "memory");
+    }
+  };
+
+  Cursor ic, cc;                                    // issue / consume cursors
+  open_chunk(ic, first);
+  open_chunk(cc, first);
+  uint32_t gi = 0, gc = 0;                          // batches issued / consumed so far (ring positions)
+  int col_cur = load_col(ic);
+  for (int d = 0; d < D; ++d) {                     // prime the ring
+    Cursor nx = ic;
+    advance(nx);
+    const int col_nx = load_col(nx);
+    issue(ic, gi, col_cur);
+    if (ic.c < p.n_chunks) ++gi;
+    ic = nx;
+    col_cur = col_nx;
+  }
+  float acc[CH][VEC];
+#pragma unroll
+  for (int ch = 0; ch < CH; ++ch)
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+
+  while (cc.c < p.n_chunks) {
+    const int s = int(gc % SLOTS);
+    const uint32_t bar = smem_u32(bars + s);
+    const uint32_t parity = (gc / SLOTS) & 1u;
+    float my_w = 0.f;
+    if (WEIGHTED) {
+      const int idx = cc.beg + cc.b * kTmaRows + lane;
+      my_w = (lane < kTmaRows && idx < cc.end) ? ld_stream(p.w + idx) : 0.f;
+    }
+    uint32_t spins = 0;
+    while (true) {
+      uint32_t ok;
+      asm volatile(
+          "{\n\t.reg .pred q;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, q;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+      if (ok) break;
+      if (++spins > (1u << 26)) __trap();
+    }
+    const int n = min(kTmaRows, cc.end - (cc.beg + cc.b * kTmaRows));
+    const uint32_t base = smem_u32(ring + size_t(s) * SLOT_BYTES) + uint32_t(lane) * 16u;
+#pragma unroll 4
+    for (int r = 0; r < n; ++r) {
+      float wgt = 1.f;
+      if (WEIGHTED) wgt = __shfl_sync(0xffffffffu, my_w, r);
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(base + uint32_t(r) * ROW_BYTES + uint32_t(ch) * 512u)
+                     : "memory");
+        Pack<T, VEC> v;
+        uint4 u = make_uint4(a0, a1, a2, a3);
+        v.v = *reinterpret_cast<decltype(v.v)*>(&u);
+        float f[VEC];
+        v.unpack(f);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[ch][k] = WEIGHTED ? fmaf(wgt, f[k], acc[ch][k]) : acc[ch][k] + f[k];
+      }
+    }
+    __syncwarp();                                  // every lane has read the slot: it may be refilled
+    ++gc;
+    {                                              // refill: the batch D ahead in the stream
+      Cursor nx = ic;
+      advance(nx);
+      const int col_nx = load_col(nx);
+      issue(ic, gi, col_cur);
+      if (ic.c < p.n_chunks) ++gi;
+      ic = nx;
+      col_cur = col_nx;
+    }
+    if (cc.b + 1 >= cc.nb) {                       // chunk complete: its fp32 partial sum
+      float* __restrict__ dst = p.out + cc.c * p.feat + lane * VEC;
+#pragma unroll
+      for (int ch = 0; ch < CH; ++ch) {
+        if constexpr (VEC == 8) {
+          reinterpret_cast<float4*>(dst + ch * 32 * VEC)[0] = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
+          reinterpret_cast<float4*>(dst + ch * 32 * VEC)[1] = make_float4(acc[ch][4], acc[ch][5], acc[ch][6], acc[ch][7]);
+        } else {
+          reinterpret_cast<float4*>(dst + ch * 32 * VEC)[0] = make_float4(acc[ch][0], acc[ch][1], acc[ch][2], acc[ch][3]);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[ch][k] = 0.f;
+      }
+    }
+    advance(cc);
+  }
+}
+
 // final in-order reduction of the hub partials: `tpr` threads per hub row, each thread owns the
 // features f = t, t+tpr, ...; chunk partials are loaded 8 at a time (independent loads) and added
 // in chunk order (fixed order => deterministic).
@@ -403,6 +582,38 @@ struct Job {
   int unroll;  // 0 = default
 };
 
+template <typename T, int VEC, int CH, int NW, int SLOTS>
+int launch_chunk_tma(Job& job, cudaStream_t st) {
+  ChunkParams& q = job.chunks;
+  CUtensorMap xmap;
+  // the C ABI does not carry the number of source rows: the map is bounded by INT32_MAX rows (col is int32), which
+  // only widens the coordinate range the engine accepts -- rows that no col entry names are never touched
+  if (int rc = row_gather_map(&xmap, q.x, 0x7fffffff, q.feat, q.ldx, sizeof(T) == 4 ? GMLM_F32 : GMLM_BF16)) return rc;
+  constexpr size_t smem = size_t(NW) * SLOTS * kTmaRows * 512 * CH + size_t(NW) * SLOTS * 8;
+  static_assert(smem <= 227 * 1024, "ring exceeds the shared memory of one SM");
+  static bool configured[kMaxDevices][2] = {};
+  const int dev = current_device();
+  if (q.n_chunks == 0) return GMLM_OK;
+  const int64_t gx = std::min<int64_t>((q.n_chunks + NW - 1) / NW, num_sms());     // persistent: one CTA per SM
+  if (job.weighted) {
+    auto k = chunk_tma_kernel<T, VEC, CH, NW, SLOTS, true>;
+    if (!configured[dev][0]) {
+      GMLM_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      configured[dev][0] = true;
+    }
+    k<<<unsigned(gx), NW * 32, smem, st>>>(xmap, q);
+  } else {
+    auto k = chunk_tma_kernel<T, VEC, CH, NW, SLOTS, false>;
+    if (!configured[dev][1]) {
+      GMLM_CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+      configured[dev][1] = true;
+    }
+    k<<<unsigned(gx), NW * 32, smem, st>>>(xmap, q);
+  }
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
 template <typename T, int VEC, int CH, int LPR, int U, int MINB>
 int launch_geo(Job& job, cudaStream_t st) {
   constexpr int GROUPS = 32 / LPR;
@@ -446,6 +657,19 @@ int launch_vec(Job& job, cudaStream_t st) {
   if (nvec <= 8) return launch_geo<T, VEC, 1, 8, 8, 3>(job, st);
   if (nvec <= 16) return launch_geo<T, VEC, 1, 16, 8, 3>(job, st);
   if (nvec <= 32) {
+    if constexpr (VEC * sizeof(T) == 16) {
+      // rows of exactly 512 bytes (F = 256 bf16 / 128 fp32), no head slabs: the hub chunks can take the
+      // bulk-copy kernel (spmm_variant 3 / 4: 8 warps x 3 slots / 12 warps x 2 slots per SM)
+      const int var = tuning_spmm_variant();
+      if (var >= 3 && job.do_chunks && nvec == 32 && job.chunks.slab_stride == 0 && job.chunks.w_stride <= 1 &&
+          job.chunks.ldx * int64_t(sizeof(T)) % 16 == 0) {
+        Job rows_only = job;
+        rows_only.do_chunks = false;
+        int rc = launch_geo<T, VEC, 1, 32, 4, 4>(rows_only, st);
+        if (rc) return rc;
+        return var == 3 ? launch_chunk_tma<T, VEC, 1, 8, 3>(job, st) : launch_chunk_tma<T, VEC, 1, 12, 2>(job, st);
+      }
+    }
     // measured on B200 (C4, bf16 F=256): U=4 at 4 CTAs/SM beats U=8 at 3 CTAs/SM by 12 %
     if (job.unroll == 8) return launch_geo<T, VEC, 1, 32, 8, 3>(job, st);
     return launch_geo<T, VEC, 1, 32, 4, 4>(job, st);

@@ -31,7 +31,7 @@ def _case(n, e, seed, kind="uniform"):
 
 
 @pytest.mark.parametrize("feat", [1, 5, 64, 96, 128, 256, 300, 512, 1000, 1703])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 def test_aggregate_fp32_widths(cuda_dev, feat, variant):
     n, ei = _case(257, 2000, seed=feat)
     et = edge_type_bucket_ref(ei, n)
@@ -48,7 +48,7 @@ def test_aggregate_fp32_widths(cuda_dev, feat, variant):
 
 
 @pytest.mark.parametrize("feat", [8, 64, 128, 256, 264, 512, 257])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 def test_aggregate_bf16_widths(cuda_dev, feat, variant):
     n, ei = _case(300, 3000, seed=feat + 1)
     et = edge_type_bucket_ref(ei, n)
@@ -67,7 +67,7 @@ def test_aggregate_bf16_widths(cuda_dev, feat, variant):
 
 
 @pytest.mark.parametrize("hub_thresh", [1, 3, 16, 100000])
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("variant", [0, 1, 3, 4])
 @pytest.mark.parametrize("quantum", [0, 7, 256])
 def test_aggregate_hub_rows_and_determinism(cuda_dev, hub_thresh, variant, quantum):
     """A star-like graph: the hub path (chunk partials + in-order final sum) must agree with the
