@@ -54,6 +54,13 @@ SIGNATURES = {
                                  _p]),
     "gmlm_gemm_nt": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int,
                             _p]),
+    "gmlm_gemm_nt_multi": (_int, [_int, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _p, _i64, _p, _p, _i64, _i64, _i64,
+                                  _p, _i64, _i64, _p, _i64, _int, _int, _p]),
+    "gmlm_basis_compose": (_int, [_p, _p, _p, C.POINTER(_i32), _int, _int, _int, _i64, _i64, _int, _p, _i64, _i64, _i64,
+                                  _p, _i64, _i64, _i64, _p]),
+    "gmlm_basis_compose_bwd_workspace_bytes": (_sz, [_int, _int, _int, _i64, _i64]),
+    "gmlm_basis_compose_bwd": (_int, [_p, _p, _p, _i64, _i64, C.POINTER(_i32), _int, _int, _int, _i64, _i64, _p, _p, _p,
+                                      _sz, _p]),
     "gmlm_gcn_edge_weights": (_int, [_p, _p, _i64, _p, _p, _p]),
     "gmlm_gat_workspace_bytes": (_sz, [_i64, _int, _int]),
     "gmlm_gat_fused_fwd": (_int, [_p, _p, _i64, _p, _int, _i64, _p, _p, _int, _int, _f32, _f32, C.c_uint64, _i32, _i64, _i64,

@@ -90,11 +90,22 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+constexpr int kMaxSources = 4;
 struct GemmParams {
-  int M, N, K, K1;        // K1: columns served by the first A descriptor (multiple of BLOCK_K)
-  int N1;                 // output columns [0,N1) go to C1, [N1,N) to C2 (multiple of BLOCK_N, or N)
+  int M, N;
+  int N1;                 // output columns [0,N1) go to C1, [N1,N) to C2 (any split; N1 = N: one output)
+  int tiles1;             // ceil(N1 / BLOCK_N): tiles [0,tiles1) cover C1, the rest C2 (B rows N1 + ...)
+  int n_tiles;            // tiles1 + ceil((N - N1) / BLOCK_N)
+  int n_src;              // A = [A_0 | .. | A_{n_src-1}]: one tensor map per source, never concatenated in memory
+  int kb_end[kMaxSources];  // cumulative 64-column block counts of the sources (a source's last block may be partial:
+  int k_off[kMaxSources];   // TMA zero-fills it); k_off = column of B where the source starts (cumulative TRUE widths)
   const float* bias;      // [N] or nullptr
+  const void* addend;     // [M, N] of the output type or nullptr: C = A.B^T + bias + addend (residual folded in)
+  int64_t ld_add;
   uint32_t idesc_formats; // a/b element format bits of the instruction descriptor (F16 = 0, BF16 = 1)
+};
+struct SourceMaps {
+  CUtensorMap m[kMaxSources];
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -146,8 +157,7 @@ constexpr size_t smem_bytes_for() {
 // The round-1 kernel ran one tile per CTA with one accumulator: on the backward shape (K = 64: ONE k-block per
 // tile) load latency, MMA and a 64 KB epilogue were serialised per tile (3.3 ms against 0.88 ms for cuBLAS).
 template <int BLOCK_N, typename OutT>
-__global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_constant__ CUtensorMap tma_a1,
-                                                              const __grid_constant__ CUtensorMap tma_a2,
+__global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_constant__ SourceMaps tma_a,
                                                               const __grid_constant__ CUtensorMap tma_b,
                                                               const __grid_constant__ CUtensorMap tma_c1,
                                                               const __grid_constant__ CUtensorMap tma_c2,
@@ -177,8 +187,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_kb = p.K / BLOCK_K;
-  const int n_tiles = p.N / BLOCK_N;
+  const int num_kb = p.kb_end[p.n_src - 1];
+  const int n_tiles = p.n_tiles;
   const int total_tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * n_tiles;
 
   if (warp == 0 && lane == 0) {
@@ -209,16 +219,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
       uint32_t kc = 0;                                   // k-blocks issued so far, across tiles
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int m0 = (t / n_tiles) * BLOCK_M;
-        const int n0 = (t % n_tiles) * BLOCK_N;
+        const int tn = t % n_tiles;
+        const int brow0 = tn < p.tiles1 ? tn * BLOCK_N : p.N1 + (tn - p.tiles1) * BLOCK_N;   // row of B = output column
+        int src = 0, kb_first = 0;                       // current A source and its first k-block
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+          while (kb >= p.kb_end[src]) kb_first = p.kb_end[src++];
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
           mbar_wait(smem_u32(empty + s), ph ^ 1);
           mbar_expect_tx(smem_u32(full + s), A_BYTES + B_BYTES);
-          const int k0 = kb * BLOCK_K;
-          if (k0 < p.K1) tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a1, smem_u32(full + s), k0, m0);
-          else tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a2, smem_u32(full + s), k0 - p.K1, m0);
-          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tma_b, smem_u32(full + s), k0, n0);
+          const int ka = (kb - kb_first) * BLOCK_K;      // column inside the source; columns past its width and rows
+          tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a.m[src], smem_u32(full + s), ka, m0);   // past M: zeros
+          tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tma_b, smem_u32(full + s), p.k_off[src] + ka, brow0);
         }
       }
     }
@@ -262,11 +274,15 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
     uint32_t it = 0, sp = 0;                               // tile counter, staging-buffer toggle
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const int m0 = (t / n_tiles) * BLOCK_M;
-      const int n0 = (t % n_tiles) * BLOCK_N;
+      const int tn = t % n_tiles;
+      const bool second = tn >= p.tiles1;
+      const int ccol0 = second ? (tn - p.tiles1) * BLOCK_N : tn * BLOCK_N;   // first column inside C1 / C2
+      const int n0 = second ? p.N1 + ccol0 : ccol0;                          // ... and of the whole product
+      const int n_end = second ? p.N : p.N1;                                 // columns at or past it are clipped
       const uint32_t buf = it & 1, aph = (it >> 1) & 1;
       float* bs = bias_s + buf * BLOCK_N;
       if (p.bias) {
-        for (int c = et; c < BLOCK_N; c += 32 * kEpiWarps) bs[c] = __ldg(p.bias + n0 + c);
+        for (int c = et; c < BLOCK_N; c += 32 * kEpiWarps) bs[c] = n0 + c < n_end ? __ldg(p.bias + n0 + c) : 0.f;
       }
       // every epilogue warp has finished tile it-1 here, hence every read of bias_s[buf] from tile it-2
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -278,9 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
         if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
         continue;
       }
-      const bool second = n0 >= p.N1;
       const CUtensorMap* cmap = second ? &tma_c2 : &tma_c1;
-      const int ccol0 = second ? n0 - p.N1 : n0;
       const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16) + buf * BLOCK_N;
 #pragma unroll 1
       for (int ch = half; ch < N_CHUNKS; ch += 2, sp ^= 1) {
@@ -315,6 +329,30 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
           for (int j = 0; j < CHUNK / 4; ++j) {
             const float4 bb = b4[j];                       // same address in every lane: a broadcast
             v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+        }
+        if (p.addend) {
+          // residual folded into the epilogue: a lane owns one output row and reads its CHUNK columns of the
+          // addend as whole 16-byte pieces (every 32-byte sector it touches is fully used)
+          const int row = m0 + quad * 32 + lane;
+          constexpr int EPA = 16 / int(sizeof(OutT));
+          const OutT* arow = static_cast<const OutT*>(p.addend) + int64_t(row) * p.ld_add + n0 + ch * CHUNK;
+#pragma unroll
+          for (int j = 0; j < CHUNK / EPA; ++j) {
+            if (row < p.M && n0 + ch * CHUNK + (j + 1) * EPA <= n_end) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(arow) + j);
+              if constexpr (sizeof(OutT) == 2) {
+                Pack<__nv_bfloat16, 8> a;
+                a.v = q;
+                float f[8];
+                a.unpack(f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[EPA * j + e] += f[e];
+              } else {
+                v[4 * j] += __uint_as_float(q.x); v[4 * j + 1] += __uint_as_float(q.y);
+                v[4 * j + 2] += __uint_as_float(q.z); v[4 * j + 3] += __uint_as_float(q.w);
+              }
+            }
           }
         }
         // one staging row per lane; its 16-byte chunk j goes to position j ^ (row & 7) (128-byte rows) or
@@ -431,8 +469,8 @@ int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int6
 }
 
 template <int BLOCK_N, typename OutT>
-int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, const CUtensorMap& c1,
-           const CUtensorMap& c2, const GemmParams& p, cudaStream_t st) {
+int launch(const SourceMaps& a, const CUtensorMap& b, const CUtensorMap& c1, const CUtensorMap& c2, GemmParams p,
+           cudaStream_t st) {
   constexpr size_t smem = smem_bytes_for<BLOCK_N>();
   static_assert(smem <= 227 * 1024, "tile configuration exceeds the shared memory of one SM");
   auto kern = gemm_nt_kernel<BLOCK_N, OutT>;
@@ -442,11 +480,116 @@ int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& b, c
     GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     configured[dev] = true;
   }
-  const int64_t tiles = int64_t((p.M + BLOCK_M - 1) / BLOCK_M) * (p.N / BLOCK_N);
+  p.tiles1 = (p.N1 + BLOCK_N - 1) / BLOCK_N;
+  p.n_tiles = p.tiles1 + (p.N - p.N1 + BLOCK_N - 1) / BLOCK_N;
+  const int64_t tiles = int64_t((p.M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles;
   const unsigned grid = unsigned(std::min<int64_t>(tiles, num_sms()));     // persistent: one CTA per SM
-  kern<<<grid, kThreads, smem, st>>>(a1, a2, b, c1, c2, p);
+  kern<<<grid, kThreads, smem, st>>>(a, b, c1, c2, p);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
+}
+
+// tile width: the widest tile whose padding (columns computed past N1 / N and clipped by the store) stays under
+// 1/8 of the product; exact divisors first (160 for N = 320, 640: two passes over A through L2 instead of five
+// with 64-wide tiles, which made that shape L2-bandwidth-bound)
+int pick_block_n(int64_t n1, int64_t n2) {
+  const int cand[5] = {256, 160, 128, 64, 32};
+  auto padded = [&](int bn) { return (n1 + bn - 1) / bn * bn + (n2 + bn - 1) / bn * bn; };
+  for (int bn : cand)
+    if (n1 % bn == 0 && n2 % bn == 0 && (bn != 160 || (n1 + n2) % 256 != 0)) return bn;
+  for (int bn : cand)
+    if (padded(bn) * 8 <= (n1 + n2) * 9) return bn;
+  return 32;
+}
+
+int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int64_t* Ks, const void* B, int64_t ldb,
+                 const float* bias, const void* addend, int64_t ld_add, int64_t M, int64_t N, void* C1, int64_t ldc1,
+                 int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream) {
+  GMLM_REQUIRE(n_src >= 1 && n_src <= kMaxSources, "gemm: 1..%d A sources", kMaxSources);
+  GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16, "gemm: operands must be GMLM_BF16 or GMLM_F16");
+  GMLM_REQUIRE(out_dtype == GMLM_F32 || out_dtype == GMLM_BF16, "gemm: out_dtype must be GMLM_F32 or GMLM_BF16");
+  const int esz = out_dtype == GMLM_F32 ? 4 : 2;
+  int64_t K = 0;
+  for (int i = 0; i < n_src; ++i) {
+    GMLM_REQUIRE(A[i] != nullptr && Ks[i] > 0, "gemm: A source %d is empty", i);
+    GMLM_REQUIRE(lda[i] >= Ks[i] && lda[i] % 8 == 0, "gemm: lda[%d] must be >= K and a multiple of 8 (16-byte row pitch)", i);
+    GMLM_REQUIRE((reinterpret_cast<uintptr_t>(A[i]) & 15) == 0, "gemm: operands must be 16-byte aligned");
+    // a source starts at column sum(K_0..K_{i-1}) of B: the TMA wants that inner coordinate on a 16-byte boundary
+    GMLM_REQUIRE(i == n_src - 1 || Ks[i] % 8 == 0, "gemm: every source but the last must be a multiple of 8 columns wide");
+    K += Ks[i];
+  }
+  GMLM_REQUIRE(M >= 0 && N > 0, "gemm: bad sizes");
+  GMLM_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 24) && K < (int64_t(1) << 30), "gemm: sizes exceed int32");
+  GMLM_REQUIRE(B && C1, "gemm: null pointer");
+  GMLM_REQUIRE(ldb >= K && ldb % 8 == 0, "gemm: ldb must be >= K and a multiple of 8 (16-byte row pitch)");
+  GMLM_REQUIRE((reinterpret_cast<uintptr_t>(B) & 15) == 0, "gemm: operands must be 16-byte aligned");
+  if (N1 <= 0 || N1 >= N) {
+    N1 = N; C2 = C1; ldc2 = ldc1;
+  } else {
+    GMLM_REQUIRE(C2 != nullptr, "gemm: second output missing");
+    GMLM_REQUIRE(addend == nullptr, "gemm: the addend goes with a single output");
+  }
+  GMLM_REQUIRE((reinterpret_cast<uintptr_t>(C1) & 15) == 0 && (reinterpret_cast<uintptr_t>(C2) & 15) == 0 &&
+                   (ldc1 * esz) % 16 == 0 && (ldc2 * esz) % 16 == 0 && ldc1 >= N1 && ldc2 >= N - N1,
+               "gemm: outputs must be 16-byte aligned with a 16-byte row pitch");
+  if (addend)
+    GMLM_REQUIRE((reinterpret_cast<uintptr_t>(addend) & 15) == 0 && (ld_add * esz) % 16 == 0 && (N * esz) % 16 == 0 &&
+                     ld_add >= N,
+                 "gemm: the addend must be 16-byte aligned with a 16-byte row pitch");
+  if (M == 0) return GMLM_OK;
+  const int bn = pick_block_n(N1, N - N1);
+  // cuTensorMapEncodeTiled is a driver entry point: it needs a current context on THIS thread (autograd worker
+  // threads may not have touched the runtime of this library yet).  The caller's current device is the device of
+  // the operands (the torch layer guards it); it is neither changed nor queried per call.
+  {
+    static thread_local bool ctx_ready[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!ctx_ready[dev]) {
+      GMLM_CUDA_TRY(cudaFree(nullptr));
+      ctx_ready[dev] = true;
+    }
+  }
+  GemmParams p{};
+  SourceMaps ma;
+  CUtensorMap mb, mc1, mc2;
+  int kb = 0, koff = 0;
+  for (int i = 0; i < kMaxSources; ++i) {
+    if (i < n_src) {
+      if (int rc = get_map(&ma.m[i], A[i], M, Ks[i], lda[i], BLOCK_M, BLOCK_K, in_dtype)) return rc;
+      p.k_off[i] = koff;
+      koff += int(Ks[i]);
+      kb += int((Ks[i] + BLOCK_K - 1) / BLOCK_K);
+    } else {
+      ma.m[i] = ma.m[0];
+      p.k_off[i] = koff;
+    }
+    p.kb_end[i] = kb;
+  }
+  int rc = get_map(&mb, B, N, K, ldb, bn, BLOCK_K, in_dtype);
+  if (rc) return rc;
+  const int chunk = bn % (128 / esz) == 0 ? 128 / esz : 64 / esz;      // chunk_cols<BLOCK_N, OutT>()
+  rc = get_map(&mc1, C1, M, N1, ldc1, 32, chunk, out_dtype);
+  if (rc) return rc;
+  rc = N1 < N ? get_map(&mc2, C2, M, N - N1, ldc2, 32, chunk, out_dtype) : (mc2 = mc1, GMLM_OK);
+  if (rc) return rc;
+  p.M = int(M); p.N = int(N); p.N1 = int(N1); p.n_src = n_src;
+  p.bias = bias;
+  p.addend = addend; p.ld_add = ld_add;
+  p.idesc_formats = in_dtype == GMLM_BF16 ? 1u : 0u;
+  cudaStream_t st = as_stream(stream);
+#define GMLM_GEMM_CASE(BN)                                                                     \
+  case BN:                                                                                     \
+    return out_dtype == GMLM_F32 ? launch<BN, float>(ma, mb, mc1, mc2, p, st)                  \
+                                 : launch<BN, __nv_bfloat16>(ma, mb, mc1, mc2, p, st);
+  switch (bn) {
+    GMLM_GEMM_CASE(256)
+    GMLM_GEMM_CASE(160)
+    GMLM_GEMM_CASE(128)
+    GMLM_GEMM_CASE(64)
+    GMLM_GEMM_CASE(32)
+  }
+#undef GMLM_GEMM_CASE
+  return fail(GMLM_ERR_INVALID, "gemm: unsupported tile");
 }
 
 }  // namespace
@@ -466,81 +609,24 @@ int row_gather_map(void* out_map, const void* base, int64_t rows, int64_t cols, 
 
 using namespace gmlm;
 
+extern "C" int gmlm_gemm_nt_multi(int num_sources, const void* const* A_host, const int64_t* lda_host,
+                                  const int64_t* K_host, const void* B, int64_t ldb, const float* bias,
+                                  const void* addend, int64_t ld_add, int64_t M, int64_t N, void* C1, int64_t ldc1,
+                                  int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream) {
+  GMLM_REQUIRE(A_host && lda_host && K_host, "gemm: null source table");
+  return gemm_general(num_sources, A_host, lda_host, K_host, B, ldb, bias, addend, ld_add, M, N, C1, ldc1, N1, C2, ldc2,
+                      in_dtype, out_dtype, stream);
+}
+
 extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                             const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1,
                             int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype,
                             void* stream) {
-  const int64_t K = K1 + K2;
-  GMLM_REQUIRE(M >= 0 && N > 0 && K1 > 0 && K2 >= 0, "gemm: bad sizes");
-  GMLM_REQUIRE(M < (int64_t(1) << 31) && N <= 65535 * 256 && K < (int64_t(1) << 31), "gemm: sizes exceed int32");
-  GMLM_REQUIRE(K1 % BLOCK_K == 0 && K2 % BLOCK_K == 0, "gemm: K1 and K2 must be multiples of 64");
-  GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16, "gemm: operands must be GMLM_BF16 or GMLM_F16");
-  GMLM_REQUIRE(out_dtype == GMLM_F32 || out_dtype == GMLM_BF16, "gemm: out_dtype must be GMLM_F32 or GMLM_BF16");
-  const int min_n = 32;
-  GMLM_REQUIRE(N % min_n == 0, "gemm: N must be a multiple of 32");
-  GMLM_REQUIRE(A1 && B && C1 && (K2 == 0 || A2), "gemm: null pointer");
-  GMLM_REQUIRE(lda1 >= K1 && (K2 == 0 || lda2 >= K2) && ldb >= K, "gemm: bad leading dimensions");
-  GMLM_REQUIRE(lda1 % 8 == 0 && (K2 == 0 || lda2 % 8 == 0) && ldb % 8 == 0, "gemm: leading dimensions must be multiples of 8");
-  GMLM_REQUIRE((reinterpret_cast<uintptr_t>(A1) & 15) == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0 &&
-                   (K2 == 0 || (reinterpret_cast<uintptr_t>(A2) & 15) == 0),
-               "gemm: operands must be 16-byte aligned");
-  if (M == 0) return GMLM_OK;
-  int bn = N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
-  if (N1 <= 0 || N1 >= N) {
-    N1 = N; C2 = C1; ldc2 = ldc1;
-    // 160-wide tiles for N = 320, 640, ... ((S+1) * Fo of the transform-first layers): two passes over A through L2
-    // instead of five with 64-wide tiles (measured: 64-wide tiles made that shape L2-bandwidth-bound)
-    if (N % 256 != 0 && N % 160 == 0) bn = 160;
-  } else {
-    GMLM_REQUIRE(C2 != nullptr, "gemm: second output missing");
-    while (bn > min_n && N1 % bn != 0) bn >>= 1;
-    GMLM_REQUIRE(N1 % bn == 0 && (N - N1) % bn == 0, "gemm: N1 must split N on a tile boundary");
-  }
-  const int esz = out_dtype == GMLM_F32 ? 4 : 2;
-  GMLM_REQUIRE((reinterpret_cast<uintptr_t>(C1) & 15) == 0 && (reinterpret_cast<uintptr_t>(C2) & 15) == 0 &&
-                   (ldc1 * esz) % 16 == 0 && (ldc2 * esz) % 16 == 0,
-               "gemm: outputs must be 16-byte aligned");
-  // cuTensorMapEncodeTiled is a driver entry point: it needs a current context on THIS thread (autograd worker
-  // threads may not have touched the runtime of this library yet).  The caller's current device is the device of
-  // the operands (the torch layer guards it); it is neither changed nor queried per call.
-  {
-    static thread_local bool ctx_ready[kMaxDevices] = {};
-    const int dev = current_device();
-    if (!ctx_ready[dev]) {
-      GMLM_CUDA_TRY(cudaFree(nullptr));
-      ctx_ready[dev] = true;
-    }
-  }
-  CUtensorMap ma1, ma2, mb, mc1, mc2;
-  int rc = get_map(&ma1, A1, M, K1, lda1, BLOCK_M, BLOCK_K, in_dtype);
-  if (rc) return rc;
-  rc = K2 ? get_map(&ma2, A2, M, K2, lda2, BLOCK_M, BLOCK_K, in_dtype) : (ma2 = ma1, GMLM_OK);
-  if (rc) return rc;
-  rc = get_map(&mb, B, N, K, ldb, bn, BLOCK_K, in_dtype);
-  if (rc) return rc;
-  const int chunk = bn % (128 / esz) == 0 ? 128 / esz : 64 / esz;      // chunk_cols<BLOCK_N, OutT>()
-  rc = get_map(&mc1, C1, M, N1, ldc1, 32, chunk, out_dtype);
-  if (rc) return rc;
-  rc = N1 < N ? get_map(&mc2, C2, M, N - N1, ldc2, 32, chunk, out_dtype) : (mc2 = mc1, GMLM_OK);
-  if (rc) return rc;
-  GemmParams p;
-  p.M = int(M); p.N = int(N); p.K = int(K); p.K1 = int(K1); p.N1 = int(N1);
-  p.bias = bias;
-  p.idesc_formats = in_dtype == GMLM_BF16 ? 1u : 0u;
-  cudaStream_t st = as_stream(stream);
-#define GMLM_GEMM_CASE(BN)                                                                                  \
-  case BN:                                                                                                  \
-    return out_dtype == GMLM_F32 ? launch<BN, float>(ma1, ma2, mb, mc1, mc2, p, st)                         \
-                                 : launch<BN, __nv_bfloat16>(ma1, ma2, mb, mc1, mc2, p, st);
-  switch (bn) {
-    GMLM_GEMM_CASE(256)
-    GMLM_GEMM_CASE(160)
-    GMLM_GEMM_CASE(128)
-    GMLM_GEMM_CASE(64)
-    GMLM_GEMM_CASE(32)
-  }
-#undef GMLM_GEMM_CASE
-  return fail(GMLM_ERR_INVALID, "gemm: unsupported tile");
+  GMLM_REQUIRE(K1 > 0 && K2 >= 0 && A1 && (K2 == 0 || A2), "gemm: bad sizes");
+  const void* A[2] = {A1, A2};
+  const int64_t lda[2] = {lda1, lda2}, Ks[2] = {K1, K2};
+  return gemm_general(K2 > 0 ? 2 : 1, A, lda, Ks, B, ldb, bias, nullptr, 0, M, N, C1, ldc1, N1, C2, ldc2, in_dtype,
+                      out_dtype, stream);
 }
 
 extern "C" int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,

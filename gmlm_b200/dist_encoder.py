@@ -56,20 +56,23 @@ class PartitionedGraphEncoder(nn.Module):
         y = self.ops.conv(conv, self.ops.exchange(x_local))
         return drop(self.ops.norm_gelu(gn, y))            # the whole graph has > 1 node here (main.py:273)
 
-    def _lin(self, lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    def _residual(self, lin: nn.Linear, x: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
+        enc = self.encoder
+        if acc.is_cuda and hasattr(enc, "_residual"):
+            return enc._residual(lin, x, acc)              # the add folded into the projection's epilogue
         if x.dtype == lin.weight.dtype or torch.is_autocast_enabled(x.device.type):
-            return lin(x)
-        return torch.nn.functional.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype))
+            return acc + lin(x).to(acc.dtype)
+        return acc + torch.nn.functional.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype)).to(acc.dtype)
 
     def forward(self, x_local: torch.Tensor, return_layers: bool = False):
         enc = self.encoder
         outs = []
         x1 = self._block(1, x_local)
         outs.append(x1)                                   # pre-residual outputs feed the fusion (main.py:279)
-        x1 = x1 + self._lin(enc.residual_proj1, x_local).to(x1.dtype)
+        x1 = self._residual(enc.residual_proj1, x_local, x1)
         x2 = self._block(2, x1)
         outs.append(x2)
-        x2 = x2 + self._lin(enc.residual_proj2, x1).to(x2.dtype)
+        x2 = self._residual(enc.residual_proj2, x1, x2)
         x3 = self._block(3, x2)
         outs.append(x3)
         x4 = self._block(4, x3)

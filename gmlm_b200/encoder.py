@@ -25,8 +25,7 @@ from torch.utils.checkpoint import checkpoint
 
 from .graph import _tensor_key, get_rel_graph
 from .nn import GraphNorm, RGCNConv
-from .ops import (edge_type_from_degree, layer_norm, layer_norm_ok, linear_nt, linear_nt_ok,
-                  soft_masking_gnn_input)
+from .ops import edge_type_from_degree, layer_norm, layer_norm_ok, linear_nt, soft_masking_gnn_input
 
 
 class MultiScaleFusion(nn.Module):
@@ -46,12 +45,17 @@ class MultiScaleFusion(nn.Module):
         w = F.softmax(self.scale_weights, dim=0)
         dt = self.projections[0].weight.dtype
         autocast = torch.is_autocast_enabled("cuda")
-        weight = torch.cat([w[i] * p.weight for i, p in enumerate(self.projections)], dim=1)
-        bias = sum(w[i] * p.bias for i, p in enumerate(self.projections))
-        xs = torch.cat([e if autocast else e.to(dt) for e in embeddings_list], dim=1)
-        if not autocast and linear_nt_ok(xs, weight.size(0)):
-            fused = linear_nt(xs, weight, bias)                      # bf16 pipeline: the tcgen05 GEMM (csrc/gemm_tcgen05.cu)
+        with torch.amp.autocast("cuda", enabled=False):
+            weight = torch.cat([w[i] * p.weight for i, p in enumerate(self.projections)], dim=1)
+            bias = sum(w[i] * p.bias for i, p in enumerate(self.projections))
+        op = _dense_op_dtype(embeddings_list[0])
+        if op is not None and len(embeddings_list) <= 4 and embeddings_list[0].is_cuda:
+            # the tcgen05 GEMM reads the layer outputs through one tensor map each: no concatenation (csrc/gemm_tcgen05.cu)
+            with torch.amp.autocast("cuda", enabled=False):
+                fused = linear_nt(list(embeddings_list), weight, bias, op_dtype=op,
+                                  out_dtype=torch.float32 if autocast else embeddings_list[0].dtype)
         else:
+            xs = torch.cat([e if autocast else e.to(dt) for e in embeddings_list], dim=1)
             fused = F.linear(xs, weight, bias)
         ln = self.layer_norm
         if autocast:                      # torch.autocast runs layer_norm in fp32
@@ -59,6 +63,15 @@ class MultiScaleFusion(nn.Module):
         if ln.elementwise_affine and ln.bias is not None and layer_norm_ok(fused):
             return layer_norm(fused, ln.weight, ln.bias, ln.eps)     # row-wise kernel (csrc/layernorm.cu)
         return ln(fused)                  # widths the kernel does not take: stock, as in the reference
+
+
+def _dense_op_dtype(x: torch.Tensor) -> Optional[torch.dtype]:
+    """Operand type of a dense projection on the tcgen05 GEMM: the autocast type under torch.amp.autocast, bf16 in
+    the bf16 pipeline; None = fp32 activations outside autocast (stock cuBLAS path)."""
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
+        return dt if dt in (torch.float16, torch.bfloat16) else None
+    return torch.bfloat16 if x.dtype == torch.bfloat16 else None
 
 
 _ET_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
@@ -119,12 +132,16 @@ class GraphEncoder(nn.Module):
             return checkpoint(self._block(k), x, graph, use_reentrant=False)
         return self._block(k)(x, graph)
 
-    def _lin(self, lin: nn.Linear, x: torch.Tensor) -> torch.Tensor:
-        if not torch.is_autocast_enabled("cuda") and linear_nt_ok(x, lin.out_features):
-            return linear_nt(x, lin.weight, lin.bias)                # bf16 pipeline: the tcgen05 GEMM
-        if torch.is_autocast_enabled("cuda") or x.dtype == lin.weight.dtype:
-            return lin(x)
-        return F.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype))
+    def _residual(self, lin: nn.Linear, x: torch.Tensor, acc: torch.Tensor) -> torch.Tensor:
+        """``acc + lin(x)`` (main.py:281-282, 294-295).  On the tcgen05 GEMM the add happens in the epilogue: the
+        projection reads ``acc`` tile by tile and writes the sum, no separate elementwise pass."""
+        op = _dense_op_dtype(x)
+        if op is not None and x.is_cuda and acc.dtype in (torch.float32, torch.bfloat16):
+            with torch.amp.autocast("cuda", enabled=False):
+                return linear_nt(x, lin.weight, lin.bias, out_dtype=acc.dtype, op_dtype=op, addend=acc)
+        if x.dtype == lin.weight.dtype:
+            return acc + lin(x).to(acc.dtype)
+        return acc + F.linear(x, lin.weight.to(x.dtype), lin.bias.to(x.dtype)).to(acc.dtype)
 
     def get_graph_embeddings(self, x_feat: torch.Tensor, edge_index: torch.Tensor,
                              edge_type: Optional[torch.Tensor] = None, return_layers: bool = False):
@@ -135,10 +152,10 @@ class GraphEncoder(nn.Module):
         outs = []
         x1 = self._run(1, x_feat, graph)
         outs.append(x1)                              # pre-residual outputs feed the fusion (main.py:279)
-        x1 = x1 + self._lin(self.residual_proj1, x_feat).to(x1.dtype)
+        x1 = self._residual(self.residual_proj1, x_feat, x1)
         x2 = self._run(2, x1, graph)
         outs.append(x2)
-        x2 = x2 + self._lin(self.residual_proj2, x1).to(x2.dtype)
+        x2 = self._residual(self.residual_proj2, x1, x2)
         x3 = self._run(3, x2, graph)
         outs.append(x3)
         x4 = self._run(4, x3, graph)

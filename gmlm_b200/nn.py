@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .graph import RelGraph, get_rel_graph
-from .ops import graph_norm, rgcn_aggregate, rgcn_transform, rgcn_transform_first, rgcn_transform_ok
+from .ops import graph_norm, rgcn_aggregate, rgcn_transform, rgcn_transform_first
 
 
 def glorot_(t: Optional[torch.Tensor]):
@@ -34,7 +34,8 @@ class RGCNConv(nn.Module):
         out_i = sum_r mean_{j in N_r(i)} x_j @ W_r  +  x_i @ root + bias,   W_r = sum_b comp[r,b] * weight[b]
 
     Execution: one cached (dst,rel)-keyed CSR (A3), one deterministic segmented-mean kernel over
-    all relations (A5), then two dense GEMMs ``[N, S*Fi] @ [S*Fi, Fo]`` and ``x @ root`` (A6).
+    all relations (A5), one composition kernel that reads the fp32 bases once and writes the GEMM operand (A4),
+    ONE tcgen05 GEMM over ``[H | x]`` with the bias in its epilogue (A6).
     Relations with no edges contribute exact zeros upstream and are skipped here; their
     ``comp`` rows receive exact-zero gradients through the index-select of the composed weight.
     """
@@ -44,7 +45,7 @@ class RGCNConv(nn.Module):
                  is_sorted: bool = False, bias: bool = True, out_dtype: Optional[torch.dtype] = None, **kwargs):
         super().__init__()
         self.out_dtype = out_dtype  # None = upstream behaviour (default dtype); bf16 for the bandwidth study
-        self.use_tcgen05 = True     # bf16 activations: dense transform on the tcgen05 GEMM (else cuBLAS)
+        self.use_tcgen05 = True     # 16-bit operand types (bf16 pipeline, autocast): dense transform on the tcgen05 GEMM
         self.transform_first = None  # None = by the byte-count model below; True / False force the formulation
         if num_blocks is not None:
             raise NotImplementedError("gmlm_b200.RGCNConv: block-diagonal decomposition is not on the reference "
@@ -116,33 +117,34 @@ class RGCNConv(nn.Module):
             raise NotImplementedError("gmlm_b200.RGCNConv: integer node-id inputs are not on the reference path")
         if x.size(1) != self.in_channels:
             raise _lib.GmlmError(f"RGCNConv: x has {x.size(1)} features, layer expects {self.in_channels}")
-        w = self.composed_weight()
         live = graph.live_rels
-        if len(live) != self.num_relations:
-            w = w.index_select(0, torch.as_tensor(live, device=w.device))
+        if self.comp is not None and (self.comp.size(0) > 64 or len(live) > 8):
+            return self._forward_torch(x, graph)     # sizes outside the composition kernel (never on the reference path)
         if self._use_transform_first(graph):
             # narrowing layer: Z = x @ [W_r | root] first, then gather Fo-wide slabs; H is never materialised
-            return rgcn_transform_first(x, graph, w, self.root, self.bias, self.out_dtype or torch.get_default_dtype())
+            return rgcn_transform_first(x, graph, self.weight, self.comp, self.root, self.bias, self.out_dtype,
+                                        self.use_tcgen05)
         h = rgcn_aggregate(x, graph)                                   # [N, S*Fi], x's dtype
         if graph.num_src != graph.num_nodes:
             # destination-row partition: x = [local rows ‖ halo rows]; the root term is over the local rows
             x = x[: graph.num_nodes]
+        # A4 + A6: composition kernel + ONE GEMM over [h | x].  Upstream accumulates into `out = torch.zeros(N, Fo)`
+        # of the default dtype (fp32) while the matmuls run in the operand dtype, or in the autocast dtype under
+        # torch.amp.autocast (main.py:446,543): fp16 operands, fp32 result here too.
+        return rgcn_transform(h, x, self.weight, self.comp, self.root, self.bias, live, self.out_dtype, self.use_tcgen05)
+
+    def _forward_torch(self, x: torch.Tensor, graph: RelGraph) -> torch.Tensor:
+        """Aggregate-first with the dense part on stock torch ops (shapes the composition kernel does not take)."""
+        w = self.composed_weight()
+        live = graph.live_rels
+        if len(live) != self.num_relations:
+            w = w.index_select(0, torch.as_tensor(live, device=w.device))
+        h = rgcn_aggregate(x, graph)
+        if graph.num_src != graph.num_nodes:
+            x = x[: graph.num_nodes]
         w = w.reshape(len(live) * self.in_channels, self.out_channels)
-        # upstream accumulates into `out = torch.zeros(N, Fo)` of the default dtype (fp32) while the
-        # matmuls run in the operand dtype, or in the autocast dtype under torch.amp.autocast
         autocast = torch.is_autocast_enabled("cuda")
         out_dtype = self.out_dtype or torch.get_default_dtype()
-        if self.use_tcgen05 and self.root is not None and out_dtype in (torch.float32, torch.bfloat16):
-            if not autocast and rgcn_transform_ok(h, x, self.out_channels):
-                # bf16 pipeline: one tcgen05 GEMM over [h | x] with the bias in its epilogue
-                return rgcn_transform(h, x, w, self.root, self.bias, out_dtype)
-            if autocast:
-                # torch.amp.autocast (main.py:446,543): the matmuls run in the autocast dtype (fp16 by default) and
-                # accumulate into the fp32 `out`; here h and x are cast once and ONE tcgen05 GEMM writes fp32
-                op = torch.get_autocast_dtype("cuda")
-                if rgcn_transform_ok(h, x, self.out_channels, op):
-                    with torch.amp.autocast("cuda", enabled=False):
-                        return rgcn_transform(h, x, w, self.root, self.bias, out_dtype, op)
 
         def mm(a, b):
             return torch.matmul(a, b) if autocast else torch.matmul(a, b.to(a.dtype))

@@ -367,7 +367,7 @@ def _plan_aggregate_impl(rows, *a):
 
 
 def _gemm_nt_op(a1, b, bias, a2, out_dtype):
-    return gemm_nt(a1, b, bias=bias, a2=a2, out_dtype=out_dtype)
+    return gemm_nt(a1, b, bias=bias, a2=a2, out_dtype=out_dtype).contiguous()
 
 
 def _csr_build_op(row, col, rel, keep, num_rows, num_cols, num_relations, slot_of_rel, num_slots):
@@ -568,95 +568,168 @@ torch.library.register_autograd("gmlm::soft_mask_fwd", _soft_mask_backward, setu
 
 
 # ------------------------------------------------------------------------------ A6 dense transform (tcgen05)
-def gemm_nt(a1: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
-            out_dtype: Optional[torch.dtype] = None, split: int = 0):
-    """``[a1 | a2] @ b.T + bias`` on the tcgen05 tensor cores (bf16 or fp16 in, fp32 accumulate).
+_OPS16 = (torch.bfloat16, torch.float16)
 
-    a1 [M,K1], a2 [M,K2] (optional), b [N,K1+K2], all bf16 (or all fp16) with unit inner stride; returns C [M,N]
-    (bf16 or fp32), or (C[:, :split], C[:, split:]) as two contiguous tensors when ``split`` > 0."""
+
+def _op_code(dt: torch.dtype) -> int:
+    return {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16, torch.float16: _lib.F16}[dt]
+
+
+def _tma_rows(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """``t`` [M, K] as a TMA-readable operand of type ``dtype``: unit inner stride, 16-byte aligned rows.  A cast
+    and / or a pitch fix is ONE copy into a buffer whose pitch is rounded up to 16 bytes (K = 300 fp16: pitch 304)."""
+    dtype = dtype or t.dtype
+    es = torch.empty((), dtype=dtype).element_size()
+    if (t.dtype == dtype and t.dim() == 2 and t.stride(1) == 1 and (t.stride(0) * es) % 16 == 0
+            and t.data_ptr() % 16 == 0 and t.stride(0) >= t.size(1)):
+        return t
+    m, k = t.shape
+    per = 16 // es
+    buf = torch.empty((m, (k + per - 1) // per * per), dtype=dtype, device=t.device)
+    view = buf[:, :k]
+    view.copy_(t)
+    return view
+
+
+def gemm_nt(a1, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None, split: int = 0, addend: Optional[torch.Tensor] = None):
+    """``[a1 | a2 | ..] @ b.T + bias (+ addend)`` on the tcgen05 tensor cores (bf16 or fp16 in, fp32 accumulate).
+
+    a1: one [M,K1] tensor or a list of up to four [M,K_i] sources (never concatenated in memory); a2 [M,K2]
+    (optional); b [N, sum K], all bf16 (or all fp16) with unit inner stride and a 16-byte row pitch (anything else is
+    copied once); any K, N.  Returns C [M,N] (bf16 or fp32), or (C[:, :split], C[:, split:]) as two contiguous tensors
+    when ``split`` > 0.  ``addend`` [M,N] of the output type is added in the epilogue (single output only)."""
     lib = _lib.load()
-    _require_cuda(a1, "a1")
-    if a1.dtype not in (torch.bfloat16, torch.float16) or b.dtype != a1.dtype or (a2 is not None and a2.dtype != a1.dtype):
+    srcs = list(a1) if isinstance(a1, (list, tuple)) else [a1]
+    if a2 is not None:
+        srcs.append(a2)
+    _require_cuda(srcs[0], "a1")
+    op = srcs[0].dtype
+    if op not in _OPS16 or b.dtype != op or any(t.dtype != op for t in srcs):
         raise _lib.GmlmError("gemm_nt: operands must all be bfloat16 or all be float16")
-    a1, b = _rowmajor(a1), _rowmajor(b)
-    a2 = _rowmajor(a2) if a2 is not None else None
-    m, k1 = a1.shape
-    k2 = int(a2.size(1)) if a2 is not None else 0
+    if not 1 <= len(srcs) <= 4:
+        raise _lib.GmlmError("gemm_nt: one to four A sources")
+    m = int(srcs[0].size(0))
+    if any(t.dim() != 2 or t.size(0) != m for t in srcs) or b.dim() != 2 or b.size(1) != sum(int(t.size(1)) for t in srcs):
+        raise _lib.GmlmError(f"gemm_nt: shape mismatch a {[tuple(t.shape) for t in srcs]} b {tuple(b.shape)}")
+    if any(t.size(1) % 8 for t in srcs[:-1]):
+        srcs = [torch.cat(srcs, dim=1)]      # a source must start on a 16-byte column boundary of b: concatenate
+    srcs = [_tma_rows(t) for t in srcs]
+    b = _tma_rows(b)
     n = int(b.size(0))
-    if b.size(1) != k1 + k2 or (a2 is not None and a2.size(0) != m):
-        raise _lib.GmlmError(f"gemm_nt: shape mismatch a1 {tuple(a1.shape)} a2 {None if a2 is None else tuple(a2.shape)} "
-                             f"b {tuple(b.shape)}")
-    out_dtype = out_dtype or (torch.bfloat16 if a1.dtype == torch.bfloat16 else torch.float32)
+    out_dtype = out_dtype or (torch.bfloat16 if op == torch.bfloat16 else torch.float32)
     if out_dtype not in _DT:
         raise _lib.GmlmError("gemm_nt: output must be float32 or bfloat16")
-    code = _DT[out_dtype]
-    in_code = _lib.BF16 if a1.dtype == torch.bfloat16 else _lib.F16
-    dev = a1.device
+    per = 16 // torch.empty((), dtype=out_dtype).element_size()
+    dev = srcs[0].device
     bias32 = bias.detach().float().contiguous() if bias is not None else None
+    if addend is not None:
+        if split or addend.shape != (m, n) or addend.dtype != out_dtype:
+            raise _lib.GmlmError("gemm_nt: addend must be [M, N] of the output type (single output)")
+        addend = _tma_rows(addend)
+
+    def alloc(cols):          # contiguous when the width allows a 16-byte pitch, else a padded buffer's view
+        if cols % per == 0:
+            return torch.empty((m, cols), dtype=out_dtype, device=dev)
+        return torch.empty((m, (cols + per - 1) // per * per), dtype=out_dtype, device=dev)[:, :cols]
+
     with torch.cuda.device(dev):
         if split and 0 < split < n:
-            c1 = torch.empty((m, split), dtype=out_dtype, device=dev)
-            c2 = torch.empty((m, n - split), dtype=out_dtype, device=dev)
+            c1, c2 = alloc(split), alloc(n - split)
         else:
             split = 0
-            c1 = torch.empty((m, n), dtype=out_dtype, device=dev)
-            c2 = None
-        _lib.check(lib.gmlm_gemm_nt(_ptr(a1), _ld(a1), k1, _ptr(a2), _ld(a2) if a2 is not None else 0, k2,
-                                    _ptr(b), _ld(b), _ptr(bias32), m, n, _ptr(c1), c1.size(1), split,
-                                    _ptr(c2), c2.size(1) if c2 is not None else 0, in_code, code, _stream(dev)),
-                   "gemm_nt")
+            c1, c2 = alloc(n), None
+        k = len(srcs)
+        ptrs = (C.c_void_p * k)(*[t.data_ptr() for t in srcs])
+        ldas = (C.c_int64 * k)(*[_ld(t) for t in srcs])
+        ks = (C.c_int64 * k)(*[int(t.size(1)) for t in srcs])
+        _lib.check(lib.gmlm_gemm_nt_multi(k, ptrs, ldas, ks, _ptr(b), _ld(b), _ptr(bias32), _ptr(addend),
+                                          _ld(addend) if addend is not None else 0, m, n, _ptr(c1), _ld(c1), split,
+                                          _ptr(c2), _ld(c2) if c2 is not None else 0, _op_code(op), _DT[out_dtype],
+                                          _stream(dev)), "gemm_nt")
     return (c1, c2) if c2 is not None else c1
 
 
-class _RGCNTransform(torch.autograd.Function):
-    """out = [h | x] @ [w ; root] + bias as ONE tcgen05 GEMM (A6; 0.81 ms vs 1.03 ms for the two cuBLAS calls at
-    M=2M, K=1280, N=64).  Backward: [dh | dx] = g @ [w ; root]^T is one more launch of the same persistent kernel,
-    its two outputs written through two tensor maps so that dh lands contiguous for the transposed aggregation;
-    dW = h^T g and droot = x^T g are reductions over all nodes and are produced in fp32.
+# ------------------------------------------------------------------------------ A4 basis composition
+def _rup(v: int, q: int) -> int:
+    return (v + q - 1) // q * q
 
-    ``op_dtype`` is the operand type of the GEMMs: bf16 for the bf16 pipeline, fp16 under ``torch.amp.autocast``
-    (what the reference's matmuls run in, main.py:446,543); h and x are cast once and saved in that type."""
 
-    @staticmethod
-    def forward(ctx, h, x, w, root, bias, out_dtype, op_dtype):
-        hq = h if h.dtype == op_dtype else h.to(op_dtype)
-        xq = x if x.dtype == op_dtype else x.to(op_dtype)
-        wc = torch.cat([w, root], dim=0).detach().to(op_dtype)          # [K1+K2, Fo]
-        out = gemm_nt(hq, wc.t().contiguous(), bias=bias, a2=xq, out_dtype=out_dtype)
-        ctx.save_for_backward(hq, xq, wc)
-        ctx.k1 = h.size(1)
-        ctx.dtypes = (w.dtype, root.dtype, None if bias is None else bias.dtype, h.dtype, x.dtype)
-        return out
+def basis_compose(weight: torch.Tensor, comp: Optional[torch.Tensor], root: Optional[torch.Tensor], live: Sequence[int],
+                  op_dtype: torch.dtype, layout: str = "agg", want_n: bool = True, want_t: bool = True):
+    """A4 in one pass over the fp32 bases: the composed weights of the populated relations ``live`` (+ ``root`` as one
+    more slab), written in ``op_dtype`` in the two layouts the dense transforms consume.
 
-    @staticmethod
-    def backward(ctx, g):
-        h, x, wc = ctx.saved_tensors
-        k1, k2 = ctx.k1, x.size(1)
-        gb = g.to(wc.dtype).contiguous()
-        fo = gb.size(1)
-        dh = dx = dw = droot = dbias = None
-        need_h, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        if need_h or need_x:
-            out_dt = torch.bfloat16 if ctx.dtypes[3] == torch.bfloat16 else torch.float32
-            if fo % 64 == 0 and k1 % 32 == 0 and k2 % 32 == 0 and ctx.dtypes[3] == ctx.dtypes[4]:
-                if need_h and need_x:
-                    dh, dx = gemm_nt(gb, wc, out_dtype=out_dt, split=k1)      # [M, Fo] x [K1+K2, Fo]^T
-                elif need_h:
-                    dh = gemm_nt(gb, wc[:k1], out_dtype=out_dt)
-                else:
-                    dx = gemm_nt(gb, wc[k1:], out_dtype=out_dt)
-            else:
-                if need_h:
-                    dh = (gb @ wc[:k1].t()).to(ctx.dtypes[3])
-                if need_x:
-                    dx = (gb @ wc[k1:].t()).to(ctx.dtypes[4])
-        if ctx.needs_input_grad[2]:
-            dw = _mm_f32(h.t(), gb).to(ctx.dtypes[0])
-        if ctx.needs_input_grad[3]:
-            droot = _mm_f32(x.t(), gb).to(ctx.dtypes[1])
-        if ctx.needs_input_grad[4]:
-            dbias = torch.ops.gmlm.colstats(gb.float() if gb.dtype == torch.float16 else gb)[0].to(ctx.dtypes[2])
-        return dh, dx, dw, droot, dbias, None, None
+    layout "agg" (aggregate-first layer, K = (S+1)*Fi):  wn [K, Fo] = [W_0; ..; W_{S-1}; root],  wt [Fo, K] = wn^T
+    layout "tf"  (transform-first layer):                wn [Fi, (S+1)*Fo] = [W_0 | .. | root],  wt = wn^T
+    Both are views with a 16-byte row pitch.  No autograd (see ``basis_compose_bwd``)."""
+    lib = _lib.load()
+    _require_cuda(weight, "weight")
+    nb, fi, fo = (int(v) for v in weight.shape)
+    S = len(live)
+    slabs = S + (1 if root is not None else 0)
+    per = 16 // torch.empty((), dtype=op_dtype).element_size()
+    dev = weight.device
+    w32 = weight.detach().float().contiguous()
+    c32 = comp.detach().float().contiguous() if comp is not None else None
+    r32 = root.detach().float().contiguous() if root is not None else None
+    rels = (C.c_int32 * max(S, 1))(*[int(v) for v in live])
+    with torch.cuda.device(dev):
+        if layout == "agg":
+            k = slabs * fi
+            ldn, ldt = _rup(fo, per), _rup(k, per)
+            wn = torch.empty((k, ldn), dtype=op_dtype, device=dev)[:, :fo] if want_n else None
+            wt = torch.empty((fo, ldt), dtype=op_dtype, device=dev)[:, :k] if want_t else None
+            n_args = (fi * ldn, ldn, S * fi * ldn)
+            t_args = (fi, ldt, S * fi)
+        elif layout == "tf":
+            k = slabs * fo
+            ldn, ldt = _rup(k, per), _rup(fi, per)
+            wn = torch.empty((fi, ldn), dtype=op_dtype, device=dev)[:, :k] if want_n else None
+            wt = torch.empty((k, ldt), dtype=op_dtype, device=dev)[:, :fi] if want_t else None
+            n_args = (fo, ldn, S * fo)
+            t_args = (fo * ldt, ldt, S * fo * ldt)
+        else:
+            raise _lib.GmlmError(f"basis_compose: unknown layout {layout!r}")
+        _lib.check(lib.gmlm_basis_compose(_ptr(c32), _ptr(w32), _ptr(r32), rels, S,
+                                          int(comp.size(0)) if comp is not None else nb, nb, fi, fo, _op_code(op_dtype),
+                                          _ptr(wn), *n_args, _ptr(wt), *t_args, _stream(dev)), "basis_compose")
+    return wn, wt
+
+
+def basis_compose_bwd(weight: torch.Tensor, comp: Optional[torch.Tensor], dw: torch.Tensor, slot_stride: int,
+                      row_stride: int, live: Sequence[int], need_weight: bool = True, need_comp: bool = True):
+    """Gradients of the composition: ``dw`` = fp32 gradient of the composed weights of the populated relations in
+    the natural strided layout ``dw[s*slot_stride + i*row_stride + o]``.  Returns (dweight [B,Fi,Fo], dcomp [R,B])."""
+    lib = _lib.load()
+    nb, fi, fo = (int(v) for v in weight.shape)
+    S = len(live)
+    dev = weight.device
+    if comp is None:                       # no basis decomposition: the gradient slabs ARE the weight gradient
+        dweight = torch.zeros_like(weight, dtype=torch.float32)
+        flat = dw.reshape(-1)
+        for s, r in enumerate(live):
+            dweight[r] = torch.as_strided(flat, (fi, fo), (row_stride, 1), s * slot_stride)
+        return dweight, None
+    w32 = weight.detach().float().contiguous()
+    c32 = comp.detach().float().contiguous()
+    R = int(comp.size(0))
+    rels = (C.c_int32 * max(S, 1))(*[int(v) for v in live])
+    with torch.cuda.device(dev):
+        dweight = torch.empty((nb, fi, fo), dtype=torch.float32, device=dev) if need_weight else None
+        dcomp = torch.empty((R, nb), dtype=torch.float32, device=dev) if need_comp else None
+        if S == 0:
+            return (dweight.zero_() if need_weight else None), (dcomp.zero_() if need_comp else None)
+        ws_bytes = lib.gmlm_basis_compose_bwd_workspace_bytes(S, R, nb, fi, fo)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_basis_compose_bwd(_ptr(c32), _ptr(w32), _ptr(dw), int(slot_stride), int(row_stride), rels,
+                                              S, R, nb, fi, fo, _ptr(dweight), _ptr(dcomp), _ptr(ws), ws_bytes,
+                                              _stream(dev)), "basis_compose_bwd")
+    return dweight, dcomp
+
+
+def _compose_bwd_ok(weight, S):
+    return weight.size(2) % 4 == 0 and 1 <= S <= 8
 
 
 def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
@@ -670,90 +743,266 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return (a @ b).float()
 
 
+def _colsum_f32(g: torch.Tensor) -> torch.Tensor:
+    """Column sums of g (a bias gradient): one pass, fp64 accumulation, fixed order."""
+    if g.dtype not in _DT:
+        g = g.float()
+    return torch.ops.gmlm.colstats(g)[0]
+
+
+class _RGCNTransform(torch.autograd.Function):
+    """out = [h | x] @ [W_live ; root] + bias  (A4 + A6) for an aggregate-first layer.
+
+    The composed weights never exist as a torch tensor: ``basis_compose`` reads the fp32 bases once and writes the
+    GEMM's B operand in both layouts; 16-bit operand types run ONE tcgen05 GEMM over the two A sources (bias in the
+    epilogue); fp32 runs on cuBLAS (TF32 cannot meet the reference's fp32 gate).  Backward: [dh | dx] = g @ [W;root]^T
+    is one more launch of the same kernel with two output maps (dh lands contiguous for the transposed aggregation);
+    dW = h^T g and droot = x^T g are reductions over all nodes, produced in fp32; ``basis_compose_bwd`` turns dW
+    into the basis and coefficient gradients in one pass over the bases.
+
+    ``op_dtype``: bf16 for the bf16 pipeline, fp16 under ``torch.amp.autocast`` (what the reference's matmuls run in,
+    main.py:446,543); h and x are cast once and saved in that type."""
+
+    @staticmethod
+    def forward(ctx, h, x, weight, comp, root, bias, live, out_dtype, op_dtype):
+        live = tuple(int(v) for v in live)
+        S, fi, fo = len(live), weight.size(1), weight.size(2)
+        k1 = S * fi
+        need_bwd_w = any(ctx.needs_input_grad[:2])
+        if op_dtype in _OPS16:
+            hq, xq = _tma_rows(h, op_dtype), (_tma_rows(x, op_dtype) if root is not None else None)
+            wn, wt = basis_compose(weight, comp, root, live, op_dtype, "agg", want_n=need_bwd_w)
+            out = gemm_nt([hq] + ([xq] if xq is not None else []), wt, bias=bias, out_dtype=out_dtype)
+        else:
+            hq, xq = h.float(), (x.float() if root is not None else None)
+            wn, _ = basis_compose(weight, comp, root, live, torch.float32, "agg", want_t=False)
+            out = hq @ wn[:k1] if bias is None else torch.addmm(bias.float(), hq, wn[:k1])
+            if xq is not None:
+                out.addmm_(xq, wn[k1:])
+            out = out.to(out_dtype)
+        ctx.save_for_backward(hq, xq, wn, weight, comp)
+        ctx.live, ctx.k1, ctx.op = live, k1, op_dtype
+        ctx.dtypes = (weight.dtype, None if comp is None else comp.dtype, None if root is None else root.dtype,
+                      None if bias is None else bias.dtype, h.dtype, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        hq, xq, wn, weight, comp = ctx.saved_tensors
+        k1, live, op = ctx.k1, ctx.live, ctx.op
+        S, fi, fo = len(live), weight.size(1), weight.size(2)
+        need_h, need_x = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and xq is not None
+        dh = dx = dweight = dcomp = droot = dbias = None
+        gb = g if (g.dtype == op and g.is_contiguous()) else g.to(op).contiguous()
+        if need_h or need_x:
+            if op in _OPS16:
+                out_dt = torch.bfloat16 if ctx.dtypes[4] == torch.bfloat16 else torch.float32
+                gq = _tma_rows(gb)
+                if need_h and need_x:
+                    dh, dx = gemm_nt(gq, wn, out_dtype=out_dt, split=k1)      # [M, Fo] x [K1+K2, Fo]^T
+                elif need_h:
+                    dh = gemm_nt(gq, wn[:k1], out_dtype=out_dt)
+                else:
+                    dx = gemm_nt(gq, wn[k1:], out_dtype=out_dt)
+            else:
+                if need_h:
+                    dh = gb @ wn[:k1].t()
+                if need_x:
+                    dx = gb @ wn[k1:].t()
+            if dh is not None and not dh.is_contiguous():
+                dh = dh.contiguous()
+            if dh is not None and dh.dtype != ctx.dtypes[4]:
+                dh = dh.to(ctx.dtypes[4])
+            if dx is not None and dx.dtype != ctx.dtypes[5]:
+                dx = dx.to(ctx.dtypes[5])
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            dw = _mm_f32(hq.t(), gb)                                          # [S*Fi, Fo] fp32
+            if _compose_bwd_ok(weight, S) or comp is None:
+                dweight, dcomp = basis_compose_bwd(weight, comp, dw, fi * fo, fo, live, ctx.needs_input_grad[2],
+                                                   ctx.needs_input_grad[3] and comp is not None)
+            else:                                                             # widths the kernel does not take
+                dws = dw.view(S, fi * fo)
+                cl = comp.detach().float()[list(live)]
+                dweight = (cl.t() @ dws).view_as(weight)
+                dcomp = torch.zeros_like(comp, dtype=torch.float32)
+                dcomp[list(live)] = dws @ weight.detach().float().view(weight.size(0), -1).t()
+            dweight = dweight.to(ctx.dtypes[0]) if dweight is not None else None
+            dcomp = dcomp.to(ctx.dtypes[1]) if dcomp is not None else None
+        if ctx.needs_input_grad[4] and xq is not None:
+            droot = _mm_f32(xq.t(), gb).to(ctx.dtypes[2])
+        if ctx.needs_input_grad[5]:
+            dbias = _colsum_f32(gb).to(ctx.dtypes[3])
+        return dh, dx, dweight, dcomp, droot, dbias, None, None, None
+
+
+class _RGCNTransformFirst(torch.autograd.Function):
+    """Z = x @ [W_0 | .. | W_{S-1} | root] (+ bias on the root slab) for a transform-first layer (A4 + A6): the same
+    composition kernel in the "tf" layout, the same GEMM; backward dx = dZ @ [W | root]^T, dW = x^T dZ (fp32)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, comp, root, bias, live, out_dtype, op_dtype):
+        live = tuple(int(v) for v in live)
+        S, fi, fo = len(live), weight.size(1), weight.size(2)
+        bias_cat = None
+        if bias is not None:
+            bias_cat = torch.cat([bias.new_zeros(S * fo), bias.detach()]).float()
+        if op_dtype in _OPS16:
+            xq = _tma_rows(x, op_dtype)
+            wn, wt = basis_compose(weight, comp, root, live, op_dtype, "tf", want_n=ctx.needs_input_grad[0])
+            z = gemm_nt(xq, wt, bias=bias_cat, out_dtype=out_dtype)
+        else:
+            xq = x.float()
+            wn, _ = basis_compose(weight, comp, root, live, torch.float32, "tf", want_t=False)
+            z = (xq @ wn if bias_cat is None else torch.addmm(bias_cat, xq, wn)).to(out_dtype)
+        ctx.save_for_backward(xq, wn, weight, comp)
+        ctx.live, ctx.op = live, op_dtype
+        ctx.dtypes = (weight.dtype, None if comp is None else comp.dtype, root.dtype,
+                      None if bias is None else bias.dtype, x.dtype)
+        return z
+
+    @staticmethod
+    def backward(ctx, gz):
+        xq, wn, weight, comp = ctx.saved_tensors
+        live, op = ctx.live, ctx.op
+        S, fi, fo = len(live), weight.size(1), weight.size(2)
+        dx = dweight = dcomp = droot = dbias = None
+        gb = gz if (gz.dtype == op and gz.is_contiguous()) else gz.to(op).contiguous()
+        if ctx.needs_input_grad[0]:
+            if op in _OPS16:
+                dx = gemm_nt(_tma_rows(gb), wn, out_dtype=torch.bfloat16 if ctx.dtypes[4] == torch.bfloat16 else torch.float32)
+                if not dx.is_contiguous():
+                    dx = dx.contiguous()
+            else:
+                dx = gb @ wn.t()
+            if dx.dtype != ctx.dtypes[4]:
+                dx = dx.to(ctx.dtypes[4])
+        if any(ctx.needs_input_grad[1:4]):
+            dwn = _mm_f32(xq.t(), gb)                                         # [Fi, (S+1)*Fo] fp32
+            ld = dwn.size(1)
+            if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+                if (_compose_bwd_ok(weight, S) and ld % 4 == 0) or comp is None:
+                    dweight, dcomp = basis_compose_bwd(weight, comp, dwn, fo, ld, live, ctx.needs_input_grad[1],
+                                                       ctx.needs_input_grad[2] and comp is not None)
+                else:
+                    dws = dwn[:, :S * fo].reshape(fi, S, fo).permute(1, 0, 2).reshape(S, fi * fo)
+                    cl = comp.detach().float()[list(live)]
+                    dweight = (cl.t() @ dws).view_as(weight)
+                    dcomp = torch.zeros_like(comp, dtype=torch.float32)
+                    dcomp[list(live)] = dws @ weight.detach().float().view(weight.size(0), -1).t()
+                dweight = dweight.to(ctx.dtypes[0]) if dweight is not None else None
+                dcomp = dcomp.to(ctx.dtypes[1]) if dcomp is not None else None
+            if ctx.needs_input_grad[3]:
+                droot = dwn[:, S * fo:].contiguous().to(ctx.dtypes[2])
+        if ctx.needs_input_grad[4]:
+            dbias = _colsum_f32(gb[:, S * fo:]).to(ctx.dtypes[3])
+        return dx, dweight, dcomp, droot, dbias, None, None, None
+
+
 def linear_nt_ok(x: torch.Tensor, n_out: int) -> bool:
-    """Shapes ``linear_nt`` runs on the tcgen05 GEMM: bf16 CUDA activations, K a multiple of 64, N of 32."""
-    return (x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and x.size(1) % 64 == 0 and x.size(1) > 0
-            and n_out % 32 == 0 and n_out > 0)
+    """Inputs ``linear_nt`` runs on the tcgen05 GEMM without an explicit operand type: bf16 CUDA activations."""
+    return x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and x.size(1) > 0 and n_out > 0
 
 
 class _LinearNT(torch.autograd.Function):
-    """y = x @ wt.T + bias on the tcgen05 GEMM (bf16 operands, fp32 accumulation).  Backward: dx on the same
-    kernel when its shape fits (K = n_out a multiple of 64), weight gradient as an fp32 reduction."""
+    """y = [x_0 | x_1 | ..] @ wt.T + bias (+ addend) on the tcgen05 GEMM (16-bit operands, fp32 accumulation).  The
+    sources are never concatenated (MultiScaleFusion, main.py:176-180); ``addend`` is a residual folded into the
+    epilogue (main.py:281-282).  Backward: dx on the same kernel, weight gradient as an fp32 reduction."""
 
     @staticmethod
-    def forward(ctx, x, wt, bias, out_dtype):
-        wtb = wt.detach().to(torch.bfloat16).contiguous()                 # [N_out, K]
-        y = gemm_nt(x, wtb, bias=bias, out_dtype=out_dtype)
-        ctx.save_for_backward(x, wtb)
-        ctx.dtypes = (wt.dtype, None if bias is None else bias.dtype)
+    def forward(ctx, wt, bias, addend, out_dtype, op_dtype, *xs):
+        xq = [_tma_rows(x, op_dtype) for x in xs]
+        wtq = _tma_rows(wt.detach(), op_dtype)                            # [N_out, K]
+        if addend is not None and addend.dtype != out_dtype:
+            addend = addend.to(out_dtype)
+        y = gemm_nt(xq, wtq, bias=bias, out_dtype=out_dtype, addend=addend)
+        ctx.save_for_backward(wtq, *xq)
+        ctx.dtypes = (wt.dtype, None if bias is None else bias.dtype, [x.dtype for x in xs])
+        ctx.op = op_dtype
         return y
 
     @staticmethod
     def backward(ctx, g):
-        x, wtb = ctx.saved_tensors
-        gb = g.to(torch.bfloat16).contiguous()
-        dx = dwt = dbias = None
+        wtq, *xq = ctx.saved_tensors
+        op = ctx.op
+        gb = g if (g.dtype == op and g.is_contiguous()) else g.to(op).contiguous()
+        dwt = dbias = dadd = None
+        dxs = [None] * len(xq)
+        if any(ctx.needs_input_grad[5:]):
+            all_bf16 = all(d == torch.bfloat16 for d in ctx.dtypes[2])
+            dx = gemm_nt(_tma_rows(gb), wtq.t().contiguous(), out_dtype=torch.bfloat16 if all_bf16 else torch.float32)
+            k0 = 0
+            for i, x in enumerate(xq):
+                if ctx.needs_input_grad[5 + i]:
+                    d = dx[:, k0:k0 + x.size(1)]
+                    dxs[i] = d if d.dtype == ctx.dtypes[2][i] else d.to(ctx.dtypes[2][i])
+                k0 += x.size(1)
         if ctx.needs_input_grad[0]:
-            if wtb.size(0) % 64 == 0 and wtb.size(1) % 32 == 0:
-                dx = gemm_nt(gb, wtb.t().contiguous())                     # [M, N_out] x [K, N_out]^T
-            else:
-                dx = gb @ wtb
+            gt = gb.t()
+            dwt = torch.cat([_mm_f32(gt, x) for x in xq], dim=1).to(ctx.dtypes[0])
         if ctx.needs_input_grad[1]:
-            dwt = _mm_f32(gb.t(), x).to(ctx.dtypes[0])
+            dbias = _colsum_f32(gb).to(ctx.dtypes[1])
         if ctx.needs_input_grad[2]:
-            dbias = torch.ops.gmlm.colstats(gb)[0].to(ctx.dtypes[1])       # one pass, fp64 accumulate, deterministic
-        return dx, dwt, dbias, None
+            dadd = g
+        return (dwt, dbias, dadd, None, None, *dxs)
 
 
-def linear_nt(x: torch.Tensor, wt: torch.Tensor, bias: Optional[torch.Tensor] = None,
-              out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    """``F.linear(x, wt, bias)`` for the bf16 pipeline (``linear_nt_ok``) on the tcgen05 GEMM."""
-    return _LinearNT.apply(x, wt, bias, out_dtype or x.dtype)
+def linear_nt(x, wt: torch.Tensor, bias: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+              op_dtype: Optional[torch.dtype] = None, addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear(cat(x, 1), wt, bias) + addend`` on the tcgen05 GEMM; ``x`` one tensor or a list of up to four
+    sources.  ``op_dtype``: operand type (default: x's when 16-bit, else bf16); ``out_dtype``: bf16 or fp32."""
+    xs = list(x) if isinstance(x, (list, tuple)) else [x]
+    op = op_dtype or (xs[0].dtype if xs[0].dtype in _OPS16 else torch.bfloat16)
+    out_dtype = out_dtype or (torch.bfloat16 if xs[0].dtype == torch.bfloat16 else torch.float32)
+    return _LinearNT.apply(wt, bias, addend, out_dtype, op, *xs)
 
 
-def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, w_live: torch.Tensor, root: torch.Tensor,
-                         bias: Optional[torch.Tensor], out_dtype: torch.dtype) -> torch.Tensor:
+def _dense_dtypes(x: torch.Tensor, out_dtype: Optional[torch.dtype]):
+    """(operand type, output type) of a dense transform called with activations x: the autocast type with fp32
+    results under torch.amp.autocast (upstream accumulates into an fp32 `out`), bf16 in the bf16 pipeline, fp32
+    otherwise."""
+    if torch.is_autocast_enabled("cuda"):
+        return torch.get_autocast_dtype("cuda"), out_dtype or torch.get_default_dtype()
+    if x.dtype == torch.bfloat16:
+        return torch.bfloat16, out_dtype or torch.get_default_dtype()
+    return torch.float32, out_dtype or torch.get_default_dtype()
+
+
+def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, weight: torch.Tensor, comp: Optional[torch.Tensor],
+                         root: torch.Tensor, bias: Optional[torch.Tensor], out_dtype: Optional[torch.dtype] = None,
+                         use_tcgen05: bool = True) -> torch.Tensor:
     """RGCNConv as TRANSFORM-then-aggregate (A5+A6 fused by linearity of the mean; include/gmlm_b200.h
     ``gmlm_dst_plan``):  Z = x @ [W_0 | .. | W_{S-1} | root] (+ bias on the root slab),
     out[i] = sum_e w_e Z[src_e, slot_e] + Z[i, S].  The [N, S*Fi] matrix H of the aggregate-first form is never
     materialised and the gather moves Fo-wide rows instead of Fi-wide ones.
 
-    x [num_src, Fi]; w_live [S, Fi, Fo] (composed weights of the populated relations); root [Fi, Fo]."""
+    x [num_src, Fi]; weight [B, Fi, Fo] / comp [R, B] (the layer's parameters); root [Fi, Fo]."""
     _require_cuda(x, "x")
-    S, fi, fo = w_live.shape
+    live = graph.live_rels
+    S, fi, fo = len(live), int(weight.size(1)), int(weight.size(2))
     if S != graph.num_slots or x.size(0) != graph.num_src or x.size(1) != fi:
         raise _lib.GmlmError("rgcn_transform_first: shape mismatch")
     fplan, bplan = graph.dst_plan()
-    wcat_t = torch.cat([w_live.permute(0, 2, 1).reshape(S * fo, fi), root.t()], dim=0)     # [(S+1)*Fo, Fi]
-    bias_cat = None
-    if bias is not None:
-        bias_cat = torch.cat([bias.new_zeros(S * fo), bias])
-    if linear_nt_ok(x, (S + 1) * fo) and not torch.is_autocast_enabled("cuda"):
-        z = linear_nt(x, wcat_t, bias_cat)
-    else:
-        z = torch.nn.functional.linear(x, wcat_t if torch.is_autocast_enabled("cuda") else wcat_t.to(x.dtype),
-                                       None if bias_cat is None else
-                                       (bias_cat if torch.is_autocast_enabled("cuda") else bias_cat.to(x.dtype)))
-        if z.dtype not in _DT:
-            z = z.float()                                   # autocast produced fp16: the kernels take fp32 / bf16
-    fl, fm = csr_pack(fplan)
-    bl, bm = csr_pack(bplan)
-    out = torch.ops.gmlm.plan_aggregate(z.view(graph.num_src * (S + 1), fo), *fl, *bl, fm + bm)
-    return out if out.dtype == out_dtype else out.to(out_dtype)
+    op, out_dt = _dense_dtypes(x, out_dtype)
+    if not use_tcgen05:
+        op = torch.float32
+    z_dt = out_dt if out_dt in _DT else torch.float32          # the gather kernels take fp32 / bf16
+    with torch.amp.autocast("cuda", enabled=False):
+        z = _RGCNTransformFirst.apply(x, weight, comp, root, bias, tuple(live), z_dt, op)
+        fl, fm = csr_pack(fplan)
+        bl, bm = csr_pack(bplan)
+        out = torch.ops.gmlm.plan_aggregate(z.view(graph.num_src * (S + 1), fo), *fl, *bl, fm + bm)
+    return out if out.dtype == out_dt else out.to(out_dt)
 
 
-def rgcn_transform_ok(h: torch.Tensor, x: torch.Tensor, fo: int, op_dtype: Optional[torch.dtype] = None) -> bool:
-    """Shapes the tcgen05 path covers: K blocks of 64, Fo a multiple of 32; activations bf16 (bf16 pipeline) or
-    anything castable when an explicit fp16 / bf16 operand type is given (autocast)."""
-    if not (h.is_cuda and h.size(1) % 64 == 0 and x.size(1) % 64 == 0 and fo % 32 == 0 and h.size(1) > 0):
-        return False
-    if op_dtype is None:
-        return h.dtype == torch.bfloat16 and x.dtype == torch.bfloat16
-    return op_dtype in (torch.bfloat16, torch.float16)
-
-
-def rgcn_transform(h, x, w, root, bias, out_dtype, op_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
-    return _RGCNTransform.apply(h, x, w, root, bias, out_dtype, op_dtype or h.dtype)
+def rgcn_transform(h: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, comp: Optional[torch.Tensor],
+                   root: Optional[torch.Tensor], bias: Optional[torch.Tensor], live: Sequence[int],
+                   out_dtype: Optional[torch.dtype] = None, use_tcgen05: bool = True) -> torch.Tensor:
+    """A4 + A6 of an aggregate-first layer: ``[h | x] @ [W_live ; root] + bias`` (see ``_RGCNTransform``)."""
+    op, out_dt = _dense_dtypes(h, out_dtype)
+    if not use_tcgen05:
+        op = torch.float32
+    with torch.amp.autocast("cuda", enabled=False):
+        return _RGCNTransform.apply(h, x, weight, comp, root, bias, tuple(live), out_dt, op)
 
 
 # ------------------------------------------------------------------------------ halo pack / unpack

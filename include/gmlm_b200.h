@@ -201,19 +201,55 @@ int gmlm_layernorm_bwd(const void* x, const void* gy, int dtype, int64_t num_row
                        int64_t ldg, const float* gamma, const float* mean, const float* rstd, void* gx,
                        int64_t ldgx, float* g_gamma, float* g_beta, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- A4  basis composition: [PyG] RGCNConv.forward `weight = (comp @ weight.view(num_bases, -1)).view(R, Fi, Fo)`
+ *          (modules built main.py:189,193,197,201; upstream recomputes it on every call) ----
+ * W_s[i,o] = sum_b comp[rel_of_slot_host[s], b] * basis[b,i,o] for the `num_slots` populated relations
+ * (comp NULL: W_s = basis[rel_of_slot_host[s]], the layer without basis decomposition), plus `root` as one more slab
+ * (NULL: none).  ONE pass over the fp32 bases writes the result in the GEMM operand type `out_dtype`
+ * (GMLM_F32 / GMLM_BF16 / GMLM_F16) and in up to two layouts (either pointer may be NULL):
+ *   out_n[s*n_slot_stride + i*n_row_stride + o]   root at n_root_off   ("natural": B operand of [dH|dx] = g W^T)
+ *   out_t[s*t_slot_stride + o*t_row_stride + i]   root at t_root_off   ("transposed": B operand of out = [H|x] W)
+ * so that neither the index_select of the populated relations, nor the concatenation with root, nor the cast, nor
+ * the transposition is a separate pass.  Strides and offsets in elements. */
+int gmlm_basis_compose(const float* comp, const float* basis, const float* root, const int32_t* rel_of_slot_host,
+                       int num_slots, int num_relations, int num_bases, int64_t in_channels, int64_t out_channels,
+                       int out_dtype, void* out_n, int64_t n_slot_stride, int64_t n_row_stride, int64_t n_root_off,
+                       void* out_t, int64_t t_slot_stride, int64_t t_row_stride, int64_t t_root_off, void* stream);
+/* backward of the composition (autograd of the matmul above): dw = gradient of the composed weights in the natural
+ * strided layout, fp32;  dbasis[b,i,o] = sum_s comp[rel_s,b] dw_s[i,o]  (NULL: skipped),
+ * dcomp[r,b] = sum_{i,o} dw_{slot(r)}[i,o] basis[b,i,o], zero rows for relations without a slot (NULL: skipped).
+ * One pass over the bases; per-CTA partials + fixed-order fp64 final sum (deterministic).  out_channels and the
+ * strides must be multiples of 4; 1..8 slots, <= 64 relations. */
+size_t gmlm_basis_compose_bwd_workspace_bytes(int num_slots, int num_relations, int num_bases, int64_t in_channels,
+                                              int64_t out_channels);
+int gmlm_basis_compose_bwd(const float* comp, const float* basis, const float* dw, int64_t slot_stride,
+                           int64_t row_stride, const int32_t* rel_of_slot_host, int num_slots, int num_relations,
+                           int num_bases, int64_t in_channels, int64_t out_channels, float* dbasis, float* dcomp,
+                           void* ws, size_t ws_bytes, void* stream);
+
 /* ---- A6  dense feature transform on tcgen05 tensor cores (TMA tiles, TMEM accumulator):
  *          [PyG] RGCNConv.forward `out += h @ W[r]` / `out += x @ root` / `+ bias`, main.py:272 ----
  * C[M,N] = [A1 | A2][M, K1+K2] * B[N, K1+K2]^T + bias[N];  A1, A2, B bf16 row-major (K contiguous),
  * fp32 accumulation, C bf16 or fp32.  Output columns [0,N1) go to C1 and [N1,N) to C2 (N1 <= 0 or
- * >= N: everything to C1).  K1, K2 multiples of 64; N multiple of 32; N1 on a tile boundary. */
+ * >= N: everything to C1).  Any K1, K2, N, N1: partial 64-column blocks of a source are zero-filled by the TMA,
+ * partial output tiles are clipped by the TMA store; row pitches must be multiples of 16 bytes. */
 int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                       const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
                       int64_t N1, void* C2, int64_t ldc2, int out_dtype, void* stream);
 /* the same with the operand type given: in_dtype = GMLM_BF16 or GMLM_F16 (fp16 is what torch.amp.autocast feeds
- * the reference's matmuls, main.py:446,543); N multiple of 32 for fp32 output, of 64 for bf16 output */
+ * the reference's matmuls, main.py:446,543) */
 int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                  const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
                  int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream);
+/* the general form: A = [A_0 | .. | A_{n-1}] from up to 4 sources (one tensor map each: the layer outputs that feed
+ * MultiScaleFusion, main.py:176-180, are never concatenated), and an optional addend [M,N] of the output type read
+ * in the epilogue: C = A B^T + bias + addend (the residual adds `x1 + residual_proj1(x_feat)`, main.py:281-282,
+ * 294-295, folded into the projection; single output only).  A_host / lda_host / K_host are HOST arrays; every
+ * source but the last must be a multiple of 8 columns wide (its columns of B start on a 16-byte boundary). */
+int gmlm_gemm_nt_multi(int num_sources, const void* const* A_host, const int64_t* lda_host, const int64_t* K_host,
+                       const void* B, int64_t ldb, const float* bias, const void* addend, int64_t ld_add, int64_t M,
+                       int64_t N, void* C1, int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int in_dtype,
+                       int out_dtype, void* stream);
 
 /* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference: semantics = upstream GCNConv /
  *      GATConv defaults, restated in oracle/pyg_ref.py) on a dst-keyed CSR with upstream's self-loop handling ----

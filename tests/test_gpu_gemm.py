@@ -49,14 +49,59 @@ def test_gemm_nt_split_outputs_and_strided_operands(cuda_dev):
     assert rel_err(c1, ref[:, :1024]) <= 1e-2 and rel_err(c2, ref[:, 1024:]) <= 1e-2
 
 
-def test_gemm_nt_rejects_bad_shapes(cuda_dev):
+def test_gemm_nt_rejects_bad_operands(cuda_dev):
     from gmlm_b200 import GmlmError
-    a = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)      # K not a multiple of 64
+    a = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)
     b = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)
     with pytest.raises(GmlmError):
-        gemm_nt(a, b)
+        gemm_nt(a.float(), b.float())                                     # fp32 operands
     with pytest.raises(GmlmError):
-        gemm_nt(a.float(), b.float())
+        gemm_nt(a, b[:, :96])                                             # K mismatch
+    with pytest.raises(GmlmError):
+        gemm_nt(a, b, addend=torch.zeros(64, 63, device=cuda_dev))        # addend shape
+
+
+@pytest.mark.parametrize("op", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,n,ks", [(300, 512, (1200, 300)), (1000, 100, (100,)), (257, 1500, (512,)), (129, 36, (70, 30, 20)),
+                                    (5000, 768, (64, 128, 256, 512)), (64, 8, (8,)), (999, 200, (72, 200))])
+def test_gemm_nt_ragged_shapes_and_sources(cuda_dev, m, n, ks, op):
+    """Any K, N: partial k-blocks of every source are zero-filled by the TMA, partial output tiles clipped by the
+    TMA store (C2/C3: Fi = 300, S*Fi = 1200); up to four A sources (the MultiScaleFusion inputs, never concatenated)."""
+    g = torch.Generator().manual_seed(m + n)
+    srcs = [torch.randn(m, k, generator=g).to(op).to(cuda_dev) for k in ks]
+    b = (torch.randn(n, sum(ks), generator=g) / sum(ks) ** 0.5).to(op).to(cuda_dev)
+    bias = torch.randn(n, generator=g).to(cuda_dev)
+    got = gemm_nt(srcs, b, bias=bias, out_dtype=torch.float32)
+    ref = torch.cat([t.float() for t in srcs], dim=1) @ b.float().t() + bias
+    assert got.shape == (m, n) and got.dtype == torch.float32
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("n,split", [(1500, 1200), (1280, 1024), (330, 30), (96, 64)])
+def test_gemm_nt_split_at_any_column(cuda_dev, n, split):
+    g = torch.Generator().manual_seed(n)
+    m, k = 1111, 512
+    a = torch.randn(m, k, generator=g).half().to(cuda_dev)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).half().to(cuda_dev)
+    c1, c2 = gemm_nt(a, b, out_dtype=torch.float32, split=split)
+    ref = a.float() @ b.float().t()
+    assert c1.shape == (m, split) and c2.shape == (m, n - split)
+    assert rel_err(c1, ref[:, :split]) <= 1e-5 and rel_err(c2, ref[:, split:]) <= 1e-5
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,n,k", [(1000, 512, 300), (4099, 64, 256), (70, 128, 64), (2500, 1024, 512)])
+def test_gemm_nt_addend_in_the_epilogue(cuda_dev, m, n, k, out_dtype):
+    """C = A B^T + bias + addend: the residual add of main.py:281-282 folded into the projection."""
+    g = torch.Generator().manual_seed(k)
+    a = torch.randn(m, k, generator=g).bfloat16().to(cuda_dev)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).bfloat16().to(cuda_dev)
+    bias = torch.randn(n, generator=g).to(cuda_dev)
+    add = torch.randn(m, n, generator=g).to(out_dtype).to(cuda_dev)
+    got = gemm_nt(a, b, bias=bias, out_dtype=out_dtype, addend=add)
+    ref = a.float() @ b.float().t() + bias + add.float()
+    assert rel_err(got, ref) <= (1e-5 if out_dtype == torch.float32 else 1e-2)
 
 
 def test_rgcn_conv_bf16_tcgen05_path_matches_cublas_path_and_oracle(cuda_dev):
