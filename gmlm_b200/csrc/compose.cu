@@ -249,16 +249,21 @@ constexpr int kMaxRelations = 64;
 struct SlotOfRel {
   int v[kMaxRelations];
 };
+// one warp per (relation, basis) pair: lane l sums the partials of CTAs l, l+32, .. in order, the 32 lane sums are
+// combined by a fixed xor tree (deterministic)
 __global__ void compose_bwd_final_kernel(const float* partial, int n_ctas, int S, int B, int R, const SlotOfRel slot_of_rel,
                                          float* dcomp) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (k >= R * B) return;
   const int r = k / B, b = k % B;
   const int s = slot_of_rel.v[r];
   double sum = 0.0;
   if (s >= 0)
-    for (int c = 0; c < n_ctas; ++c) sum += double(partial[(int64_t(c) * S + s) * B + b]);
-  dcomp[k] = float(sum);
+    for (int c = lane; c < n_ctas; c += 32) sum += double(partial[(int64_t(c) * S + s) * B + b]);
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) dcomp[k] = float(sum);
 }
 
 int bwd_grid(int64_t n4) {
@@ -368,7 +373,7 @@ extern "C" int gmlm_basis_compose_bwd(const float* comp, const float* basis, con
   }
   if (dcomp) {
     const int n = num_relations * num_bases;
-    compose_bwd_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(p.partial, grid, num_slots, num_bases, num_relations,
+    compose_bwd_final_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(p.partial, grid, num_slots, num_bases, num_relations,
                                                               slot_of_rel, dcomp);
     GMLM_LAUNCH_CHECK();
   }

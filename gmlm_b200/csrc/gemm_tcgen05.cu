@@ -592,6 +592,236 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
   return fail(GMLM_ERR_INVALID, "gemm: unsupported tile");
 }
 
+// ================================================================== TN product: weight gradients
+// D[Ka, N] (fp32) = [A_0 | A_1 | ..]^T[Ka, M] . G[M, N]: the reduction over all M nodes that gives dW = H^T g and
+// droot = x^T g of the RGCN layer (autograd of [PyG] RGCNConv.forward's `h @ weight[r]` / `x @ root`, main.py:272;
+// SURVEY §8a row A14 "dW_r = h_r^T g") and the weight gradients of the residual / fusion linears.
+//
+// Both operands are read as they lie in memory — row-major [M, .] activations — i.e. MN-major for the tensor core:
+// TMA boxes of 64 columns x 64 rows (128-byte swizzle) ARE the canonical MN-major SWIZZLE_128B layout
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units: a shared-memory row is one node (k), eight rows form a
+// 1024-byte swizzle atom (SBO), the next 64 channels live one box further (LBO = 8 KB); the instruction descriptor
+// sets a_major = b_major = MN.  One UMMA covers 16 nodes = two atoms, so the k-advance inside a stage is +2 KB.
+//
+// Schedule: output tiles are 128 (channels of A) x BN (channels of G); the M range is cut into `splits` pieces so
+// that tiles x splits fill the SMs (the layer shapes have 2..40 tiles but millions of rows).  CTA b works on tile
+// b mod tiles of split b / tiles: the CTAs that run together walk the same rows, so A and G are read from HBM once
+// and from L2 by the other tiles.  Each CTA accumulates its piece in TMEM and writes fp32 either straight to D
+// (splits = 1) or to its slab of the workspace, which a second kernel sums in split order (deterministic).
+constexpr int TN_BK = 64;                     // nodes per pipeline stage
+constexpr int kTnThreads = 192;               // warp 0: TMA, warp 1: MMA, warps 2-5: epilogue (one per TMEM lane quarter)
+constexpr uint32_t TN_BOX_BYTES = 64 * TN_BK * 2;   // one 64-channel x 64-node box
+
+struct TnParams {
+  int M, N;
+  int n_src;
+  int tile_end[kMaxSources];   // cumulative 128-channel tile counts of the A sources
+  int k_off[kMaxSources];      // first row of D each source writes (cumulative true widths)
+  int k_len[kMaxSources];      // its width
+  int ka_tiles, n_tiles, splits, kb_per_split;
+  float* out;                  // D (splits == 1) or the workspace [splits][Ka][ldo]
+  int64_t ldo, slab;           // row pitch and slab stride (elements)
+  uint32_t idesc_formats;
+};
+
+// MN-major SWIZZLE_128B operand: LBO = byte distance between 64-channel boxes, SBO = 1024 (8 nodes x 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr & 0x3FFFFu) >> 4);
+  d |= uint64_t(TN_BOX_BYTES >> 4) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
+
+template <int BN>
+constexpr int tn_stages() { return BN >= 256 ? 4 : (BN >= 128 ? 6 : 8); }
+template <int BN>
+constexpr size_t tn_smem_bytes() {
+  return size_t(tn_stages<BN>()) * (2 * TN_BOX_BYTES + (BN / 64) * TN_BOX_BYTES) + (2 * tn_stages<BN>() + 1) * 8 + 16 + 1024;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kTnThreads, 1) gemm_tn_kernel(const __grid_constant__ SourceMaps tma_a,
+                                                                const __grid_constant__ CUtensorMap tma_g,
+                                                                const TnParams p) {
+  constexpr int STAGES = tn_stages<BN>();
+  constexpr uint32_t A_BYTES = 2 * TN_BOX_BYTES;
+  constexpr uint32_t B_BYTES = (BN / 64) * TN_BOX_BYTES;
+  constexpr uint32_t TMEM_COLS = BN < 32 ? 32u : uint32_t(BN);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem_a + STAGES * A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles = p.ka_tiles * p.n_tiles;
+  const int tile = blockIdx.x % tiles, split = blockIdx.x / tiles;
+  const int kt = tile / p.n_tiles, nt = tile % p.n_tiles;
+  int src = 0;
+  while (kt >= p.tile_end[src]) ++src;
+  const int ka0 = (kt - (src ? p.tile_end[src - 1] : 0)) * BLOCK_M;      // first channel inside the source
+  const int n0 = nt * BN;
+  const int total_kb = (p.M + TN_BK - 1) / TN_BK;
+  const int kb_lo = split * p.kb_per_split;
+  const int kb_hi = min(total_kb, kb_lo + p.kb_per_split);
+  const int num_kb = max(0, kb_hi - kb_lo);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(full + s), 1);
+      mbar_init(smem_u32(empty + s), 1);
+    }
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(smem_u32(empty + s), ph ^ 1);
+        mbar_expect_tx(smem_u32(full + s), A_BYTES + B_BYTES);
+        const int m0 = (kb_lo + i) * TN_BK;            // rows past M and channels past a source's width: zeros
+        tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a.m[src], smem_u32(full + s), ka0, m0);
+        tma_load_2d(smem_u32(smem_a + s * A_BYTES + TN_BOX_BYTES), &tma_a.m[src], smem_u32(full + s), ka0 + 64, m0);
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j)
+          tma_load_2d(smem_u32(smem_b + s * B_BYTES + j * TN_BOX_BYTES), &tma_g, smem_u32(full + s), n0 + 64 * j, m0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(BLOCK_M, BN, p.idesc_formats) | (1u << 15) | (1u << 16);   // MN-major A and B
+      for (int i = 0; i < num_kb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(smem_u32(full + s), ph);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_mn(smem_u32(smem_a + s * A_BYTES));
+        const uint64_t db = make_smem_desc_mn(smem_u32(smem_b + s * B_BYTES));
+#pragma unroll
+        for (int k = 0; k < TN_BK / UMMA_K; ++k) {
+          // 16 nodes further = two swizzle atoms = +2048 bytes = +128 in the address field
+          umma(tmem_base, da + uint64_t(128 * k), db + uint64_t(128 * k), idesc, (i | k) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(empty + s));
+      }
+      umma_commit(smem_u32(acc_full));
+    }
+  } else {
+    // ---------------- epilogue: warp w reads TMEM lanes [32*(w%4), +32) = 32 rows (channels of A) of the tile
+    const int quad = warp & 3;
+    const int row_in_src = ka0 + quad * 32 + lane;
+    const bool row_ok = row_in_src < p.k_len[src];
+    float* dst = p.out + int64_t(split) * p.slab + int64_t(p.k_off[src] + row_in_src) * p.ldo + n0;
+    if (num_kb > 0) {
+      mbar_wait(smem_u32(acc_full), 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      if (num_kb > 0) {
+        tmem_ld32_nowait(tmem_base + (uint32_t(quad * 32) << 16) + uint32_t(c0), r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;          // an empty split still owns (zeroes) its slab
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = n0 + c0 + j;
+          if (col + 4 <= p.N) {
+            *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < p.N) dst[c0 + j + e] = __uint_as_float(r[j + e]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// D = sum over splits (in order) of the workspace slabs
+__global__ void gemm_tn_reduce_kernel(const float* __restrict__ ws, int splits, int64_t slab, int64_t rows, int64_t n4,
+                                      int64_t ld_ws, float* __restrict__ out, int64_t ldo) {
+  const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * n4) return;
+  const int64_t r = i / n4, c = (i % n4) * 4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(ws + s * slab + r * ld_ws + c));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(out + r * ldo + c) = acc;
+}
+
+struct TnPlan {
+  int bn, ka_tiles, n_tiles, splits, kb_per_split;
+  int64_t ka, ld_ws;
+};
+TnPlan tn_plan(int n_src, const int64_t* Ks, int64_t M, int64_t N) {
+  TnPlan t{};
+  t.bn = N > 128 ? 256 : (N > 64 ? 128 : 64);
+  for (int i = 0; i < n_src; ++i) {
+    t.ka_tiles += int((Ks[i] + BLOCK_M - 1) / BLOCK_M);
+    t.ka += Ks[i];
+  }
+  t.n_tiles = int((N + t.bn - 1) / t.bn);
+  const int total_kb = int((M + TN_BK - 1) / TN_BK);
+  const int tiles = t.ka_tiles * t.n_tiles;
+  // fill the SMs once: the workspace traffic (splits x Ka x N x 8 bytes) stays far below the operand traffic
+  int splits = std::max(1, num_sms() / std::max(tiles, 1));
+  splits = std::min(splits, std::max(1, total_kb / 8));       // at least 8 k-blocks (512 nodes) per split
+  t.kb_per_split = (total_kb + splits - 1) / std::max(splits, 1);
+  t.splits = std::max(1, (total_kb + std::max(t.kb_per_split, 1) - 1) / std::max(t.kb_per_split, 1));
+  t.ld_ws = (N + 3) / 4 * 4;
+  return t;
+}
+
+template <int BN>
+int launch_tn(const SourceMaps& a, const CUtensorMap& g, const TnParams& p, cudaStream_t st) {
+  constexpr size_t smem = tn_smem_bytes<BN>();
+  static_assert(smem <= 227 * 1024, "tile configuration exceeds the shared memory of one SM");
+  auto kern = gemm_tn_kernel<BN>;
+  static bool configured[kMaxDevices] = {};
+  const int dev = current_device();
+  if (!configured[dev]) {
+    GMLM_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    configured[dev] = true;
+  }
+  kern<<<unsigned(p.ka_tiles * p.n_tiles * p.splits), kTnThreads, smem, st>>>(a, g, p);
+  GMLM_LAUNCH_CHECK();
+  return GMLM_OK;
+}
+
 }  // namespace
 
 // row-gather tensor map for the aggregation kernels (spmm.cu): [rows, cols] matrix, box = one whole row, no swizzle
@@ -634,4 +864,85 @@ extern "C" int gmlm_gemm_nt_bf16(const void* A1, int64_t lda1, int64_t K1, const
                                  int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int out_dtype, void* stream) {
   return gmlm_gemm_nt(A1, lda1, K1, A2, lda2, K2, B, ldb, bias, M, N, C1, ldc1, N1, C2, ldc2, GMLM_BF16, out_dtype,
                       stream);
+}
+
+extern "C" size_t gmlm_gemm_tn_workspace_bytes(int num_sources, const int64_t* K_host, int64_t M, int64_t N) {
+  if (!K_host || num_sources < 1 || num_sources > kMaxSources || M <= 0 || N <= 0) return 256;
+  const TnPlan t = tn_plan(num_sources, K_host, M, N);
+  return t.splits > 1 ? size_t(t.splits) * size_t(t.ka) * size_t(t.ld_ws) * sizeof(float) + 256 : 256;
+}
+
+extern "C" int gmlm_gemm_tn(int num_sources, const void* const* A_host, const int64_t* lda_host, const int64_t* K_host,
+                            const void* G, int64_t ldg, int64_t M, int64_t N, float* D, int64_t ldd, int in_dtype,
+                            void* ws, size_t ws_bytes, void* stream) {
+  GMLM_REQUIRE(A_host && lda_host && K_host, "gemm_tn: null source table");
+  GMLM_REQUIRE(num_sources >= 1 && num_sources <= kMaxSources, "gemm_tn: 1..%d A sources", kMaxSources);
+  GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16, "gemm_tn: operands must be GMLM_BF16 or GMLM_F16");
+  GMLM_REQUIRE(M >= 0 && N > 0 && M < (int64_t(1) << 31) && N < (int64_t(1) << 24), "gemm_tn: bad sizes");
+  GMLM_REQUIRE(G && D && ldg >= N && ldg % 8 == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0,
+               "gemm_tn: G must be 16-byte aligned with a 16-byte row pitch");
+  GMLM_REQUIRE(ldd >= N && ldd % 4 == 0 && (reinterpret_cast<uintptr_t>(D) & 15) == 0,
+               "gemm_tn: D must be 16-byte aligned with a 16-byte row pitch");
+  int64_t ka = 0;
+  for (int i = 0; i < num_sources; ++i) {
+    GMLM_REQUIRE(A_host[i] != nullptr && K_host[i] > 0, "gemm_tn: A source %d is empty", i);
+    GMLM_REQUIRE(lda_host[i] >= K_host[i] && lda_host[i] % 8 == 0 && (reinterpret_cast<uintptr_t>(A_host[i]) & 15) == 0,
+                 "gemm_tn: A sources must be 16-byte aligned with a 16-byte row pitch");
+    ka += K_host[i];
+  }
+  GMLM_REQUIRE(ka < (int64_t(1) << 24), "gemm_tn: too many channels");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0) {
+    GMLM_CUDA_TRY(cudaMemset2DAsync(D, size_t(ldd) * sizeof(float), 0, size_t(N) * sizeof(float), size_t(ka), st));
+    return GMLM_OK;
+  }
+  const TnPlan t = tn_plan(num_sources, K_host, M, N);
+  GMLM_REQUIRE(ws_bytes >= gmlm_gemm_tn_workspace_bytes(num_sources, K_host, M, N) && (t.splits == 1 || ws),
+               "gemm_tn: workspace too small");
+  {
+    static thread_local bool ctx_ready[kMaxDevices] = {};
+    const int dev = current_device();
+    if (!ctx_ready[dev]) {
+      GMLM_CUDA_TRY(cudaFree(nullptr));
+      ctx_ready[dev] = true;
+    }
+  }
+  TnParams p{};
+  SourceMaps ma;
+  CUtensorMap mg;
+  int tiles = 0, koff = 0;
+  for (int i = 0; i < kMaxSources; ++i) {
+    if (i < num_sources) {
+      if (int rc = get_map(&ma.m[i], A_host[i], M, K_host[i], lda_host[i], TN_BK, 64, in_dtype)) return rc;
+      p.k_off[i] = koff;
+      p.k_len[i] = int(K_host[i]);
+      koff += int(K_host[i]);
+      tiles += int((K_host[i] + BLOCK_M - 1) / BLOCK_M);
+    } else {
+      ma.m[i] = ma.m[0];
+      p.k_off[i] = koff;
+      p.k_len[i] = 0;
+    }
+    p.tile_end[i] = tiles;
+  }
+  if (int rc = get_map(&mg, G, M, N, ldg, TN_BK, 64, in_dtype)) return rc;
+  p.M = int(M); p.N = int(N); p.n_src = num_sources;
+  p.ka_tiles = t.ka_tiles; p.n_tiles = t.n_tiles; p.splits = t.splits; p.kb_per_split = t.kb_per_split;
+  p.idesc_formats = in_dtype == GMLM_BF16 ? 1u : 0u;
+  if (t.splits == 1) {
+    p.out = D; p.ldo = ldd; p.slab = 0;
+  } else {
+    p.out = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~uintptr_t(255));
+    p.ldo = t.ld_ws; p.slab = ka * t.ld_ws;
+  }
+  int rc = t.bn == 256 ? launch_tn<256>(ma, mg, p, st) : (t.bn == 128 ? launch_tn<128>(ma, mg, p, st) : launch_tn<64>(ma, mg, p, st));
+  if (rc) return rc;
+  if (t.splits > 1) {
+    const int64_t n4 = (N + 3) / 4;
+    GMLM_REQUIRE(ldd >= n4 * 4, "gemm_tn: D row pitch must cover N rounded up to 4");
+    const int64_t total = ka * n4;
+    gemm_tn_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, st>>>(p.out, t.splits, p.slab, ka, n4, t.ld_ws, D, ldd);
+    GMLM_LAUNCH_CHECK();
+  }
+  return GMLM_OK;
 }

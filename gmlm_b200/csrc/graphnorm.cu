@@ -148,17 +148,48 @@ __global__ void __launch_bounds__(kCta) colstats_kernel(const T* __restrict__ x,
   }
 }
 
-__global__ void colstats_final_kernel(const double* __restrict__ partial, int row_blocks, int64_t C,
-                                      double* __restrict__ out0, double* __restrict__ out1) {
-  const int64_t c = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// 32 channels x 8 row-block ranges per CTA: group g sums the partials y in [g*span, (g+1)*span) in order (eight
+// independent loads ahead of the adds), the eight range sums are combined in group order: a fixed summation tree
+// (deterministic) whose serial chain is row_blocks / 8 long (one thread per channel walking all ~1000 partials made
+// this tiny kernel cost as much as the statistics pass on L2-resident graphs)
+constexpr int kFinalGroups = 8;
+__global__ void __launch_bounds__(32 * kFinalGroups) colstats_final_kernel(const double* __restrict__ partial,
+                                                                           int row_blocks, int64_t C,
+                                                                           double* __restrict__ out0,
+                                                                           double* __restrict__ out1) {
+  __shared__ double sh[2][kFinalGroups][32];
+  const int cx = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int64_t c = int64_t(blockIdx.x) * 32 + cx;
+  const int span = (row_blocks + kFinalGroups - 1) / kFinalGroups;
+  const int y0 = g * span, y1 = min(row_blocks, y0 + span);
   double a = 0.0, b = 0.0;
-  for (int y = 0; y < row_blocks; ++y) {
-    a += partial[(int64_t(y) * 2 + 0) * C + c];
-    b += partial[(int64_t(y) * 2 + 1) * C + c];
+  if (c < C) {
+    int y = y0;
+    for (; y + 4 <= y1; y += 4) {
+      double va[4], vb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        va[k] = partial[(int64_t(y + k) * 2 + 0) * C + c];
+        vb[k] = partial[(int64_t(y + k) * 2 + 1) * C + c];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { a += va[k]; b += vb[k]; }
+    }
+    for (; y < y1; ++y) {
+      a += partial[(int64_t(y) * 2 + 0) * C + c];
+      b += partial[(int64_t(y) * 2 + 1) * C + c];
+    }
   }
-  if (out0) out0[c] = a;
-  if (out1) out1[c] = b;
+  sh[0][g][cx] = a;
+  sh[1][g][cx] = b;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    double ta = 0.0, tb = 0.0;
+#pragma unroll
+    for (int k = 0; k < kFinalGroups; ++k) { ta += sh[0][k][cx]; tb += sh[1][k][cx]; }
+    if (out0) out0[c] = ta;
+    if (out1) out1[c] = tb;
+  }
 }
 
 // ---------------------------------------------------------------- forward
@@ -482,7 +513,7 @@ static int colstats_impl(const void* x, int dtype, int64_t N, int64_t C, int64_t
     return GMLM_OK;
   });
   if (rc) return rc;
-  colstats_final_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(partial, row_blocks, C, out0, out1);
+  colstats_final_kernel<<<unsigned((C + 31) / 32), 32 * kFinalGroups, 0, st>>>(partial, row_blocks, C, out0, out1);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }
@@ -538,7 +569,7 @@ int gmlm_graphnorm_bwd_stats(const void* x, const void* gy, int dtype, int64_t N
     return GMLM_OK;
   });
   if (rc) return rc;
-  colstats_final_kernel<<<unsigned((C + 255) / 256), 256, 0, st>>>(partial, row_blocks, C, sum_g, sum_go);
+  colstats_final_kernel<<<unsigned((C + 31) / 32), 32 * kFinalGroups, 0, st>>>(partial, row_blocks, C, sum_g, sum_go);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }

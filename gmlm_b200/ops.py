@@ -650,6 +650,36 @@ def gemm_nt(a1, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Option
     return (c1, c2) if c2 is not None else c1
 
 
+def gemm_tn(srcs, g: torch.Tensor) -> torch.Tensor:
+    """``cat(srcs, 1).T @ g`` -> fp32 [sum K_i, N] on the tcgen05 tensor cores: the weight-gradient reduction over all
+    rows (dW = H^T g, droot = x^T g in ONE launch over the two sources; dWt = g^T x of the linears).  ``srcs``: one
+    to four [M, K_i] tensors, ``g`` [M, N], all bf16 or all fp16; operands are read as they lie (no transposes)."""
+    lib = _lib.load()
+    srcs = list(srcs) if isinstance(srcs, (list, tuple)) else [srcs]
+    _require_cuda(g, "g")
+    op = g.dtype
+    if op not in _OPS16 or any(t.dtype != op for t in srcs) or not 1 <= len(srcs) <= 4:
+        raise _lib.GmlmError("gemm_tn: one to four sources, all operands bfloat16 or all float16")
+    m, n = int(g.size(0)), int(g.size(1))
+    if any(t.dim() != 2 or t.size(0) != m for t in srcs):
+        raise _lib.GmlmError("gemm_tn: row count mismatch")
+    srcs = [_tma_rows(t) for t in srcs]
+    g = _tma_rows(g)
+    dev = g.device
+    k = len(srcs)
+    ka = sum(int(t.size(1)) for t in srcs)
+    with torch.cuda.device(dev):
+        out = torch.empty((ka, _rup(n, 4)), dtype=torch.float32, device=dev)
+        ptrs = (C.c_void_p * k)(*[t.data_ptr() for t in srcs])
+        ldas = (C.c_int64 * k)(*[_ld(t) for t in srcs])
+        ks = (C.c_int64 * k)(*[int(t.size(1)) for t in srcs])
+        ws_bytes = lib.gmlm_gemm_tn_workspace_bytes(k, ks, m, n)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.gmlm_gemm_tn(k, ptrs, ldas, ks, _ptr(g), _ld(g), m, n, _ptr(out), out.size(1), _op_code(op),
+                                    _ptr(ws), ws_bytes, _stream(dev)), "gemm_tn")
+    return out if out.size(1) == n else out[:, :n]
+
+
 # ------------------------------------------------------------------------------ A4 basis composition
 def _rup(v: int, q: int) -> int:
     return (v + q - 1) // q * q
@@ -815,8 +845,14 @@ class _RGCNTransform(torch.autograd.Function):
                 dh = dh.to(ctx.dtypes[4])
             if dx is not None and dx.dtype != ctx.dtypes[5]:
                 dx = dx.to(ctx.dtypes[5])
+        dwcat = None
+        if op in _OPS16 and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
+            # dW = h^T g and droot = x^T g: ONE tcgen05 reduction over the two sources, fp32 result
+            dwcat = gemm_tn([hq] + ([xq] if xq is not None else []), gb)
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            dw = _mm_f32(hq.t(), gb)                                          # [S*Fi, Fo] fp32
+            dw = dwcat[:k1] if dwcat is not None else _mm_f32(hq.t(), gb)    # [S*Fi, Fo] fp32
+            if not dw.is_contiguous():
+                dw = dw.contiguous()
             if _compose_bwd_ok(weight, S) or comp is None:
                 dweight, dcomp = basis_compose_bwd(weight, comp, dw, fi * fo, fo, live, ctx.needs_input_grad[2],
                                                    ctx.needs_input_grad[3] and comp is not None)
@@ -829,7 +865,7 @@ class _RGCNTransform(torch.autograd.Function):
             dweight = dweight.to(ctx.dtypes[0]) if dweight is not None else None
             dcomp = dcomp.to(ctx.dtypes[1]) if dcomp is not None else None
         if ctx.needs_input_grad[4] and xq is not None:
-            droot = _mm_f32(xq.t(), gb).to(ctx.dtypes[2])
+            droot = (dwcat[k1:] if dwcat is not None else _mm_f32(xq.t(), gb)).contiguous().to(ctx.dtypes[2])
         if ctx.needs_input_grad[5]:
             dbias = _colsum_f32(gb).to(ctx.dtypes[3])
         return dh, dx, dweight, dcomp, droot, dbias, None, None, None
@@ -877,7 +913,9 @@ class _RGCNTransformFirst(torch.autograd.Function):
             if dx.dtype != ctx.dtypes[4]:
                 dx = dx.to(ctx.dtypes[4])
         if any(ctx.needs_input_grad[1:4]):
-            dwn = _mm_f32(xq.t(), gb)                                         # [Fi, (S+1)*Fo] fp32
+            dwn = gemm_tn([xq], gb) if op in _OPS16 else _mm_f32(xq.t(), gb)  # [Fi, (S+1)*Fo] fp32
+            if not dwn.is_contiguous():
+                dwn = dwn.contiguous()
             ld = dwn.size(1)
             if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
                 if (_compose_bwd_ok(weight, S) and ld % 4 == 0) or comp is None:
@@ -937,8 +975,8 @@ class _LinearNT(torch.autograd.Function):
                     dxs[i] = d if d.dtype == ctx.dtypes[2][i] else d.to(ctx.dtypes[2][i])
                 k0 += x.size(1)
         if ctx.needs_input_grad[0]:
-            gt = gb.t()
-            dwt = torch.cat([_mm_f32(gt, x) for x in xq], dim=1).to(ctx.dtypes[0])
+            # dWt = g^T [x_0 | x_1 | ..] as ([x..]^T g)^T: one tcgen05 reduction over the sources
+            dwt = gemm_tn(xq, gb).t().contiguous().to(ctx.dtypes[0])
         if ctx.needs_input_grad[1]:
             dbias = _colsum_f32(gb).to(ctx.dtypes[1])
         if ctx.needs_input_grad[2]:

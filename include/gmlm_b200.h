@@ -251,6 +251,17 @@ int gmlm_gemm_nt_multi(int num_sources, const void* const* A_host, const int64_t
                        int64_t N, void* C1, int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int in_dtype,
                        int out_dtype, void* stream);
 
+/* ---- A14 weight gradients on the tensor cores: D[sum K_i, N] (fp32) = [A_0 | A_1 | ..]^T . G, the reduction over all
+ *      M rows (nodes) that autograd of [PyG] RGCNConv.forward's `h @ weight[r]`, `x @ root` (main.py:272) and of the
+ *      residual / fusion linears (main.py:176-180, 205-207) needs: dW = H^T g, droot = x^T g, dWt = g^T x.
+ * A_i [M, K_i] and G [M, N] are read as they lie in memory (row-major activations = MN-major tensor-core operands,
+ * 64x64 TMA boxes), bf16 or fp16, fp32 accumulation in TMEM.  The M range is split over CTAs; partial sums go
+ * through `ws` and are added in split order (deterministic).  Any sizes; row pitches multiples of 16 bytes. */
+size_t gmlm_gemm_tn_workspace_bytes(int num_sources, const int64_t* K_host, int64_t M, int64_t N);
+int gmlm_gemm_tn(int num_sources, const void* const* A_host, const int64_t* lda_host, const int64_t* K_host,
+                 const void* G, int64_t ldg, int64_t M, int64_t N, float* D, int64_t ldd, int in_dtype, void* ws,
+                 size_t ws_bytes, void* stream);
+
 /* ---- A8 / A9 (extensions named by north_star; no counterpart in /root/reference: semantics = upstream GCNConv /
  *      GATConv defaults, restated in oracle/pyg_ref.py) on a dst-keyed CSR with upstream's self-loop handling ----
  * gcn_edge_weights: w[e] = deg[col[e]]^-1/2 * deg[row]^-1/2, deg = CSR row length (self-loops included); the GCN

@@ -3,7 +3,7 @@ against a plain PyTorch fp32 reference of the same op on the same bf16 inputs.""
 import pytest
 import torch
 
-from gmlm_b200.ops import gemm_nt
+from gmlm_b200.ops import gemm_nt, gemm_tn
 
 from conftest import rel_err
 
@@ -102,6 +102,32 @@ def test_gemm_nt_addend_in_the_epilogue(cuda_dev, m, n, k, out_dtype):
     got = gemm_nt(a, b, bias=bias, out_dtype=out_dtype, addend=add)
     ref = a.float() @ b.float().t() + bias + add.float()
     assert rel_err(got, ref) <= (1e-5 if out_dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("op", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("m,ks,n", [(1000, (64,), 64), (100000, (1024, 256), 64), (5000, (1200, 300), 512),
+                                    (70000, (256,), 320), (777, (100, 36), 200), (30000, (64, 128, 256, 512), 768),
+                                    (200, (8,), 8), (37, (130,), 70), (22662, (2560,), 1024), (64, (128,), 256),
+                                    (300000, (320,), 64)])
+def test_gemm_tn_weight_gradient_reduction(cuda_dev, m, ks, n, op):
+    """D = [A_0 | ..]^T G (dW = H^T g, droot = x^T g in one launch): MN-major tcgen05 operands, split over the rows,
+    against an fp64 product of the same 16-bit inputs; deterministic."""
+    g = torch.Generator().manual_seed(m + n)
+    srcs = [torch.randn(m, k, generator=g).to(op).to(cuda_dev) for k in ks]
+    gg = torch.randn(m, n, generator=g).to(op).to(cuda_dev)
+    got = gemm_tn(srcs, gg)
+    ref = torch.cat([t.double() for t in srcs], dim=1).t() @ gg.double()
+    assert got.shape == (sum(ks), n) and got.dtype == torch.float32
+    assert rel_err(got, ref) <= 1e-4          # an fp32 tensor-core accumulation up to 22 662 rows deep (one split)
+    assert torch.equal(gemm_tn(srcs, gg), got)
+
+
+def test_gemm_tn_strided_operands(cuda_dev):
+    g = torch.Generator().manual_seed(3)
+    big = torch.randn(5000, 512, generator=g).bfloat16().to(cuda_dev)
+    a, gg = big[:, 64:192], big[:, 256:320]                  # column slices: leading dimension 512
+    got = gemm_tn([a], gg)
+    assert rel_err(got, a.double().t() @ gg.double()) <= 2e-5
 
 
 def test_rgcn_conv_bf16_tcgen05_path_matches_cublas_path_and_oracle(cuda_dev):

@@ -38,3 +38,19 @@ for (m, n, k1, k2) in [(2_000_000, 64, 1024, 256), (2_000_000, 128, 256, 64), (2
     print(f"M={m} N={n} K={k1}+{k2}: tcgen05 {ms_tc:.3f} ms ({bytes_/ms_tc/1e6:.0f} GB/s, "
           f"{2*m*n*(k1+k2)/ms_tc/1e9:.0f} TFLOP/s)  cuBLAS {ms_cb:.3f} ms ({bytes_/ms_cb/1e6:.0f} GB/s)", flush=True)
     del a1, a2, b
+
+# ---- weight-gradient reductions: D = [A_0 | A_1]^T G (tcgen05, MN-major operands) vs cuBLAS split-K
+from gmlm_b200.ops import gemm_tn  # noqa: E402
+for (m, ks, n, dt) in [(2_000_000, (1024, 256), 64, torch.bfloat16), (2_000_000, (256, 64), 128, torch.bfloat16),
+                       (2_000_000, (512, 128), 256, torch.bfloat16), (2_000_000, (1024, 256), 512, torch.bfloat16),
+                       (2_000_000, (256,), 320, torch.bfloat16), (2_000_000, (64, 128, 256, 512), 768, torch.bfloat16),
+                       (22_662, (8192, 2048), 4096, torch.float16), (22_662, (1200, 300), 512, torch.float16)]:
+    srcs = [torch.randn(m, k, device=dev).to(dt) for k in ks]
+    g = torch.randn(m, n, device=dev).to(dt)
+    ms_tc = t(lambda: gemm_tn(srcs, g))
+    ms_cb = t(lambda: [torch.mm(s_.t(), g, out_dtype=torch.float32) for s_ in srcs])
+    bytes_ = (m * sum(ks) + m * n) * 2
+    fl = 2 * m * n * sum(ks)
+    print(f"TN M={m} K={ks} N={n} {dt}: tcgen05 {ms_tc:.3f} ms ({bytes_/ms_tc/1e6:.0f} GB/s, {fl/ms_tc/1e9:.0f} TFLOP/s)"
+          f"  cuBLAS {ms_cb:.3f} ms", flush=True)
+    del srcs, g
