@@ -259,7 +259,10 @@ def test_aggregate_property_random_graphs(cuda_dev, n, e, feat, seed, hub_thresh
     ei = torch.randint(0, n, (2, e), generator=g_)
     et = edge_type_bucket_ref(ei, n)
     dtype = torch.bfloat16 if bf16 else torch.float32
-    tol = BF16_TOL if bf16 else FP32_TOL
+    # an fp32 running sum over a row of L terms carries up to L/2 ulp: the 1e-5 gate holds for rows up to a few
+    # hundred entries; degenerate examples (N = 1 with 3000 self-loops: every term identical, no cancellation of the
+    # rounding errors, found by brute force over this space) get the bound of the summation itself
+    tol = BF16_TOL if bf16 else max(FP32_TOL, 0.5 * max(e, 1) / max(n, 1) * 2.0 ** -24 * 4)
     x = torch.randn(n, feat, generator=g_).to(dtype)
     g = G.RelGraph.build(ei.to(cuda_dev), et.to(cuda_dev), n, 5, hub_thresh=hub_thresh, quantum=quantum)
     assert int(g.fwd.rowptr[-1]) == e and int(g.bwd.rowptr[-1]) == e
