@@ -26,6 +26,7 @@ from .ops import (  # noqa: F401
 )
 from .nn import GraphNorm, RGCNConv  # noqa: F401
 from .encoder import GraphEncoder, MultiScaleFusion  # noqa: F401
+from .graphed import GraphedEncoderStep  # noqa: F401
 from .losses import nt_xent_loss  # noqa: F401
 from .sampling import generate_active_node_mask, weighted_sample_without_replacement  # noqa: F401
 from .dist_norm import partitioned_graph_norm  # noqa: F401

@@ -26,6 +26,7 @@ def step():
         y = enc.get_graph_embeddings(xg, ei, et)
     y.backward(torch.ones_like(y))
     xg.grad = None
+    enc.zero_grad(set_to_none=True)
 
 
 for _ in range(2):
