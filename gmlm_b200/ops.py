@@ -773,6 +773,21 @@ def _mm_f32(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
         return (a @ b).float()
 
 
+_ONES: dict = {}
+
+
+def _ones_source(m: int, dtype: torch.dtype, dev: torch.device) -> torch.Tensor:
+    """[M, 8] of ones: appended as one more source of a weight-gradient reduction, its rows of the result are the
+    column sums of g = the bias gradient, so the reduction that already streams g produces it (no extra pass)."""
+    key = (m, dtype, dev)
+    t = _ONES.get(key)
+    if t is None:
+        if len(_ONES) > 8:
+            _ONES.clear()
+        t = _ONES[key] = torch.ones((m, 8), dtype=dtype, device=dev)
+    return t
+
+
 def _colsum_f32(g: torch.Tensor) -> torch.Tensor:
     """Column sums of g (a bias gradient): one pass, fp64 accumulation, fixed order."""
     if g.dtype not in _DT:
@@ -846,9 +861,15 @@ class _RGCNTransform(torch.autograd.Function):
             if dx is not None and dx.dtype != ctx.dtypes[5]:
                 dx = dx.to(ctx.dtypes[5])
         dwcat = None
+        k2 = xq.size(1) if xq is not None else 0
         if op in _OPS16 and (ctx.needs_input_grad[2] or ctx.needs_input_grad[3] or ctx.needs_input_grad[4]):
-            # dW = h^T g and droot = x^T g: ONE tcgen05 reduction over the two sources, fp32 result
-            dwcat = gemm_tn([hq] + ([xq] if xq is not None else []), gb)
+            # dW = h^T g, droot = x^T g (and dbias = 1^T g): ONE tcgen05 reduction over the sources, fp32 result
+            srcs = [hq] + ([xq] if xq is not None else [])
+            if ctx.needs_input_grad[5]:
+                srcs.append(_ones_source(gb.size(0), op, gb.device))
+            dwcat = gemm_tn(srcs, gb)
+            if ctx.needs_input_grad[5]:
+                dbias = dwcat[k1 + k2].to(ctx.dtypes[3])
         if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
             dw = dwcat[:k1] if dwcat is not None else _mm_f32(hq.t(), gb)    # [S*Fi, Fo] fp32
             if not dw.is_contiguous():
@@ -865,8 +886,8 @@ class _RGCNTransform(torch.autograd.Function):
             dweight = dweight.to(ctx.dtypes[0]) if dweight is not None else None
             dcomp = dcomp.to(ctx.dtypes[1]) if dcomp is not None else None
         if ctx.needs_input_grad[4] and xq is not None:
-            droot = (dwcat[k1:] if dwcat is not None else _mm_f32(xq.t(), gb)).contiguous().to(ctx.dtypes[2])
-        if ctx.needs_input_grad[5]:
+            droot = (dwcat[k1:k1 + k2] if dwcat is not None else _mm_f32(xq.t(), gb)).contiguous().to(ctx.dtypes[2])
+        if ctx.needs_input_grad[5] and dbias is None:
             dbias = _colsum_f32(gb).to(ctx.dtypes[3])
         return dh, dx, dweight, dcomp, droot, dbias, None, None, None
 
@@ -913,7 +934,13 @@ class _RGCNTransformFirst(torch.autograd.Function):
             if dx.dtype != ctx.dtypes[4]:
                 dx = dx.to(ctx.dtypes[4])
         if any(ctx.needs_input_grad[1:4]):
-            dwn = gemm_tn([xq], gb) if op in _OPS16 else _mm_f32(xq.t(), gb)  # [Fi, (S+1)*Fo] fp32
+            if op in _OPS16:                                                  # [Fi, (S+1)*Fo] fp32 (+ 1^T g rows)
+                dwn = gemm_tn([xq] + ([_ones_source(gb.size(0), op, gb.device)] if ctx.needs_input_grad[4] else []), gb)
+                if ctx.needs_input_grad[4]:
+                    dbias = dwn[fi, S * fo:].to(ctx.dtypes[3])
+                dwn = dwn[:fi]
+            else:
+                dwn = _mm_f32(xq.t(), gb)
             if not dwn.is_contiguous():
                 dwn = dwn.contiguous()
             ld = dwn.size(1)
@@ -931,7 +958,7 @@ class _RGCNTransformFirst(torch.autograd.Function):
                 dcomp = dcomp.to(ctx.dtypes[1]) if dcomp is not None else None
             if ctx.needs_input_grad[3]:
                 droot = dwn[:, S * fo:].contiguous().to(ctx.dtypes[2])
-        if ctx.needs_input_grad[4]:
+        if ctx.needs_input_grad[4] and dbias is None:
             dbias = _colsum_f32(gb[:, S * fo:]).to(ctx.dtypes[3])
         return dx, dweight, dcomp, droot, dbias, None, None, None
 
@@ -975,9 +1002,14 @@ class _LinearNT(torch.autograd.Function):
                     dxs[i] = d if d.dtype == ctx.dtypes[2][i] else d.to(ctx.dtypes[2][i])
                 k0 += x.size(1)
         if ctx.needs_input_grad[0]:
-            # dWt = g^T [x_0 | x_1 | ..] as ([x..]^T g)^T: one tcgen05 reduction over the sources
-            dwt = gemm_tn(xq, gb).t().contiguous().to(ctx.dtypes[0])
-        if ctx.needs_input_grad[1]:
+            # dWt = g^T [x_0 | x_1 | ..] as ([x..]^T g)^T: one tcgen05 reduction over the sources (+ 1^T g = dbias)
+            with_bias = ctx.needs_input_grad[1] and len(xq) < 4
+            d = gemm_tn(list(xq) + ([_ones_source(gb.size(0), op, gb.device)] if with_bias else []), gb)
+            kx = sum(int(x.size(1)) for x in xq)
+            if with_bias:
+                dbias = d[kx].to(ctx.dtypes[1])
+            dwt = d[:kx].t().contiguous().to(ctx.dtypes[0])
+        if ctx.needs_input_grad[1] and dbias is None:
             dbias = _colsum_f32(gb).to(ctx.dtypes[1])
         if ctx.needs_input_grad[2]:
             dadd = g
