@@ -31,7 +31,7 @@ namespace gmlm {
 namespace {
 
 constexpr int kMaxSlots = 8;      // slots per launch (the reference has 4 populated relations)
-constexpr int kTileI = 32;        // rows (input channels) per CTA tile
+constexpr int kTileI = 16;        // rows (input channels) per CTA tile
 constexpr int kThreads = 256;
 
 template <typename OutT>
@@ -57,9 +57,12 @@ struct ComposeParams {
   int with_root;          // this launch also writes the root slab
 };
 
-// tile = 32 input channels x 16*VEC output channels; thread (tx, ty) owns rows ty and ty+16, VEC adjacent columns
-template <typename OutT, int VEC>
-__global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const ComposeParams p) {
+// tile = 16 input channels x 16*VEC output channels; thread (tx, ty) owns row ty, VEC adjacent columns.  One row and
+// MAXS (4 or 8) slots per thread keep the kernel at <= 64 registers (4 CTAs of 256 threads per SM), and the basis
+// loop is unrolled ten deep: 32 warps x 10 independent 16-byte loads per lane in flight per SM (the first version --
+// two rows, eight slots, 126 registers, 2 CTAs per SM -- measured 41 % of DRAM peak under ncu: latency-bound).
+template <typename OutT, int VEC, int MAXS>
+__global__ void __launch_bounds__(kThreads, MAXS == 4 ? 4 : 3) compose_fwd_kernel(const ComposeParams p) {
   constexpr int TILE_O = 16 * VEC;
   extern __shared__ float smem_f[];
   float* comp_s = smem_f;                              // [S][B]
@@ -67,47 +70,35 @@ __global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const ComposePara
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int o0 = blockIdx.x * TILE_O + tx * VEC;
   const int i0 = blockIdx.y * kTileI;
-  for (int k = threadIdx.x; k < p.S * p.B; k += kThreads) {
+  for (int k = threadIdx.x; k < kMaxSlots * p.B; k += kThreads) {
     const int s = k / p.B, b = k % p.B;
-    comp_s[k] = p.comp ? __ldg(p.comp + int64_t(p.rel_of_slot[s]) * p.B + b) : (b == p.rel_of_slot[s] ? 1.f : 0.f);
+    comp_s[k] = s >= p.S ? 0.f
+                : (p.comp ? __ldg(p.comp + int64_t(p.rel_of_slot[s]) * p.B + b) : (b == p.rel_of_slot[s] ? 1.f : 0.f));
   }
   __syncthreads();
-  float acc[kMaxSlots][2][VEC];
+  float acc[MAXS][VEC];
 #pragma unroll
-  for (int s = 0; s < kMaxSlots; ++s)
+  for (int s = 0; s < MAXS; ++s)
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) acc[s][r][k] = 0.f;
-  const bool col_ok = o0 < p.Fo;                       // Fo is a multiple of VEC: a pack is in or out as a whole
-  const bool row_ok[2] = {i0 + ty < p.Fi, i0 + ty + 16 < p.Fi};
+    for (int k = 0; k < VEC; ++k) acc[s][k] = 0.f;
+  const bool ok = o0 < p.Fo && i0 + ty < p.Fi;         // Fo is a multiple of VEC: a pack is in or out as a whole
   const int64_t plane = int64_t(p.Fi) * p.Fo;
-  const float* src[2] = {p.basis + int64_t(i0 + ty) * p.Fo + o0, p.basis + int64_t(i0 + ty + 16) * p.Fo + o0};
-#pragma unroll 6
-  for (int b = 0; b < p.B; ++b) {
-    float v[2][VEC];
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      if (col_ok && row_ok[r]) {
-        if constexpr (VEC == 4) {
-          const float4 q = __ldcs(reinterpret_cast<const float4*>(src[r] + b * plane));
-          v[r][0] = q.x; v[r][1] = q.y; v[r][2] = q.z; v[r][3] = q.w;
-        } else {
-          v[r][0] = __ldcs(src[r] + b * plane);
-        }
+  const float* src = p.basis + int64_t(i0 + ty) * p.Fo + o0;
+  if (ok) {
+#pragma unroll 10
+    for (int b = 0; b < p.B; ++b) {
+      float v[VEC];
+      if constexpr (VEC == 4) {
+        const float4 q = __ldcs(reinterpret_cast<const float4*>(src + b * plane));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
       } else {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) v[r][k] = 0.f;
+        v[0] = __ldcs(src + b * plane);
       }
-    }
 #pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s) {
-      if (s < p.S) {
-        const float c = comp_s[s * p.B + b];
+      for (int s = 0; s < MAXS; ++s) {
+        const float c = comp_s[s * p.B + b];             // slots past S hold zeros (never written out)
 #pragma unroll
-        for (int r = 0; r < 2; ++r)
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) acc[s][r][k] = fmaf(c, v[r][k], acc[s][r][k]);
+        for (int k = 0; k < VEC; ++k) acc[s][k] = fmaf(c, v[k], acc[s][k]);
       }
     }
   }
@@ -116,46 +107,34 @@ __global__ void __launch_bounds__(kThreads) compose_fwd_kernel(const ComposePara
   const int n_slabs = p.S + (p.with_root ? 1 : 0);
 #pragma unroll 1
   for (int s = 0; s < n_slabs; ++s) {
-    float v[2][VEC];
+    float v[VEC];
     const bool is_root = s == p.S;
     if (is_root) {
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k)
-          v[r][k] = (col_ok && row_ok[r]) ? __ldg(p.root + int64_t(i0 + ty + 16 * r) * p.Fo + o0 + k) : 0.f;
+      for (int k = 0; k < VEC; ++k) v[k] = ok ? __ldg(p.root + int64_t(i0 + ty) * p.Fo + o0 + k) : 0.f;
     } else {
       // acc is indexed by a loop variable: select with a fully unrolled compare so it stays in registers
 #pragma unroll
-      for (int q = 0; q < kMaxSlots; ++q)
+      for (int q = 0; q < MAXS; ++q)
         if (q == s) {
 #pragma unroll
-          for (int r = 0; r < 2; ++r)
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) v[r][k] = acc[q][r][k];
+          for (int k = 0; k < VEC; ++k) v[k] = acc[q][k];
         }
     }
-    if (out_n) {
+    if (out_n && ok) {
       const int64_t base = is_root ? p.n_root_off : int64_t(p.slot0 + s) * p.n_slot_stride;
+      OutT* d = out_n + base + int64_t(i0 + ty) * p.n_row_stride + o0;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (col_ok && row_ok[r]) {
-          OutT* d = out_n + base + int64_t(i0 + ty + 16 * r) * p.n_row_stride + o0;
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) d[k] = cvt<OutT>(v[r][k]);
-        }
-      }
+      for (int k = 0; k < VEC; ++k) d[k] = cvt<OutT>(v[k]);
     }
     if (out_t) {
       __syncthreads();                                   // the previous slab has left the tile
 #pragma unroll
-      for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) tile[(tx * VEC + k) * (kTileI + 1) + ty + 16 * r] = v[r][k];
+      for (int k = 0; k < VEC; ++k) tile[(tx * VEC + k) * (kTileI + 1) + ty] = v[k];
       __syncthreads();
       const int64_t base = is_root ? p.t_root_off : int64_t(p.slot0 + s) * p.t_slot_stride;
-      const int li = threadIdx.x & 31;                   // consecutive threads -> consecutive input channels
-      for (int lo = threadIdx.x >> 5; lo < TILE_O; lo += kThreads / 32) {
+      const int li = threadIdx.x & (kTileI - 1);         // consecutive threads -> consecutive input channels
+      for (int lo = threadIdx.x / kTileI; lo < TILE_O; lo += kThreads / kTileI) {
         const int o = blockIdx.x * TILE_O + lo;
         if (o < p.Fo && i0 + li < p.Fi)
           out_t[base + int64_t(o) * p.t_row_stride + i0 + li] = cvt<OutT>(tile[lo * (kTileI + 1) + li]);
@@ -181,7 +160,9 @@ struct ComposeBwdParams {
 constexpr int kBwdWarps = kThreads / 32;
 constexpr int kMaxBPerWarp = 4;     // bases per warp per launch: 32 bases per launch (the reference has 30)
 
-__global__ void __launch_bounds__(kThreads, 2) compose_bwd_kernel(const ComposeBwdParams p, int b_base, int b_count) {
+template <int MAXS>
+__global__ void __launch_bounds__(kThreads, MAXS == 4 ? 3 : 2) compose_bwd_kernel(const ComposeBwdParams p, int b_base,
+                                                                                 int b_count) {
   extern __shared__ float comp_s[];                    // [S][b_count]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < p.S * b_count; k += kThreads) {
@@ -189,11 +170,11 @@ __global__ void __launch_bounds__(kThreads, 2) compose_bwd_kernel(const ComposeB
     comp_s[k] = __ldg(p.comp + int64_t(p.rel_of_slot[s]) * p.B + b_base + b);
   }
   __syncthreads();
-  float acc[kMaxBPerWarp][kMaxSlots];
+  float acc[kMaxBPerWarp][MAXS];
 #pragma unroll
   for (int j = 0; j < kMaxBPerWarp; ++j)
 #pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s) acc[j][s] = 0.f;
+    for (int s = 0; s < MAXS; ++s) acc[j][s] = 0.f;
   const int fo4 = p.Fo >> 2;
   const int64_t n4 = int64_t(p.Fi) * fo4;
   const int64_t plane = int64_t(p.Fi) * p.Fo;
@@ -202,9 +183,9 @@ __global__ void __launch_bounds__(kThreads, 2) compose_bwd_kernel(const ComposeB
     const bool ok = q < n4;
     const int64_t i = ok ? q / fo4 : 0;
     const int o = ok ? int(q % fo4) * 4 : 0;
-    float4 g[kMaxSlots];
+    float4 g[MAXS];
 #pragma unroll
-    for (int s = 0; s < kMaxSlots; ++s) {
+    for (int s = 0; s < MAXS; ++s) {
       g[s] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (s < p.S && ok) g[s] = *reinterpret_cast<const float4*>(p.dw + s * p.slot_stride + i * p.row_stride + o);
     }
@@ -216,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 2) compose_bwd_kernel(const ComposeB
         const float4 w = __ldcs(reinterpret_cast<const float4*>(p.basis + off));
         float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int s = 0; s < kMaxSlots; ++s) {
+        for (int s = 0; s < MAXS; ++s) {
           if (s < p.S) {
             const float c = comp_s[s * b_count + b];
             d.x = fmaf(c, g[s].x, d.x); d.y = fmaf(c, g[s].y, d.y); d.z = fmaf(c, g[s].z, d.z); d.w = fmaf(c, g[s].w, d.w);
@@ -232,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 2) compose_bwd_kernel(const ComposeB
     for (int j = 0; j < kMaxBPerWarp; ++j) {
       const int b = warp + j * kBwdWarps;
 #pragma unroll
-      for (int s = 0; s < kMaxSlots; ++s) {
+      for (int s = 0; s < MAXS; ++s) {
         float v = acc[j][s];
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -268,7 +249,7 @@ __global__ void compose_bwd_final_kernel(const float* partial, int n_ctas, int S
 
 int bwd_grid(int64_t n4) {
   const int64_t want = (n4 + 31) / 32;
-  return int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(num_sms()) * 6)));
+  return int(std::max<int64_t>(1, std::min<int64_t>(want, int64_t(num_sms()) * 9)));
 }
 
 template <typename OutT>
@@ -277,10 +258,11 @@ int launch_fwd(const ComposeParams& p, cudaStream_t st) {
   const size_t smem_vec1 = (size_t(kMaxSlots) * p.B + 16 * (kTileI + 1)) * sizeof(float);
   if (p.Fo % 4 == 0) {
     dim3 grid((p.Fo + 63) / 64, (p.Fi + kTileI - 1) / kTileI);
-    compose_fwd_kernel<OutT, 4><<<grid, kThreads, smem_vec4, st>>>(p);
+    if (p.S <= 4) compose_fwd_kernel<OutT, 4, 4><<<grid, kThreads, smem_vec4, st>>>(p);
+    else compose_fwd_kernel<OutT, 4, 8><<<grid, kThreads, smem_vec4, st>>>(p);
   } else {
     dim3 grid((p.Fo + 15) / 16, (p.Fi + kTileI - 1) / kTileI);
-    compose_fwd_kernel<OutT, 1><<<grid, kThreads, smem_vec1, st>>>(p);
+    compose_fwd_kernel<OutT, 1, 8><<<grid, kThreads, smem_vec1, st>>>(p);
   }
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
@@ -368,7 +350,8 @@ extern "C" int gmlm_basis_compose_bwd(const float* comp, const float* basis, con
   constexpr int kPerLaunch = kBwdWarps * kMaxBPerWarp;
   for (int b0 = 0; b0 < num_bases; b0 += kPerLaunch) {
     const int cnt = std::min(kPerLaunch, num_bases - b0);
-    compose_bwd_kernel<<<grid, kThreads, size_t(num_slots) * cnt * sizeof(float), st>>>(p, b0, cnt);
+    if (num_slots <= 4) compose_bwd_kernel<4><<<grid, kThreads, size_t(num_slots) * cnt * sizeof(float), st>>>(p, b0, cnt);
+    else compose_bwd_kernel<8><<<grid, kThreads, size_t(num_slots) * cnt * sizeof(float), st>>>(p, b0, cnt);
     GMLM_LAUNCH_CHECK();
   }
   if (dcomp) {

@@ -54,3 +54,17 @@ for (m, ks, n, dt) in [(2_000_000, (1024, 256), 64, torch.bfloat16), (2_000_000,
     print(f"TN M={m} K={ks} N={n} {dt}: tcgen05 {ms_tc:.3f} ms ({bytes_/ms_tc/1e6:.0f} GB/s, {fl/ms_tc/1e9:.0f} TFLOP/s)"
           f"  cuBLAS {ms_cb:.3f} ms", flush=True)
     del srcs, g
+
+# ---- basis composition (A4) at the reference's widths: HBM floor = one pass over the fp32 bases
+from gmlm_b200.ops import basis_compose, basis_compose_bwd  # noqa: E402
+for (fi, fo) in [(2048, 4096), (1024, 2048), (300, 512), (256, 64)]:
+    weight = torch.randn(30, fi, fo, device=dev)
+    comp = torch.randn(5, 30, device=dev)
+    root = torch.randn(fi, fo, device=dev)
+    dw = torch.randn(4 * fi, fo, device=dev)
+    ms_f = t(lambda: basis_compose(weight, comp, root, (0, 1, 2, 3), torch.float16, "agg"))
+    ms_b = t(lambda: basis_compose_bwd(weight, comp, dw, fi * fo, fo, (0, 1, 2, 3)))
+    gb = 30 * fi * fo * 4 / 1e9
+    print(f"compose Fi={fi} Fo={fo}: fwd {ms_f:.3f} ms ({(gb + 5 * fi * fo * 4 / 1e9) / ms_f * 1e3:.0f} GB/s)  "
+          f"bwd {ms_b:.3f} ms ({(2 * gb + 4 * fi * fo * 4 / 1e9) / ms_b * 1e3:.0f} GB/s)", flush=True)
+    del weight, root, dw
