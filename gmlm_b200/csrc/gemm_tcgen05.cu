@@ -129,11 +129,17 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
       : "r"(taddr));
 }
 
-constexpr int stages_for(int block_n) { return block_n >= 256 ? 3 : (block_n >= 128 ? 4 : (block_n >= 64 ? 6 : 7)); }
+// 256-wide tiles: FOUR 48 KB stages (three left the tensor pipe 65 % active on the K = 960 fusion product: two
+// k-blocks of prefetch do not cover the L2 / HBM latency); the shared memory for the fourth stage comes from
+// single-buffering the epilogue's staging rows, which have slack (4 us of MMAs per tile against ~2 us of epilogue)
+constexpr int stages_for(int block_n) { return block_n >= 256 ? 4 : (block_n >= 128 ? 4 : (block_n >= 64 ? 6 : 7)); }
+constexpr int staging_bufs_for(int block_n) { return block_n >= 256 ? 1 : 2; }
 constexpr uint32_t tmem_cols_for(int block_n) {
   return 2 * block_n <= 32 ? 32u : (2 * block_n <= 64 ? 64u : (2 * block_n <= 128 ? 128u : (2 * block_n <= 256 ? 256u : 512u)));
 }
-constexpr int kStagingBytes = kEpiWarps * 2 * 32 * 128;   // 8 epilogue warps x 2 buffers x (32 rows x 128 B)
+constexpr int staging_bytes_for(int block_n) {           // 8 epilogue warps x 1-2 buffers x (32 rows x 128 B)
+  return kEpiWarps * staging_bufs_for(block_n) * 32 * 128;
+}
 // output columns per staging row: a full 128-byte swizzle row when the tile width allows it, else 64 bytes
 template <int BLOCK_N, typename OutT>
 constexpr int chunk_cols() {
@@ -141,8 +147,9 @@ constexpr int chunk_cols() {
 }
 template <int BLOCK_N>
 constexpr size_t smem_bytes_for() {
-  return size_t(stages_for(BLOCK_N)) * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + kStagingBytes +
-         2 * BLOCK_N * sizeof(float) + (2 * stages_for(BLOCK_N) + 4) * 8 + 16 + 1024;
+  // no alignment slack: the dynamic shared memory is declared __align__(1024) (checked at kernel entry)
+  return size_t(stages_for(BLOCK_N)) * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + staging_bytes_for(BLOCK_N) +
+         2 * BLOCK_N * sizeof(float) + (2 * stages_for(BLOCK_N) + 4) * 8 + 16;
 }
 
 // PERSISTENT kernel: every CTA (one per SM) walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the
@@ -171,9 +178,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
   constexpr int N_CHUNKS = BLOCK_N / CHUNK;
   static_assert(BLOCK_N % CHUNK == 0 && (ROWB == 128 || ROWB == 64) && (CHUNK == 32 || CHUNK == 64),
                 "tile width must be a multiple of one staging row");
-  extern __shared__ uint8_t smem_raw[];
+  constexpr int STG_BUFS = staging_bufs_for(BLOCK_N);
+  constexpr int kStagingBytes = staging_bytes_for(BLOCK_N);
+  extern __shared__ __align__(1024) uint8_t smem_nt[];
   // 1024-byte alignment for the 128B-swizzled tiles
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_nt;
+  if (smem_u32(smem) & 1023u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + STAGES * A_BYTES;
   uint8_t* staging = smem_b + STAGES * B_BYTES;                       // 1024-aligned: A_BYTES, B_BYTES are
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int et = int(threadIdx.x) - 64;                  // 0..255 among the epilogue threads
-    uint8_t* stg = staging + (warp - 2) * (2 * 32 * 128);
+    uint8_t* stg = staging + (warp - 2) * (STG_BUFS * 32 * 128);
     constexpr int LAST0 = ((N_CHUNKS - 1) / 2) * 2;        // last chunk of the even warp
     constexpr int LAST1 = N_CHUNKS >= 2 ? ((N_CHUNKS - 2) / 2) * 2 + 1 : -1;
     const int my_last = half == 0 ? LAST0 : LAST1;
@@ -297,10 +307,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
       const CUtensorMap* cmap = second ? &tma_c2 : &tma_c1;
       const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16) + buf * BLOCK_N;
 #pragma unroll 1
-      for (int ch = half; ch < N_CHUNKS; ch += 2, sp ^= 1) {
+      for (int ch = half; ch < N_CHUNKS; ch += 2, sp ^= (STG_BUFS - 1)) {
         uint8_t* sb = stg + sp * (32 * 128);
-        // the TMA store issued from this buffer two chunks ago must have finished READING it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        // the TMA store last issued from this buffer (two chunks ago; the previous chunk when the tile shape leaves
+        // room for one buffer only) must have finished READING it
+        if (lane == 0) {
+          if constexpr (STG_BUFS == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         __syncwarp();
         float v[CHUNK];
         {
