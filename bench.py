@@ -65,7 +65,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -278,8 +278,10 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
     clocks = sampler.stop()
     total_ms = t_start.elapsed_time(t_end)
     ms_per_step = total_ms / args.steps
-    fwd_ms = statistics.mean(a.elapsed_time(b) for a, b, _ in ev)
-    bwd_ms = statistics.mean(b.elapsed_time(c) for _, b, c in ev)
+    fwd_all = [a.elapsed_time(b) for a, b, _ in ev]
+    bwd_all = [b.elapsed_time(c) for _, b, c in ev]
+    fwd_ms = statistics.mean(fwd_all)
+    bwd_ms = statistics.mean(bwd_all)
     value = e / (ms_per_step * 1e-3)
 
     fwd_b, bwd_b = algorithmic_bytes(n, e, feat, esize, S)
@@ -295,7 +297,7 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
     roof = {"bound": "hbm", "kernel": "forward aggregate (A5): rows_kernel + chunk_kernel + hub_final_kernel",
             "achieved": fwd_b / (fwd_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
             "frac": fwd_b / (fwd_ms * 1e-3) / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-            "algorithmic_bytes": fwd_b, "ms": fwd_ms}
+            "algorithmic_bytes": fwd_b, "ms": fwd_ms, "ms_min_max": [min(fwd_all), max(fwd_all)]}
     if traffic:
         roof["traffic_source"] = ("stored ncu figure (dram__bytes_read.sum + dram__bytes_write.sum of the same kernels on "
                                   "this workload, profiles/traffic.json), NOT measured in this run")
