@@ -87,6 +87,14 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
       ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -132,24 +140,29 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 // 256-wide tiles: FOUR 48 KB stages (three left the tensor pipe 65 % active on the K = 960 fusion product: two
 // k-blocks of prefetch do not cover the L2 / HBM latency); the shared memory for the fourth stage comes from
 // single-buffering the epilogue's staging rows, which have slack (4 us of MMAs per tile against ~2 us of epilogue)
-constexpr int stages_for(int block_n) { return block_n >= 256 ? 4 : (block_n >= 128 ? 4 : (block_n >= 64 ? 6 : 7)); }
-constexpr int staging_bufs_for(int block_n) { return block_n >= 256 ? 1 : 2; }
+// fp32 operands (3xTF32, see gemm_nt_kernel): a stage also holds the low-part copies of both tiles, tiles <= 128 wide
+constexpr int stages_for(int block_n, bool x3 = false) {
+  if (x3) return block_n >= 128 ? 3 : (block_n >= 64 ? 3 : 4);
+  return block_n >= 256 ? 4 : (block_n >= 128 ? 4 : (block_n >= 64 ? 6 : 7));
+}
+constexpr int staging_bufs_for(int block_n, bool x3 = false) { return (block_n >= 256 || (x3 && block_n >= 128)) ? 1 : 2; }
 constexpr uint32_t tmem_cols_for(int block_n) {
   return 2 * block_n <= 32 ? 32u : (2 * block_n <= 64 ? 64u : (2 * block_n <= 128 ? 128u : (2 * block_n <= 256 ? 256u : 512u)));
 }
-constexpr int staging_bytes_for(int block_n) {           // 8 epilogue warps x 1-2 buffers x (32 rows x 128 B)
-  return kEpiWarps * staging_bufs_for(block_n) * 32 * 128;
+constexpr int staging_bytes_for(int block_n, bool x3 = false) {   // 8 epilogue warps x 1-2 buffers x (32 rows x 128 B)
+  return kEpiWarps * staging_bufs_for(block_n, x3) * 32 * 128;
 }
 // output columns per staging row: a full 128-byte swizzle row when the tile width allows it, else 64 bytes
 template <int BLOCK_N, typename OutT>
 constexpr int chunk_cols() {
   return BLOCK_N % (128 / int(sizeof(OutT))) == 0 ? 128 / int(sizeof(OutT)) : 64 / int(sizeof(OutT));
 }
-template <int BLOCK_N>
+template <int BLOCK_N, bool X3 = false>
 constexpr size_t smem_bytes_for() {
-  // no alignment slack: the dynamic shared memory is declared __align__(1024) (checked at kernel entry)
-  return size_t(stages_for(BLOCK_N)) * (BLOCK_M * BLOCK_K * 2 + BLOCK_N * BLOCK_K * 2) + staging_bytes_for(BLOCK_N) +
-         2 * BLOCK_N * sizeof(float) + (2 * stages_for(BLOCK_N) + 4) * 8 + 16;
+  // no alignment slack: the dynamic shared memory is declared __align__(1024) (checked at kernel entry); one
+  // operand row of a stage is 128 bytes whatever the element type (64 bf16 / fp16 or 32 fp32)
+  return size_t(stages_for(BLOCK_N, X3)) * (X3 ? 2 : 1) * (BLOCK_M * 128 + BLOCK_N * 128) +
+         staging_bytes_for(BLOCK_N, X3) + 2 * BLOCK_N * sizeof(float) + (3 * stages_for(BLOCK_N, X3) + 4) * 8 + 16;
 }
 
 // PERSISTENT kernel: every CTA (one per SM) walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... of the
@@ -163,37 +176,54 @@ constexpr size_t smem_bytes_for() {
 //                           lane quarter split the column chunks (the epilogue, not the MMA, paces K <= 128 shapes)
 // The round-1 kernel ran one tile per CTA with one accumulator: on the backward shape (K = 64: ONE k-block per
 // tile) load latency, MMA and a 64 KB epilogue were serialised per tile (3.3 ms against 0.88 ms for cuBLAS).
-template <int BLOCK_N, typename OutT>
-__global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_constant__ SourceMaps tma_a,
+//
+// X3 = fp32 operands on the tf32 tensor cores with fp32-grade accuracy ("3xTF32"): TMA lands the fp32 tiles, four
+// CONVERTER warps (10-13) split every element in place into hi = the tf32-representable top 19 bits and write
+// lo = x - hi (exact) to a second copy of the stage at the same swizzled offsets, and the MMA warp issues
+// lo.hi + hi.lo + hi.hi per k-step (the dropped lo.lo term and the tf32 rounding of lo are 2^-22 relative): the
+// reference's fp32 eval mode (main.py:603) meets the 1e-5 gate that plain TF32 (2^-11) cannot.
+template <int BLOCK_N, typename OutT, bool X3 = false>
+__global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads, 1) gemm_nt_kernel(const __grid_constant__ SourceMaps tma_a,
                                                               const __grid_constant__ CUtensorMap tma_b,
                                                               const __grid_constant__ CUtensorMap tma_c1,
                                                               const __grid_constant__ CUtensorMap tma_c2,
                                                               const GemmParams p) {
-  constexpr int STAGES = stages_for(BLOCK_N);
-  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr uint32_t TMEM_COLS = tmem_cols_for(BLOCK_N);
+  constexpr int STAGES = stages_for(BLOCK_N, X3);
+  constexpr int BK = X3 ? 32 : BLOCK_K;              // elements per k-block: one 128-byte swizzle row
+  constexpr uint32_t A_BYTES = BLOCK_M * 128;
+  constexpr uint32_t B_BYTES = BLOCK_N * 128;
+  // X3: ONE tile in flight, split over all of tensor memory: k-block kb adds its hi.hi product to accumulator
+  // kb mod X3_MAIN (3 for 128-wide tiles, 7 for narrower ones), the small lo.hi + hi.lo terms go to one more.  The
+  // tensor core adds into an fp32 accumulator with truncation, a bias that grows linearly with the number of
+  // accumulations (3 MMAs x K/32 into ONE accumulator measured 1.2e-5 at K = 1500, 2e-6 split over four); the
+  // epilogue adds the accumulators with round-to-nearest
+  constexpr int X3_MAIN = BLOCK_N >= 128 ? 3 : 7;
+  constexpr uint32_t TMEM_COLS = X3 ? uint32_t((X3_MAIN + 1) * BLOCK_N) : tmem_cols_for(BLOCK_N);
+  static_assert(!X3 || (TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0), "accumulators exceed tensor memory");
   constexpr int CHUNK = chunk_cols<BLOCK_N, OutT>();      // output columns per staging row (128 or 64 bytes)
   constexpr int ROWB = CHUNK * int(sizeof(OutT));
   constexpr int N_CHUNKS = BLOCK_N / CHUNK;
   static_assert(BLOCK_N % CHUNK == 0 && (ROWB == 128 || ROWB == 64) && (CHUNK == 32 || CHUNK == 64),
                 "tile width must be a multiple of one staging row");
-  constexpr int STG_BUFS = staging_bufs_for(BLOCK_N);
-  constexpr int kStagingBytes = staging_bytes_for(BLOCK_N);
+  constexpr int STG_BUFS = staging_bufs_for(BLOCK_N, X3);
+  constexpr int kStagingBytes = staging_bytes_for(BLOCK_N, X3);
   extern __shared__ __align__(1024) uint8_t smem_nt[];
   // 1024-byte alignment for the 128B-swizzled tiles
   uint8_t* smem = smem_nt;
   if (smem_u32(smem) & 1023u) __trap();
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem_a + STAGES * A_BYTES;
-  uint8_t* staging = smem_b + STAGES * B_BYTES;                       // 1024-aligned: A_BYTES, B_BYTES are
+  uint8_t* smem_alo = smem_b + STAGES * B_BYTES;                      // X3 only: low parts of the A / B tiles
+  uint8_t* smem_blo = smem_alo + (X3 ? STAGES * A_BYTES : 0);
+  uint8_t* staging = smem_blo + (X3 ? STAGES * B_BYTES : 0);          // 1024-aligned: A_BYTES, B_BYTES are
   float* bias_s = reinterpret_cast<float*>(staging + kStagingBytes);  // [2][BLOCK_N]
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + 2 * BLOCK_N);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* conv = bars + 2 * STAGES;                                 // X3 only: stage split into hi / lo
+  uint64_t* tmem_full = bars + 3 * STAGES;
+  uint64_t* tmem_empty = bars + 3 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -205,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(full + s), 1);
       mbar_init(smem_u32(empty + s), 1);
+      mbar_init(smem_u32(conv + s), 4);                   // one arrival per converter warp
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(smem_u32(tmem_full + b), 1);
@@ -238,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
           const uint32_t ph = (kc / STAGES) & 1;
           mbar_wait(smem_u32(empty + s), ph ^ 1);
           mbar_expect_tx(smem_u32(full + s), A_BYTES + B_BYTES);
-          const int ka = (kb - kb_first) * BLOCK_K;      // column inside the source; columns past its width and rows
+          const int ka = (kb - kb_first) * BK;           // column inside the source; columns past its width and rows
           tma_load_2d(smem_u32(smem_a + s * A_BYTES), &tma_a.m[src], smem_u32(full + s), ka, m0);   // past M: zeros
           tma_load_2d(smem_u32(smem_b + s * B_BYTES), &tma_b, smem_u32(full + s), p.k_off[src] + ka, brow0);
         }
@@ -247,28 +278,71 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer (single thread)
-      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, p.idesc_formats);
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, X3 ? 2u : p.idesc_formats);   // 2 = TF32
       uint32_t kc = 0, it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
-        const uint32_t buf = it & 1, aph = (it >> 1) & 1;
+        const uint32_t buf = X3 ? 0u : (it & 1), aph = X3 ? (it & 1) : ((it >> 1) & 1);
         mbar_wait(smem_u32(tmem_empty + buf), aph ^ 1);   // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb, ++kc) {
           const int s = kc % STAGES;
           const uint32_t ph = (kc / STAGES) & 1;
-          mbar_wait(smem_u32(full + s), ph);
+          mbar_wait(smem_u32(X3 ? conv + s : full + s), ph);
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_BYTES));
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_BYTES));
+          if constexpr (X3) {
+            const uint64_t dal = make_smem_desc(smem_u32(smem_alo + s * A_BYTES));
+            const uint64_t dbl = make_smem_desc(smem_u32(smem_blo + s * B_BYTES));
+            const uint32_t d_main = tmem_base + uint32_t(kb % X3_MAIN) * BLOCK_N;
+            const uint32_t d_small = tmem_base + uint32_t(X3_MAIN) * BLOCK_N;
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advancing 16 elements along K inside the swizzle atom = +32 bytes = +2 in the address field
-            umma(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) {                  // 8 fp32 per UMMA = 32 bytes = +2 in the address field
+              umma_tf32(d_small, dal + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+              umma_tf32(d_small, da + uint64_t(2 * k), dbl + uint64_t(2 * k), idesc, 1u);
+              umma_tf32(d_main, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb >= X3_MAIN || k) ? 1u : 0u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              // advancing 16 elements along K inside the swizzle atom = +32 bytes = +2 in the address field
+              umma(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+            }
           }
           umma_commit(smem_u32(empty + s));      // frees the smem stage once these MMAs have read it
         }
         umma_commit(smem_u32(tmem_full + buf));  // accumulator complete
+      }
+    }
+  } else if (X3 && warp >= 2 + kEpiWarps) {
+    // ---------------- converter (fp32 operands): hi = x & 0xffffe000 in place, lo = x - hi into the stage's second
+    // copy, same byte offsets (the swizzle is a permutation of 16-byte chunks: element-wise work is layout-blind)
+    const int ct = int(threadIdx.x) - 32 * (2 + kEpiWarps);     // 0..127
+    uint32_t kc = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++kc) {
+        const int s = kc % STAGES;
+        const uint32_t ph = (kc / STAGES) & 1;
+        mbar_wait(smem_u32(full + s), ph);
+        auto split = [&](uint8_t* hi, uint8_t* lo, int n16) {
+#pragma unroll 4
+          for (int i = ct; i < n16; i += 128) {
+            uint4 v = *reinterpret_cast<uint4*>(hi + 16 * i);
+            uint4 h = make_uint4(v.x & 0xffffe000u, v.y & 0xffffe000u, v.z & 0xffffe000u, v.w & 0xffffe000u);
+            uint4 l = make_uint4(__float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x)),
+                                 __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y)),
+                                 __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z)),
+                                 __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w)));
+            *reinterpret_cast<uint4*>(hi + 16 * i) = h;
+            *reinterpret_cast<uint4*>(lo + 16 * i) = l;
+          }
+        };
+        split(smem_a + s * A_BYTES, smem_alo + s * A_BYTES, int(A_BYTES / 16));
+        split(smem_b + s * B_BYTES, smem_blo + s * B_BYTES, int(B_BYTES / 16));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(conv + s));
       }
     }
   } else {
@@ -289,8 +363,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
       const int ccol0 = second ? (tn - p.tiles1) * BLOCK_N : tn * BLOCK_N;   // first column inside C1 / C2
       const int n0 = second ? p.N1 + ccol0 : ccol0;                          // ... and of the whole product
       const int n_end = second ? p.N : p.N1;                                 // columns at or past it are clipped
-      const uint32_t buf = it & 1, aph = (it >> 1) & 1;
-      float* bs = bias_s + buf * BLOCK_N;
+      const uint32_t buf = X3 ? 0u : (it & 1), aph = X3 ? (it & 1) : ((it >> 1) & 1);
+      float* bs = bias_s + (it & 1) * BLOCK_N;
       if (p.bias) {
         for (int c = et; c < BLOCK_N; c += 32 * kEpiWarps) bs[c] = n0 + c < n_end ? __ldg(p.bias + n0 + c) : 0.f;
       }
@@ -317,7 +391,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_nt_kernel(const __grid_const
         }
         __syncwarp();
         float v[CHUNK];
-        {
+        if constexpr (X3) {                                // CHUNK == 32 (fp32 output): sum the accumulators in use
+          static_assert(!X3 || CHUNK == 32, "fp32 operands give fp32 output");
+          uint32_t r0[32], r1[32];
+          tmem_ld32_nowait(t_lane + uint32_t(X3_MAIN * BLOCK_N + ch * CHUNK), r0);     // small terms first
+          tmem_ld32_nowait(t_lane + uint32_t(ch * CHUNK), r1);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r0[j]) + __uint_as_float(r1[j]);
+          for (int a = 1; a < X3_MAIN && a < num_kb; ++a) {
+            tmem_ld32_nowait(t_lane + uint32_t(a * BLOCK_N + ch * CHUNK), r1);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r1[j]);
+          }
+        } else {
           uint32_t r0[32];
           tmem_ld32_nowait(t_lane + uint32_t(ch * CHUNK), r0);
           if constexpr (CHUNK == 64) {
@@ -482,12 +570,12 @@ int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int6
   return GMLM_OK;
 }
 
-template <int BLOCK_N, typename OutT>
+template <int BLOCK_N, typename OutT, bool X3 = false>
 int launch(const SourceMaps& a, const CUtensorMap& b, const CUtensorMap& c1, const CUtensorMap& c2, GemmParams p,
            cudaStream_t st) {
-  constexpr size_t smem = smem_bytes_for<BLOCK_N>();
+  constexpr size_t smem = smem_bytes_for<BLOCK_N, X3>();
   static_assert(smem <= 227 * 1024, "tile configuration exceeds the shared memory of one SM");
-  auto kern = gemm_nt_kernel<BLOCK_N, OutT>;
+  auto kern = gemm_nt_kernel<BLOCK_N, OutT, X3>;
   static bool configured[kMaxDevices] = {};          // per device: the opt-in is a per-device function attribute
   const int dev = current_device();
   if (!configured[dev]) {
@@ -498,7 +586,7 @@ int launch(const SourceMaps& a, const CUtensorMap& b, const CUtensorMap& c1, con
   p.n_tiles = p.tiles1 + (p.N - p.N1 + BLOCK_N - 1) / BLOCK_N;
   const int64_t tiles = int64_t((p.M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles;
   const unsigned grid = unsigned(std::min<int64_t>(tiles, num_sms()));     // persistent: one CTA per SM
-  kern<<<grid, kThreads, smem, st>>>(a, b, c1, c2, p);
+  kern<<<grid, X3 ? kThreads + 128 : kThreads, smem, st>>>(a, b, c1, c2, p);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }
@@ -506,13 +594,16 @@ int launch(const SourceMaps& a, const CUtensorMap& b, const CUtensorMap& c1, con
 // tile width: the widest tile whose padding (columns computed past N1 / N and clipped by the store) stays under
 // 1/8 of the product; exact divisors first (160 for N = 320, 640: two passes over A through L2 instead of five
 // with 64-wide tiles, which made that shape L2-bandwidth-bound)
-int pick_block_n(int64_t n1, int64_t n2) {
+int pick_block_n(int64_t n1, int64_t n2, bool x3) {
   const int cand[5] = {256, 160, 128, 64, 32};
+  const int first = x3 ? 2 : 0;                      // fp32 operands: tiles up to 128 wide (a stage holds hi and lo)
   auto padded = [&](int bn) { return (n1 + bn - 1) / bn * bn + (n2 + bn - 1) / bn * bn; };
-  for (int bn : cand)
+  for (int i = first; i < 5; ++i) {
+    const int bn = cand[i];
     if (n1 % bn == 0 && n2 % bn == 0 && (bn != 160 || (n1 + n2) % 256 != 0)) return bn;
-  for (int bn : cand)
-    if (padded(bn) * 8 <= (n1 + n2) * 9) return bn;
+  }
+  for (int i = first; i < 5; ++i)
+    if (padded(cand[i]) * 8 <= (n1 + n2) * 9) return cand[i];
   return 32;
 }
 
@@ -520,22 +611,27 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
                  const float* bias, const void* addend, int64_t ld_add, int64_t M, int64_t N, void* C1, int64_t ldc1,
                  int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream) {
   GMLM_REQUIRE(n_src >= 1 && n_src <= kMaxSources, "gemm: 1..%d A sources", kMaxSources);
-  GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16, "gemm: operands must be GMLM_BF16 or GMLM_F16");
+  GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16 || in_dtype == GMLM_F32,
+               "gemm: operands must be GMLM_BF16, GMLM_F16 or GMLM_F32");
   GMLM_REQUIRE(out_dtype == GMLM_F32 || out_dtype == GMLM_BF16, "gemm: out_dtype must be GMLM_F32 or GMLM_BF16");
+  const bool x3 = in_dtype == GMLM_F32;               // fp32 operands: the 3xTF32 kernel, fp32 output
+  GMLM_REQUIRE(!x3 || out_dtype == GMLM_F32, "gemm: fp32 operands give an fp32 output");
   const int esz = out_dtype == GMLM_F32 ? 4 : 2;
+  const int per16 = x3 ? 4 : 8;                       // operand elements per 16 bytes
+  const int bk = x3 ? 32 : BLOCK_K;                   // operand elements per 128-byte k-block
   int64_t K = 0;
   for (int i = 0; i < n_src; ++i) {
     GMLM_REQUIRE(A[i] != nullptr && Ks[i] > 0, "gemm: A source %d is empty", i);
-    GMLM_REQUIRE(lda[i] >= Ks[i] && lda[i] % 8 == 0, "gemm: lda[%d] must be >= K and a multiple of 8 (16-byte row pitch)", i);
+    GMLM_REQUIRE(lda[i] >= Ks[i] && lda[i] % per16 == 0, "gemm: lda[%d] must be >= K with a 16-byte row pitch", i);
     GMLM_REQUIRE((reinterpret_cast<uintptr_t>(A[i]) & 15) == 0, "gemm: operands must be 16-byte aligned");
     // a source starts at column sum(K_0..K_{i-1}) of B: the TMA wants that inner coordinate on a 16-byte boundary
-    GMLM_REQUIRE(i == n_src - 1 || Ks[i] % 8 == 0, "gemm: every source but the last must be a multiple of 8 columns wide");
+    GMLM_REQUIRE(i == n_src - 1 || Ks[i] % per16 == 0, "gemm: every source but the last must be a multiple of 16 bytes wide");
     K += Ks[i];
   }
   GMLM_REQUIRE(M >= 0 && N > 0, "gemm: bad sizes");
   GMLM_REQUIRE(M < (int64_t(1) << 31) && N < (int64_t(1) << 24) && K < (int64_t(1) << 30), "gemm: sizes exceed int32");
   GMLM_REQUIRE(B && C1, "gemm: null pointer");
-  GMLM_REQUIRE(ldb >= K && ldb % 8 == 0, "gemm: ldb must be >= K and a multiple of 8 (16-byte row pitch)");
+  GMLM_REQUIRE(ldb >= K && ldb % per16 == 0, "gemm: ldb must be >= K with a 16-byte row pitch");
   GMLM_REQUIRE((reinterpret_cast<uintptr_t>(B) & 15) == 0, "gemm: operands must be 16-byte aligned");
   if (N1 <= 0 || N1 >= N) {
     N1 = N; C2 = C1; ldc2 = ldc1;
@@ -551,7 +647,7 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
                      ld_add >= N,
                  "gemm: the addend must be 16-byte aligned with a 16-byte row pitch");
   if (M == 0) return GMLM_OK;
-  const int bn = pick_block_n(N1, N - N1);
+  const int bn = pick_block_n(N1, N - N1, x3);
   // cuTensorMapEncodeTiled is a driver entry point: it needs a current context on THIS thread (autograd worker
   // threads may not have touched the runtime of this library yet).  The caller's current device is the device of
   // the operands (the torch layer guards it); it is neither changed nor queried per call.
@@ -569,17 +665,17 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
   int kb = 0, koff = 0;
   for (int i = 0; i < kMaxSources; ++i) {
     if (i < n_src) {
-      if (int rc = get_map(&ma.m[i], A[i], M, Ks[i], lda[i], BLOCK_M, BLOCK_K, in_dtype)) return rc;
+      if (int rc = get_map(&ma.m[i], A[i], M, Ks[i], lda[i], BLOCK_M, bk, in_dtype)) return rc;
       p.k_off[i] = koff;
       koff += int(Ks[i]);
-      kb += int((Ks[i] + BLOCK_K - 1) / BLOCK_K);
+      kb += int((Ks[i] + bk - 1) / bk);
     } else {
       ma.m[i] = ma.m[0];
       p.k_off[i] = koff;
     }
     p.kb_end[i] = kb;
   }
-  int rc = get_map(&mb, B, N, K, ldb, bn, BLOCK_K, in_dtype);
+  int rc = get_map(&mb, B, N, K, ldb, bn, bk, in_dtype);
   if (rc) return rc;
   const int chunk = bn % (128 / esz) == 0 ? 128 / esz : 64 / esz;      // chunk_cols<BLOCK_N, OutT>()
   rc = get_map(&mc1, C1, M, N1, ldc1, 32, chunk, out_dtype);
@@ -591,6 +687,14 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
   p.addend = addend; p.ld_add = ld_add;
   p.idesc_formats = in_dtype == GMLM_BF16 ? 1u : 0u;
   cudaStream_t st = as_stream(stream);
+  if (x3) {
+    switch (bn) {
+      case 128: return launch<128, float, true>(ma, mb, mc1, mc2, p, st);
+      case 64: return launch<64, float, true>(ma, mb, mc1, mc2, p, st);
+      case 32: return launch<32, float, true>(ma, mb, mc1, mc2, p, st);
+    }
+    return fail(GMLM_ERR_INVALID, "gemm: unsupported tile");
+  }
 #define GMLM_GEMM_CASE(BN)                                                                     \
   case BN:                                                                                     \
     return out_dtype == GMLM_F32 ? launch<BN, float>(ma, mb, mc1, mc2, p, st)                  \

@@ -593,7 +593,8 @@ def _tma_rows(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Ten
 
 def gemm_nt(a1, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Optional[torch.Tensor] = None,
             out_dtype: Optional[torch.dtype] = None, split: int = 0, addend: Optional[torch.Tensor] = None):
-    """``[a1 | a2 | ..] @ b.T + bias (+ addend)`` on the tcgen05 tensor cores (bf16 or fp16 in, fp32 accumulate).
+    """``[a1 | a2 | ..] @ b.T + bias (+ addend)`` on the tcgen05 tensor cores: bf16 / fp16 operands (fp32 accumulate), or
+    fp32 operands as 3xTF32 (hi/lo split in shared memory, three MMAs per k-step: fp32-grade accuracy, 1e-5 gate).
 
     a1: one [M,K1] tensor or a list of up to four [M,K_i] sources (never concatenated in memory); a2 [M,K2]
     (optional); b [N, sum K], all bf16 (or all fp16) with unit inner stride and a 16-byte row pitch (anything else is
@@ -605,21 +606,21 @@ def gemm_nt(a1, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Option
         srcs.append(a2)
     _require_cuda(srcs[0], "a1")
     op = srcs[0].dtype
-    if op not in _OPS16 or b.dtype != op or any(t.dtype != op for t in srcs):
-        raise _lib.GmlmError("gemm_nt: operands must all be bfloat16 or all be float16")
+    if op not in _OPS16 + (torch.float32,) or b.dtype != op or any(t.dtype != op for t in srcs):
+        raise _lib.GmlmError("gemm_nt: operands must all be bfloat16, all float16 or all float32")
     if not 1 <= len(srcs) <= 4:
         raise _lib.GmlmError("gemm_nt: one to four A sources")
     m = int(srcs[0].size(0))
     if any(t.dim() != 2 or t.size(0) != m for t in srcs) or b.dim() != 2 or b.size(1) != sum(int(t.size(1)) for t in srcs):
         raise _lib.GmlmError(f"gemm_nt: shape mismatch a {[tuple(t.shape) for t in srcs]} b {tuple(b.shape)}")
-    if any(t.size(1) % 8 for t in srcs[:-1]):
+    if any(t.size(1) % (16 // t.element_size()) for t in srcs[:-1]):
         srcs = [torch.cat(srcs, dim=1)]      # a source must start on a 16-byte column boundary of b: concatenate
     srcs = [_tma_rows(t) for t in srcs]
     b = _tma_rows(b)
     n = int(b.size(0))
     out_dtype = out_dtype or (torch.bfloat16 if op == torch.bfloat16 else torch.float32)
-    if out_dtype not in _DT:
-        raise _lib.GmlmError("gemm_nt: output must be float32 or bfloat16")
+    if out_dtype not in _DT or (op == torch.float32 and out_dtype != torch.float32):
+        raise _lib.GmlmError("gemm_nt: output must be float32 or bfloat16 (float32 for float32 operands)")
     per = 16 // torch.empty((), dtype=out_dtype).element_size()
     dev = srcs[0].device
     bias32 = bias.detach().float().contiguous() if bias is not None else None
@@ -809,15 +810,22 @@ class _RGCNTransform(torch.autograd.Function):
     main.py:446,543); h and x are cast once and saved in that type."""
 
     @staticmethod
-    def forward(ctx, h, x, weight, comp, root, bias, live, out_dtype, op_dtype):
+    def forward(ctx, h, x, weight, comp, root, bias, live, out_dtype, op_dtype, stock=False):
         live = tuple(int(v) for v in live)
         S, fi, fo = len(live), weight.size(1), weight.size(2)
         k1 = S * fi
+        ctx.stock = bool(stock)       # fp32 on stock cuBLAS (A/B switch RGCNConv.use_tcgen05 = False)
         need_bwd_w = any(ctx.needs_input_grad[:2])
         if op_dtype in _OPS16:
             hq, xq = _tma_rows(h, op_dtype), (_tma_rows(x, op_dtype) if root is not None else None)
             wn, wt = basis_compose(weight, comp, root, live, op_dtype, "agg", want_n=need_bwd_w)
             out = gemm_nt([hq] + ([xq] if xq is not None else []), wt, bias=bias, out_dtype=out_dtype)
+        elif op_dtype == torch.float32 and h.is_cuda and out_dtype == torch.float32 and not stock:
+            # fp32 activations outside autocast (the reference's eval mode, main.py:603): the same ONE GEMM, fp32
+            # operands on the tf32 tensor cores as 3xTF32 (fp32-grade accuracy)
+            hq, xq = _tma_rows(h, torch.float32), (_tma_rows(x, torch.float32) if root is not None else None)
+            wn, wt = basis_compose(weight, comp, root, live, torch.float32, "agg", want_n=True)
+            out = gemm_nt([hq] + ([xq] if xq is not None else []), wt, bias=bias, out_dtype=torch.float32)
         else:
             hq, xq = h.float(), (x.float() if root is not None else None)
             wn, _ = basis_compose(weight, comp, root, live, torch.float32, "agg", want_t=False)
@@ -849,6 +857,14 @@ class _RGCNTransform(torch.autograd.Function):
                     dh = gemm_nt(gq, wn[:k1], out_dtype=out_dt)
                 else:
                     dx = gemm_nt(gq, wn[k1:], out_dtype=out_dt)
+            elif op == torch.float32 and gb.is_cuda and not ctx.stock:
+                gq = _tma_rows(gb)
+                if need_h and need_x:
+                    dh, dx = gemm_nt(gq, wn, out_dtype=torch.float32, split=k1)
+                elif need_h:
+                    dh = gemm_nt(gq, wn[:k1], out_dtype=torch.float32)
+                else:
+                    dx = gemm_nt(gq, wn[k1:], out_dtype=torch.float32)
             else:
                 if need_h:
                     dh = gb @ wn[:k1].t()
@@ -889,7 +905,7 @@ class _RGCNTransform(torch.autograd.Function):
             droot = (dwcat[k1:k1 + k2] if dwcat is not None else _mm_f32(xq.t(), gb)).contiguous().to(ctx.dtypes[2])
         if ctx.needs_input_grad[5] and dbias is None:
             dbias = _colsum_f32(gb).to(ctx.dtypes[3])
-        return dh, dx, dweight, dcomp, droot, dbias, None, None, None
+        return dh, dx, dweight, dcomp, droot, dbias, None, None, None, None
 
 
 class _RGCNTransformFirst(torch.autograd.Function):
@@ -1072,7 +1088,7 @@ def rgcn_transform(h: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, comp:
     if not use_tcgen05:
         op = torch.float32
     with torch.amp.autocast("cuda", enabled=False):
-        return _RGCNTransform.apply(h, x, weight, comp, root, bias, tuple(live), out_dt, op)
+        return _RGCNTransform.apply(h, x, weight, comp, root, bias, tuple(live), out_dt, op, not use_tcgen05)
 
 
 # ------------------------------------------------------------------------------ halo pack / unpack

@@ -54,7 +54,9 @@ def test_gemm_nt_rejects_bad_operands(cuda_dev):
     a = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)
     b = torch.zeros(64, 100, dtype=torch.bfloat16, device=cuda_dev)
     with pytest.raises(GmlmError):
-        gemm_nt(a.float(), b.float())                                     # fp32 operands
+        gemm_nt(a, b.half())                                              # mixed operand types
+    with pytest.raises(GmlmError):
+        gemm_nt(a.float(), b.float(), out_dtype=torch.bfloat16)           # fp32 operands give fp32
     with pytest.raises(GmlmError):
         gemm_nt(a, b[:, :96])                                             # K mismatch
     with pytest.raises(GmlmError):
@@ -76,6 +78,42 @@ def test_gemm_nt_ragged_shapes_and_sources(cuda_dev, m, n, ks, op):
     assert got.shape == (m, n) and got.dtype == torch.float32
     assert torch.isfinite(got).all()
     assert rel_err(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("m,n,ks", [(300, 512, (1200, 300)), (4097, 64, (1024, 256)), (1000, 100, (100,)), (50000, 128, (256, 64)),
+                                    (777, 36, (72, 20)), (2000, 4096, (512,)), (64, 8, (4,)), (22662, 512, (1200, 300)),
+                                    (9000, 320, (1703,))])
+@pytest.mark.parametrize("use_bias", [False, True])
+def test_gemm_nt_fp32_operands_3xtf32(cuda_dev, m, n, ks, use_bias):
+    """fp32 operands (the reference's eval mode, main.py:603) on the tf32 tensor cores as 3xTF32 -- hi/lo split in
+    shared memory, three MMAs per k-step -- against an fp64 product: the 1e-5 gate plain TF32 (2^-11) cannot meet."""
+    g = torch.Generator().manual_seed(m + n)
+    srcs = [torch.randn(m, k, generator=g).to(cuda_dev) for k in ks]
+    b = (torch.randn(n, sum(ks), generator=g) / sum(ks) ** 0.5).to(cuda_dev)
+    bias = torch.randn(n, generator=g).to(cuda_dev) if use_bias else None
+    got = gemm_nt(srcs, b, bias=bias)
+    ref = torch.cat([t.double() for t in srcs], dim=1) @ b.double().t()
+    if bias is not None:
+        ref = ref + bias.double()
+    assert got.shape == (m, n) and got.dtype == torch.float32
+    assert rel_err(got, ref) <= 2e-6
+    # per element, against |ref| + rms(ref): a dot product's rounding error scales with sum |a_k b_k| (~ rms of the
+    # outputs), not with a result that cancelled to nearly zero
+    from conftest import elementwise_err
+    assert elementwise_err(got, ref, atol_frac=1.0) <= 1e-5
+
+
+def test_gemm_nt_fp32_split_and_addend(cuda_dev):
+    g = torch.Generator().manual_seed(9)
+    m, k, n = 3000, 512, 1500
+    a = torch.randn(m, k, generator=g).to(cuda_dev)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).to(cuda_dev)
+    c1, c2 = gemm_nt(a, b, split=1200)
+    ref = a.double() @ b.double().t()
+    assert rel_err(c1, ref[:, :1200]) <= 2e-6 and rel_err(c2, ref[:, 1200:]) <= 2e-6
+    add = torch.randn(m, n, generator=g).to(cuda_dev)
+    got = gemm_nt(a, b, addend=add)
+    assert rel_err(got, ref + add.double()) <= 2e-6
 
 
 @pytest.mark.parametrize("n,split", [(1500, 1200), (1280, 1024), (330, 30), (96, 64)])
