@@ -913,14 +913,15 @@ class _RGCNTransformFirst(torch.autograd.Function):
     composition kernel in the "tf" layout, the same GEMM; backward dx = dZ @ [W | root]^T, dW = x^T dZ (fp32)."""
 
     @staticmethod
-    def forward(ctx, x, weight, comp, root, bias, live, out_dtype, op_dtype):
+    def forward(ctx, x, weight, comp, root, bias, live, out_dtype, op_dtype, stock=False):
         live = tuple(int(v) for v in live)
         S, fi, fo = len(live), weight.size(1), weight.size(2)
         bias_cat = None
         if bias is not None:
             bias_cat = torch.cat([bias.new_zeros(S * fo), bias.detach()]).float()
-        if op_dtype in _OPS16:
-            xq = _tma_rows(x, op_dtype)
+        ctx.stock = bool(stock)
+        if op_dtype in _OPS16 or (op_dtype == torch.float32 and out_dtype == torch.float32 and not stock):
+            xq = _tma_rows(x, op_dtype)                   # fp32 operands: 3xTF32 (the reference's eval mode)
             wn, wt = basis_compose(weight, comp, root, live, op_dtype, "tf", want_n=ctx.needs_input_grad[0])
             z = gemm_nt(xq, wt, bias=bias_cat, out_dtype=out_dtype)
         else:
@@ -941,7 +942,7 @@ class _RGCNTransformFirst(torch.autograd.Function):
         dx = dweight = dcomp = droot = dbias = None
         gb = gz if (gz.dtype == op and gz.is_contiguous()) else gz.to(op).contiguous()
         if ctx.needs_input_grad[0]:
-            if op in _OPS16:
+            if op in _OPS16 or (op == torch.float32 and gb.is_cuda and not ctx.stock):
                 dx = gemm_nt(_tma_rows(gb), wn, out_dtype=torch.bfloat16 if ctx.dtypes[4] == torch.bfloat16 else torch.float32)
                 if not dx.is_contiguous():
                     dx = dx.contiguous()
@@ -976,7 +977,7 @@ class _RGCNTransformFirst(torch.autograd.Function):
                 droot = dwn[:, S * fo:].contiguous().to(ctx.dtypes[2])
         if ctx.needs_input_grad[4] and dbias is None:
             dbias = _colsum_f32(gb[:, S * fo:]).to(ctx.dtypes[3])
-        return dx, dweight, dcomp, droot, dbias, None, None, None
+        return dx, dweight, dcomp, droot, dbias, None, None, None, None
 
 
 def linear_nt_ok(x: torch.Tensor, n_out: int) -> bool:
@@ -1073,7 +1074,7 @@ def rgcn_transform_first(x: torch.Tensor, graph: RelGraph, weight: torch.Tensor,
         op = torch.float32
     z_dt = out_dt if out_dt in _DT else torch.float32          # the gather kernels take fp32 / bf16
     with torch.amp.autocast("cuda", enabled=False):
-        z = _RGCNTransformFirst.apply(x, weight, comp, root, bias, tuple(live), z_dt, op)
+        z = _RGCNTransformFirst.apply(x, weight, comp, root, bias, tuple(live), z_dt, op, not use_tcgen05)
         fl, fm = csr_pack(fplan)
         bl, bm = csr_pack(bplan)
         out = torch.ops.gmlm.plan_aggregate(z.view(graph.num_src * (S + 1), fo), *fl, *bl, fm + bm)
