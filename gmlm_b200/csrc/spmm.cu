@@ -242,6 +242,166 @@ __global__ void __launch_bounds__(256, MINB) rows_kernel(const RowsParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------ rows kernel, narrow rows
+// Rows of at most 16 packs (F <= 64 / 128 bf16): 8- or 16-lane groups, two or four groups per warp.  The general
+// kernel above walks its rows in batches of LPR: with 8-lane groups and 79 % empty (dst,rel) rows one batch is
+// eight rows, two of them with edges, and the per-batch bookkeeping (row extents, ballots, run detection, one
+// flush per row) is paid per ~12 units of work; the groups of a warp also leave their inner loops at different
+// trip counts.  ncu (C4, F = 64): 727 M warp instructions for 21 M units, 13.4 of 32 lanes active per
+// instruction, DRAM 13 % busy (profiles/r2b_narrow_rows.md).  Four row loads per batch at 4 CTAs per SM (64
+// registers) beat eight at 3 (bwd F = 64: 1.21 vs 1.77 ms) and two at 5 (1.29 ms).  Here a group
+//   1. zero-fills ALL its rows with one coalesced 16-byte store per lane and row (warp-uniform loop),
+//   2. walks its edges [rowptr[r_lo], rowptr[r_hi]) in batches of U with the batch loop uniform over the warp,
+//      column indices / weights read with group-uniform (broadcast) loads one batch ahead, U row loads in flight,
+//   3. on a row end scales / packs / stores the accumulator over the zeros and finds the next NON-EMPTY row with one
+//      cooperative look-ahead (LPR row ends per load + ballot): empty rows cost nothing in the edge walk.
+// Same per-row summation order as the general kernel (CSR order, fp32): bit-identical results.
+template <typename T, int VEC, int LPR, int U, int MINB, bool WEIGHTED>
+__global__ void __launch_bounds__(256, MINB) rows_narrow_kernel(const RowsParams p) {
+  static_assert(LPR < 32, "narrow rows: several groups per warp");
+  constexpr int GROUPS = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % LPR;
+  const int g = lane / LPR;
+  const unsigned gmask = ((1u << LPR) - 1u) << (g * LPR);
+  // (Re-cutting the rows of a warp's groups at equal EDGE counts -- the plan balances rows + edges -- measured 8 %
+  // slower: the groups of a warp are balanced well enough, the binary searches cost more than they save.)
+  const int64_t group_id = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + g;
+  int64_t r_lo = 0, r_hi = 0;                       // a group past the plan keeps running with no rows (warp-wide votes)
+  if (group_id < p.n_groups) {
+    if (p.grp_row != nullptr) {
+      r_lo = __ldg(p.grp_row + group_id);
+      r_hi = __ldg(p.grp_row + group_id + 1);
+    } else {
+      r_lo = group_id * LPR;
+      r_hi = min(r_lo + LPR, p.num_rows);
+    }
+  }
+  const bool fvalid = gl * VEC < p.feat;
+  const T* __restrict__ xf = static_cast<const T*>(p.x) + gl * VEC;
+  T* __restrict__ outf = static_cast<T*>(p.out) + gl * VEC;
+  const uint32_t row_bytes = uint32_t(p.ldx) * uint32_t(sizeof(T));
+
+  // ---- 1. zeros
+  const int n_rows = int(r_hi - r_lo);
+  int t1 = n_rows;
+#pragma unroll
+  for (int d = LPR; d < 32; d <<= 1) t1 = max(t1, __shfl_xor_sync(0xffffffffu, t1, d));
+  for (int i = 0; i < t1; ++i) {
+    if (i < n_rows && fvalid) {
+      Pack<T, VEC> z;
+      z.zero();
+      z.store(outf + (r_lo + i) * p.ldo);
+    }
+  }
+
+  // ---- 2. edges
+  int e = 0, e_end = 0;
+  if (n_rows > 0) {
+    e = __ldg(p.rowptr + r_lo);
+    e_end = __ldg(p.rowptr + r_hi);
+  }
+  int64_t cur = r_lo - 1;                            // current row; its extent [cur_beg, cur_end)
+  int cur_beg = e, cur_end = e;
+  bool hub = false;
+  float acc[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+
+  // edge `at` starts the next non-empty row after `cur` (every row in between is empty): find it with a cooperative
+  // look-ahead (LPR row ends per load + ballot).  (A register window of row ends with the next window prefetched
+  // measured no faster: the row-end load is not what the walk waits for.)
+  auto advance = [&](int at) {
+    if (at >= e_end) {
+      cur = r_hi;
+      cur_beg = cur_end = e_end;
+      hub = false;
+      return;
+    }
+    int64_t base = cur + 1;
+    while (true) {
+      const int64_t r = base + gl;
+      const int v = r < r_hi ? __ldg(p.rowptr + r + 1) : 0x7fffffff;
+      const unsigned bits = (__ballot_sync(gmask, v > at) >> (g * LPR)) & ((1u << LPR) - 1u);
+      if (bits) {
+        const int j = __ffs(bits) - 1;
+        cur = base + j;
+        cur_end = __shfl_sync(gmask, v, j, LPR);
+        break;
+      }
+      base += LPR;
+    }
+    cur_beg = at;
+    hub = (cur_end - cur_beg) > p.hub_thresh;        // hub rows belong to the chunk path: walked over, not gathered
+  };
+  auto flush = [&]() {
+    if (!hub && fvalid) {
+      const float scale = (p.mean && cur_end - cur_beg > 1) ? 1.0f / float(cur_end - cur_beg) : 1.0f;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) acc[k] *= scale;
+      Pack<T, VEC> o;
+      o.pack(acc);
+      o.store(outf + cur * p.ldo);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) acc[k] = 0.f;
+  };
+
+  advance(e);
+  // column indices / weights: group-uniform (broadcast) loads, one batch ahead.  (One coalesced load per batch and
+  // group + shuffle broadcast -- the general kernel's scheme -- measured 30 % slower here: the shuffles sit in the
+  // dependency chain of every row load.)
+  int c_next[U];
+  float w_next[U];
+  int pre_at = -1;                                   // edge the prefetched indices start at
+  while (__any_sync(0xffffffffu, e < e_end)) {
+    while (hub && e < e_end) {                       // skip a hub row's edges
+      e = cur_end;
+      advance(e);
+    }
+    if (pre_at != e) {                               // first batch, or the cursor jumped over a hub row
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int ee = e + u;
+        c_next[u] = ee < e_end ? ld_stream(p.col + ee) : 0;
+        if (WEIGHTED) w_next[u] = ee < e_end ? ld_stream(p.w + ee) : 0.f;
+      }
+    }
+    Pack<T, VEC> v[U];
+    float wv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      wv[u] = WEIGHTED ? w_next[u] : 1.f;
+      if (e + u < e_end && fvalid) v[u].load(row_ptr(xf, c_next[u], row_bytes));
+    }
+    pre_at = e + U;                                  // the next batch's indices, under the row loads
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ee = pre_at + u;
+      c_next[u] = ee < e_end ? ld_stream(p.col + ee) : 0;
+      if (WEIGHTED) w_next[u] = ee < e_end ? ld_stream(p.w + ee) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ee = e + u;
+      if (ee < e_end) {
+        if (ee >= cur_end) {                         // the previous row is complete
+          flush();
+          advance(ee);
+        }
+        if (!hub && fvalid) {
+          float f[VEC];
+          v[u].unpack(f);
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) acc[k] = WEIGHTED ? fmaf(wv[u], f[k], acc[k]) : acc[k] + f[k];
+        }
+      }
+    }
+    if (e < e_end) e += U;
+  }
+  if (cur < r_hi && cur_end > cur_beg) flush();      // the last row with edges
+}
+
 // ------------------------------------------------------------------------------ chunk kernel
 // one group per hub chunk: out[c, :] = sum_{e in chunk c} w[e] * x[col[e], :]  (fp32 partial)
 template <typename T, int VEC, int CH, int LPR, int U, int MINB, bool WEIGHTED>
@@ -649,13 +809,36 @@ int launch_geo(Job& job, cudaStream_t st) {
   return GMLM_OK;
 }
 
+// narrow rows: rows_narrow_kernel for the rows, the general chunk kernel for the hub chunks
+template <typename T, int VEC, int LPR, int U, int MINB>
+int launch_narrow(Job& job, cudaStream_t st) {
+  constexpr int GROUPS = 32 / LPR;
+  const int64_t groups_per_cta = int64_t(256 / 32) * GROUPS;
+  RowsParams& p = job.rows;
+  if (p.grp_row == nullptr) p.n_groups = (p.num_rows + LPR - 1) / LPR;
+  const int64_t gx = (p.n_groups + groups_per_cta - 1) / groups_per_cta;
+  GMLM_REQUIRE(gx <= 0x7fffffffLL, "spmm: grid too large");
+  if (gx > 0) {
+    if (job.weighted) rows_narrow_kernel<T, VEC, LPR, U, MINB, true><<<unsigned(gx), 256, 0, st>>>(p);
+    else rows_narrow_kernel<T, VEC, LPR, U, MINB, false><<<unsigned(gx), 256, 0, st>>>(p);
+    GMLM_LAUNCH_CHECK();
+  }
+  if (!job.do_chunks) return GMLM_OK;
+  Job chunks_only = job;
+  chunks_only.do_rows = false;
+  return launch_geo<T, VEC, 1, LPR, U, MINB>(chunks_only, st);
+}
+
 template <typename T, int VEC>
 int launch_vec(Job& job, cudaStream_t st) {
   const int64_t width = job.rows.slab_width ? job.rows.slab_width : job.rows.feat;
   const int64_t nvec = (width + VEC - 1) / VEC;
   if (job.rows.slab_width) GMLM_REQUIRE(nvec <= 128, "spmm: per-head width above 128 packs is not supported");
-  if (nvec <= 8) return launch_geo<T, VEC, 1, 8, 8, 3>(job, st);
-  if (nvec <= 16) return launch_geo<T, VEC, 1, 16, 8, 3>(job, st);
+  // narrow rows without head slabs: the warp-uniform edge walk (spmm_variant 2 keeps the general kernel for A/B)
+  const bool narrow = job.do_rows && job.rows.slab_stride == 0 && job.rows.w_stride <= 1 && !job.rows.single &&
+                      tuning_spmm_variant() != 2;
+  if (nvec <= 8) return narrow ? launch_narrow<T, VEC, 8, 4, 4>(job, st) : launch_geo<T, VEC, 1, 8, 8, 3>(job, st);
+  if (nvec <= 16) return narrow ? launch_narrow<T, VEC, 16, 4, 4>(job, st) : launch_geo<T, VEC, 1, 16, 8, 3>(job, st);
   if (nvec <= 32) {
     if constexpr (VEC * sizeof(T) == 16) {
       // rows of exactly 512 bytes (F = 256 bf16 / 128 fp32), no head slabs: the hub chunks can take the

@@ -17,7 +17,8 @@ et = G.edge_type_from_degree(ei, n)
 g = G.get_rel_graph(ei, et, n, 5)
 S = g.num_slots
 a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-for feat in (64, 128, 256):
+import os
+for feat in [int(v) for v in os.environ.get("NARROW_FEATS", "64,128,256").split(",")]:
     x = synth.make_features(n, feat, device=dev, dtype=torch.bfloat16)
     gh = synth.make_features(n * S, feat, device=dev, seed=7, dtype=torch.bfloat16)
     for _ in range(2):
