@@ -52,6 +52,21 @@ def algorithmic_bytes(n_nodes, n_edges, feat, esize, live_rels):
     return fwd, bwd
 
 
+_ONES_CACHE = {}
+
+
+def _ones_like(y):
+    """Upstream gradient of the context legs, created once per shape: in training it comes out of the loss; a fresh
+    `ones_like` per step would put a [N, out] fill (0.8 ms at 2M x 768) inside every timed step."""
+    key = (tuple(y.shape), y.dtype, y.device)
+    t = _ONES_CACHE.get(key)
+    if t is None:
+        if len(_ONES_CACHE) > 4:
+            _ONES_CACHE.clear()
+        t = _ONES_CACHE[key] = torch.ones_like(y)
+    return t
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -371,7 +386,7 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
 
             def layer_step():
                 y = norm(conv(xg, g), fuse_gelu=True)
-                y.backward(torch.ones_like(y))
+                y.backward(_ones_like(y))
                 xg.grad = None
                 conv.zero_grad(set_to_none=True)     # as optimizer.zero_grad() does every step (main.py:439,530):
                 norm.zero_grad(set_to_none=True)     # gradients are written, not accumulated into last step's
@@ -409,7 +424,7 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
             def enc_step():
                 with torch.amp.autocast("cuda", enabled=use_autocast):
                     y = enc.get_graph_embeddings(xg, ei, et)
-                y.backward(torch.ones_like(y))
+                y.backward(_ones_like(y))
                 xg.grad = None
                 enc.zero_grad(set_to_none=True)      # optimizer.zero_grad() of the reference's loops (main.py:439,530)
 
@@ -498,7 +513,7 @@ def measure_small(args, key: str, with_stock: bool):
     def enc_step(m=enc):
         with torch.amp.autocast("cuda"):
             y = m.get_graph_embeddings(xg, ei)
-        y.backward(torch.ones_like(y))
+        y.backward(_ones_like(y))
         xg.grad = None
         m.zero_grad(set_to_none=True)                # optimizer.zero_grad() of the reference's loops (main.py:439,530)
 
@@ -527,7 +542,7 @@ def measure_small(args, key: str, with_stock: bool):
 
         def gat_step(m=gat):
             y = m(xg, ei)
-            y.backward(torch.ones_like(y))
+            y.backward(_ones_like(y))
             xg.grad = None
             m.zero_grad(set_to_none=True)
 
@@ -542,7 +557,7 @@ def measure_small(args, key: str, with_stock: bool):
             def ref_step():
                 with torch.amp.autocast("cuda"):
                     y = ref(xg, ei)
-                y.backward(torch.ones_like(y))
+                y.backward(_ones_like(y))
                 xg.grad = None
                 ref.zero_grad(set_to_none=True)
 
@@ -555,7 +570,7 @@ def measure_small(args, key: str, with_stock: bool):
 
                 def gref_step():
                     y = gref(xg, ei)
-                    y.backward(torch.ones_like(y))
+                    y.backward(_ones_like(y))
                     xg.grad = None
                     gref.zero_grad(set_to_none=True)
 

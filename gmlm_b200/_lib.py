@@ -54,8 +54,8 @@ SIGNATURES = {
                                  _p]),
     "gmlm_gemm_nt": (_int, [_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _p, _i64, _i64, _p, _i64, _i64, _p, _i64, _int, _int,
                             _p]),
-    "gmlm_gemm_nt_multi": (_int, [_int, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _p, _i64, _p, _p, _i64, _i64, _i64,
-                                  _p, _i64, _i64, _p, _i64, _int, _int, _p]),
+    "gmlm_gemm_nt_multi": (_int, [_int, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _p, _i64, _p, _p, _i64, _i64, _int,
+                                  C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _int, _int, _p]),
     "gmlm_gemm_tn_workspace_bytes": (_sz, [_int, C.POINTER(_i64), _i64, _i64]),
     "gmlm_gemm_tn": (_int, [_int, C.POINTER(_p), C.POINTER(_i64), C.POINTER(_i64), _p, _i64, _i64, _i64, _p, _i64, _int, _p,
                             _sz, _p]),

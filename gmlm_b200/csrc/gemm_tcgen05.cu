@@ -107,6 +107,8 @@ struct GemmParams {
   int n_src;              // A = [A_0 | .. | A_{n_src-1}]: one tensor map per source, never concatenated in memory
   int kb_end[kMaxSources];  // cumulative 64-column block counts of the sources (a source's last block may be partial:
   int k_off[kMaxSources];   // TMA zero-fills it); k_off = column of B where the source starts (cumulative TRUE widths)
+  int n_route;            // > 0: the N columns go to n_route outputs cut at route_end[] (multiples of 64 columns): every
+  int route_end[kMaxSources];  // 64- / 32-column epilogue chunk is routed to its output's tensor map (tiles may straddle)
   const float* bias;      // [N] or nullptr
   const void* addend;     // [M, N] of the output type or nullptr: C = A.B^T + bias + addend (residual folded in)
   int64_t ld_add;
@@ -185,8 +187,7 @@ constexpr size_t smem_bytes_for() {
 template <int BLOCK_N, typename OutT, bool X3 = false>
 __global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads, 1) gemm_nt_kernel(const __grid_constant__ SourceMaps tma_a,
                                                               const __grid_constant__ CUtensorMap tma_b,
-                                                              const __grid_constant__ CUtensorMap tma_c1,
-                                                              const __grid_constant__ CUtensorMap tma_c2,
+                                                              const __grid_constant__ SourceMaps tma_c,
                                                               const GemmParams p) {
   constexpr int STAGES = stages_for(BLOCK_N, X3);
   constexpr int BK = X3 ? 32 : BLOCK_K;              // elements per k-block: one 128-byte swizzle row
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads, 1) gemm_nt_ker
         if (lane == 0) mbar_arrive(smem_u32(tmem_empty + buf));
         continue;
       }
-      const CUtensorMap* cmap = second ? &tma_c2 : &tma_c1;
+      const CUtensorMap* cmap = second ? &tma_c.m[1] : &tma_c.m[0];
       const uint32_t t_lane = tmem_base + (uint32_t(quad * 32) << 16) + buf * BLOCK_N;
 #pragma unroll 1
       for (int ch = half; ch < N_CHUNKS; ch += 2, sp ^= (STG_BUFS - 1)) {
@@ -479,7 +480,14 @@ __global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads, 1) gemm_nt_ker
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA
         __syncwarp();
         if (lane == 0) {
-          tma_store_2d(cmap, smem_u32(sb), ccol0 + ch * CHUNK, m0 + quad * 32);
+          if (p.n_route > 0) {                             // route this chunk to the output that owns its columns
+            const int col = n0 + ch * CHUNK;
+            int o = 0;
+            while (o + 1 < p.n_route && col >= p.route_end[o]) ++o;
+            tma_store_2d(&tma_c.m[o], smem_u32(sb), col - (o ? p.route_end[o - 1] : 0), m0 + quad * 32);
+          } else {
+            tma_store_2d(cmap, smem_u32(sb), ccol0 + ch * CHUNK, m0 + quad * 32);
+          }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
@@ -571,8 +579,7 @@ int get_map(CUtensorMap* out, const void* base, int64_t rows, int64_t cols, int6
 }
 
 template <int BLOCK_N, typename OutT, bool X3 = false>
-int launch(const SourceMaps& a, const CUtensorMap& b, const CUtensorMap& c1, const CUtensorMap& c2, GemmParams p,
-           cudaStream_t st) {
+int launch(const SourceMaps& a, const CUtensorMap& b, const SourceMaps& c, GemmParams p, cudaStream_t st) {
   constexpr size_t smem = smem_bytes_for<BLOCK_N, X3>();
   static_assert(smem <= 227 * 1024, "tile configuration exceeds the shared memory of one SM");
   auto kern = gemm_nt_kernel<BLOCK_N, OutT, X3>;
@@ -586,7 +593,7 @@ int launch(const SourceMaps& a, const CUtensorMap& b, const CUtensorMap& c1, con
   p.n_tiles = p.tiles1 + (p.N - p.N1 + BLOCK_N - 1) / BLOCK_N;
   const int64_t tiles = int64_t((p.M + BLOCK_M - 1) / BLOCK_M) * p.n_tiles;
   const unsigned grid = unsigned(std::min<int64_t>(tiles, num_sms()));     // persistent: one CTA per SM
-  kern<<<grid, X3 ? kThreads + 128 : kThreads, smem, st>>>(a, b, c1, c2, p);
+  kern<<<grid, X3 ? kThreads + 128 : kThreads, smem, st>>>(a, b, c, p);
   GMLM_LAUNCH_CHECK();
   return GMLM_OK;
 }
@@ -607,9 +614,26 @@ int pick_block_n(int64_t n1, int64_t n2, bool x3) {
   return 32;
 }
 
+// outputs: n_out = 1 or 2 with any column split (tiles never straddle: the second output starts a new tile row of B),
+// or up to four outputs cut at multiples of 64 columns (tiles straddle, every epilogue chunk is routed)
 int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int64_t* Ks, const void* B, int64_t ldb,
-                 const float* bias, const void* addend, int64_t ld_add, int64_t M, int64_t N, void* C1, int64_t ldc1,
-                 int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream) {
+                 const float* bias, const void* addend, int64_t ld_add, int64_t M, int n_out, void* const* Cs,
+                 const int64_t* ldcs, const int64_t* Ns, int in_dtype, int out_dtype, void* stream) {
+  GMLM_REQUIRE(n_out >= 1 && n_out <= kMaxSources && Cs && ldcs && Ns, "gemm: 1..%d outputs", kMaxSources);
+  int64_t N = 0;
+  for (int i = 0; i < n_out; ++i) {
+    GMLM_REQUIRE(Cs[i] != nullptr && Ns[i] > 0, "gemm: output %d is empty", i);
+    N += Ns[i];
+  }
+  const bool route = n_out > 2;
+  if (route)
+    for (int i = 0; i + 1 < n_out; ++i)
+      GMLM_REQUIRE(Ns[i] % 64 == 0, "gemm: with more than two outputs every output but the last must be a multiple of 64 columns wide");
+  void* C1 = Cs[0];
+  int64_t ldc1 = ldcs[0];
+  int64_t N1 = (n_out == 2) ? Ns[0] : N;
+  void* C2 = n_out == 2 ? Cs[1] : nullptr;
+  int64_t ldc2 = n_out == 2 ? ldcs[1] : 0;
   GMLM_REQUIRE(n_src >= 1 && n_src <= kMaxSources, "gemm: 1..%d A sources", kMaxSources);
   GMLM_REQUIRE(in_dtype == GMLM_BF16 || in_dtype == GMLM_F16 || in_dtype == GMLM_F32,
                "gemm: operands must be GMLM_BF16, GMLM_F16 or GMLM_F32");
@@ -639,9 +663,14 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
     GMLM_REQUIRE(C2 != nullptr, "gemm: second output missing");
     GMLM_REQUIRE(addend == nullptr, "gemm: the addend goes with a single output");
   }
-  GMLM_REQUIRE((reinterpret_cast<uintptr_t>(C1) & 15) == 0 && (reinterpret_cast<uintptr_t>(C2) & 15) == 0 &&
-                   (ldc1 * esz) % 16 == 0 && (ldc2 * esz) % 16 == 0 && ldc1 >= N1 && ldc2 >= N - N1,
-               "gemm: outputs must be 16-byte aligned with a 16-byte row pitch");
+  if (!route)
+    GMLM_REQUIRE((reinterpret_cast<uintptr_t>(C1) & 15) == 0 && (reinterpret_cast<uintptr_t>(C2) & 15) == 0 &&
+                     (ldc1 * esz) % 16 == 0 && (ldc2 * esz) % 16 == 0 && ldc1 >= N1 && ldc2 >= N - N1,
+                 "gemm: outputs must be 16-byte aligned with a 16-byte row pitch");
+  for (int i = 0; route && i < n_out; ++i)
+    GMLM_REQUIRE((reinterpret_cast<uintptr_t>(Cs[i]) & 15) == 0 && (ldcs[i] * esz) % 16 == 0 && ldcs[i] >= Ns[i],
+                 "gemm: outputs must be 16-byte aligned with a 16-byte row pitch");
+  GMLM_REQUIRE(!(route && addend), "gemm: the addend goes with a single output");
   if (addend)
     GMLM_REQUIRE((reinterpret_cast<uintptr_t>(addend) & 15) == 0 && (ld_add * esz) % 16 == 0 && (N * esz) % 16 == 0 &&
                      ld_add >= N,
@@ -661,7 +690,8 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
   }
   GemmParams p{};
   SourceMaps ma;
-  CUtensorMap mb, mc1, mc2;
+  CUtensorMap mb;
+  SourceMaps mc;
   int kb = 0, koff = 0;
   for (int i = 0; i < kMaxSources; ++i) {
     if (i < n_src) {
@@ -678,10 +708,26 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
   int rc = get_map(&mb, B, N, K, ldb, bn, bk, in_dtype);
   if (rc) return rc;
   const int chunk = bn % (128 / esz) == 0 ? 128 / esz : 64 / esz;      // chunk_cols<BLOCK_N, OutT>()
-  rc = get_map(&mc1, C1, M, N1, ldc1, 32, chunk, out_dtype);
-  if (rc) return rc;
-  rc = N1 < N ? get_map(&mc2, C2, M, N - N1, ldc2, 32, chunk, out_dtype) : (mc2 = mc1, GMLM_OK);
-  if (rc) return rc;
+  if (route) {
+    int end = 0;
+    for (int i = 0; i < kMaxSources; ++i) {
+      if (i < n_out) {
+        if (int rc2 = get_map(&mc.m[i], Cs[i], M, Ns[i], ldcs[i], 32, chunk, out_dtype)) return rc2;
+        end += int(Ns[i]);
+      } else {
+        mc.m[i] = mc.m[0];
+      }
+      p.route_end[i] = end;
+    }
+    p.n_route = n_out;
+  } else {
+    rc = get_map(&mc.m[0], C1, M, N1, ldc1, 32, chunk, out_dtype);
+    if (rc) return rc;
+    rc = N1 < N ? get_map(&mc.m[1], C2, M, N - N1, ldc2, 32, chunk, out_dtype) : (mc.m[1] = mc.m[0], GMLM_OK);
+    if (rc) return rc;
+    mc.m[2] = mc.m[3] = mc.m[0];
+    p.n_route = 0;
+  }
   p.M = int(M); p.N = int(N); p.N1 = int(N1); p.n_src = n_src;
   p.bias = bias;
   p.addend = addend; p.ld_add = ld_add;
@@ -689,16 +735,16 @@ int gemm_general(int n_src, const void* const* A, const int64_t* lda, const int6
   cudaStream_t st = as_stream(stream);
   if (x3) {
     switch (bn) {
-      case 128: return launch<128, float, true>(ma, mb, mc1, mc2, p, st);
-      case 64: return launch<64, float, true>(ma, mb, mc1, mc2, p, st);
-      case 32: return launch<32, float, true>(ma, mb, mc1, mc2, p, st);
+      case 128: return launch<128, float, true>(ma, mb, mc, p, st);
+      case 64: return launch<64, float, true>(ma, mb, mc, p, st);
+      case 32: return launch<32, float, true>(ma, mb, mc, p, st);
     }
     return fail(GMLM_ERR_INVALID, "gemm: unsupported tile");
   }
 #define GMLM_GEMM_CASE(BN)                                                                     \
   case BN:                                                                                     \
-    return out_dtype == GMLM_F32 ? launch<BN, float>(ma, mb, mc1, mc2, p, st)                  \
-                                 : launch<BN, __nv_bfloat16>(ma, mb, mc1, mc2, p, st);
+    return out_dtype == GMLM_F32 ? launch<BN, float>(ma, mb, mc, p, st)                  \
+                                 : launch<BN, __nv_bfloat16>(ma, mb, mc, p, st);
   switch (bn) {
     GMLM_GEMM_CASE(256)
     GMLM_GEMM_CASE(160)
@@ -959,21 +1005,26 @@ using namespace gmlm;
 
 extern "C" int gmlm_gemm_nt_multi(int num_sources, const void* const* A_host, const int64_t* lda_host,
                                   const int64_t* K_host, const void* B, int64_t ldb, const float* bias,
-                                  const void* addend, int64_t ld_add, int64_t M, int64_t N, void* C1, int64_t ldc1,
-                                  int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream) {
+                                  const void* addend, int64_t ld_add, int64_t M, int num_outputs, void* const* C_host,
+                                  const int64_t* ldc_host, const int64_t* N_host, int in_dtype, int out_dtype,
+                                  void* stream) {
   GMLM_REQUIRE(A_host && lda_host && K_host, "gemm: null source table");
-  return gemm_general(num_sources, A_host, lda_host, K_host, B, ldb, bias, addend, ld_add, M, N, C1, ldc1, N1, C2, ldc2,
-                      in_dtype, out_dtype, stream);
+  return gemm_general(num_sources, A_host, lda_host, K_host, B, ldb, bias, addend, ld_add, M, num_outputs, C_host,
+                      ldc_host, N_host, in_dtype, out_dtype, stream);
 }
 
 extern "C" int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64_t lda2, int64_t K2,
                             const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1,
                             int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype,
                             void* stream) {
-  GMLM_REQUIRE(K1 > 0 && K2 >= 0 && A1 && (K2 == 0 || A2), "gemm: bad sizes");
+  GMLM_REQUIRE(K1 > 0 && K2 >= 0 && A1 && (K2 == 0 || A2) && N > 0, "gemm: bad sizes");
   const void* A[2] = {A1, A2};
   const int64_t lda[2] = {lda1, lda2}, Ks[2] = {K1, K2};
-  return gemm_general(K2 > 0 ? 2 : 1, A, lda, Ks, B, ldb, bias, nullptr, 0, M, N, C1, ldc1, N1, C2, ldc2, in_dtype,
+  const bool two = N1 > 0 && N1 < N;
+  GMLM_REQUIRE(!two || C2 != nullptr, "gemm: second output missing");
+  void* Cs[2] = {C1, C2};
+  const int64_t ldcs[2] = {ldc1, ldc2}, Ns[2] = {two ? N1 : N, N - N1};
+  return gemm_general(K2 > 0 ? 2 : 1, A, lda, Ks, B, ldb, bias, nullptr, 0, M, two ? 2 : 1, Cs, ldcs, Ns, in_dtype,
                       out_dtype, stream);
 }
 

@@ -599,7 +599,8 @@ def gemm_nt(a1, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Option
     a1: one [M,K1] tensor or a list of up to four [M,K_i] sources (never concatenated in memory); a2 [M,K2]
     (optional); b [N, sum K], all bf16 (or all fp16) with unit inner stride and a 16-byte row pitch (anything else is
     copied once); any K, N.  Returns C [M,N] (bf16 or fp32), or (C[:, :split], C[:, split:]) as two contiguous tensors
-    when ``split`` > 0.  ``addend`` [M,N] of the output type is added in the epilogue (single output only)."""
+    when ``split`` > 0, or a list of up to four tensors when ``split`` is a list of column widths (more than two:
+    multiples of 64).  ``addend`` [M,N] of the output type is added in the epilogue (single output only)."""
     lib = _lib.load()
     srcs = list(a1) if isinstance(a1, (list, tuple)) else [a1]
     if a2 is not None:
@@ -634,21 +635,34 @@ def gemm_nt(a1, b: torch.Tensor, bias: Optional[torch.Tensor] = None, a2: Option
             return torch.empty((m, cols), dtype=out_dtype, device=dev)
         return torch.empty((m, (cols + per - 1) // per * per), dtype=out_dtype, device=dev)[:, :cols]
 
+    if isinstance(split, (list, tuple)):
+        widths = [int(v) for v in split]
+        if sum(widths) != n or any(v <= 0 for v in widths) or not 1 <= len(widths) <= 4:
+            raise _lib.GmlmError(f"gemm_nt: output widths {widths} do not add up to N = {n}")
+        if len(widths) > 2 and any(v % 64 for v in widths[:-1]):
+            raise _lib.GmlmError("gemm_nt: more than two outputs must be cut at multiples of 64 columns")
+    elif split and 0 < split < n:
+        widths = [int(split), n - int(split)]
+    else:
+        widths = [n]
+    if addend is not None and len(widths) > 1:
+        raise _lib.GmlmError("gemm_nt: the addend goes with a single output")
     with torch.cuda.device(dev):
-        if split and 0 < split < n:
-            c1, c2 = alloc(split), alloc(n - split)
-        else:
-            split = 0
-            c1, c2 = alloc(n), None
+        outs = [alloc(v) for v in widths]
         k = len(srcs)
         ptrs = (C.c_void_p * k)(*[t.data_ptr() for t in srcs])
         ldas = (C.c_int64 * k)(*[_ld(t) for t in srcs])
         ks = (C.c_int64 * k)(*[int(t.size(1)) for t in srcs])
+        no = len(outs)
+        cptrs = (C.c_void_p * no)(*[t.data_ptr() for t in outs])
+        ldcs = (C.c_int64 * no)(*[_ld(t) for t in outs])
+        ns = (C.c_int64 * no)(*widths)
         _lib.check(lib.gmlm_gemm_nt_multi(k, ptrs, ldas, ks, _ptr(b), _ld(b), _ptr(bias32), _ptr(addend),
-                                          _ld(addend) if addend is not None else 0, m, n, _ptr(c1), _ld(c1), split,
-                                          _ptr(c2), _ld(c2) if c2 is not None else 0, _op_code(op), _DT[out_dtype],
-                                          _stream(dev)), "gemm_nt")
-    return (c1, c2) if c2 is not None else c1
+                                          _ld(addend) if addend is not None else 0, m, no, cptrs, ldcs, ns,
+                                          _op_code(op), _DT[out_dtype], _stream(dev)), "gemm_nt")
+    if isinstance(split, (list, tuple)):
+        return outs
+    return tuple(outs) if len(outs) > 1 else outs[0]
 
 
 def gemm_tn(srcs, g: torch.Tensor) -> torch.Tensor:
@@ -1011,13 +1025,22 @@ class _LinearNT(torch.autograd.Function):
         dxs = [None] * len(xq)
         if any(ctx.needs_input_grad[5:]):
             all_bf16 = all(d == torch.bfloat16 for d in ctx.dtypes[2])
-            dx = gemm_nt(_tma_rows(gb), wtq.t().contiguous(), out_dtype=torch.bfloat16 if all_bf16 else torch.float32)
-            k0 = 0
-            for i, x in enumerate(xq):
+            widths = [int(x.size(1)) for x in xq]
+            odt = torch.bfloat16 if all_bf16 else torch.float32
+            wt_t = wtq.t().contiguous()
+            if len(widths) <= 2 or all(v % 64 == 0 for v in widths[:-1]):
+                # one launch, one CONTIGUOUS gradient per source (epilogue chunks routed to up to four tensor maps):
+                # autograd's sums with the other gradients of a layer output stay vectorised
+                parts = gemm_nt(_tma_rows(gb), wt_t, out_dtype=odt, split=widths)
+            else:
+                dx = gemm_nt(_tma_rows(gb), wt_t, out_dtype=odt)
+                parts, k0 = [], 0
+                for v in widths:
+                    parts.append(dx[:, k0:k0 + v])
+                    k0 += v
+            for i, d in enumerate(parts):
                 if ctx.needs_input_grad[5 + i]:
-                    d = dx[:, k0:k0 + x.size(1)]
                     dxs[i] = d if d.dtype == ctx.dtypes[2][i] else d.to(ctx.dtypes[2][i])
-                k0 += x.size(1)
         if ctx.needs_input_grad[0]:
             # dWt = g^T [x_0 | x_1 | ..] as ([x..]^T g)^T: one tcgen05 reduction over the sources (+ 1^T g = dbias)
             with_bias = ctx.needs_input_grad[1] and len(xq) < 4

@@ -242,14 +242,17 @@ int gmlm_gemm_nt(const void* A1, int64_t lda1, int64_t K1, const void* A2, int64
                  const void* B, int64_t ldb, const float* bias, int64_t M, int64_t N, void* C1, int64_t ldc1,
                  int64_t N1, void* C2, int64_t ldc2, int in_dtype, int out_dtype, void* stream);
 /* the general form: A = [A_0 | .. | A_{n-1}] from up to 4 sources (one tensor map each: the layer outputs that feed
- * MultiScaleFusion, main.py:176-180, are never concatenated), and an optional addend [M,N] of the output type read
- * in the epilogue: C = A B^T + bias + addend (the residual adds `x1 + residual_proj1(x_feat)`, main.py:281-282,
- * 294-295, folded into the projection; single output only).  A_host / lda_host / K_host are HOST arrays; every
- * source but the last must be a multiple of 8 columns wide (its columns of B start on a 16-byte boundary). */
+ * MultiScaleFusion, main.py:176-180, are never concatenated), operands GMLM_BF16 / GMLM_F16 or GMLM_F32 (fp32 operands
+ * run as 3xTF32: hi/lo split in shared memory, three tf32 MMAs per k-step; fp32 output), and an optional addend [M,N]
+ * of the output type read in the epilogue: C = A B^T + bias + addend (the residual adds `x1 + residual_proj1(x_feat)`,
+ * main.py:281-282, 294-295, folded into the projection; single output only).  The N = sum N_i output columns go to
+ * `num_outputs` matrices: one, two with any split, or up to four cut at multiples of 64 columns (the input gradients of
+ * the fusion land contiguous per layer).  A_host / lda_host / K_host / C_host / ldc_host / N_host are HOST arrays;
+ * every source but the last must be a multiple of 16 bytes wide (its columns of B start on a 16-byte boundary). */
 int gmlm_gemm_nt_multi(int num_sources, const void* const* A_host, const int64_t* lda_host, const int64_t* K_host,
                        const void* B, int64_t ldb, const float* bias, const void* addend, int64_t ld_add, int64_t M,
-                       int64_t N, void* C1, int64_t ldc1, int64_t N1, void* C2, int64_t ldc2, int in_dtype,
-                       int out_dtype, void* stream);
+                       int num_outputs, void* const* C_host, const int64_t* ldc_host, const int64_t* N_host,
+                       int in_dtype, int out_dtype, void* stream);
 
 /* ---- A14 weight gradients on the tensor cores: D[sum K_i, N] (fp32) = [A_0 | A_1 | ..]^T . G, the reduction over all
  *      M rows (nodes) that autograd of [PyG] RGCNConv.forward's `h @ weight[r]`, `x @ root` (main.py:272) and of the

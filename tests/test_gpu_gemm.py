@@ -129,6 +129,26 @@ def test_gemm_nt_split_at_any_column(cuda_dev, n, split):
 
 
 @pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("widths", [(64, 128, 256, 512), (128, 64, 40), (256, 256, 256, 192), (64, 64, 64)])
+def test_gemm_nt_up_to_four_routed_outputs(cuda_dev, widths, out_dtype):
+    """More than two outputs: tiles straddle the cuts (multiples of 64 columns), every epilogue chunk is routed to its
+    output's tensor map -- the input gradients of MultiScaleFusion land contiguous per layer."""
+    g = torch.Generator().manual_seed(sum(widths))
+    m, k, n = 3001, 768, sum(widths)
+    a = torch.randn(m, k, generator=g).bfloat16().to(cuda_dev)
+    b = (torch.randn(n, k, generator=g) / k ** 0.5).bfloat16().to(cuda_dev)
+    outs = gemm_nt(a, b, out_dtype=out_dtype, split=list(widths))
+    ref = a.float() @ b.float().t()
+    assert len(outs) == len(widths)
+    c0 = 0
+    for o, w in zip(outs, widths):
+        assert o.shape == (m, w) and o.dtype == out_dtype
+        assert o.is_contiguous() or w % (16 // o.element_size()) != 0
+        assert rel_err(o, ref[:, c0:c0 + w]) <= (1e-5 if out_dtype == torch.float32 else 1e-2)
+        c0 += w
+
+
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("m,n,k", [(1000, 512, 300), (4099, 64, 256), (70, 128, 64), (2500, 1024, 512)])
 def test_gemm_nt_addend_in_the_epilogue(cuda_dev, m, n, k, out_dtype):
     """C = A B^T + bias + addend: the residual add of main.py:281-282 folded into the projection."""
