@@ -12,6 +12,8 @@
 // as accurate as the reference's two-pass form.
 #include <algorithm>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace gmlm {
@@ -101,9 +103,12 @@ __global__ void __launch_bounds__(kCta) colstats_kernel(const T* __restrict__ x,
   const int64_t cp = int64_t(blockIdx.x) * tpr + tx;
   const int64_t c0 = cp * VEC;
   const bool cvalid = c0 < C;
-  double s[VEC], q[VEC];
+  // per-thread running sums: fp64 for fp32 activations (the 1e-5 gate); bf16 activations (resolution 4e-3, ~100
+  // rows per thread) keep them in fp32 and widen only for the cross-thread / cross-CTA reduction
+  using AccT = typename std::conditional<sizeof(T) == 2, float, double>::type;
+  AccT s[VEC], q[VEC];
 #pragma unroll
-  for (int k = 0; k < VEC; ++k) s[k] = q[k] = 0.0;
+  for (int k = 0; k < VEC; ++k) s[k] = q[k] = AccT(0);
   if (cvalid) {
     // kU row loads in flight per thread (latency, not issue, bounds a one-load loop); fp32 partials
     // over those rows, flushed into the fp64 accumulators: error of a partial <= kU ulp(fp32)
@@ -129,14 +134,14 @@ __global__ void __launch_bounds__(kCta) colstats_kernel(const T* __restrict__ x,
         for (int k = 0; k < VEC; ++k) { ps[k] += f[k]; pq[k] = fmaf(f[k], f[k], pq[k]); }
       }
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) { s[k] += double(ps[k]); q[k] += double(pq[k]); }
+      for (int k = 0; k < VEC; ++k) { s[k] += AccT(ps[k]); q[k] += AccT(pq[k]); }
     }
   }
   // reduce over ty in fixed order
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
-    sh[0][threadIdx.x] = s[k];
-    sh[1][threadIdx.x] = q[k];
+    sh[0][threadIdx.x] = double(s[k]);
+    sh[1][threadIdx.x] = double(q[k]);
     __syncthreads();
     if (ty == 0 && cvalid) {
       double a = 0.0, b = 0.0;
