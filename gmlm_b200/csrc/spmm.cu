@@ -258,12 +258,12 @@ __global__ void __launch_bounds__(256, MINB) rows_kernel(const RowsParams p) {
 // Same per-row summation order as the general kernel (CSR order, fp32): bit-identical results.
 template <typename T, int VEC, int LPR, int U, int MINB, bool WEIGHTED>
 __global__ void __launch_bounds__(256, MINB) rows_narrow_kernel(const RowsParams p) {
-  static_assert(LPR < 32, "narrow rows: several groups per warp");
   constexpr int GROUPS = 32 / LPR;
+  constexpr unsigned kLprMask = LPR == 32 ? 0xffffffffu : ((1u << (LPR & 31)) - 1u);
   const int lane = threadIdx.x & 31;
   const int gl = lane % LPR;
   const int g = lane / LPR;
-  const unsigned gmask = ((1u << LPR) - 1u) << (g * LPR);
+  const unsigned gmask = kLprMask << (g * LPR);
   // (Re-cutting the rows of a warp's groups at equal EDGE counts -- the plan balances rows + edges -- measured 8 %
   // slower: the groups of a warp are balanced well enough, the binary searches cost more than they save.)
   const int64_t group_id = (int64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS + g;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256, MINB) rows_narrow_kernel(const RowsParams
     while (true) {
       const int64_t r = base + gl;
       const int v = r < r_hi ? __ldg(p.rowptr + r + 1) : 0x7fffffff;
-      const unsigned bits = (__ballot_sync(gmask, v > at) >> (g * LPR)) & ((1u << LPR) - 1u);
+      const unsigned bits = (__ballot_sync(gmask, v > at) >> (g * LPR)) & kLprMask;
       if (bits) {
         const int j = __ffs(bits) - 1;
         cur = base + j;
@@ -853,6 +853,9 @@ int launch_vec(Job& job, cudaStream_t st) {
         return var == 3 ? launch_chunk_tma<T, VEC, 1, 8, 3>(job, st) : launch_chunk_tma<T, VEC, 1, 12, 2>(job, st);
       }
     }
+    // (the edge-walk kernel instantiated for 32-lane rows measured slower than the general kernel: C4 F = 256 pair
+    // 3.07 + 2.74 ms against 2.99 + 2.50 ms, C5 forward 32.9 against 17.7 ms -- with one group per warp there is no
+    // divergence to remove, and zero-filling 40 M rows up front is a second pass over the output)
     // measured on B200 (C4, bf16 F=256): U=4 at 4 CTAs/SM beats U=8 at 3 CTAs/SM by 12 %
     if (job.unroll == 8) return launch_geo<T, VEC, 1, 32, 8, 3>(job, st);
     return launch_geo<T, VEC, 1, 32, 4, 4>(job, st);
