@@ -3,12 +3,13 @@
 // backward gather, and the hub plan that keeps power-law rows balanced and deterministic.
 //
 // All integer work: results are bit-exact against oracle/csr_ref.py and oracle/pyg_ref.py.
-// The radix sort / scan / select primitives are CUB (header library shipped with the CUDA
-// toolkit); everything graph-specific is written here.  This is HBM-bound byte shuffling:
-// coalesced 64-bit index reads, int32 outputs, grid sized in multiples of the SM count.
-#include <cub/cub.cuh>
+// The stable radix sort / exclusive scan / ordered selection are this library's own (primitives.cuh; round 1 used
+// CUB).  This is HBM-bound byte shuffling: coalesced 64-bit index reads, int32 outputs, grid sized in multiples of
+// the SM count.
+#include <algorithm>
 
 #include "common.cuh"
+#include "primitives.cuh"
 
 namespace gmlm {
 
@@ -242,12 +243,6 @@ __global__ void dst_plan_kernel(const int32_t* __restrict__ rowptr, const int32_
 }
 
 // ------------------------------------------------------------------ hub plan
-struct IsHub {
-  const int32_t* rowptr;
-  int32_t thresh;
-  __device__ __forceinline__ bool operator()(const int32_t& r) const { return rowptr[r + 1] - rowptr[r] > thresh; }
-};
-
 __global__ void hub_count_kernel(const int32_t* __restrict__ rowptr, int64_t num_rows, int32_t thresh,
                                  unsigned long long* __restrict__ counts) {
   unsigned long long hubs = 0, chunks = 0;
@@ -298,26 +293,9 @@ int bits_for(uint64_t n_keys) {  // number of key bits needed to represent value
   return b;
 }
 
-size_t sort_temp_bytes(int64_t E) {
-  size_t bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
-                                  (const int32_t*)nullptr, (int32_t*)nullptr, int(E), 0, 32, (cudaStream_t)0);
-  return bytes;
-}
-
-size_t scan_temp_bytes(int64_t n) {
-  size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, (const int32_t*)nullptr, (int32_t*)nullptr, int(n), (cudaStream_t)0);
-  return bytes;
-}
-
-size_t select_temp_bytes(int64_t n) {
-  size_t bytes = 0;
-  cub::CountingInputIterator<int32_t> it(0);
-  IsHub pred{nullptr, 0};
-  cub::DeviceSelect::If(nullptr, bytes, it, (int32_t*)nullptr, (int32_t*)nullptr, int(n), pred, (cudaStream_t)0);
-  return bytes;
-}
+size_t sort_temp_bytes(int64_t E) { return prim::sort_temp_bytes(E); }
+size_t scan_temp_bytes(int64_t n) { return prim::scan_temp_bytes(n); }
+size_t select_temp_bytes(int64_t n) { return prim::select_temp_bytes(n); }
 
 }  // namespace
 }  // namespace gmlm
@@ -470,14 +448,11 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
                                                         keys_in, vals_in, seg_of_edge, rowptr, d_flag);
   GMLM_LAUNCH_CHECK();
   // counts -> exclusive prefix (in place); entry [rows] is 0 on input so rowptr[rows] = E
-  size_t need = scan_temp_bytes(rows + 1);
-  GMLM_REQUIRE(need <= cub_bytes, "csr_build: scan workspace");
-  GMLM_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, need, rowptr, rowptr, int(rows + 1), st));
-  need = sort_temp_bytes(E);
-  GMLM_REQUIRE(need <= cub_bytes, "csr_build: sort workspace");
-  // LSD radix sort is stable: equal (dst,slot) keys keep the original edge order
-  GMLM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, need, keys_in, keys_out, vals_in, perm, int(E), 0,
-                                                bits_for(uint64_t(rows) + (keep ? 1 : 0)), st));
+  if (int rc = prim::exclusive_scan_i32(rowptr, rowptr, rows + 1, cub_ws, cub_bytes, st)) return rc;
+  // the LSD radix sort is stable: equal (dst,slot) keys keep the original edge order
+  if (int rc = prim::radix_sort_pairs(keys_in, vals_in, keys_out, perm, E, bits_for(uint64_t(rows) + (keep ? 1 : 0)),
+                                      cub_ws, cub_bytes, st))
+    return rc;
   gather_col_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, perm, E, col);
   GMLM_LAUNCH_CHECK();
   int flag = 0;
@@ -515,13 +490,10 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
   make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, keep, E, num_rows, keys_in, vals_in, rowptr_t,
                                                           d_flag);
   GMLM_LAUNCH_CHECK();
-  size_t need = scan_temp_bytes(num_rows + 1);
-  GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: scan workspace");
-  GMLM_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, need, rowptr_t, rowptr_t, int(num_rows + 1), st));
-  need = sort_temp_bytes(E);
-  GMLM_REQUIRE(need <= cub_bytes, "csr_transpose: sort workspace");
-  GMLM_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_ws, need, keys_in, keys_out, vals_in, perm_t, int(E), 0,
-                                                bits_for(uint64_t(num_rows) + (keep ? 1 : 0)), st));
+  if (int rc = prim::exclusive_scan_i32(rowptr_t, rowptr_t, num_rows + 1, cub_ws, cub_bytes, st)) return rc;
+  if (int rc = prim::radix_sort_pairs(keys_in, vals_in, keys_out, perm_t, E,
+                                      bits_for(uint64_t(num_rows) + (keep ? 1 : 0)), cub_ws, cub_bytes, st))
+    return rc;
   gather_payload_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(payload, edge_w, fwd_rowptr, perm_t, keep, E, payload_t,
                                                                w_t);
   GMLM_LAUNCH_CHECK();
@@ -575,18 +547,13 @@ int gmlm_hub_fill(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64
   void* cub_ws = cv.take<char>(0);
   GMLM_REQUIRE(ws_bytes > cv.used(), "hub_fill: workspace too small");
   size_t cub_bytes = ws_bytes - cv.used();
-  // ascending list of hub rows (DeviceSelect keeps input order)
-  cub::CountingInputIterator<int32_t> it(0);
-  IsHub pred{rowptr, thresh};
-  size_t need = select_temp_bytes(num_rows);
-  GMLM_REQUIRE(need <= cub_bytes, "hub_fill: select workspace");
-  GMLM_CUDA_TRY(cub::DeviceSelect::If(cub_ws, need, it, hub_row, d_num, int(num_rows), pred, st));
+  // ascending list of hub rows (the selection keeps input order)
+  (void)d_num;
+  if (int rc = prim::select_rows(rowptr, num_rows, thresh, hub_row, n_hub, cub_ws, cub_bytes, st)) return rc;
   hub_nchunks_kernel<<<int((n_hub + 1 + kThreads - 1) / kThreads), kThreads, 0, st>>>(rowptr, hub_row, n_hub, thresh,
                                                                                    hub_chunk_ptr);
   GMLM_LAUNCH_CHECK();
-  need = scan_temp_bytes(n_hub + 1);
-  GMLM_REQUIRE(need <= cub_bytes, "hub_fill: scan workspace");
-  GMLM_CUDA_TRY(cub::DeviceScan::ExclusiveSum(cub_ws, need, hub_chunk_ptr, hub_chunk_ptr, int(n_hub + 1), st));
+  if (int rc = prim::exclusive_scan_i32(hub_chunk_ptr, hub_chunk_ptr, n_hub + 1, cub_ws, cub_bytes, st)) return rc;
   int64_t threads = n_hub * 32;
   hub_fill_chunks_kernel<<<int((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(
       rowptr, hub_row, hub_chunk_ptr, n_hub, thresh, chunk_beg, chunk_end);
