@@ -100,6 +100,36 @@ def test_rel_csr_bit_exact(cuda_dev, name, hub_thresh):
                 assert np.all(e - b <= hub_thresh) and np.all(e - b > 0)
 
 
+@pytest.mark.parametrize("n,e,hub_thresh", [(3_000_000, 12_000_000, 256), (700_001, 5_000_003, 16)])
+def test_rel_csr_bit_exact_at_scale(cuda_dev, n, e, hub_thresh):
+    """The library's own scan / stable radix sort / selection at sizes with several scan levels (12 M keys = 2930 sort
+    tiles, a 750 k-entry digit table, 12 M segment counters) against torch's stable sort on the same device."""
+    ei = synth.rmat_edges(n, e, seed=13).to(cuda_dev)
+    et = G.edge_type_from_degree(ei, n)
+    g = G.RelGraph.build(ei, et, n, 5, hub_thresh=hub_thresh)
+    live = torch.tensor(g.live_rels, device=cuda_dev)
+    slot = torch.searchsorted(live, et)
+    S = len(g.live_rels)
+    key = ei[1] * S + slot
+    order = torch.sort(key, stable=True).indices
+    counts = torch.bincount(key, minlength=n * S)
+    rowptr = torch.zeros(n * S + 1, dtype=torch.int64, device=cuda_dev)
+    rowptr[1:] = torch.cumsum(counts, 0)
+    assert torch.equal(g.fwd.rowptr.long(), rowptr)
+    assert torch.equal(g.fwd.perm.long(), order)
+    assert torch.equal(g.fwd.col.long(), ei[0][order])
+    order_t = torch.sort(ei[0], stable=True).indices                    # transposed CSR: rows = source nodes
+    rowptr_t = torch.zeros(n + 1, dtype=torch.int64, device=cuda_dev)
+    rowptr_t[1:] = torch.cumsum(torch.bincount(ei[0], minlength=n), 0)
+    assert torch.equal(g.bwd.rowptr.long(), rowptr_t)
+    assert torch.equal(g.bwd.perm.long(), order_t)
+    assert torch.equal(g.bwd.col.long(), key[order_t])
+    hubs = torch.nonzero(counts > hub_thresh).flatten()
+    assert g.fwd.n_hub == hubs.numel()
+    if hubs.numel():
+        assert torch.equal(g.fwd.hub_row.long(), hubs)
+
+
 def test_csr_rejects_bad_indices(cuda_dev):
     ei = torch.tensor([[0, 1, 9], [1, 2, 0]]).to(cuda_dev)
     et = torch.tensor([0, 1, 2]).to(cuda_dev)
