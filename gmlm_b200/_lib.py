@@ -107,7 +107,7 @@ def load():
         fn.argtypes = args
     _lib = lib
     import os
-    for key in ("spmm_variant", "spmm_unroll"):          # A/B switches for measurements (development)
+    for key in ("spmm_variant", "spmm_unroll", "spmm_overlap"):          # A/B switches for measurements (development)
         val = os.environ.get("GMLM_" + key.upper())
         if val is not None:
             lib.gmlm_set_tuning(key.encode(), int(val))

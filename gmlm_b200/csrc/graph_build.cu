@@ -20,6 +20,8 @@ char* err_buf() {
 
 static int g_spmm_variant = 1;   // 0 = one row per walk, 1 = flat walk over runs of rows (default)
 static int g_spmm_unroll = 0;
+static int g_spmm_overlap = 0;   // 1 = the hub chunks (chunk + final kernels) run on a side stream beside the rows kernel
+int tuning_spmm_overlap() { return g_spmm_overlap; }
 int tuning_spmm_variant() { return g_spmm_variant; }
 int tuning_spmm_unroll() { return g_spmm_unroll; }
 static int g_halo_pull_ctas = 0;
@@ -312,6 +314,7 @@ int gmlm_set_tuning(const char* key, int value) {
   int old = -1;
   if (!strcmp(key, "spmm_variant")) { old = g_spmm_variant; g_spmm_variant = value; }
   else if (!strcmp(key, "spmm_unroll")) { old = g_spmm_unroll; g_spmm_unroll = value; }
+  else if (!strcmp(key, "spmm_overlap")) { old = g_spmm_overlap; g_spmm_overlap = value; }
   else if (!strcmp(key, "halo_pull_ctas")) { old = g_halo_pull_ctas; g_halo_pull_ctas = value; }
   else if (!strcmp(key, "halo_pull_threads")) { old = g_halo_pull_threads; g_halo_pull_threads = value; }
   return old;

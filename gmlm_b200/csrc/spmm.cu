@@ -36,6 +36,7 @@ namespace gmlm {
 int row_gather_map(void* out_map, const void* base, int64_t rows, int64_t cols, int64_t ld, int dtype);  // gemm_tcgen05.cu
 int tuning_spmm_variant();
 int tuning_spmm_unroll();
+int tuning_spmm_overlap();
 
 namespace {
 
@@ -740,7 +741,26 @@ struct Job {
   bool do_rows;
   bool do_chunks;
   int unroll;  // 0 = default
+  cudaStream_t chunk_stream = nullptr;   // where the chunk kernel goes (the caller's stream unless the hub path is forked)
+  bool forked = false;
 };
+
+// fork / join resources of the overlapped hub path: per host thread and device (events are reused across calls)
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static thread_local SideStream s[kMaxDevices];
+  SideStream& r = s[current_device()];
+  if (!r.stream) {
+    if (cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    if (cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming) != cudaSuccess)
+      return nullptr;
+  }
+  return &r;
+}
 
 template <typename T, int VEC, int CH, int NW, int SLOTS>
 int launch_chunk_tma(Job& job, cudaStream_t st) {
@@ -801,8 +821,9 @@ int launch_geo(Job& job, cudaStream_t st) {
     GMLM_REQUIRE(gx <= 0x7fffffffLL && gy <= 65535, "spmm: grid too large");
     if (gx > 0) {
       dim3 grid((unsigned)gx, (unsigned)gy);
-      if (job.weighted) chunk_kernel<T, VEC, CH, LPR, U, MINB, true><<<grid, 256, 0, st>>>(q);
-      else chunk_kernel<T, VEC, CH, LPR, U, MINB, false><<<grid, 256, 0, st>>>(q);
+      cudaStream_t cs = job.chunk_stream ? job.chunk_stream : st;
+      if (job.weighted) chunk_kernel<T, VEC, CH, LPR, U, MINB, true><<<grid, 256, 0, cs>>>(q);
+      else chunk_kernel<T, VEC, CH, LPR, U, MINB, false><<<grid, 256, 0, cs>>>(q);
       GMLM_LAUNCH_CHECK();
     }
   }
@@ -826,7 +847,7 @@ int launch_narrow(Job& job, cudaStream_t st) {
   if (!job.do_chunks) return GMLM_OK;
   Job chunks_only = job;
   chunks_only.do_rows = false;
-  return launch_geo<T, VEC, 1, LPR, U, MINB>(chunks_only, st);
+  return launch_geo<T, VEC, 1, LPR, U, MINB>(chunks_only, st);     // same stream (see gmlm_spmm_csr: never forked)
 }
 
 template <typename T, int VEC>
@@ -935,11 +956,30 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   q.w_stride = w_heads; q.slab_stride = head_width; q.slab_width = head_width;
   q.n_chunks = n_chunks; q.out = hub_ws;
 
+  // Overlapped hub path (tuning "spmm_overlap", default off): the chunk + final kernels work on rows the rows kernel
+  // skips, so they can be forked onto a side stream.  Measured: C5 32.45 -> 32.34 ms/step, C4 5.46 -> 5.33 -- the rows
+  // kernel fills every SM, the side stream only gets its tail, and both kernels already sit at the same ~70 % of DRAM
+  // peak (the LDG row-gather ceiling of profiles/r2_row_gather_tma_vs_ldg.log), so there is no idle resource to fill.
+  // Not for the narrow-row kernel (it zero-fills every row first, the hub rows included).
+  SideStream* side = nullptr;
+  {
+    const int64_t nvec_rows = (feat + fullvec - 1) / fullvec;
+    const bool narrow_path = aligned ? (nvec_rows <= 16 && head_width == 0 && w_heads <= 1) : (feat <= 16 && w_heads <= 1);
+    if (tuning_spmm_overlap() && n_hub > 0 && !narrow_path) side = side_stream();
+  }
+  if (side) {
+    GMLM_CUDA_TRY(cudaEventRecord(side->fork, st));
+    GMLM_CUDA_TRY(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    job.chunk_stream = side->stream;
+    job.forked = true;
+  }
   int rc;
   if (dtype == GMLM_F32) rc = aligned ? launch_vec<float, 4>(job, st) : launch_vec<float, 1>(job, st);
   else rc = aligned ? launch_vec<__nv_bfloat16, 8>(job, st) : launch_vec<__nv_bfloat16, 1>(job, st);
   if (rc) return rc;
   if (n_hub == 0) return GMLM_OK;
+  cudaStream_t st_rows = st;
+  if (side) st = side->stream;                       // the final kernel follows the chunk kernel
 
   int tpr = 256;
   if (feat <= 128) tpr = int((feat + 31) / 32) * 32;
@@ -953,5 +993,9 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
     hub_final_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(hub_ws, feat, rowptr, hub_row, hub_chunk_ptr, n_hub, tpr,
                                                             p.mean, static_cast<__nv_bfloat16*>(out), ldo);
   GMLM_LAUNCH_CHECK();
+  if (side) {                                        // join: the caller's stream continues after both branches
+    GMLM_CUDA_TRY(cudaEventRecord(side->join, side->stream));
+    GMLM_CUDA_TRY(cudaStreamWaitEvent(st_rows, side->join, 0));
+  }
   return GMLM_OK;
 }

@@ -42,7 +42,7 @@ extern "C" {
 
 int gmlm_abi_version(void);
 const char* gmlm_last_error(void);
-/* tuning knobs for A/B measurements: key in {"spmm_variant","spmm_unroll","halo_pull_ctas","halo_pull_threads"};
+/* tuning knobs for A/B measurements: key in {"spmm_variant","spmm_unroll","spmm_overlap","halo_pull_ctas","halo_pull_threads"};
  * returns old value (halo_pull_*: launch shape of gmlm_gather_rows_ptr when a pull shares the GPU with an aggregation) */
 int gmlm_set_tuning(const char* key, int value);
 
