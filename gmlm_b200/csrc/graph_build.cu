@@ -405,10 +405,10 @@ size_t gmlm_csr_workspace_bytes(int64_t E, int64_t num_rows) {
   size_t t = sort_temp_bytes(E);
   size_t s = scan_temp_bytes(num_rows + 1);
   size_t sel = select_temp_bytes(num_rows);
-  size_t cub_bytes = t > s ? t : s;
-  if (sel > cub_bytes) cub_bytes = sel;
+  size_t prim_bytes = t > s ? t : s;
+  if (sel > prim_bytes) prim_bytes = sel;
   // keys_in, keys_out (u32), vals_in (i32) + hub scratch (2 x u64) + the per-call error flag + alignment slack
-  return cub_bytes + 3 * (size_t(E) * 4 + 256) + 4096;
+  return prim_bytes + 3 * (size_t(E) * 4 + 256) + 4096;
 }
 
 int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_type, const uint8_t* keep, int64_t E,
@@ -443,18 +443,18 @@ int gmlm_csr_build(const int64_t* src, const int64_t* dst, const int64_t* edge_t
   uint32_t* keys_out = cv.take<uint32_t>(E);
   int32_t* vals_in = cv.take<int32_t>(E);
   int* d_flag = cv.take<int>(1);
-  void* cub_ws = cv.take<char>(0);
-  size_t cub_bytes = ws_bytes - cv.used();
+  void* prim_ws = cv.take<char>(0);
+  size_t prim_bytes = ws_bytes - cv.used();
 
   GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   make_keys_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, dst, edge_type, keep, E, N, Nsrc, edge_type ? R : 1, sm, S,
                                                         keys_in, vals_in, seg_of_edge, rowptr, d_flag);
   GMLM_LAUNCH_CHECK();
   // counts -> exclusive prefix (in place); entry [rows] is 0 on input so rowptr[rows] = E
-  if (int rc = prim::exclusive_scan_i32(rowptr, rowptr, rows + 1, cub_ws, cub_bytes, st)) return rc;
+  if (int rc = prim::exclusive_scan_i32(rowptr, rowptr, rows + 1, prim_ws, prim_bytes, st)) return rc;
   // the LSD radix sort is stable: equal (dst,slot) keys keep the original edge order
   if (int rc = prim::radix_sort_pairs(keys_in, vals_in, keys_out, perm, E, bits_for(uint64_t(rows) + (keep ? 1 : 0)),
-                                      cub_ws, cub_bytes, st))
+                                      prim_ws, prim_bytes, st))
     return rc;
   gather_col_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(src, perm, E, col);
   GMLM_LAUNCH_CHECK();
@@ -486,16 +486,16 @@ int gmlm_csr_transpose(const int64_t* row_of_edge, const int32_t* payload, const
   uint32_t* keys_out = cv.take<uint32_t>(E);
   int32_t* vals_in = cv.take<int32_t>(E);
   int* d_flag = cv.take<int>(1);
-  void* cub_ws = cv.take<char>(0);
-  size_t cub_bytes = ws_bytes - cv.used();
+  void* prim_ws = cv.take<char>(0);
+  size_t prim_bytes = ws_bytes - cv.used();
 
   GMLM_CUDA_TRY(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
   make_keys_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(row_of_edge, keep, E, num_rows, keys_in, vals_in, rowptr_t,
                                                           d_flag);
   GMLM_LAUNCH_CHECK();
-  if (int rc = prim::exclusive_scan_i32(rowptr_t, rowptr_t, num_rows + 1, cub_ws, cub_bytes, st)) return rc;
+  if (int rc = prim::exclusive_scan_i32(rowptr_t, rowptr_t, num_rows + 1, prim_ws, prim_bytes, st)) return rc;
   if (int rc = prim::radix_sort_pairs(keys_in, vals_in, keys_out, perm_t, E,
-                                      bits_for(uint64_t(num_rows) + (keep ? 1 : 0)), cub_ws, cub_bytes, st))
+                                      bits_for(uint64_t(num_rows) + (keep ? 1 : 0)), prim_ws, prim_bytes, st))
     return rc;
   gather_payload_t_kernel<<<grid_for(E, 2), kThreads, 0, st>>>(payload, edge_w, fwd_rowptr, perm_t, keep, E, payload_t,
                                                                w_t);
@@ -547,16 +547,16 @@ int gmlm_hub_fill(const int32_t* rowptr, int64_t num_rows, int32_t thresh, int64
   cudaStream_t st = as_stream(stream);
   Carver cv(ws);
   int32_t* d_num = cv.take<int32_t>(1);
-  void* cub_ws = cv.take<char>(0);
+  void* prim_ws = cv.take<char>(0);
   GMLM_REQUIRE(ws_bytes > cv.used(), "hub_fill: workspace too small");
-  size_t cub_bytes = ws_bytes - cv.used();
+  size_t prim_bytes = ws_bytes - cv.used();
   // ascending list of hub rows (the selection keeps input order)
   (void)d_num;
-  if (int rc = prim::select_rows(rowptr, num_rows, thresh, hub_row, n_hub, cub_ws, cub_bytes, st)) return rc;
+  if (int rc = prim::select_rows(rowptr, num_rows, thresh, hub_row, n_hub, prim_ws, prim_bytes, st)) return rc;
   hub_nchunks_kernel<<<int((n_hub + 1 + kThreads - 1) / kThreads), kThreads, 0, st>>>(rowptr, hub_row, n_hub, thresh,
                                                                                    hub_chunk_ptr);
   GMLM_LAUNCH_CHECK();
-  if (int rc = prim::exclusive_scan_i32(hub_chunk_ptr, hub_chunk_ptr, n_hub + 1, cub_ws, cub_bytes, st)) return rc;
+  if (int rc = prim::exclusive_scan_i32(hub_chunk_ptr, hub_chunk_ptr, n_hub + 1, prim_ws, prim_bytes, st)) return rc;
   int64_t threads = n_hub * 32;
   hub_fill_chunks_kernel<<<int((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(
       rowptr, hub_row, hub_chunk_ptr, n_hub, thresh, chunk_beg, chunk_end);
