@@ -260,9 +260,16 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
 
     launches_per_step = 2 + (2 if g.fwd.n_hub else 0) + (2 if g.bwd.n_hub else 0)
 
+    # the two outputs live in buffers allocated ONCE (as a training loop's steady state does through the caching
+    # allocator): a fresh 20 GB `torch.empty` per call made single steps of the timed loop stall for ~100 ms whenever
+    # the allocator had to return cached blocks to the driver (cudaFree synchronises) -- one run in four measured a
+    # 28-30 ms forward mean against 17.7 ms for exactly the same kernels (per-step min / max are in the line)
+    h_buf = torch.empty((n * S, feat), dtype=dtype, device=dev)
+    gx_buf = torch.empty((n, feat), dtype=dtype, device=dev)
+
     def step():
-        h = G.spmm(x, g.fwd, _lib.AGG_MEAN)             # A5  forward propagate (all relations)
-        gx = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)       # A14 backward propagate
+        h = G.spmm(x, g.fwd, _lib.AGG_MEAN, out=h_buf)             # A5  forward propagate (all relations)
+        gx = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED, out=gx_buf)      # A14 backward propagate
         return h, gx
 
     sampler = ClockSampler(0)
@@ -283,9 +290,9 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
     t_start.record()
     for k in range(args.steps):
         ev[k][0].record()
-        h = G.spmm(x, g.fwd, _lib.AGG_MEAN)
+        h = G.spmm(x, g.fwd, _lib.AGG_MEAN, out=h_buf)
         ev[k][1].record()
-        gx = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED)
+        gx = G.spmm(gh, g.bwd, _lib.AGG_WEIGHTED, out=gx_buf)
         ev[k][2].record()
     t_end.record()
     torch.cuda.synchronize()
@@ -330,6 +337,7 @@ def measure_single(args, key: str, extras: bool, with_cpu: bool):
     roof_step = {"achieved": (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9, "peak": peak,
                  "frac": (fwd_b + bwd_b) / (ms_per_step * 1e-3) / 1e9 / peak, "unit": "GB/s"}
 
+    del h, gx, h_buf, gx_buf                     # 25 GB on C5: the legs below allocate their own
     # ---- e2e: public autograd API, x from pinned host memory every step, scalar result read back
     #      (a copy stream double-buffers the next step's H2D under the current step's kernels)
     x_host = x.cpu().pin_memory()

@@ -956,6 +956,10 @@ extern "C" int gmlm_spmm_csr(const void* x, int dtype, int64_t feat, int64_t ldx
   q.w_stride = w_heads; q.slab_stride = head_width; q.slab_width = head_width;
   q.n_chunks = n_chunks; q.out = hub_ws;
 
+  // (Also measured and not kept: `prefetch.global.L2` of the rows the NEXT index batch gathers, issued by each lane while
+  // the current batch is in flight -- bytes in flight towards L2 without registers: C5 forward 17.7 -> 18.8 ms in the
+  // rows kernel alone, 32 ms with the chunk kernel prefetching too: the extra instructions and the L2 churn cost more
+  // than the earlier arrival buys.)
   // Overlapped hub path (tuning "spmm_overlap", default off): the chunk + final kernels work on rows the rows kernel
   // skips, so they can be forked onto a side stream.  Measured: C5 32.45 -> 32.34 ms/step, C4 5.46 -> 5.33 -- the rows
   // kernel fills every SM, the side stream only gets its tail, and both kernels already sit at the same ~70 % of DRAM
