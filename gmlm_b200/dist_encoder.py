@@ -18,7 +18,6 @@ refuse CPU tensors.
 """
 from __future__ import annotations
 
-from typing import Optional
 
 import torch
 import torch.distributed as dist

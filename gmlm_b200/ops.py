@@ -994,11 +994,6 @@ class _RGCNTransformFirst(torch.autograd.Function):
         return dx, dweight, dcomp, droot, dbias, None, None, None, None
 
 
-def linear_nt_ok(x: torch.Tensor, n_out: int) -> bool:
-    """Inputs ``linear_nt`` runs on the tcgen05 GEMM without an explicit operand type: bf16 CUDA activations."""
-    return x.is_cuda and x.dim() == 2 and x.dtype == torch.bfloat16 and x.size(1) > 0 and n_out > 0
-
-
 class _LinearNT(torch.autograd.Function):
     """y = [x_0 | x_1 | ..] @ wt.T + bias (+ addend) on the tcgen05 GEMM (16-bit operands, fp32 accumulation).  The
     sources are never concatenated (MultiScaleFusion, main.py:176-180); ``addend`` is a residual folded into the
