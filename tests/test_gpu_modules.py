@@ -358,6 +358,51 @@ def test_rgcn_conv_arbitrary_relation_ids_and_no_basis(cuda_dev):
             assert rel_err(mod.comp.grad, ref.comp.grad) <= 2e-5 and torch.count_nonzero(mod.comp.grad[4]) > 0
 
 
+@pytest.mark.parametrize("mode", ["fp32", "autocast", "bf16"])
+@pytest.mark.parametrize("root_weight,bias", [(False, True), (True, False), (False, False)])
+def test_rgcn_conv_without_root_or_bias(cuda_dev, mode, root_weight, bias):
+    """Upstream's root_weight=False / bias=False (not used by the reference, part of the constructor it calls): the
+    single-source GEMM, the weight-gradient reduction without the x source and without the ones source."""
+    torch.manual_seed(9)
+    n, e, fi, fo = 600, 7000, 64, 128
+    ei = synth.rmat_edges(n, e, seed=8)
+    et = edge_type_bucket_ref(ei, n)
+    ref = RGCNConvRef(fi, fo, 5, 30).double()
+    with torch.no_grad():
+        ref.bias.uniform_(-0.1, 0.1)
+        if not root_weight:
+            ref.root.zero_()
+        if not bias:
+            ref.bias.zero_()
+    dt = torch.bfloat16 if mode == "bf16" else torch.float32
+    mod = G.RGCNConv(fi, fo, 5, 30, root_weight=root_weight, bias=bias, out_dtype=dt if mode == "bf16" else None)
+    sd = {k: v.float() for k, v in ref.state_dict().items()}
+    if not root_weight:
+        sd.pop("root")
+    if not bias:
+        sd.pop("bias")
+    mod.load_state_dict(sd)
+    mod = mod.to(cuda_dev)
+    x = torch.randn(n, fi).to(dt)
+    gout = torch.randn(n, fo).to(dt)
+    x64 = x.double().requires_grad_(True)
+    y_ref = ref(x64, ei, et)
+    y_ref.backward(gout.double())
+    xg = x.to(cuda_dev).requires_grad_(True)
+    with torch.amp.autocast("cuda", enabled=mode == "autocast"):
+        y = mod(xg, ei.to(cuda_dev), et.to(cuda_dev))
+    y.backward(gout.to(cuda_dev).to(y.dtype))
+    tol = {"fp32": 1e-5, "autocast": 2e-3, "bf16": 2e-2}[mode]
+    gtol = {"fp32": 2e-5, "autocast": 5e-3, "bf16": 2e-2}[mode]
+    assert rel_err(y, y_ref) <= tol
+    assert rel_err(xg.grad, x64.grad) <= tol
+    assert rel_err(mod.weight.grad, ref.weight.grad) <= gtol and rel_err(mod.comp.grad, ref.comp.grad) <= gtol
+    if root_weight:
+        assert rel_err(mod.root.grad, ref.root.grad) <= gtol
+    if bias:
+        assert rel_err(mod.bias.grad, ref.bias.grad) <= gtol
+
+
 def test_mask_sampler_on_cuda(cuda_dev):
     """§8f N2 on the device: the exponential-race sampler reproduces torch.multinomial for the same seed, and
     generate_active_node_mask (degrees from the gmlm_degree kernel) selects exactly num_select base nodes with
