@@ -176,6 +176,21 @@ def transpose_csr(row_of_edge: torch.Tensor, payload: torch.Tensor, num_rows: in
 
 
 @dataclass
+class SegPlan:
+    """Segment-compact view of a RelGraph (``RelGraph.seg_plan``): ``fwd`` rows = non-empty (dst, slot) segments in
+    slot-major order (slot s owns rows ``slot_start[s] .. slot_start[s] + slot_count[s]``), gather index = source
+    node; ``bwd`` rows = source nodes, gather index = compact row, weight = 1/|segment|; ``dst[k]`` = destination
+    node of compact row k."""
+    fwd: CSR
+    bwd: CSR
+    slot_start: List[int]
+    slot_count: List[int]
+    dst: torch.Tensor
+    num_rows: int
+    num_segments: int
+
+
+@dataclass
 class RelGraph:
     """Typed graph prepared for relational mean aggregation.
 
@@ -192,6 +207,7 @@ class RelGraph:
     seg_of_edge: Optional[torch.Tensor] = None   # int32 [E] forward segment of each ORIGINAL edge (kept on request)
     _keepalive: list = field(default_factory=list, repr=False)
     _dst_plan: Optional[tuple] = field(default=None, repr=False)
+    _seg_plan: Optional["SegPlan"] = field(default=None, repr=False)
 
     def __post_init__(self):
         if self.num_src < 0:
@@ -227,6 +243,61 @@ class RelGraph:
         b = transpose_csr(col_d.long(), dst_d, self.num_src * (S + 1), edge_w=w_d, hub_thresh=fwd.hub_thresh)
         self._dst_plan = (f, b)
         return self._dst_plan
+
+    def seg_plan(self) -> "SegPlan":
+        """The SEGMENT-COMPACT formulation (built on first use, kept with the graph): only the non-empty (dst, slot)
+        segments become rows, ordered slot-major, so that the dense transform of relation s is ONE GEMM over the
+        contiguous compact rows of slot s and multiplies no zero rows (79 % of the (dst, rel) rows of a power-law graph
+        with degree-bucket relations are empty; 64 % on the Roman-empire shape).  The edges of a compact row keep their
+        CSR order: its mean is bit-identical to the dense row's."""
+        if self._seg_plan is not None:
+            return self._seg_plan
+        fwd, S, N = self.fwd, self.num_slots, self.num_nodes
+        dev = fwd.rowptr.device
+        rp = fwd.rowptr.long()
+        lens = rp[1:] - rp[:-1]
+        sid = torch.nonzero(lens > 0).flatten()                      # non-empty segments, dst-major
+        slot, dst = sid % S, sid // S
+        order = torch.argsort(slot * N + dst)                        # slot-major (keys are unique)
+        cseg, dst_c, slot_c = sid[order], dst[order], slot[order]
+        counts = torch.bincount(slot_c, minlength=S).cpu().tolist()  # one host read per graph
+        # every slot starts on a multiple of 8 compact rows (a 16-byte boundary of the GEMM operand whatever the row
+        # width); the padding rows are empty
+        starts, rows = [], 0
+        for c in counts:
+            starts.append(rows)
+            rows += (c + 7) // 8 * 8
+        pos = torch.empty(cseg.numel(), dtype=torch.int64, device=dev)   # compact row of each non-empty segment
+        off = 0
+        for s_, c in enumerate(counts):
+            pos[off:off + c] = torch.arange(starts[s_], starts[s_] + c, device=dev)
+            off += c
+        lens_c = torch.zeros(rows, dtype=torch.int64, device=dev)
+        lens_c[pos] = lens[cseg]
+        rowptr_c = torch.zeros(rows + 1, dtype=torch.int64, device=dev)
+        rowptr_c[1:] = torch.cumsum(lens_c, 0)
+        E = int(rowptr_c[-1].item()) if rows else 0
+        old_start = torch.zeros(rows, dtype=torch.int64, device=dev)
+        old_start[pos] = rp[cseg]
+        e_idx = torch.repeat_interleave(old_start - rowptr_c[:-1], lens_c) + torch.arange(E, device=dev)
+        col_c = fwd.col[e_idx].contiguous()
+        crow = torch.repeat_interleave(torch.arange(rows, device=dev), lens_c).int()
+        f = CSR(rowptr=rowptr_c.int(), col=col_c, num_rows=rows, hub_thresh=fwd.hub_thresh)
+        f.plan_hubs()
+        f.plan_groups()
+        b = transpose_csr(col_c.long(), crow, self.num_src, fwd_rowptr=f.rowptr, hub_thresh=fwd.hub_thresh)
+        dst_rows = torch.zeros(rows, dtype=torch.int64, device=dev)
+        dst_rows[pos] = dst_c
+        self._seg_plan = SegPlan(fwd=f, bwd=b, slot_start=starts, slot_count=counts, dst=dst_rows, num_rows=rows,
+                                 num_segments=int(cseg.numel()))
+        return self._seg_plan
+
+    @property
+    def num_nonempty_segments(self) -> int:
+        if getattr(self, "_nseg", None) is None:
+            rp = self.fwd.rowptr
+            self._nseg = int((rp[1:] > rp[:-1]).sum().item())
+        return self._nseg
 
     @staticmethod
     def build(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int, num_relations: int,

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from . import _lib
 from .graph import RelGraph, get_rel_graph
-from .ops import graph_norm, rgcn_aggregate, rgcn_transform, rgcn_transform_first
+from .ops import graph_norm, rgcn_aggregate, rgcn_segment_compact, rgcn_transform, rgcn_transform_first
 
 
 def glorot_(t: Optional[torch.Tensor]):
@@ -47,6 +47,7 @@ class RGCNConv(nn.Module):
         self.out_dtype = out_dtype  # None = upstream behaviour (default dtype); bf16 for the bandwidth study
         self.use_tcgen05 = True     # 16-bit operand types (bf16 pipeline, autocast): dense transform on the tcgen05 GEMM
         self.transform_first = None  # None = by the byte-count model below; True / False force the formulation
+        self.segment_compact = None  # None = by the FLOP / byte model below; True / False force it
         if num_blocks is not None:
             raise NotImplementedError("gmlm_b200.RGCNConv: block-diagonal decomposition is not on the reference "
                                       "path (main.py uses num_bases=30)")
@@ -106,6 +107,25 @@ class RGCNConv(nn.Module):
         tr_first = 2 * graph.num_src * (S + 1) * fo + (graph.num_edges + graph.num_nodes) * fo
         return tr_first < 0.8 * agg_first
 
+    def _use_segment_compact(self, graph: RelGraph, x: torch.Tensor) -> bool:
+        """The segment-compact formulation (one GEMM per populated relation over the non-empty segments only) pays when
+        the layer is FLOP-bound and most (dst, rel) segments are empty: the reference's own graphs at its shipped
+        widths.  Dense cost ~ N*S*Fi*Fo flops against (N*S*Fi + N*Fo) operand bytes."""
+        if self.root is None or not x.is_cuda:
+            return False
+        if not (torch.is_autocast_enabled("cuda") or x.dtype == torch.bfloat16):
+            return False                                   # 16-bit operand types only
+        if self.segment_compact is not None:
+            return bool(self.segment_compact)
+        n, S, fi, fo = graph.num_nodes, graph.num_slots, self.in_channels, self.out_channels
+        if n == 0 or fi * fo < 128 * 128:
+            return False
+        flop_s = 2.0 * n * S * fi * fo / 1.2e15
+        byte_s = (2.0 * n * S * fi + 4.0 * n * fo) / 6.0e12
+        if flop_s < 2.0 * byte_s:
+            return False
+        return graph.num_nonempty_segments <= 0.6 * n * S
+
     def forward(self, x: torch.Tensor, edge_index, edge_type: Optional[torch.Tensor] = None) -> torch.Tensor:
         if isinstance(edge_index, RelGraph):
             graph = edge_index
@@ -120,6 +140,8 @@ class RGCNConv(nn.Module):
         live = graph.live_rels
         if self.comp is not None and (self.comp.size(0) > 64 or len(live) > 8):
             return self._forward_torch(x, graph)     # sizes outside the composition kernel (never on the reference path)
+        if self.use_tcgen05 and self._use_segment_compact(graph, x) and not self._use_transform_first(graph):
+            return rgcn_segment_compact(x, graph, self.weight, self.comp, self.root, self.bias, self.out_dtype)
         if self._use_transform_first(graph):
             # narrowing layer: Z = x @ [W_r | root] first, then gather Fo-wide slabs; H is never materialised
             return rgcn_transform_first(x, graph, self.weight, self.comp, self.root, self.bias, self.out_dtype,

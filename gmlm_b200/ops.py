@@ -922,6 +922,123 @@ class _RGCNTransform(torch.autograd.Function):
         return dh, dx, dweight, dcomp, droot, dbias, None, None, None, None
 
 
+class _RGCNSegCompact(torch.autograd.Function):
+    """RGCNConv on the SEGMENT-COMPACT view of the graph (``RelGraph.seg_plan``; A5 + A4 + A6 of one layer):
+
+        H_c   = mean over the edges of every NON-EMPTY (dst, slot) segment            [rows_c, Fi]   (slot-major)
+        out   = x @ root + bias;   out[dst of slot s's rows] += H_c[slot s] @ W_s      one GEMM per populated slot
+
+    The dense form multiplies the zero rows of H: on the reference's own graphs most (dst, rel) segments are empty
+    (Roman-empire shape: 22.7k nodes x 4 slots = 90.6k segments, at most 32.9k with an edge), and at the shipped widths
+    (H = 512) the layer is FLOP-bound, so half of the forward, the [dH | dx] and the dW products are spent on zeros.
+    Here every product runs over the compact rows only.  Backward: g rows gathered per slot, dH_c = g_s @ W_s^T,
+    dW_s = H_c[s]^T g_s, [droot; dbias] = [x | 1]^T g, dx = g @ root^T + (transposed compact aggregation of dH_c).
+    A compact row's edges keep their CSR order, so H_c equals the dense H's rows bit for bit; the per-destination sum
+    over slots runs in slot order (the dense GEMM sums along K in the same slot order, with other roundings)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, comp, root, bias, plan, num_nodes, live, out_dtype, op_dtype):
+        live = tuple(int(v) for v in live)
+        S, fi, fo = len(live), weight.size(1), weight.size(2)
+        h_c = _spmm_csr(x, plan.fwd.rowptr, plan.fwd.col, None, plan.fwd.num_rows, _lib.AGG_MEAN, plan.fwd.grp_row,
+                        plan.fwd.hub_thresh, plan.fwd.hub_row, plan.fwd.hub_chunk_ptr, plan.fwd.chunk_beg,
+                        plan.fwd.chunk_end)
+        hq = _tma_rows(h_c, op_dtype)
+        xq = _tma_rows(x[:num_nodes], op_dtype)
+        wn, wt = basis_compose(weight, comp, root, live, op_dtype, "agg")
+        out = gemm_nt(xq, wt[:, S * fi:], bias=bias, out_dtype=out_dtype)          # root term + bias
+        for s in range(S):
+            a, c = plan.slot_start[s], plan.slot_count[s]
+            if c:
+                y = gemm_nt(hq[a:a + c], wt[:, s * fi:(s + 1) * fi], out_dtype=out_dtype)
+                scatter_add_rows_(out, plan.dst[a:a + c], y)
+        ctx.save_for_backward(hq, xq, wn, weight, comp)
+        ctx.plan, ctx.live, ctx.op, ctx.num_nodes = plan, live, op_dtype, num_nodes
+        ctx.dtypes = (weight.dtype, None if comp is None else comp.dtype, root.dtype,
+                      None if bias is None else bias.dtype, x.dtype)
+        ctx.num_src = x.size(0)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        hq, xq, wn, weight, comp = ctx.saved_tensors
+        plan, live, op, n = ctx.plan, ctx.live, ctx.op, ctx.num_nodes
+        S, fi, fo = len(live), weight.size(1), weight.size(2)
+        g = g.contiguous()
+        gq = _tma_rows(g, op)
+        acc_dt = torch.bfloat16 if ctx.dtypes[4] == torch.bfloat16 else torch.float32
+        dx = dweight = dcomp = droot = dbias = None
+        need_x = ctx.needs_input_grad[0]
+        need_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        g_src = g if g.dtype in _DT else g.float()                         # the row gather takes fp32 / bf16
+        dh_parts, dw = [], None
+        if need_w:
+            dw = torch.zeros((S * fi, fo), dtype=torch.float32, device=g.device)
+        rows_done = 0
+        for s in range(S):
+            a, c = plan.slot_start[s], plan.slot_count[s]
+            pad = (plan.slot_start[s + 1] if s + 1 < S else plan.num_rows) - a - c
+            if c:
+                gs = _tma_rows(gather_rows(g_src, plan.dst[a:a + c]), op)
+                if need_x:
+                    dh_parts.append(gemm_nt(gs, wn[s * fi:(s + 1) * fi], out_dtype=acc_dt))
+                if need_w:
+                    dw[s * fi:(s + 1) * fi] = gemm_tn([hq[a:a + c]], gs)
+            if need_x and pad:
+                dh_parts.append(torch.zeros((pad, fi), dtype=acc_dt, device=g.device))
+            rows_done = a + c + pad
+        if need_x:
+            dh_c = torch.cat(dh_parts, dim=0) if dh_parts else torch.zeros((0, fi), dtype=acc_dt, device=g.device)
+            b = plan.bwd
+            if dh_c.size(0) == 0:                                                         # a graph without edges
+                dx = torch.zeros((ctx.num_src, fi), dtype=acc_dt, device=g.device)
+            else:
+                dx = _spmm_csr(dh_c, b.rowptr, b.col, b.w, b.num_rows, _lib.AGG_WEIGHTED, b.grp_row, b.hub_thresh,
+                               b.hub_row, b.hub_chunk_ptr, b.chunk_beg, b.chunk_end)      # [num_src, Fi]
+            dxr = gemm_nt(gq, wn[S * fi:], out_dtype=acc_dt)                              # root term, local rows
+            if dx.size(0) == dxr.size(0):
+                dx = dx + dxr
+            else:
+                dx[:n] += dxr
+            if dx.dtype != ctx.dtypes[4]:
+                dx = dx.to(ctx.dtypes[4])
+        if ctx.needs_input_grad[3] or ctx.needs_input_grad[4]:
+            srcs = [xq] + ([_ones_source(gq.size(0), op, gq.device)] if ctx.needs_input_grad[4] else [])
+            d = gemm_tn(srcs, gq)
+            if ctx.needs_input_grad[3]:
+                droot = d[:fi].contiguous().to(ctx.dtypes[2])
+            if ctx.needs_input_grad[4]:
+                dbias = d[fi].to(ctx.dtypes[3])
+        if need_w:
+            if _compose_bwd_ok(weight, S) or comp is None:
+                dweight, dcomp = basis_compose_bwd(weight, comp, dw, fi * fo, fo, live, ctx.needs_input_grad[1],
+                                                   ctx.needs_input_grad[2] and comp is not None)
+            else:
+                dws = dw.view(S, fi * fo)
+                cl = comp.detach().float()[list(live)]
+                dweight = (cl.t() @ dws).view_as(weight)
+                dcomp = torch.zeros_like(comp, dtype=torch.float32)
+                dcomp[list(live)] = dws @ weight.detach().float().view(weight.size(0), -1).t()
+            dweight = dweight.to(ctx.dtypes[0]) if dweight is not None else None
+            dcomp = dcomp.to(ctx.dtypes[1]) if dcomp is not None else None
+        return dx, dweight, dcomp, droot, dbias, None, None, None, None, None
+
+
+def rgcn_segment_compact(x: torch.Tensor, graph: RelGraph, weight: torch.Tensor, comp: Optional[torch.Tensor],
+                         root: torch.Tensor, bias: Optional[torch.Tensor],
+                         out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """RGCNConv over the non-empty segments only (see ``_RGCNSegCompact``); 16-bit operand types."""
+    _require_cuda(x, "x")
+    op, out_dt = _dense_dtypes(x, out_dtype)
+    if op not in _OPS16 or out_dt not in _DT:
+        raise _lib.GmlmError("rgcn_segment_compact: 16-bit operand types (bf16 pipeline or autocast) only")
+    if x.dtype not in _DT:
+        x = x.float()
+    with torch.amp.autocast("cuda", enabled=False):
+        return _RGCNSegCompact.apply(x, weight, comp, root, bias, graph.seg_plan(), graph.num_nodes,
+                                     tuple(graph.live_rels), out_dt, op)
+
+
 class _RGCNTransformFirst(torch.autograd.Function):
     """Z = x @ [W_0 | .. | W_{S-1} | root] (+ bias on the root slab) for a transform-first layer (A4 + A6): the same
     composition kernel in the "tf" layout, the same GEMM; backward dx = dZ @ [W | root]^T, dW = x^T dZ (fp32)."""
