@@ -280,7 +280,10 @@ from hypothesis import HealthCheck, given, settings, strategies as st  # noqa: E
 @given(n=st.integers(1, 300), e=st.integers(0, 3000), feat=st.sampled_from([3, 8, 20, 64, 72, 256]),
        seed=st.integers(0, 10_000), hub_thresh=st.sampled_from([2, 17, 256]), quantum=st.sampled_from([0, 5, 64]),
        bf16=st.booleans())
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+# derandomize: the suite draws the same 40 examples on every box (a gate that fails one run in fifty is no gate);
+# the random exploration of this space is tools/fuzz_spmm.py (thousands of examples per run)
+@settings(max_examples=40, deadline=None, derandomize=True, database=None,
+          suppress_health_check=[HealthCheck.function_scoped_fixture])
 def test_aggregate_property_random_graphs(cuda_dev, n, e, feat, seed, hub_thresh, quantum, bf16):
     """Random graphs (isolated nodes, multi-edges, self-loops, empty relations, N=1), random widths and
     every plan setting: forward and backward agree with the oracle and the integer structure is consistent."""
