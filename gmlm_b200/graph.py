@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import List, Optional
@@ -369,14 +370,30 @@ class RelGraph:
 #     what makes the advertised one-line import swap hit -- the reference builds a FRESH edge_type tensor on
 #     every get_graph_embeddings call (main.py:255), so identity alone would rebuild the CSR (two radix sorts,
 #     four host syncs) per layer call.  A content lookup costs one pass over the indices and one host read.
-# Entries hold strong references to the tensors of their FIRST key so that storage cannot be recycled under a
-# stale identity key; `_version` catches in-place edits.  Graphs are read-only after construction (checkpoint
-# recompute / autograd threads only read).
+# Alias entries hold strong references to their key tensors so that storage cannot be recycled under a stale
+# identity key; `_version` catches in-place edits.  What they pin is bounded in BYTES as well as in count: under
+# the import swap every call brings a fresh edge_type (8 bytes per edge -- 1.6 GB at 2e8 edges), so the oldest
+# aliases are dropped once the table holds more than `GMLM_GRAPH_ALIAS_BYTES` (default 1 GiB; the newest alias
+# always stays -- dropping an alias costs one checksum pass on the next call, never a rebuild).  Graphs are
+# read-only after construction; the tables themselves are guarded by a lock (checkpoint recompute and backward
+# run on autograd engine threads, one per device).
 _CACHE: "OrderedDict[tuple, RelGraph]" = OrderedDict()           # content key -> graph
-_ALIAS: "OrderedDict[tuple, tuple]" = OrderedDict()              # identity key -> (content key, keepalive tensors)
+_ALIAS: "OrderedDict[tuple, tuple]" = OrderedDict()              # identity key -> (content key, keepalive tensors, bytes)
 _CACHE_SIZE = int(os.environ.get("GMLM_GRAPH_CACHE", "4"))
 _ALIAS_SIZE = 64
+_ALIAS_BYTES = int(os.environ.get("GMLM_GRAPH_ALIAS_BYTES", str(1 << 30)))
+_LOCK = threading.RLock()
 cache_stats = {"identity_hits": 0, "content_hits": 0, "builds": 0}
+
+
+def _alias_put(ikey: tuple, ckey: tuple, tensors: tuple) -> None:
+    """Record identity key -> content key, keeping `tensors` alive; evict oldest-first by count and by bytes."""
+    nbytes = sum(t.numel() * t.element_size() for t in tensors if t is not None)
+    _ALIAS.pop(ikey, None)
+    _ALIAS[ikey] = (ckey, tensors, nbytes)
+    held = sum(v[2] for v in _ALIAS.values())
+    while len(_ALIAS) > 1 and (len(_ALIAS) > _ALIAS_SIZE or held > _ALIAS_BYTES):
+        held -= _ALIAS.popitem(last=False)[1][2]
 
 
 def _tensor_key(t: Optional[torch.Tensor]):
@@ -400,30 +417,30 @@ def _content_key(t: Optional[torch.Tensor]):
 def get_rel_graph(edge_index: torch.Tensor, edge_type: Optional[torch.Tensor], num_nodes: int,
                   num_relations: int) -> RelGraph:
     ikey = (_tensor_key(edge_index), _tensor_key(edge_type), int(num_nodes), int(num_relations))
-    hit = _ALIAS.get(ikey)
-    if hit is not None and hit[0] in _CACHE:
-        _ALIAS.move_to_end(ikey)
-        _CACHE.move_to_end(hit[0])
-        cache_stats["identity_hits"] += 1
-        return _CACHE[hit[0]]
-    _require_cuda(edge_index, "edge_index")
-    ckey = (_content_key(edge_index), _content_key(edge_type), int(num_nodes), int(num_relations))
-    g = _CACHE.get(ckey)
-    if g is None:
-        g = RelGraph.build(edge_index, edge_type, num_nodes, num_relations)
-        _CACHE[ckey] = g
-        cache_stats["builds"] += 1
-        while len(_CACHE) > _CACHE_SIZE:
-            _CACHE.popitem(last=False)
-    else:
-        _CACHE.move_to_end(ckey)
-        cache_stats["content_hits"] += 1
-    _ALIAS[ikey] = (ckey, (edge_index, edge_type))              # keep the key tensors alive with the alias
-    while len(_ALIAS) > _ALIAS_SIZE:
-        _ALIAS.popitem(last=False)
-    return g
+    with _LOCK:
+        hit = _ALIAS.get(ikey)
+        if hit is not None and hit[0] in _CACHE:
+            _ALIAS.move_to_end(ikey)
+            _CACHE.move_to_end(hit[0])
+            cache_stats["identity_hits"] += 1
+            return _CACHE[hit[0]]
+        _require_cuda(edge_index, "edge_index")
+        ckey = (_content_key(edge_index), _content_key(edge_type), int(num_nodes), int(num_relations))
+        g = _CACHE.get(ckey)
+        if g is None:
+            g = RelGraph.build(edge_index, edge_type, num_nodes, num_relations)
+            _CACHE[ckey] = g
+            cache_stats["builds"] += 1
+            while len(_CACHE) > _CACHE_SIZE:
+                _CACHE.popitem(last=False)
+        else:
+            _CACHE.move_to_end(ckey)
+            cache_stats["content_hits"] += 1
+        _alias_put(ikey, ckey, (edge_index, edge_type))           # keep the key tensors alive with the alias
+        return g
 
 
 def clear_graph_cache():
-    _CACHE.clear()
-    _ALIAS.clear()
+    with _LOCK:
+        _CACHE.clear()
+        _ALIAS.clear()
