@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .graph import CSR, _ptr, _require_cuda, _stream, _tensor_key, build_csr, transpose_csr
+from .graph import _LOCK, CSR, _ptr, _require_cuda, _stream, _tensor_key, build_csr, transpose_csr
 from .nn import glorot_
 from .ops import _dtype_code, _ld, _rowmajor, spmm
 
@@ -64,15 +64,16 @@ _LOOP_CACHE: "OrderedDict[tuple, tuple]" = OrderedDict()
 
 def get_loop_graph(edge_index: torch.Tensor, num_nodes: int) -> LoopGraph:
     key = (_tensor_key(edge_index), int(num_nodes))
-    hit = _LOOP_CACHE.get(key)
-    if hit is not None:
-        _LOOP_CACHE.move_to_end(key)
-        return hit[0]
-    g = LoopGraph.build(edge_index, num_nodes)
-    _LOOP_CACHE[key] = (g, edge_index)
-    while len(_LOOP_CACHE) > 4:
-        _LOOP_CACHE.popitem(last=False)
-    return g
+    with _LOCK:
+        hit = _LOOP_CACHE.get(key)
+        if hit is not None:
+            _LOOP_CACHE.move_to_end(key)
+            return hit[0]
+        g = LoopGraph.build(edge_index, num_nodes)
+        _LOOP_CACHE[key] = (g, edge_index)
+        while len(_LOOP_CACHE) > 4:
+            _LOOP_CACHE.popitem(last=False)
+        return g
 
 
 def _with_w(csr: CSR, w: torch.Tensor) -> CSR:

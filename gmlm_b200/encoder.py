@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint
 
-from .graph import _tensor_key, get_rel_graph
+from .graph import _LOCK, _tensor_key, get_rel_graph
 from .nn import GraphNorm, RGCNConv
 from .ops import edge_type_from_degree, layer_norm, layer_norm_ok, linear_nt, soft_masking_gnn_input
 
@@ -82,15 +82,16 @@ def cached_edge_type(edge_index: torch.Tensor, num_nodes: int) -> torch.Tensor:
     identity of ``edge_index`` (the reference passes the same ``data.edge_index`` every call); the SAME tensor is
     returned on a hit, so the graph cache behind it hits on identity as well."""
     key = (_tensor_key(edge_index), int(num_nodes))
-    hit = _ET_CACHE.get(key)
-    if hit is not None:
-        _ET_CACHE.move_to_end(key)
-        return hit[0]
-    et = edge_type_from_degree(edge_index, num_nodes)
-    _ET_CACHE[key] = (et, edge_index)          # keep the key tensor alive (see graph.py cache note)
-    while len(_ET_CACHE) > 4:
-        _ET_CACHE.popitem(last=False)
-    return et
+    with _LOCK:                                    # autograd threads recompute checkpointed layers
+        hit = _ET_CACHE.get(key)
+        if hit is not None:
+            _ET_CACHE.move_to_end(key)
+            return hit[0]
+        et = edge_type_from_degree(edge_index, num_nodes)
+        _ET_CACHE[key] = (et, edge_index)          # keep the key tensor alive (see graph.py cache note)
+        while len(_ET_CACHE) > 4:
+            _ET_CACHE.popitem(last=False)
+        return et
 
 
 class GraphEncoder(nn.Module):
