@@ -1,5 +1,7 @@
 #!/usr/bin/env bash
-# compute-sanitizer passes over the kernel tests (run on a GPU box; slow: use the small-shape tests only):
+# compute-sanitizer passes over the kernel tests (run on a GPU box; slow: use the small-shape tests only).
+# NOTE: this pool's gpurun refuses compute-sanitizer ("closed on this pool", rc 86, gpurun_out/r2g_memcheck_dense.log),
+# so there is no sanitizer log under profiles/; bounds are covered by the out-of-range / ragged / empty-input tests.
 #   gpurun --timeout 900 -- 'bash tools/sanitize.sh'
 # Writes gpurun_out/sanitize_{memcheck,racecheck,initcheck}.log; exit code != 0 if any tool reports an error.
 set -u
