@@ -40,6 +40,16 @@ golden vectors under tests/golden/ generated *from this oracle* by
 ``tests/golden/make_golden.py`` (they pin the oracle against regressions, not
 against PyG).
 
+One pin comes from outside this code: ``tests/test_known_answers.py`` holds known
+answers worked out by hand from the published operator definitions (two- and
+three-node graphs: ``degree`` -- upstream's own unit-test vector --, ``RGCNConv``
+forward and backward with bases / duplicate edge / self-loop / empty relations,
+``GraphNorm`` with a non-unit ``mean_scale`` and its backward against finite
+differences of the scalar definition, ``GCNConv``, ``GATConv``).  The oracle meets
+them to 1e-12 and the CUDA modules are checked against the same numbers directly.
+That is evidence that the restatement follows the published formulas; it is still
+not an output of torch_geometric itself, so the header above stands.
+
 Who may import this package: ``tests/``, ``__graft_entry__.smoke()`` and
 ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs — as the checker or the
 timed CPU baseline, never as the product.
